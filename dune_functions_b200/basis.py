@@ -1,0 +1,421 @@
+"""Host-side mirror of the reference's interface for the element-loop path.
+
+Names follow dune-functions (BasisFactory: makeBasis / lagrange / lagrangeDG /
+power / composite / taylorHood and the four index-merging tags; interpolate;
+makeDiscreteGlobalBasisFunction; subspaceBasis), cf.
+  dune/functions/functionspacebases/defaultglobalbasis.hh:205-209
+  dune/functions/functionspacebases/basistags.hh:192-225
+  dune/functions/functionspacebases/interpolate.hh:204-302
+  dune/functions/gridfunctions/discreteglobalbasisfunction.hh:457-478
+  dune/python/functions/globalbasis.hh:141-252 (the Python front door)
+Everything computes through the C ABI (include/dfx.h) on device memory held in
+torch tensors; torch is used for allocation, streams and torch.distributed only.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+
+
+# ---- index merging strategy tags (basistags.hh:192-225) ----------------------
+def flatLexicographic():
+    return capi.IMS_FLAT_LEXICOGRAPHIC
+
+
+def flatInterleaved():
+    return capi.IMS_FLAT_INTERLEAVED
+
+
+def blockedLexicographic():
+    return capi.IMS_BLOCKED_LEXICOGRAPHIC
+
+
+def blockedInterleaved():
+    return capi.IMS_BLOCKED_INTERLEAVED
+
+
+# ---- pre-basis factories -----------------------------------------------------
+@dataclass
+class PreBasisFactory:
+    kind: int
+    order: int = 0
+    ims: int = capi.IMS_NONE
+    children: List["PreBasisFactory"] = field(default_factory=list)
+    exponent: int = 0
+
+    def nodes(self):
+        """preorder dfx_tree_node list"""
+        if self.kind == capi.NODE_POWER:
+            return [(self.kind, 0, self.exponent, self.ims)] + self.children[0].nodes()
+        if self.kind == capi.NODE_COMPOSITE:
+            out = [(self.kind, 0, len(self.children), self.ims)]
+            for c in self.children:
+                out += c.nodes()
+            return out
+        return [(self.kind, self.order, 0, capi.IMS_NONE)]
+
+
+def lagrange(k):
+    """lagrange<k>() / lagrange(k): lagrangebasis.hh:1006-1027"""
+    return PreBasisFactory(capi.NODE_LAGRANGE, order=int(k))
+
+
+def lagrangeDG(k):
+    """lagrangeDG<k>() / lagrangeDG(k): lagrangedgbasis.hh:150-170"""
+    return PreBasisFactory(capi.NODE_LAGRANGE_DG, order=int(k))
+
+
+def power(child, exponent, ims=None):
+    """power<k>(child, ims): powerbasis.hh:140-171.  The reference deprecates the
+    implicit default; it is BlockedInterleaved (powerbasis.hh:160-171)."""
+    if ims is None:
+        ims = capi.IMS_BLOCKED_INTERLEAVED
+    return PreBasisFactory(capi.NODE_POWER, ims=ims, children=[child], exponent=int(exponent))
+
+
+def composite(*args):
+    """composite(children..., ims): compositebasis.hh:420-445 (default BlockedLexicographic)."""
+    args = list(args)
+    ims = capi.IMS_BLOCKED_LEXICOGRAPHIC
+    if args and isinstance(args[-1], int):
+        ims = args.pop()
+    return PreBasisFactory(capi.NODE_COMPOSITE, ims=ims, children=args)
+
+
+def taylorHood():
+    """taylorHood(): taylorhoodbasis.hh:330-335"""
+    return PreBasisFactory(capi.NODE_TAYLOR_HOOD)
+
+
+# ---- grid --------------------------------------------------------------------
+@dataclass
+class YaspGrid:
+    """Unrefined equidistant structured grid (Dune::YaspGrid<dim>(L, N) stand-in).
+
+    `local_begin/local_n` select the box of elements owned by this rank; see
+    dfx_grid_desc in include/dfx.h."""
+    n: Sequence[int]
+    upper: Optional[Sequence[float]] = None
+    lower: Optional[Sequence[float]] = None
+    local_begin: Optional[Sequence[int]] = None
+    local_n: Optional[Sequence[int]] = None
+
+    @property
+    def dim(self):
+        return len(self.n)
+
+    def desc(self):
+        d = self.dim
+        g = capi.GridDesc()
+        g.dim = d
+        lo = list(self.lower) if self.lower is not None else [0.0] * d
+        up = list(self.upper) if self.upper is not None else [1.0] * d
+        lb = list(self.local_begin) if self.local_begin is not None else [0] * d
+        ln = list(self.local_n) if self.local_n is not None else list(self.n)
+        for j in range(3):
+            g.n_global[j] = self.n[j] if j < d else 1
+            g.local_begin[j] = lb[j] if j < d else 0
+            g.local_n[j] = ln[j] if j < d else 1
+            g.lower[j] = lo[j] if j < d else 0.0
+            g.upper[j] = up[j] if j < d else 1.0
+        return g
+
+    def slab(self, rank, world):
+        """z-slab (last direction) of this grid for `rank` of `world`."""
+        d = self.dim
+        nz = self.n[d - 1]
+        b = (nz * rank) // world
+        e = (nz * (rank + 1)) // world
+        lb = [0] * d
+        ln = list(self.n)
+        lb[d - 1] = b
+        ln[d - 1] = e - b
+        return YaspGrid(self.n, self.upper, self.lower, lb, ln)
+
+
+def tree_array(factory):
+    nodes = factory.nodes()
+    arr = (capi.TreeNode * len(nodes))()
+    for i, (k, o, c, m) in enumerate(nodes):
+        arr[i].kind, arr[i].order, arr[i].n_children, arr[i].ims = k, o, c, m
+    return arr, len(nodes)
+
+
+# ---- functions ---------------------------------------------------------------
+def make_function(fn_id, n_comp=1, params=()):
+    f = capi.Function()
+    f.id = fn_id
+    f.n_comp = n_comp
+    for i, p in enumerate(params):
+        f.p[i] = float(p)
+    return f
+
+
+def gaussian(a=1.0):
+    """x -> exp(-a |x|^2)   (examples/interpolation.cc:49-52)"""
+    return make_function(capi.FN_GAUSSIAN, 1, [a])
+
+
+def identity(n_comp):
+    """x -> x   (examples/interpolation.cc:93-95)"""
+    return make_function(capi.FN_IDENTITY, n_comp)
+
+
+def constant(*values):
+    return make_function(capi.FN_CONSTANT, len(values), values)
+
+
+def coord(j):
+    return make_function(capi.FN_COORD, 1, [j])
+
+
+def quadratic(c0, lin, quad):
+    """c0 + lin.x + sum_{i<=j} quad[(i,j)] x_i x_j, quad order (00,01,02,11,12,22)"""
+    return make_function(capi.FN_QUADRATIC, 1, [c0] + list(lin) + list(quad))
+
+
+def sinprod(w):
+    return make_function(capi.FN_SINPROD, 1, [w])
+
+
+def gaussian_vec(n_comp, a=1.0):
+    return make_function(capi.FN_GAUSSIAN_VEC, n_comp, [a])
+
+
+# ---- basis -------------------------------------------------------------------
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class GlobalBasis:
+    """DefaultGlobalBasis (defaultglobalbasis.hh:51-191) over the C ABI."""
+
+    def __init__(self, grid: YaspGrid, factory: PreBasisFactory, device: int = 0):
+        self.grid = grid
+        self.factory = factory
+        self.device = device
+        self._lib = capi.lib()
+        self._desc = grid.desc()
+        arr, n = tree_array(factory)
+        h = C.c_void_p()
+        capi.check(self._lib.dfx_basis_create(C.byref(self._desc), arr, n, device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.dfx_basis_destroy(h)
+            self._h = None
+
+    # GlobalBasis concept
+    def dimension(self):
+        return int(self._lib.dfx_basis_dimension(self._h))
+
+    def size(self, prefix=()):
+        p = (C.c_uint64 * max(1, len(prefix)))(*prefix)
+        return int(self._lib.dfx_basis_size(self._h, p, len(prefix)))
+
+    def maxNodeSize(self):
+        return int(self._lib.dfx_basis_max_node_size(self._h))
+
+    def maxMultiIndexSize(self):
+        return int(self._lib.dfx_basis_max_multi_index_size(self._h))
+
+    def minMultiIndexSize(self):
+        return int(self._lib.dfx_basis_min_multi_index_size(self._h))
+
+    def numElements(self):
+        return int(self._lib.dfx_basis_num_elements(self._h))
+
+    def numLeaves(self):
+        return int(self._lib.dfx_basis_num_leaves(self._h))
+
+    def numTreeNodes(self):
+        return int(self._lib.dfx_basis_num_tree_nodes(self._h))
+
+    def nodeInfo(self, node):
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        capi.check(self._lib.dfx_basis_node_info(self._h, node, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(local_offset=a.value, size=b.value, first_leaf=c.value, n_leaves=d.value)
+
+    def child(self, node, *path):
+        """tree node id reached from `node` along a child path (TypeTree::child)"""
+        for c in path:
+            node = int(self._lib.dfx_basis_node_child(self._h, node, c))
+            if node < 0:
+                raise capi.RangeError("no such child")
+        return node
+
+    def localIndexSizes(self):
+        out = (C.c_uint8 * self.maxNodeSize())()
+        capi.check(self._lib.dfx_basis_local_index_sizes(self._h, out))
+        return np.frombuffer(out, dtype=np.uint8).copy()
+
+    # batched LocalView::bind + index
+    def indices(self, elem_begin=0, elem_end=None, dtype=None):
+        """multi-indices of all local DOFs: tensor [ne, n_loc, maxMultiIndexSize]"""
+        import torch
+        ne_all = self.numElements()
+        elem_end = ne_all if elem_end is None else elem_end
+        ne = elem_end - elem_begin
+        stride = self.maxMultiIndexSize()
+        dtype = dtype or torch.int32
+        out = torch.empty((ne, self.maxNodeSize(), stride), dtype=dtype, device=f"cuda:{self.device}")
+        fn = self._lib.dfx_indices_multi if dtype == torch.int32 else self._lib.dfx_indices_multi_u64
+        capi.check(fn(self._h, elem_begin, elem_end, _ptr(out), stride, _stream()))
+        return out
+
+    def flatIndices(self, elem_begin=0, elem_end=None, dtype=None):
+        """flat container positions of all local DOFs: tensor [ne, n_loc]"""
+        import torch
+        ne_all = self.numElements()
+        elem_end = ne_all if elem_end is None else elem_end
+        ne = elem_end - elem_begin
+        dtype = dtype or torch.int32
+        out = torch.empty((ne, self.maxNodeSize()), dtype=dtype, device=f"cuda:{self.device}")
+        fn = self._lib.dfx_indices_flat if dtype == torch.int32 else self._lib.dfx_indices_flat_u64
+        capi.check(fn(self._h, elem_begin, elem_end, _ptr(out), _stream()))
+        return out
+
+    def newVector(self, fill=None):
+        import torch
+        v = torch.empty(self.dimension(), dtype=torch.float64, device=f"cuda:{self.device}")
+        if fill is not None:
+            v.fill_(fill)
+        return v
+
+
+def makeBasis(grid, factory, device=0):
+    """BasisFactory::makeBasis, defaultglobalbasis.hh:205-209"""
+    return GlobalBasis(grid, factory, device)
+
+
+class SubspaceBasis:
+    """subspaceBasis(rootBasis, path...), subspacebasis.hh:27-157: same root indices,
+    tree = child at the prefix path; dimension()/size() are the root's."""
+
+    def __init__(self, root: GlobalBasis, *path):
+        self.root = root
+        self.path = path
+        self.node = root.child(0, *path)
+
+    def dimension(self):
+        return self.root.dimension()
+
+
+def subspaceBasis(root, *path):
+    return SubspaceBasis(root, *path)
+
+
+def _root_and_node(basis):
+    if isinstance(basis, SubspaceBasis):
+        return basis.root, basis.node
+    return basis, 0
+
+
+def interpolate(basis, coeff, f, mask=None):
+    """interpolate(basis, coeff, f[, bitVector]) — interpolate.hh:204-302.
+
+    coeff: float64 CUDA tensor of basis.dimension() entries (flat container order),
+    f: a dfx_function from the registry (gaussian(), identity(n), ...),
+    mask: optional uint8/bool CUDA tensor in the same order."""
+    root, node = _root_and_node(basis)
+    if coeff.numel() != root.dimension():
+        raise capi.RangeError("coefficient vector size does not match basis.dimension()")
+    m = None
+    if mask is not None:
+        import torch
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    capi.check(root._lib.dfx_interpolate(root._h, node, C.byref(f), _ptr(coeff), _ptr(m), _stream()))
+    return coeff
+
+
+def interpolationPoints(basis):
+    """positions of all interpolation nodes and the leaf of every coefficient (form 2 of f)"""
+    import torch
+    n = basis.dimension()
+    xyz = torch.empty((n, basis.grid.dim), dtype=torch.float64, device=f"cuda:{basis.device}")
+    leaf = torch.empty(n, dtype=torch.int32, device=f"cuda:{basis.device}")
+    capi.check(basis._lib.dfx_interpolation_points(basis._h, _ptr(xyz), _ptr(leaf), _stream()))
+    return xyz, leaf
+
+
+def interpolateFromValues(basis, coeff, values, mask=None):
+    root, node = _root_and_node(basis)
+    capi.check(root._lib.dfx_interpolate_from_values(root._h, node, _ptr(values), _ptr(coeff), _ptr(mask), _stream()))
+    return coeff
+
+
+class DiscreteGlobalBasisFunction:
+    """makeDiscreteGlobalBasisFunction<R>(basis, coeff) — discreteglobalbasisfunction.hh:281-478.
+
+    evaluate(xhat) is localFunction(f) bound to every element in turn and evaluated
+    at the reference-element points xhat [n_q, dim]:
+       values    [ne, n_q, n_comp]
+       jacobians [ne, n_q, n_comp, dim]   (derivative(localFunction), :495-677)"""
+
+    def __init__(self, basis, coeff):
+        self.basis = basis
+        self.root, self.node = _root_and_node(basis)
+        if coeff.numel() != self.root.dimension():
+            raise capi.RangeError("coefficient vector size does not match basis.dimension()")
+        self.coeff = coeff
+
+    def nComp(self):
+        return self.root.nodeInfo(self.node)["n_leaves"]
+
+    def evaluate(self, xhat, values=True, jacobians=False, elem_begin=0, elem_end=None, out_values=None,
+                 out_jacobians=None):
+        import torch
+        root = self.root
+        xh = np.ascontiguousarray(np.asarray(xhat, dtype=np.float64).reshape(-1, root.grid.dim))
+        nq = xh.shape[0]
+        ne_all = root.numElements()
+        elem_end = ne_all if elem_end is None else elem_end
+        ne = elem_end - elem_begin
+        nc = self.nComp()
+        dev = f"cuda:{root.device}"
+        v = j = None
+        if values:
+            v = out_values if out_values is not None else torch.empty((ne, nq, nc), dtype=torch.float64, device=dev)
+        if jacobians:
+            j = out_jacobians if out_jacobians is not None else torch.empty((ne, nq, nc, root.grid.dim),
+                                                                           dtype=torch.float64, device=dev)
+        capi.check(root._lib.dfx_evaluate(root._h, self.node, _ptr(self.coeff),
+                                          xh.ctypes.data_as(C.POINTER(C.c_double)), nq,
+                                          elem_begin, elem_end, _ptr(v), _ptr(j), _stream()))
+        if values and jacobians:
+            return v, j
+        return v if values else j
+
+
+def makeDiscreteGlobalBasisFunction(basis, coeff):
+    return DiscreteGlobalBasisFunction(basis, coeff)
+
+
+# ---- quadrature helpers (tensor Gauss-Legendre on [0,1]^d) --------------------
+def gauss_points_1d(m):
+    x, w = np.polynomial.legendre.leggauss(m)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def tensor_gauss(dim, m, last_fastest=True):
+    """Tensor Gauss rule with m points per direction.  dune-geometry's tensor-product
+    rule runs the LAST coordinate fastest."""
+    x1, w1 = gauss_points_1d(m)
+    pts, wts = [], []
+    idx = np.indices((m,) * dim).reshape(dim, -1).T
+    for mi in idx:
+        # np.indices varies the last axis fastest
+        mi = mi if last_fastest else mi[::-1]
+        pts.append([x1[i] for i in mi])
+        wts.append(np.prod([w1[i] for i in mi]))
+    return np.array(pts), np.array(wts)

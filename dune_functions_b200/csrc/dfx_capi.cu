@@ -1,0 +1,458 @@
+// dfx_capi.cu — the extern "C" boundary declared in include/dfx.h.
+#include <cstring>
+
+#include "dfx_eval_fast.h"
+#include "dfx_launch.h"
+
+using namespace dfx;
+
+namespace {
+
+int g_forcedPath = -1;
+
+int ensureDevice(const dfx_basis* b) {
+  if (!b) return fail(DFX_ERR_INVALID, "null basis handle");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(DFX_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (b->device < 0 || b->device >= n) return fail(DFX_ERR_CUDA, "device ordinal out of range");
+  DFX_CUDA(cudaSetDevice(b->device));
+  return DFX_OK;
+}
+
+int subtree(const dfx_basis* b, int node, int& firstLeaf, int& nLeaves) {
+  if (node < 0 || node >= (int)b->nodes.size()) return fail(DFX_ERR_INVALID, "tree node id out of range");
+  firstLeaf = b->nodes[node].firstLeaf;
+  nLeaves = b->nodes[node].nLeaves;
+  return DFX_OK;
+}
+
+int growScratch(dfx_basis* b, int slot, size_t bytes) {
+  if (b->dScratchBytes[slot] >= bytes) return DFX_OK;
+  if (b->dScratch[slot]) cudaFree(b->dScratch[slot]);
+  b->dScratch[slot] = nullptr; b->dScratchBytes[slot] = 0;
+  DFX_CUDA(cudaMalloc(&b->dScratch[slot], bytes));
+  b->dScratchBytes[slot] = bytes;
+  return DFX_OK;
+}
+
+int privateStream(dfx_basis* b, cudaStream_t& st) {
+  if (!b->stream) {
+    cudaStream_t s;
+    DFX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    b->stream = (void*)s;
+  }
+  st = (cudaStream_t)b->stream;
+  return DFX_OK;
+}
+
+// Host shape tables for the points: per layout used below the subtree,
+//   shape[q][i]          = prod_j l_{alpha_j}(x_j)          (evaluateFunction)
+//   dshape[q][i][d]      = prod_j (j==d ? l' : l)(x_j)       (evaluateJacobian)
+// with the k = 0 / k = 1 special cases of LagrangeCubeLocalBasis.
+int prepareShape(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, ShapeOffsets& so,
+                 const double*& dShape, const double*& dDShape, cudaStream_t st) {
+  const DevBasis& D = b->dev;
+  const int dim = D.grid.dim;
+  bool used[kMaxLayouts] = {false, false, false, false};
+  for (int l = 0; l < nLeaves; ++l) used[D.leaves[firstLeaf + l].layout] = true;
+  size_t tot = 0;
+  for (int q = 0; q < D.nLayouts; ++q) {
+    so.v[q] = so.d[q] = 0;
+    if (!used[q]) continue;
+    so.v[q] = (unsigned)tot; tot += (size_t)nq * D.layouts[q].nloc;
+  }
+  const size_t valTot = tot;
+  for (int q = 0; q < D.nLayouts; ++q) {
+    if (!used[q]) continue;
+    so.d[q] = (unsigned)(tot - valTot); tot += (size_t)nq * D.layouts[q].nloc * dim;
+  }
+  const bool cached = b->lastShapeNode == node && (int)b->lastXhat.size() == nq * dim &&
+                      std::memcmp(b->lastXhat.data(), xhat, sizeof(double) * nq * dim) == 0 && b->dShape;
+  if (!cached) {
+    std::vector<double> h(tot);
+    for (int q = 0; q < D.nLayouts; ++q) {
+      if (!used[q]) continue;
+      const DevLayout& L = D.layouts[q];
+      const int k = L.k;
+      for (int p = 0; p < nq; ++p) {
+        const double* x = xhat + (size_t)p * dim;
+        for (int i = 0; i < L.nloc; ++i) {
+          int a[3] = {0, 0, 0};
+          { int ii = i; for (int j = 0; j < dim; ++j) { a[j] = ii % (k + 1); ii /= (k + 1); } }
+          double* v = &h[so.v[q] + (size_t)p * L.nloc + i];
+          double* dv = &h[valTot + so.d[q] + ((size_t)p * L.nloc + i) * dim];
+          if (k == 0) { *v = 1; for (int d = 0; d < dim; ++d) dv[d] = 0; continue; }
+          if (k == 1) {
+            *v = 1;
+            for (int j = 0; j < dim; ++j) *v *= (i & (1 << j)) ? x[j] : 1 - x[j];
+            for (int d = 0; d < dim; ++d) {
+              dv[d] = (i & (1 << d)) ? 1 : -1;
+              for (int j = 0; j < dim; ++j) if (j != d) dv[d] *= (i & (1 << j)) ? x[j] : 1 - x[j];
+            }
+            continue;
+          }
+          *v = 1.0;
+          for (int j = 0; j < dim; ++j) *v *= lagrangeP(k, a[j], x[j]);
+          for (int d = 0; d < dim; ++d) {
+            dv[d] = 1.0;
+            for (int j = 0; j < dim; ++j) dv[d] *= (j == d) ? lagrangeDP(k, a[j], x[j]) : lagrangeP(k, a[j], x[j]);
+          }
+        }
+      }
+    }
+    if (b->dShapeBytes < tot * sizeof(double)) {
+      if (b->dShape) cudaFree(b->dShape);
+      b->dShape = nullptr; b->dShapeBytes = 0;
+      DFX_CUDA(cudaMalloc(&b->dShape, tot * sizeof(double)));
+      b->dShapeBytes = tot * sizeof(double);
+    }
+    DFX_CUDA(cudaMemcpyAsync(b->dShape, h.data(), tot * sizeof(double), cudaMemcpyHostToDevice, st));
+    DFX_CUDA(cudaStreamSynchronize(st));     // h goes out of scope; tables are tiny
+    b->lastXhat.assign(xhat, xhat + (size_t)nq * dim);
+    b->lastShapeNode = node;
+  }
+  dShape = (const double*)b->dShape;
+  dDShape = (const double*)b->dShape + valTot;
+  return DFX_OK;
+}
+
+u64 haloCount(const dfx_basis* b) {
+  const DevBasis& D = b->dev;
+  const int dz = D.grid.dim - 1;
+  u64 n = 0;
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const DevLayout& L = D.layouts[D.leaves[l].layout];
+    if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) continue;
+    for (int q = 0; q < L.ncomp; ++q) {
+      const int s = L.order[q];
+      if ((s >> dz) & 1) continue;
+      n += L.compCount[s] / (u64)L.csize[s][dz];
+    }
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfx_abi_version(void) { return DFX_ABI_VERSION; }
+const char* dfx_last_error(void) { return lastErrorCStr(); }
+uint64_t dfx_kernel_launch_count(void) { return g_launchCount.load(); }
+
+int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_host, int32_t n_nodes, int32_t device,
+                     dfx_basis** out) {
+  dfx_basis_impl* impl = nullptr;
+  int rc = buildBasis(grid_host, tree_host, n_nodes, device, &impl);
+  if (rc) return rc;
+  *out = static_cast<dfx_basis*>(impl);
+  return DFX_OK;
+}
+
+void dfx_basis_destroy(dfx_basis* b) {
+  if (!b) return;
+  if (b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
+    cudaSetDevice(b->device);
+    if (b->dShape) cudaFree(b->dShape);
+    if (b->pinned) cudaFreeHost(b->pinned);
+    for (int i = 0; i < 3; ++i) if (b->dScratch[i]) cudaFree(b->dScratch[i]);
+    if (b->stream) cudaStreamDestroy((cudaStream_t)b->stream);
+  }
+  delete b;
+}
+
+uint64_t dfx_basis_dimension(const dfx_basis* b) { return b ? b->dimension : 0; }
+uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t len) {
+  if (!b || len < 0 || (len > 0 && !prefix_host)) return 0;
+  return preSize(b, (const u64*)prefix_host, len);
+}
+int32_t dfx_basis_max_node_size(const dfx_basis* b) { return b ? b->dev.nlocTotal : 0; }
+int32_t dfx_basis_max_multi_index_size(const dfx_basis* b) { return b ? b->maxDigits : 0; }
+int32_t dfx_basis_min_multi_index_size(const dfx_basis* b) { return b ? b->minDigits : 0; }
+uint64_t dfx_basis_num_elements(const dfx_basis* b) {
+  return b ? (u64)b->dev.grid.N[0] * b->dev.grid.N[1] * b->dev.grid.N[2] : 0;
+}
+int32_t dfx_basis_num_leaves(const dfx_basis* b) { return b ? b->dev.nLeaves : 0; }
+int32_t dfx_basis_num_tree_nodes(const dfx_basis* b) { return b ? (int32_t)b->nodes.size() : 0; }
+
+int dfx_basis_node_info(const dfx_basis* b, int32_t node, int32_t* local_offset, int32_t* size, int32_t* first_leaf,
+                        int32_t* n_leaves) {
+  if (!b || node < 0 || node >= (int)b->nodes.size()) return fail(DFX_ERR_INVALID, "tree node id out of range");
+  const HostNode& n = b->nodes[node];
+  if (local_offset) *local_offset = n.localOffset;
+  if (size) *size = n.size;
+  if (first_leaf) *first_leaf = n.firstLeaf;
+  if (n_leaves) *n_leaves = n.nLeaves;
+  return DFX_OK;
+}
+
+int32_t dfx_basis_node_child(const dfx_basis* b, int32_t node, int32_t child) {
+  if (!b || node < 0 || node >= (int)b->nodes.size()) return -1;
+  const HostNode& n = b->nodes[node];
+  if (child < 0 || child >= (int)n.children.size()) return -1;
+  return n.children[child];
+}
+
+int dfx_basis_local_index_sizes(const dfx_basis* b, uint8_t* sizes_host) {
+  if (!b || !sizes_host) return fail(DFX_ERR_INVALID, "null argument");
+  for (int l = 0; l < b->dev.nLeaves; ++l)
+    for (int i = 0; i < b->dev.leaves[l].nloc; ++i)
+      sizes_host[b->dev.leaves[l].localOffset + i] = (uint8_t)b->dev.leaves[l].ndig;
+  return DFX_OK;
+}
+
+// ---- indices ------------------------------------------------------------------
+static int checkRange(const dfx_basis* b, uint64_t e0, uint64_t e1) {
+  if (e0 > e1 || e1 > dfx_basis_num_elements(b)) return fail(DFX_ERR_RANGE, "element range outside the local box");
+  return DFX_OK;
+}
+
+int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, int32_t stride, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
+  if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_multi_u64");
+  return indicesMulti32(b, e0, e1, out, stride, (cudaStream_t)stream);
+}
+int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, int32_t stride, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
+  return indicesMulti64(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
+}
+int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_flat_u64");
+  return indicesFlat32(b, e0, e1, out, (cudaStream_t)stream);
+}
+int dfx_indices_flat_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  return indicesFlat64(b, e0, e1, (u64*)out, (cudaStream_t)stream);
+}
+
+// ---- interpolate -----------------------------------------------------------------
+static int checkFunction(const dfx_function* f, int nLeaves) {
+  if (!f) return fail(DFX_ERR_INVALID, "null function");
+  if (f->id < DFX_FN_CONSTANT || f->id > DFX_FN_GAUSSIAN_VEC) return fail(DFX_ERR_INVALID, "unknown function id");
+  if (f->n_comp < 1 || f->n_comp > DFX_MAX_LEAVES) return fail(DFX_ERR_INVALID, "bad number of range entries");
+  // HierarchicNodeToRangeMap: a scalar is used for every leaf, otherwise leaf l takes entry l
+  if (f->n_comp != 1 && f->n_comp != nLeaves)
+    return fail(DFX_ERR_RANGE, "range of f does not match the leaves of the (sub)tree");
+  return DFX_OK;
+}
+
+int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
+                    void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if ((rc = checkFunction(f, nl))) return rc;
+  if (!coeff) return fail(DFX_ERR_INVALID, "null coefficient vector");
+  return interpolateRegistry(b, fl, nl, *f, coeff, mask, (cudaStream_t)stream);
+}
+
+int dfx_interpolation_points(const dfx_basis* b, double* out_xyz, int32_t* out_leaf, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!out_xyz || !out_leaf) return fail(DFX_ERR_INVALID, "null output");
+  return interpolationPoints(b, out_xyz, out_leaf, (cudaStream_t)stream);
+}
+
+int dfx_interpolate_from_values(const dfx_basis* b, int32_t node, const double* values, double* coeff,
+                                const uint8_t* mask, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if (!values || !coeff) return fail(DFX_ERR_INVALID, "null argument");
+  return interpolateFromValues(b, fl, nl, values, coeff, mask, (cudaStream_t)stream);
+}
+
+// ---- evaluate ---------------------------------------------------------------------
+void dfx_set_eval_path(int32_t path) { g_forcedPath = path; }
+
+int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host, int32_t n_q, int32_t want_jac) {
+  if (!b || !xhat_host || n_q < 1) return -1;
+  int fl, nl;
+  if (subtree(b, node, fl, nl)) return -1;
+  FastPlan plan;
+  return planFastEval(b, fl, nl, xhat_host, n_q, want_jac != 0, g_forcedPath, plan);
+}
+
+int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const double* xhat_host, int32_t n_q,
+                 uint64_t e0, uint64_t e1, double* out_values, double* out_jac, void* stream) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (!coeff || !xhat_host || n_q < 1) return fail(DFX_ERR_INVALID, "null argument");
+  if (!out_values && !out_jac) return DFX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FastPlan plan;
+  const int path = planFastEval(b, fl, nl, xhat_host, n_q, out_jac != nullptr, g_forcedPath, plan);
+  if (path > 0) return runFastEval(b, plan, fl, nl, coeff, e0, e1, out_values, out_jac, st);
+  if (g_forcedPath > 0) return fail(DFX_ERR_NOT_IMPLEMENTED, "forced evaluation path does not apply to this configuration");
+  ShapeOffsets so; const double *dS, *dDS;
+  if ((rc = prepareShape(b, node, fl, nl, xhat_host, n_q, so, dS, dDS, st))) return rc;
+  return evalGeneric(b, fl, nl, coeff, dS, dDS, so, n_q, e0, e1, out_values, out_jac, st);
+}
+
+// ---- host-buffer entry points -------------------------------------------------------
+int dfx_interpolate_host(const dfx_basis* cb, int32_t node, const dfx_function* f, double* coeff_host,
+                         const uint8_t* mask_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!coeff_host) return fail(DFX_ERR_INVALID, "null coefficient vector");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  if ((rc = growScratch(b, 0, n * sizeof(double)))) return rc;
+  double* dC = (double*)b->dScratch[0];
+  uint8_t* dM = nullptr;
+  // entries outside the mask / the subtree keep their value: bring them over first
+  if (mask_host || node != 0)
+    DFX_CUDA(cudaMemcpyAsync(dC, coeff_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mask_host) {
+    if ((rc = growScratch(b, 1, n))) return rc;
+    dM = (uint8_t*)b->dScratch[1];
+    DFX_CUDA(cudaMemcpyAsync(dM, mask_host, n, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = dfx_interpolate(b, node, f, dC, dM, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(coeff_host, dC, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
+int dfx_evaluate_host(const dfx_basis* cb, int32_t node, const double* coeff_host, const double* xhat_host,
+                      int32_t n_q, uint64_t e0, uint64_t e1, double* out_values_host, double* out_jac_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (!coeff_host || !xhat_host || n_q < 1) return fail(DFX_ERR_INVALID, "null argument");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  const int dim = b->dev.grid.dim;
+  if ((rc = growScratch(b, 0, n * sizeof(double)))) return rc;
+  double* dC = (double*)b->dScratch[0];
+  DFX_CUDA(cudaMemcpyAsync(dC, coeff_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  // element chunks bound the device scratch (<= 1 GiB of values per chunk)
+  const size_t perElemV = (size_t)n_q * nl * sizeof(double);
+  const size_t perElemJ = perElemV * dim;
+  u64 chunk = std::max<u64>(1, (1ull << 30) / perElemV);
+  chunk = std::min<u64>(chunk, std::max<u64>(1, e1 - e0));
+  if (out_values_host && (rc = growScratch(b, 1, chunk * perElemV))) return rc;
+  if (out_jac_host && (rc = growScratch(b, 2, chunk * perElemJ))) return rc;
+  double* dV = out_values_host ? (double*)b->dScratch[1] : nullptr;
+  double* dJ = out_jac_host ? (double*)b->dScratch[2] : nullptr;
+  for (u64 c0 = e0; c0 < e1; c0 += chunk) {
+    const u64 c1 = std::min<u64>(e1, c0 + chunk);
+    if ((rc = dfx_evaluate(b, node, dC, xhat_host, n_q, c0, c1, dV, dJ, st))) return rc;
+    if (dV) DFX_CUDA(cudaMemcpyAsync((char*)out_values_host + (c0 - e0) * perElemV, dV, (c1 - c0) * perElemV,
+                                     cudaMemcpyDeviceToHost, st));
+    if (dJ) DFX_CUDA(cudaMemcpyAsync((char*)out_jac_host + (c0 - e0) * perElemJ, dJ, (c1 - c0) * perElemJ,
+                                     cudaMemcpyDeviceToHost, st));
+  }
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
+int dfx_indices_flat_host(const dfx_basis* cb, uint64_t e0, uint64_t e1, uint32_t* out_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (!out_host) return fail(DFX_ERR_INVALID, "null output");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t bytes = (e1 - e0) * (size_t)b->dev.nlocTotal * sizeof(uint32_t);
+  if (bytes == 0) return DFX_OK;
+  if ((rc = growScratch(b, 1, bytes))) return rc;
+  if ((rc = dfx_indices_flat(b, e0, e1, (uint32_t*)b->dScratch[1], st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(out_host, b->dScratch[1], bytes, cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
+// ---- slab partition helpers ------------------------------------------------------------
+int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint64_t* out_count, int32_t max_ranges,
+                    int32_t* n) {
+  if (!b || !out_begin || !out_count || !n) return fail(DFX_ERR_INVALID, "null argument");
+  const DevBasis& D = b->dev;
+  const int dz = D.grid.dim - 1;
+  int cnt = 0;
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const DevLeaf& leaf = D.leaves[l];
+    const DevLayout& L = D.layouts[leaf.layout];
+    if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) continue;
+    if (leaf.posA != 1) return fail(DFX_ERR_NOT_IMPLEMENTED, "interleaved layout: use dfx_halo_pack/unpack");
+    for (int q = 0; q < L.ncomp; ++q) {
+      const int s = L.order[q];
+      if ((s >> dz) & 1) continue;
+      const u64 plane = L.compCount[s] / (u64)L.csize[s][dz];
+      if (cnt >= max_ranges) return fail(DFX_ERR_RANGE, "max_ranges too small");
+      out_begin[cnt] = leaf.posB + L.compOffset[s] + plane * (u64)(side ? L.csize[s][dz] - 1 : 0);
+      out_count[cnt] = plane;
+      ++cnt;
+    }
+  }
+  *n = cnt;
+  return DFX_OK;
+}
+
+uint64_t dfx_halo_size(const dfx_basis* b) { return b ? haloCount(b) : 0; }
+
+int dfx_halo_pack(const dfx_basis* b, int32_t side, const double* coeff, double* buf, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  return haloCopy(b, side, true, const_cast<double*>(coeff), buf, haloCount(b), (cudaStream_t)stream);
+}
+int dfx_halo_unpack(const dfx_basis* b, int32_t side, const double* buf, double* coeff, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  return haloCopy(b, side, false, coeff, const_cast<double*>(buf), haloCount(b), (cudaStream_t)stream);
+}
+
+int dfx_owned_ranges(const dfx_basis* b, uint64_t* local_begin, uint64_t* count, uint64_t* global_begin,
+                     int32_t max_ranges, int32_t* n) {
+  if (!b || !local_begin || !count || !global_begin || !n) return fail(DFX_ERR_INVALID, "null argument");
+  const DevBasis& D = b->dev;
+  const int dim = D.grid.dim, dz = dim - 1;
+  for (int j = 0; j < dz; ++j)
+    if (D.grid.off[j] != 0 || D.grid.N[j] != D.grid.G[j])
+      return fail(DFX_ERR_NOT_IMPLEMENTED, "owned ranges need a slab partition along the last direction");
+  // the same tree on the whole grid gives the global numbering
+  dfx_grid_desc gg = b->gridDesc;
+  for (int j = 0; j < dim; ++j) { gg.local_begin[j] = 0; gg.local_n[j] = gg.n_global[j]; }
+  dfx_basis_impl* gimpl = nullptr;
+  int rc = buildBasis(&gg, b->treeDesc.data(), (int)b->treeDesc.size(), b->device, &gimpl);
+  if (rc) return rc;
+  std::unique_ptr<dfx_basis> gb(static_cast<dfx_basis*>(gimpl));
+  const DevBasis& G = gb->dev;
+  const bool last = D.grid.off[dz] + D.grid.N[dz] == D.grid.G[dz];
+  int cnt = 0;
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const DevLeaf& leaf = D.leaves[l];
+    const DevLeaf& gleaf = G.leaves[l];
+    if (leaf.posA != 1 || gleaf.posA != 1)
+      return fail(DFX_ERR_NOT_IMPLEMENTED, "owned ranges need a non-interleaved flat layout");
+    const DevLayout& L = D.layouts[leaf.layout];
+    const DevLayout& GL = G.layouts[gleaf.layout];
+    for (int q = 0; q < L.ncomp; ++q) {
+      const int s = L.order[q];
+      const u64 plane = L.compCount[s] / (u64)L.csize[s][dz];    // same in the global layout
+      u64 layers = (u64)L.csize[s][dz];
+      if (!((s >> dz) & 1) && !last && L.kind != DFX_NODE_LAGRANGE_DG) layers -= 1;   // top plane: upper neighbour's
+      if (cnt >= max_ranges) return fail(DFX_ERR_RANGE, "max_ranges too small");
+      local_begin[cnt] = leaf.posB + L.compOffset[s];
+      count[cnt] = plane * layers;
+      global_begin[cnt] = gleaf.posB + GL.compOffset[s] + plane * (u64)D.grid.off[dz];
+      ++cnt;
+    }
+  }
+  *n = cnt;
+  return DFX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// dfx_eval_fast.h — specialised evaluation kernels (sum factorisation, TMA bulk
+// stores, FP64 tensor-core contraction) and the planner that picks one.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dfx_internal.h"
+
+namespace dfx {
+
+constexpr int kMaxQ1 = 8;     // quadrature points per direction handled by the fast paths
+constexpr int kMaxN1 = 8;     // (order+1) handled by the fast paths
+
+// A tensor-product point set: xhat[q] = (x1[0][q0], x1[1][q1], x1[2][q2]) with
+// q = q0 + m0*(q1 + m1*q2) when firstFastest, q = q2 + m2*(q1 + m1*q0) otherwise.
+struct FastPlan {
+  int path = 0;               // 0 generic, 1 register sum-factorisation, 2 shared-memory sum-factorisation, 3 DMMA
+  int dim = 0, k = 0, m = 0;  // order and points per direction (same in every direction)
+  bool firstFastest = false;
+  bool jac = false;
+  int nq = 0;
+  // 1-d tables A[q][a] = l_a(x_q), Dm[q][a] = l_a'(x_q) per direction
+  double A[3][kMaxQ1][kMaxN1];
+  double Dm[3][kMaxQ1][kMaxN1];
+  std::vector<double> xhat;   // the points (dense DMMA path builds its table from them)
+};
+
+// returns the path that will run (0 = generic) and fills `plan` when > 0
+int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
+                 FastPlan& plan);
+int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
+                double* values, double* jac, cudaStream_t st);
+
+}  // namespace dfx

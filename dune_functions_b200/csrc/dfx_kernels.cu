@@ -1,0 +1,326 @@
+// dfx_kernels.cu — generic (any dimension / order / tree) kernels of the path.
+// The specialised fast paths live in dfx_eval_fast.cu.
+//
+//   k_indices          DefaultLocalView::bind -> PreBasis::indices     (defaultlocalview.hh:95-101)
+//   k_interpolate      interpolate element loop, owner-writes          (interpolate.hh:254-259, :151-173)
+//   k_points           positions of the interpolation nodes            (form (2) of f, include/dfx.h)
+//   k_from_values      masked copy of caller-evaluated nodal values
+//   k_eval_generic     LocalFunction::bind + operator() (+derivative)  (discreteglobalbasisfunction.hh:124-148,
+//                                                                        :336-371, :583-627)
+//   k_halo_pack/unpack one lattice plane of shared DOFs <-> contiguous buffer
+#include <atomic>
+
+#include "dfx_device.cuh"
+#include "dfx_launch.h"
+
+namespace dfx {
+
+std::atomic<unsigned long long> g_launchCount{0};
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int findLeaf(const DevBasis& B, int li) {
+  int l = 0;
+  while (l + 1 < B.nLeaves && li >= B.leaves[l + 1].localOffset) ++l;
+  return l;
+}
+
+// One thread per (element, local index).  T = uint32_t / uint64_t.
+template <class T, bool MULTI>
+__global__ void __launch_bounds__(256)
+k_indices(const __grid_constant__ DevBasis B, u64 e0, u64 total, T* __restrict__ out, int stride) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const unsigned nloc = (unsigned)B.nlocTotal;
+  const u64 el = t / nloc;
+  const int li = (int)(t - el * nloc);
+  const u64 e = e0 + el;
+  int ec[3];
+  ec[0] = (int)(e % (u64)B.grid.N[0]);
+  const u64 r = e / (u64)B.grid.N[0];
+  ec[1] = (int)(r % (u64)B.grid.N[1]);
+  ec[2] = (int)(r / (u64)B.grid.N[1]);
+  const int l = findLeaf(B, li);
+  const DevLeaf& leaf = B.leaves[l];
+  const DevLayout& L = B.layouts[leaf.layout];
+  const int i = li - leaf.localOffset;
+  int a[3];
+  localAlpha(L.k, i, a);
+  const u64 j = layoutIndex(L, B.grid, ec, a, i);
+  if (MULTI) {
+    for (int p = 0; p < stride; ++p)
+      out[t * (u64)stride + p] = p < leaf.ndig ? (T)(leaf.digA[p] * j + leaf.digB[p]) : (T)0;
+  } else {
+    out[t] = (T)(leaf.posA * j + leaf.posB);
+  }
+}
+
+template <class T, bool MULTI>
+static int launchIndices(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
+  const u64 total = (e1 - e0) * (u64)b->dev.nlocTotal;
+  if (total == 0) return DFX_OK;
+  const u64 blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  k_indices<T, MULTI><<<(unsigned)blocks, 256, 0, st>>>(b->dev, e0, total, out, stride);
+  return postLaunch("k_indices");
+}
+
+int indicesMulti32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, int stride, cudaStream_t st) {
+  return launchIndices<uint32_t, true>(b, e0, e1, out, stride, st);
+}
+int indicesMulti64(const dfx_basis* b, u64 e0, u64 e1, u64* out, int stride, cudaStream_t st) {
+  return launchIndices<u64, true>(b, e0, e1, out, stride, st);
+}
+int indicesFlat32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, cudaStream_t st) {
+  return launchIndices<uint32_t, false>(b, e0, e1, out, 1, st);
+}
+int indicesFlat64(const dfx_basis* b, u64 e0, u64 e1, u64* out, cudaStream_t st) {
+  return launchIndices<u64, false>(b, e0, e1, out, 1, st);
+}
+
+// ---------------------------------------------------------------------------
+// Position of the interpolation node of scalar DOF t of layout L, as the LAST
+// element (in grid-view iteration order of the global grid) that contains the
+// node computes it: that element's write is the one that survives in the
+// reference loop (interpolate.hh:254-259 visits elements in order and :166-171
+// overwrites).  Returns false if t is out of range.
+__device__ __forceinline__ void nodePosition(const DevBasis& B, const DevLayout& L, u64 t, double x[3]) {
+  const DevGrid& g = B.grid;
+  int ie[3] = {0, 0, 0}, a[3] = {0, 0, 0};
+  const int k = L.k;
+  if (L.kind == DFX_NODE_LAGRANGE_DG) {
+    const u64 e = t / (u64)L.nloc;
+    const int i = (int)(t - e * (u64)L.nloc);
+    localAlpha(k, i, a);
+    ie[0] = (int)(e % (u64)g.N[0]) + g.off[0];
+    const u64 r = e / (u64)g.N[0];
+    ie[1] = (int)(r % (u64)g.N[1]) + g.off[1];
+    ie[2] = (int)(r / (u64)g.N[1]) + g.off[2];
+  } else {
+    // component of t
+    int s = L.order[0];
+    for (int q = 1; q < L.ncomp; ++q)
+      if (t >= L.compOffset[L.order[q]]) s = L.order[q];
+    const u64 r = t - L.compOffset[s];
+    const u64 ent = r / (u64)L.blk[s];
+    unsigned fr = (unsigned)(r - ent * (u64)L.blk[s]);
+    int c[3];
+    c[0] = (int)(ent % (u64)L.csize[s][0]);
+    const u64 r2 = ent / (u64)L.csize[s][0];
+    c[1] = (int)(r2 % (u64)L.csize[s][1]);
+    c[2] = (int)(r2 / (u64)L.csize[s][1]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= g.dim) continue;
+      if ((s >> j) & 1) {            // node strictly inside the entity along j
+        ie[j] = g.off[j] + c[j];
+        if (k > 1) { a[j] = (int)(fr % (unsigned)(k - 1)) + 1; fr /= (unsigned)(k - 1); }
+      } else {                       // node on a lattice plane: owner = upper neighbour if any
+        const int gc = g.off[j] + c[j];
+        if (gc < g.G[j]) { ie[j] = gc; a[j] = 0; } else { ie[j] = g.G[j] - 1; a[j] = k; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= g.dim) { x[j] = 0.0; continue; }
+    // Lagrange node alpha/k (the element centre for k = 0), LagrangeCubeLocalInterpolation
+    const double xhat = k == 0 ? 0.5 : __ddiv_rn(__dmul_rn(1.0, (double)a[j]), (double)k);
+    x[j] = elementGlobal(g, j, ie[j], xhat);
+  }
+}
+
+// One thread per scalar DOF of one layout; f evaluated once per node and scattered to
+// every leaf of the subtree that lives on this lattice (a power node's components).
+template <class F>
+__global__ void __launch_bounds__(256)
+k_interpolate(const __grid_constant__ DevBasis B, int layoutId, int firstLeaf, int nLeaves, const F f,
+              double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
+  const DevLayout& L = B.layouts[layoutId];
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.dimension) return;
+  double x[3], y[DFX_MAX_LEAVES];
+  nodePosition(B, L, t, x);
+  f(x, y);
+  const bool scalar = f.ncomp() == 1;
+  for (int l = 0; l < nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[firstLeaf + l];
+    if (leaf.layout != layoutId) continue;
+    const u64 p = leaf.posA * t + leaf.posB;
+    if (mask == nullptr || mask[p]) coeff[p] = scalar ? y[0] : y[l];
+  }
+}
+
+int interpolateRegistry(const dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
+                        const uint8_t* mask, cudaStream_t st) {
+  RegistryFn f; f.f = fn; f.dim = b->dev.grid.dim;
+  for (int q = 0; q < b->dev.nLayouts; ++q) {
+    bool used = false;
+    for (int l = 0; l < nLeaves; ++l) used = used || b->dev.leaves[firstLeaf + l].layout == q;
+    if (!used) continue;
+    const u64 n = b->dev.layouts[q].dimension;
+    const u64 blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
+    k_interpolate<RegistryFn><<<(unsigned)blocks, 256, 0, st>>>(b->dev, q, firstLeaf, nLeaves, f, coeff, mask);
+    int rc = postLaunch("k_interpolate");
+    if (rc) return rc;
+  }
+  return DFX_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_points(const __grid_constant__ DevBasis B, int layoutId, double* __restrict__ xyz, int* __restrict__ leafOut) {
+  const DevLayout& L = B.layouts[layoutId];
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.dimension) return;
+  double x[3];
+  nodePosition(B, L, t, x);
+  for (int l = 0; l < B.nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[l];
+    if (leaf.layout != layoutId) continue;
+    const u64 p = leaf.posA * t + leaf.posB;
+    for (int j = 0; j < B.grid.dim; ++j) xyz[p * B.grid.dim + j] = x[j];
+    leafOut[p] = l;
+  }
+}
+
+int interpolationPoints(const dfx_basis* b, double* xyz, int* leafOut, cudaStream_t st) {
+  for (int q = 0; q < b->dev.nLayouts; ++q) {
+    const u64 n = b->dev.layouts[q].dimension;
+    const u64 blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
+    k_points<<<(unsigned)blocks, 256, 0, st>>>(b->dev, q, xyz, leafOut);
+    int rc = postLaunch("k_points");
+    if (rc) return rc;
+  }
+  return DFX_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_from_values(const __grid_constant__ DevBasis B, int leafId, const double* __restrict__ values,
+              double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
+  const DevLeaf& leaf = B.leaves[leafId];
+  const u64 n = B.layouts[leaf.layout].dimension;
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const u64 p = leaf.posA * t + leaf.posB;
+  if (mask == nullptr || mask[p]) coeff[p] = values[p];
+}
+
+int interpolateFromValues(const dfx_basis* b, int firstLeaf, int nLeaves, const double* values, double* coeff,
+                          const uint8_t* mask, cudaStream_t st) {
+  for (int l = firstLeaf; l < firstLeaf + nLeaves; ++l) {
+    const u64 n = b->dev.layouts[b->dev.leaves[l].layout].dimension;
+    const u64 blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
+    k_from_values<<<(unsigned)blocks, 256, 0, st>>>(b->dev, l, values, coeff, mask);
+    int rc = postLaunch("k_from_values");
+    if (rc) return rc;
+  }
+  return DFX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Generic evaluation: one thread per (element, point); shape tables
+// shape[layout][q][i], dshape[layout][q][i][dim] precomputed on the host exactly as
+// LagrangeCubeLocalBasis::evaluateFunction / evaluateJacobian produce them.
+// Sums run over i ascending like the reference's axpy loop.
+template <bool VAL, bool JAC>
+__global__ void __launch_bounds__(128)
+k_eval_generic(const __grid_constant__ DevBasis B, int firstLeaf, int nLeaves, const double* __restrict__ coeff,
+               const double* __restrict__ shape, const double* __restrict__ dshape, ShapeOffsets so, int nq, u64 e0,
+               u64 total, double* __restrict__ values, double* __restrict__ jac) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const DevGrid& g = B.grid;
+  const u64 el = t / (u64)nq;
+  const int q = (int)(t - el * (u64)nq);
+  const u64 e = e0 + el;
+  int ec[3];
+  ec[0] = (int)(e % (u64)g.N[0]);
+  const u64 r = e / (u64)g.N[0];
+  ec[1] = (int)(r % (u64)g.N[1]);
+  ec[2] = (int)(r / (u64)g.N[1]);
+  double jinv[3] = {0, 0, 0};
+  if (JAC)
+    for (int j = 0; j < g.dim; ++j) jinv[j] = elementJacInv(g, j, g.off[j] + ec[j]);
+  for (int l = 0; l < nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[firstLeaf + l];
+    const DevLayout& L = B.layouts[leaf.layout];
+    const double* sh = shape + so.v[leaf.layout] + (size_t)q * L.nloc;
+    const double* dsh = dshape + so.d[leaf.layout] + (size_t)q * L.nloc * g.dim;
+    double v = 0, rj[3] = {0, 0, 0};
+    for (int i = 0; i < L.nloc; ++i) {
+      int a[3];
+      localAlpha(L.k, i, a);
+      const u64 j = layoutIndex(L, g, ec, a, i);
+      const double c = coeff[leaf.posA * j + leaf.posB];
+      if (VAL) v = __dadd_rn(v, __dmul_rn(c, sh[i]));
+      if (JAC)
+        for (int d = 0; d < g.dim; ++d) rj[d] = __dadd_rn(rj[d], __dmul_rn(c, dsh[i * g.dim + d]));
+    }
+    if (VAL) values[t * (u64)nLeaves + l] = v;
+    if (JAC)
+      for (int d = 0; d < g.dim; ++d) jac[(t * (u64)nLeaves + l) * g.dim + d] = __dmul_rn(rj[d], jinv[d]);
+  }
+}
+
+int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* shape,
+                const double* dshape, const ShapeOffsets& so, int nq, u64 e0, u64 e1, double* values, double* jac,
+                cudaStream_t st) {
+  const u64 total = (e1 - e0) * (u64)nq;
+  if (total == 0) return DFX_OK;
+  const u64 blocks = (total + 127) / 128;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  if (values && jac)
+    k_eval_generic<true, true><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, shape, dshape, so, nq, e0, total, values, jac);
+  else if (values)
+    k_eval_generic<true, false><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, shape, dshape, so, nq, e0, total, values, jac);
+  else
+    k_eval_generic<false, true><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, shape, dshape, so, nq, e0, total, values, jac);
+  return postLaunch("k_eval_generic");
+}
+
+// ---------------------------------------------------------------------------
+// Halo: the lowest (side 0) / highest (side 1) lattice plane in the last direction.
+// Buffer order: leaves in tree order, per leaf the index-set components that lie in
+// the plane (shift bit of the last direction clear) in layout order.
+__device__ __forceinline__ bool haloLocate(const DevBasis& B, int side, u64 t, u64& p) {
+  const int dz = B.grid.dim - 1;
+  for (int l = 0; l < B.nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[l];
+    const DevLayout& L = B.layouts[leaf.layout];
+    if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) continue;
+    for (int q = 0; q < L.ncomp; ++q) {
+      const int s = L.order[q];
+      if ((s >> dz) & 1) continue;
+      const u64 plane = L.compCount[s] / (u64)L.csize[s][dz];
+      if (t < plane) {
+        const u64 j = L.compOffset[s] + plane * (u64)(side ? L.csize[s][dz] - 1 : 0) + t;
+        p = leaf.posA * j + leaf.posB;
+        return true;
+      }
+      t -= plane;
+    }
+  }
+  return false;
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+k_halo(const __grid_constant__ DevBasis B, int side, u64 total, double* __restrict__ coeff, double* __restrict__ buf) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  u64 p;
+  if (!haloLocate(B, side, t, p)) return;
+  if (PACK) buf[t] = coeff[p]; else coeff[p] = buf[t];
+}
+
+int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st) {
+  if (total == 0) return DFX_OK;
+  const u64 blocks = (total + 255) / 256;
+  if (pack) k_halo<true><<<(unsigned)blocks, 256, 0, st>>>(b->dev, side, total, coeff, buf);
+  else k_halo<false><<<(unsigned)blocks, 256, 0, st>>>(b->dev, side, total, coeff, buf);
+  return postLaunch("k_halo");
+}
+
+}  // namespace dfx

@@ -1,0 +1,49 @@
+// dfx_launch.h — host-side launcher prototypes (kernels are defined in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "dfx_internal.h"
+
+namespace dfx {
+
+extern std::atomic<unsigned long long> g_launchCount;
+const char* lastErrorCStr();
+
+// offsets (in doubles) of each layout's shape / shape-jacobian table
+struct ShapeOffsets { unsigned v[kMaxLayouts]; unsigned d[kMaxLayouts]; };
+
+inline int postLaunch(const char* what) {
+  g_launchCount.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DFX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+  return DFX_OK;
+}
+inline int cudaFail(cudaError_t e, const char* what) {
+  return fail(DFX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define DFX_CUDA(call)                                         \
+  do {                                                         \
+    cudaError_t e_ = (call);                                   \
+    if (e_ != cudaSuccess) return ::dfx::cudaFail(e_, #call);  \
+  } while (0)
+
+int indicesMulti32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, int stride, cudaStream_t st);
+int indicesMulti64(const dfx_basis* b, u64 e0, u64 e1, u64* out, int stride, cudaStream_t st);
+int indicesFlat32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, cudaStream_t st);
+int indicesFlat64(const dfx_basis* b, u64 e0, u64 e1, u64* out, cudaStream_t st);
+int interpolateRegistry(const dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
+                        const uint8_t* mask, cudaStream_t st);
+int interpolationPoints(const dfx_basis* b, double* xyz, int* leafOut, cudaStream_t st);
+int interpolateFromValues(const dfx_basis* b, int firstLeaf, int nLeaves, const double* values, double* coeff,
+                          const uint8_t* mask, cudaStream_t st);
+int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* shape,
+                const double* dshape, const ShapeOffsets& so, int nq, u64 e0, u64 e1, double* values, double* jac,
+                cudaStream_t st);
+int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
+
+}  // namespace dfx

@@ -1,0 +1,253 @@
+/* dfx.h — C ABI of the B200-native element-loop hot path of dune-functions.
+ *
+ * This is the drop-in boundary.  The reference (dune-functions, header-only C++)
+ * has no FFI of its own; its "operator API" for this path is the set of C++
+ * concepts and free functions cited next to each entry point below
+ * (paths relative to the reference checkout).  A C++ façade that keeps the
+ * reference's names on top of this ABI lives in include/dfx/dune_functions.hh;
+ * INTEGRATION.md shows how a maintainer binds it.
+ *
+ * Conventions
+ *  - every function returns a dfx_status (0 = ok); dfx_last_error() gives the
+ *    text of the last failure on the calling thread.  No exception crosses
+ *    the ABI.
+ *  - pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *  - `stream` is a cudaStream_t passed as void*; all device work is
+ *    stream-ordered, nothing synchronises unless documented.
+ *  - buffers are caller-owned; the library never reallocates them.
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    DFX_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Coefficient-vector layout ("flat container position"): the basis' index
+ * tree is laid out contiguously in lexicographic order of the multi-indices,
+ * i.e. exactly how nested ISTL containers resolve `vector[multiIndex]`
+ * (reference: dune/functions/backends/istlvectorbackend.hh:267-277,
+ * dune/functions/common/indexaccess.hh:376-403).  Flat bases: position ==
+ * the single index digit.  Blocked bases: e.g. BL(BI) Taylor-Hood
+ * (0,i,c) -> 3*i+c, (1,j) -> 3*n2+j.
+ */
+#ifndef DFX_H
+#define DFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFX_ABI_VERSION 1
+#define DFX_MAX_DIM 3
+#define DFX_MAX_DIGITS 6      /* longest multi-index the ABI represents          */
+#define DFX_MAX_LEAVES 16     /* leaf nodes of one basis tree                    */
+#define DFX_MAX_FN_PARAMS 16
+
+typedef enum {
+  DFX_OK = 0,
+  DFX_ERR_INVALID = 1,        /* malformed descriptor / argument                 */
+  DFX_ERR_RANGE = 2,          /* Dune::RangeError equivalents (bad order, ...)    */
+  DFX_ERR_NOT_IMPLEMENTED = 3,/* Dune::NotImplemented equivalents                 */
+  DFX_ERR_CUDA = 4,           /* CUDA runtime failure / no device                 */
+  DFX_ERR_NCCL = 5
+} dfx_status;
+
+/* ---- grid: an unrefined equidistant YaspGrid-style box --------------------
+ * n_global/lower/upper describe the whole grid; [local_begin, local_begin +
+ * local_n) is the box of elements this handle (one GPU rank) works on.  The
+ * basis is numbered over the LOCAL box (like a basis built on that rank's grid
+ * view) while node coordinates and the last-writer rule of interpolate() are
+ * those of the GLOBAL grid, so a slab-partitioned run reproduces the serial
+ * one bit for bit.  Unpartitioned: local_begin = 0, local_n = n_global.
+ * Replaces: Dune::YaspGrid<dim>(L, N) + leafGridView() as consumed by
+ * lagrangebasis.hh:783-797 (MCMGMapper over the grid view's index set).     */
+typedef struct {
+  int32_t dim;                      /* 1..3                                    */
+  int32_t n_global[DFX_MAX_DIM];    /* elements per direction, whole grid      */
+  int32_t local_begin[DFX_MAX_DIM];
+  int32_t local_n[DFX_MAX_DIM];
+  double  lower[DFX_MAX_DIM];       /* lower-left corner of the whole grid     */
+  double  upper[DFX_MAX_DIM];       /* upper-right corner of the whole grid    */
+} dfx_grid_desc;
+
+/* ---- basis tree: preorder array of nodes ----------------------------------
+ * Replaces the compile-time pre-basis types
+ *   LagrangePreBasis<GV,k,R>      lagrangebasis.hh:740-742
+ *   LagrangeDGPreBasis<GV,k,R>    lagrangedgbasis.hh:48-50
+ *   PowerPreBasis<IMS,SPB,C>      powerbasis.hh:51-53  (one child subtree follows)
+ *   CompositePreBasis<IMS,SPB...> compositebasis.hh:55-56 (n_children subtrees follow)
+ *   TaylorHoodPreBasis<GV>        taylorhoodbasis.hh:59-281 (no children in the array)
+ */
+typedef enum {
+  DFX_NODE_LAGRANGE = 0,
+  DFX_NODE_LAGRANGE_DG = 1,
+  DFX_NODE_POWER = 2,
+  DFX_NODE_COMPOSITE = 3,
+  DFX_NODE_TAYLOR_HOOD = 4
+} dfx_node_kind;
+
+/* index-merging strategies, functionspacebases/basistags.hh:52-184 */
+typedef enum {
+  DFX_IMS_NONE = 0,
+  DFX_IMS_FLAT_LEXICOGRAPHIC = 1,
+  DFX_IMS_FLAT_INTERLEAVED = 2,
+  DFX_IMS_BLOCKED_LEXICOGRAPHIC = 3,
+  DFX_IMS_BLOCKED_INTERLEAVED = 4
+} dfx_ims;
+
+typedef struct {
+  int32_t kind;        /* dfx_node_kind                                         */
+  int32_t order;       /* polynomial order k (leaves)                           */
+  int32_t n_children;  /* power: exponent C; composite: number of children      */
+  int32_t ims;         /* dfx_ims (inner nodes)                                 */
+} dfx_tree_node;
+
+/* ---- functions f for interpolate() ----------------------------------------
+ * A host callable cannot run on the device, so f crosses the ABI either as
+ * (1) an entry of the built-in registry of __device__ functors below, or
+ * (2) nodal values produced by the caller (dfx_interpolation_points +
+ *     dfx_interpolate_from_values), or
+ * (3) for C++ callers compiling with nvcc: the header template
+ *     dfx::interpolate(basis, coeff, DeviceFunctor) (include/dfx/device_functor.cuh).
+ * Replaces the callable argument of interpolate(), interpolate.hh:204-211.   */
+typedef enum {
+  DFX_FN_CONSTANT = 0,     /* y_c = p[c]                      (n_comp values)        */
+  DFX_FN_GAUSSIAN = 1,     /* y   = exp(-p[0] * |x|^2)         examples/interpolation.cc:49-52 */
+  DFX_FN_IDENTITY = 2,     /* y_c = x_c                        examples/interpolation.cc:93-95 */
+  DFX_FN_COORD = 3,        /* y   = x[(int)p[0]]               gridviewfunctionspacebasistest.cc */
+  DFX_FN_QUADRATIC = 4,    /* y = p0 + sum p[1+j] x_j + sum_{i<=j} p[4+idx(i,j)] x_i x_j,
+                              idx order (00,01,02,11,12,22)   cf. discreteglobalbasisfunctionderivativetest.cc:89-91 */
+  DFX_FN_SINPROD = 5,      /* y = prod_j sin(p[0] * x_j)                              */
+  DFX_FN_GAUSSIAN_VEC = 6  /* y_c = x_c * exp(-p[0]*|x|^2)     (vector valued, smooth) */
+} dfx_fn_id;
+
+typedef struct {
+  int32_t id;              /* dfx_fn_id                                          */
+  int32_t n_comp;          /* number of range entries; 1 = scalar (broadcast)    */
+  double  p[DFX_MAX_FN_PARAMS];
+} dfx_function;
+
+typedef struct dfx_basis dfx_basis;   /* opaque, caller-owned, explicit destroy */
+
+/* ---- life cycle ------------------------------------------------------------*/
+int         dfx_abi_version(void);
+const char* dfx_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process    */
+uint64_t    dfx_kernel_launch_count(void);
+
+/* makeBasis(gridView, preBasisFactory): defaultglobalbasis.hh:205-209, ctor :89-95.
+ * `device` is the CUDA ordinal the handle is bound to.                        */
+int  dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_host,
+                      int32_t n_nodes, int32_t device, dfx_basis** out);
+void dfx_basis_destroy(dfx_basis* b);
+
+/* ---- GlobalBasis concept: functionspacebases/concepts.hh:253-273 -----------*/
+uint64_t dfx_basis_dimension(const dfx_basis* b);                 /* defaultglobalbasis.hh:144-147 */
+uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t len); /* :150-160 */
+int32_t  dfx_basis_max_node_size(const dfx_basis* b);             /* LocalView::maxSize, defaultlocalview.hh:147-150 */
+int32_t  dfx_basis_max_multi_index_size(const dfx_basis* b);      /* PreBasis::maxMultiIndexSize */
+int32_t  dfx_basis_min_multi_index_size(const dfx_basis* b);
+uint64_t dfx_basis_num_elements(const dfx_basis* b);              /* elements(gridView) of the local box */
+int32_t  dfx_basis_num_leaves(const dfx_basis* b);
+int32_t  dfx_basis_num_tree_nodes(const dfx_basis* b);            /* nodes of the expanded local ansatz tree */
+/* node tree (nodes.hh:130-209): for expanded-tree node `node` (preorder
+ * "treeIndex"), its first local index, its size and its leaf range.           */
+int dfx_basis_node_info(const dfx_basis* b, int32_t node, int32_t* local_offset,
+                        int32_t* size, int32_t* first_leaf, int32_t* n_leaves);
+/* child `child` of expanded-tree node `node` -> node id (or -1)                */
+int32_t dfx_basis_node_child(const dfx_basis* b, int32_t node, int32_t child);
+/* multi-index length of local index i (same for every element)                */
+int dfx_basis_local_index_sizes(const dfx_basis* b, uint8_t* sizes_host /*[max_node_size]*/);
+
+/* ---- LocalView::bind + index, batched over elements ------------------------
+ * Replaces DefaultLocalView::bind (defaultlocalview.hh:95-101) -> PreBasis::indices
+ * (lagrangebasis.hh:843-873, lagrangedgbasis.hh:120-130, dynamicpowerbasis.hh:263-371,
+ * compositebasis.hh:293-338, taylorhoodbasis.hh:229-251) for elements
+ * [elem_begin, elem_end) of the local box in grid-view iteration order
+ * (x fastest).  out_digits[(e-elem_begin)*n_loc*stride + i*stride + p] is digit
+ * p of localView.index(i); digits past the multi-index length are 0.          */
+int dfx_indices_multi(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                      uint32_t* out_digits, int32_t stride, void* stream);
+int dfx_indices_multi_u64(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                          uint64_t* out_digits, int32_t stride, void* stream);
+/* flat container position of every local index: out[(e-elem_begin)*n_loc + i]  */
+int dfx_indices_flat(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                     uint32_t* out, void* stream);
+int dfx_indices_flat_u64(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                         uint64_t* out, void* stream);
+
+/* ---- interpolate(basis, coeff, f [, bitVector]) ----------------------------
+ * Replaces interpolate.hh:204-302 (+ Imp::interpolateLocal :151-173,
+ * AnalyticGridViewFunction analyticgridviewfunction.hh:77-109,
+ * HierarchicNodeToRangeMap hierarchicnodetorangemap.hh:33-48).
+ * `subtree_node` = expanded-tree node whose leaves are interpolated (0 = whole
+ * basis; otherwise what subspaceBasis(basis, path) selects, subspacebasis.hh:147-157).
+ * Leaf number l (within the subtree) takes range entry l of f, a scalar f is
+ * broadcast.  coeff has dimension() doubles; entries of other leaves and
+ * entries whose mask byte is 0 are left untouched (mask may be NULL = all).   */
+int dfx_interpolate(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
+                    double* coeff, const uint8_t* mask, void* stream);
+/* form (2): positions of the interpolation nodes and range entry of every
+ * coefficient, in flat container order; then a masked copy of caller values. */
+int dfx_interpolation_points(const dfx_basis* b, double* out_xyz /*[dimension][dim]*/,
+                             int32_t* out_leaf /*[dimension]*/, void* stream);
+int dfx_interpolate_from_values(const dfx_basis* b, int32_t subtree_node, const double* values,
+                                double* coeff, const uint8_t* mask, void* stream);
+
+/* ---- DiscreteGlobalBasisFunction local evaluation --------------------------
+ * Replaces LocalFunctionBase::bind (discreteglobalbasisfunction.hh:124-148),
+ * LocalFunction::operator() (:336-371) and
+ * DiscreteGlobalBasisFunctionDerivative::LocalFunction::operator() (:583-627)
+ * for all elements [elem_begin, elem_end) at the n_q reference-element points
+ * xhat_host[q*dim + j].
+ *   out_values[(e-elem_begin)*n_q*n_comp + q*n_comp + c]          (may be NULL)
+ *   out_jacobians[((e-elem_begin)*n_q + q)*n_comp*dim + c*dim + j]  (may be NULL)
+ * n_comp = number of leaves below subtree_node (range entry per leaf).        */
+int dfx_evaluate(const dfx_basis* b, int32_t subtree_node, const double* coeff,
+                 const double* xhat_host, int32_t n_q,
+                 uint64_t elem_begin, uint64_t elem_end,
+                 double* out_values, double* out_jacobians, void* stream);
+/* which kernel family dfx_evaluate picks for this configuration:
+ * 0 generic, 1 sum-factorised register kernel, 2 sum-factorised shared-memory
+ * (TMA bulk) kernel, 3 dense FP64 tensor-core (DMMA) kernel.
+ * dfx_set_eval_path forces one (-1 = automatic).                               */
+int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xhat_host,
+                      int32_t n_q, int32_t want_jacobians);
+void dfx_set_eval_path(int32_t path);
+
+/* ---- host-buffer entry points (what a CPU caller of the reference uses) ----
+ * Same semantics with HOST buffers; the copies are staged through pinned
+ * memory on the handle's stream and the call returns when the result is in
+ * the host buffer.                                                            */
+int dfx_interpolate_host(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
+                         double* coeff_host, const uint8_t* mask_host);
+int dfx_evaluate_host(const dfx_basis* b, int32_t subtree_node, const double* coeff_host,
+                      const double* xhat_host, int32_t n_q,
+                      uint64_t elem_begin, uint64_t elem_end,
+                      double* out_values_host, double* out_jacobians_host);
+int dfx_indices_flat_host(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                          uint32_t* out_host);
+
+/* ---- slab partition helpers (multi-GPU, one handle per rank) ---------------
+ * When the local box spans the whole grid in every direction but the last,
+ * the DOFs of one z-layer of every Yasp index-set component are contiguous.
+ * dfx_halo_ranges lists, per leaf, the contiguous flat-position ranges of the
+ * lowest (`side`=0) or highest (`side`=1) lattice plane of the local box:
+ * the data one rank sends to / receives from its z-neighbour.
+ * out_begin/out_count: [max_ranges]; returns the number of ranges in *n.     */
+int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin_host,
+                    uint64_t* out_count_host, int32_t max_ranges, int32_t* n);
+/* pack/unpack those ranges to/from one contiguous buffer (device)            */
+uint64_t dfx_halo_size(const dfx_basis* b);
+int dfx_halo_pack(const dfx_basis* b, int32_t side, const double* coeff, double* buf, void* stream);
+int dfx_halo_unpack(const dfx_basis* b, int32_t side, const double* buf, double* coeff, void* stream);
+/* owned range bookkeeping for gathering a distributed vector: per leaf and
+ * index-set component, (local flat begin, count, global flat begin) of the
+ * DOFs this rank owns (the top plane belongs to the upper neighbour unless
+ * this is the last slab).                                                     */
+int dfx_owned_ranges(const dfx_basis* b, uint64_t* local_begin_host, uint64_t* count_host,
+                     uint64_t* global_begin_host, int32_t max_ranges, int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFX_H */

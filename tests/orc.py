@@ -1,0 +1,124 @@
+"""ctypes binding of the CPU oracle (oracle/dfx_oracle.cpp).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from dune_functions_b200 import _capi as capi
+from dune_functions_b200.basis import tree_array
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_PATH = os.path.join(ROOT, "oracle", "_build", "liborc.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORC_PATH):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        L = C.CDLL(ORC_PATH)
+        vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
+        L.orc_basis_create.restype = vp
+        L.orc_basis_create.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), i32]
+        L.orc_basis_destroy.argtypes = [vp]
+        L.orc_dimension.restype = u64
+        L.orc_dimension.argtypes = [vp]
+        L.orc_size_prefix.restype = u64
+        L.orc_size_prefix.argtypes = [vp, C.POINTER(u64), i32]
+        for n in ("orc_max_node_size", "orc_max_digits", "orc_min_digits", "orc_num_leaves", "orc_num_nodes"):
+            getattr(L, n).restype = i32
+            getattr(L, n).argtypes = [vp]
+        L.orc_num_elements.restype = u64
+        L.orc_num_elements.argtypes = [vp]
+        L.orc_node_info.argtypes = [vp, i32, C.POINTER(i32)]
+        L.orc_indices.argtypes = [vp, u64, u64, vp, vp, i32]
+        L.orc_indices_flat.argtypes = [vp, u64, u64, vp]
+        L.orc_interpolate.argtypes = [vp, i32, C.POINTER(capi.Function), vp, vp, i32]
+        L.orc_evaluate.argtypes = [vp, i32, vp, vp, i32, u64, u64, vp, vp, i32]
+        L.orc_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+class OracleBasis:
+    def __init__(self, grid, factory):
+        self.grid = grid
+        self._desc = grid.desc()
+        arr, n = tree_array(factory)
+        self._h = lib().orc_basis_create(C.byref(self._desc), arr, n)
+        if not self._h:
+            raise ValueError("oracle: bad tree")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_basis_destroy(self._h)
+            self._h = None
+
+    def dimension(self):
+        return int(lib().orc_dimension(self._h))
+
+    def size(self, prefix=()):
+        p = (C.c_uint64 * max(1, len(prefix)))(*prefix)
+        return int(lib().orc_size_prefix(self._h, p, len(prefix)))
+
+    def maxNodeSize(self):
+        return int(lib().orc_max_node_size(self._h))
+
+    def maxMultiIndexSize(self):
+        return int(lib().orc_max_digits(self._h))
+
+    def minMultiIndexSize(self):
+        return int(lib().orc_min_digits(self._h))
+
+    def numElements(self):
+        return int(lib().orc_num_elements(self._h))
+
+    def numLeaves(self):
+        return int(lib().orc_num_leaves(self._h))
+
+    def numTreeNodes(self):
+        return int(lib().orc_num_nodes(self._h))
+
+    def nodeInfo(self, node):
+        out = (C.c_int32 * 4)()
+        lib().orc_node_info(self._h, node, out)
+        return dict(local_offset=out[0], size=out[1], first_leaf=out[2], n_leaves=out[3])
+
+    def indices(self, e0=0, e1=None):
+        """(digits [ne,nloc,maxlen] uint64, lens [ne,nloc] uint8)"""
+        e1 = self.numElements() if e1 is None else e1
+        nl, st = self.maxNodeSize(), self.maxMultiIndexSize()
+        dig = np.zeros((e1 - e0, nl, st), dtype=np.uint64)
+        lens = np.zeros((e1 - e0, nl), dtype=np.uint8)
+        lib().orc_indices(self._h, e0, e1, dig.ctypes.data, lens.ctypes.data, st)
+        return dig, lens
+
+    def flatIndices(self, e0=0, e1=None):
+        e1 = self.numElements() if e1 is None else e1
+        out = np.zeros((e1 - e0, self.maxNodeSize()), dtype=np.uint64)
+        lib().orc_indices_flat(self._h, e0, e1, out.ctypes.data)
+        return out
+
+    def interpolate(self, f, coeff=None, mask=None, node=0, nthreads=1):
+        if coeff is None:
+            coeff = np.zeros(self.dimension(), dtype=np.float64)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().orc_interpolate(self._h, node, C.byref(f), coeff.ctypes.data,
+                              None if m is None else m.ctypes.data, nthreads)
+        return coeff
+
+    def evaluate(self, coeff, xhat, node=0, values=True, jacobians=False, e0=0, e1=None, nthreads=1):
+        e1 = self.numElements() if e1 is None else e1
+        xh = np.ascontiguousarray(np.asarray(xhat, dtype=np.float64).reshape(-1, self.grid.dim))
+        nq = xh.shape[0]
+        nc = self.nodeInfo(node)["n_leaves"]
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        v = np.zeros((e1 - e0, nq, nc)) if values else None
+        j = np.zeros((e1 - e0, nq, nc, self.grid.dim)) if jacobians else None
+        lib().orc_evaluate(self._h, node, coeff.ctypes.data, xh.ctypes.data, nq, e0, e1,
+                           None if v is None else v.ctypes.data, None if j is None else j.ctypes.data, nthreads)
+        if values and jacobians:
+            return v, j
+        return v if values else j

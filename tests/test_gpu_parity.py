@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs.  Bar: multi-indices / flat positions bit-exact; coefficients and evaluations
+<= 1e-12 relative (|a-b| / max(1, max|ref|) per array)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+from cases import GRIDS, trees, th_variant
+import dune_functions_b200 as dfx
+from dune_functions_b200 import _capi as capi
+from dune_functions_b200 import (YaspGrid, lagrange, lagrangeDG, power, composite, taylorHood, tensor_gauss,
+                                 flatLexicographic as FL, flatInterleaved as FI,
+                                 blockedLexicographic as BL, blockedInterleaved as BI)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, ref):
+    return np.abs(a - ref).max() / max(1.0, np.abs(ref).max())
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    yield
+    capi.lib().dfx_set_eval_path(-1)
+
+
+def all_cases():
+    for gname, grid in GRIDS.items():
+        for name, tree in trees(grid.dim).items():
+            if "TH_" in name and grid.dim != 3:
+                continue
+            yield pytest.param(grid, tree, id=f"{gname}-{name}")
+
+
+# ---- bind + index -----------------------------------------------------------------------
+@pytest.mark.parametrize("grid,tree", list(all_cases()))
+def test_indices_bit_exact(grid, tree):
+    import torch
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    dig, lens = o.indices()
+    got = b.indices().cpu().numpy().astype(np.uint64)
+    assert (got == dig).all()
+    got64 = b.indices(dtype=torch.int64).cpu().numpy().astype(np.uint64)
+    assert (got64 == dig).all()
+    assert (b.localIndexSizes() == lens[0]).all()
+    flat = b.flatIndices().cpu().numpy().astype(np.uint64)
+    assert (flat == o.flatIndices()).all()
+    # an element sub-range
+    ne = b.numElements()
+    if ne > 2:
+        sub = b.flatIndices(1, ne - 1).cpu().numpy().astype(np.uint64)
+        assert (sub == flat[1:ne - 1]).all()
+
+
+def test_indices_host_entry_point():
+    grid, tree = GRIDS["3d_3x4x5"], taylorHood()
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    out = np.zeros((b.numElements(), b.maxNodeSize()), dtype=np.uint32)
+    capi.check(capi.lib().dfx_indices_flat_host(b._h, 0, b.numElements(), out.ctypes.data))
+    assert (out.astype(np.uint64) == o.flatIndices()).all()
+
+
+# ---- interpolate ----------------------------------------------------------------------------
+FUNCS = {
+    "gaussian": dfx.gaussian(1.0),
+    "coord0": dfx.coord(0),
+    "quadratic": dfx.quadratic(0.5, [1, -2, 3], [42, 7, 1, 13, -3, 5]),
+    "sinprod": dfx.sinprod(3.0),
+    "const": dfx.constant(1.0),
+}
+
+
+@pytest.mark.parametrize("grid,tree", list(all_cases()))
+@pytest.mark.parametrize("fname", ["gaussian", "quadratic"])
+def test_interpolate_scalar_function(grid, tree, fname):
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    f = FUNCS[fname]
+    x = b.newVector(-5.0)
+    dfx.interpolate(b, x, f)
+    ref = o.interpolate(f, coeff=np.full(o.dimension(), -5.0))
+    assert rel(x.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_2x1x3"])
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 5])
+def test_interpolate_coordinate_is_bit_exact(gname, k):
+    """x[0] involves no transcendental: the GPU reproduces the last writer's coordinate bit for bit"""
+    grid = GRIDS[gname]
+    for tree in (lagrange(k), lagrangeDG(k)):
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        for f in (dfx.coord(0), dfx.coord(grid.dim - 1)):
+            x = b.newVector(0.0)
+            dfx.interpolate(b, x, f)
+            assert (x.cpu().numpy() == o.interpolate(f)).all()
+
+
+def test_interpolate_vector_valued_and_subspaces():
+    """examples/interpolation.cc:71-96: Taylor-Hood FL(FL), velocity subspace <- f(x) = x,
+    pressure subspace <- exp(-|x|^2)"""
+    grid = GRIDS["3d_3x4x5"]
+    for tree in (th_variant(FL, FL, 3), th_variant(BL, BI, 3), taylorHood(), th_variant(FL, BI, 3)):
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        x = b.newVector(3.0)
+        ref = np.full(o.dimension(), 3.0)
+        vel = dfx.subspaceBasis(b, 0)
+        pre = dfx.subspaceBasis(b, 1)
+        dfx.interpolate(vel, x, dfx.identity(3))
+        o.interpolate(dfx.identity(3), coeff=ref, node=vel.node)
+        assert (x.cpu().numpy() == ref).all()
+        dfx.interpolate(pre, x, dfx.gaussian(1.0))
+        o.interpolate(dfx.gaussian(1.0), coeff=ref, node=pre.node)
+        assert rel(x.cpu().numpy(), ref) <= TOL
+        # single velocity component: subspaceBasis(basis, 0, 1)
+        comp = dfx.subspaceBasis(b, 0, 1)
+        dfx.interpolate(comp, x, dfx.sinprod(2.0))
+        o.interpolate(dfx.sinprod(2.0), coeff=ref, node=comp.node)
+        assert rel(x.cpu().numpy(), ref) <= TOL
+        # whole tree with a 4-component range
+        dfx.interpolate(b, x, dfx.gaussian_vec(4, 0.5))
+        o.interpolate(dfx.gaussian_vec(4, 0.5), coeff=ref)
+        assert rel(x.cpu().numpy(), ref) <= TOL
+
+
+def test_interpolate_masked():
+    import torch
+    grid = GRIDS["2d_10x10"]
+    tree = power(lagrange(2), 2, BI())
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    rng = np.random.default_rng(1)
+    mask = (rng.uniform(size=b.dimension()) < 0.3).astype(np.uint8)
+    x = b.newVector(7.0)
+    dfx.interpolate(b, x, dfx.identity(2), mask=torch.from_numpy(mask).cuda())
+    ref = o.interpolate(dfx.identity(2), coeff=np.full(o.dimension(), 7.0), mask=mask)
+    got = x.cpu().numpy()
+    assert (got == ref).all()
+    assert (got[mask == 0] == 7.0).all()
+
+
+def test_interpolate_wrong_range_raises():
+    b = dfx.makeBasis(GRIDS["2d_3x2"], power(lagrange(1), 2, FI()))
+    with pytest.raises(capi.RangeError):
+        dfx.interpolate(b, b.newVector(0.0), dfx.identity(3))
+    import torch
+    with pytest.raises(capi.RangeError):
+        dfx.interpolate(b, torch.zeros(3, dtype=torch.float64, device="cuda"), dfx.identity(2))
+
+
+def test_interpolation_points_and_from_values():
+    """form (2) of f: node positions out, caller-evaluated values in"""
+    grid = GRIDS["3d_2x1x3"]
+    tree = composite(power(lagrange(2), 3, BI()), lagrangeDG(1))
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    xyz, leaf = dfx.interpolationPoints(b)
+    xyz, leaf = xyz.cpu().numpy(), leaf.cpu().numpy()
+    # f(x) = (x0, x1, x2, exp(-|x|^2)) evaluated by the caller
+    vals = np.where(leaf < 3, xyz[np.arange(len(leaf)), np.minimum(leaf, 2)], np.exp(-(xyz ** 2).sum(1)))
+    import torch
+    x = b.newVector(0.0)
+    dfx.interpolateFromValues(b, x, torch.from_numpy(vals).cuda())
+    ref = np.zeros(o.dimension())
+    o.interpolate(dfx.identity(3), coeff=ref, node=1)
+    o.interpolate(dfx.gaussian(1.0), coeff=ref, node=b.child(0, 1))
+    assert rel(x.cpu().numpy(), ref) <= TOL
+
+
+def test_interpolate_host_entry_point():
+    grid, tree = GRIDS["3d_3x4x5"], lagrange(2)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    out = np.zeros(b.dimension())
+    f = dfx.gaussian(1.0)
+    capi.check(capi.lib().dfx_interpolate_host(b._h, 0, C.byref(f), out.ctypes.data, None))
+    assert rel(out, o.interpolate(f)) <= TOL
+    # masked: untouched entries survive the round trip through the device
+    mask = (np.arange(b.dimension()) % 3 == 0).astype(np.uint8)
+    out2 = np.full(b.dimension(), 4.0)
+    capi.check(capi.lib().dfx_interpolate_host(b._h, 0, C.byref(f), out2.ctypes.data, mask.ctypes.data))
+    ref2 = o.interpolate(f, coeff=np.full(b.dimension(), 4.0), mask=mask)
+    assert rel(out2, ref2) <= TOL and (out2[mask == 0] == 4.0).all()
+
+
+# ---- DiscreteGlobalBasisFunction evaluation ---------------------------------------------------
+def random_coeff(n, seed=12345):
+    return np.random.default_rng(seed).uniform(-1, 1, n)
+
+
+def eval_both(grid, tree, pts, node=0, jac=True, path=-1):
+    import torch
+    capi.lib().dfx_set_eval_path(path)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    c = random_coeff(b.dimension())
+    f = dfx.makeDiscreteGlobalBasisFunction(b if node == 0 else _Sub(b, node), torch.from_numpy(c).cuda())
+    v, j = f.evaluate(pts, jacobians=True) if jac else (f.evaluate(pts), None)
+    vr, jr = o.evaluate(c, pts, node=node, jacobians=True) if jac else (o.evaluate(c, pts, node=node), None)
+    capi.lib().dfx_set_eval_path(-1)
+    return v.cpu().numpy(), (j.cpu().numpy() if jac else None), vr, jr
+
+
+class _Sub(dfx.SubspaceBasis):
+    def __init__(self, root, node):
+        self.root, self.node, self.path = root, node, ()
+
+
+@pytest.mark.parametrize("grid,tree", list(all_cases()))
+def test_evaluate_generic_random_points(grid, tree):
+    """arbitrary (non tensor-product) points -> generic kernel"""
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(0, 1, (5, grid.dim))
+    v, j, vr, jr = eval_both(grid, tree, pts, path=0)
+    assert rel(v, vr) <= TOL
+    assert rel(j, jr) <= TOL
+
+
+@pytest.mark.parametrize("grid,tree", list(all_cases()))
+@pytest.mark.parametrize("m,last_fastest", [(3, True), (2, False)])
+def test_evaluate_tensor_gauss_points(grid, tree, m, last_fastest):
+    """tensor Gauss points -> whichever path the planner picks"""
+    pts, _ = tensor_gauss(grid.dim, m, last_fastest)
+    v, j, vr, jr = eval_both(grid, tree, pts)
+    assert rel(v, vr) <= TOL
+    assert rel(j, jr) <= TOL
+
+
+def test_evaluate_subspace_and_element_range():
+    import torch
+    grid = GRIDS["3d_3x4x5"]
+    tree = taylorHood()
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    c = random_coeff(b.dimension())
+    ct = torch.from_numpy(c).cuda()
+    pts, _ = tensor_gauss(3, 3)
+    for path in ((0,), (1,), (0, 2)):
+        sb = dfx.subspaceBasis(b, *path)
+        f = dfx.makeDiscreteGlobalBasisFunction(sb, ct)
+        v = f.evaluate(pts, elem_begin=7, elem_end=41).cpu().numpy()
+        vr = o.evaluate(c, pts, node=sb.node, e0=7, e1=41)
+        assert v.shape == vr.shape and rel(v, vr) <= TOL
+
+
+def test_evaluate_host_entry_point():
+    grid, tree = GRIDS["3d_3x4x5"], lagrange(2)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    c = random_coeff(b.dimension())
+    pts, _ = tensor_gauss(3, 3)
+    ne = b.numElements()
+    v = np.zeros((ne, 27, 1))
+    j = np.zeros((ne, 27, 1, 3))
+    capi.check(capi.lib().dfx_evaluate_host(b._h, 0, c.ctypes.data, pts.ctypes.data_as(C.POINTER(C.c_double)), 27,
+                                            0, ne, v.ctypes.data, j.ctypes.data))
+    vr, jr = o.evaluate(c, pts, jacobians=True)
+    assert rel(v, vr) <= TOL and rel(j, jr) <= TOL
+
+
+# ---- the reference's known answers, now through the GPU path ------------------------------------
+@pytest.mark.parametrize("tree", [lagrange(0), lagrange(1), lagrange(2), lagrange(3), lagrange(4),
+                                  lagrangeDG(1), lagrangeDG(2), lagrangeDG(3)])
+@pytest.mark.parametrize("n", [[7], [10, 10], [4, 3, 5]])
+def test_integral_of_interpolated_x0_is_half(tree, n):
+    """gridviewfunctionspacebasistest.cc:115-183"""
+    b = dfx.makeBasis(YaspGrid(n), tree)
+    x = dfx.interpolate(b, b.newVector(0.0), dfx.coord(0))
+    pts, w = tensor_gauss(len(n), 3)
+    v = dfx.makeDiscreteGlobalBasisFunction(b, x).evaluate(pts).cpu().numpy()
+    integral = np.einsum("eqc,q->", v, w) / b.numElements()
+    assert abs(integral - 0.5) < 1e-10
+
+
+def test_round_trip_basis_function_interpolation():
+    """discreteglobalbasisfunctiontest.cc:49-77: interpolate(basis, y, makeDGBF(basis, x)) == x,
+    done here by evaluating at the Lagrange nodes and scattering with the flat index table"""
+    import torch
+    grid = GRIDS["3d_2x1x3"]
+    tree = power(lagrange(2), 2, BI())
+    b = dfx.makeBasis(grid, tree)
+    x = torch.from_numpy(random_coeff(b.dimension())).cuda()
+    nodes = np.array([[(i % 3) / 2, ((i // 3) % 3) / 2, (i // 9) / 2] for i in range(27)])
+    v = dfx.makeDiscreteGlobalBasisFunction(b, x).evaluate(nodes)          # [ne, 27, 2]
+    flat = b.flatIndices().long()                                           # [ne, 54] = [comp0 | comp1]
+    y = torch.zeros_like(x)
+    y[flat[:, :27].reshape(-1)] = v[:, :, 0].reshape(-1)
+    y[flat[:, 27:].reshape(-1)] = v[:, :, 1].reshape(-1)
+    assert (y - x).abs().max().item() < 1e-10
+
+
+def test_derivative_of_q3_interpolant():
+    """discreteglobalbasisfunctionderivativetest.cc:80-158 on its own 10x42 grid"""
+    grid = YaspGrid([10, 42])
+    b = dfx.makeBasis(grid, lagrange(3))
+    f = dfx.quadratic(0.0, [0, 0, 0], [42, 7, 0, 13, 0, 0])
+    x = dfx.interpolate(b, b.newVector(0.0), f)
+    pts, w = tensor_gauss(2, 3)
+    v, j = dfx.makeDiscreteGlobalBasisFunction(b, x).evaluate(pts, jacobians=True)
+    v, j = v.cpu().numpy(), j.cpu().numpy()
+    e = np.arange(420)
+    X = ((e % 10)[:, None] + pts[None, :, 0]) / 10
+    Y = ((e // 10)[:, None] + pts[None, :, 1]) / 42
+    l2 = np.sqrt(np.einsum("eq,q->", (j[:, :, 0, 0] - (84 * X + 7 * Y)) ** 2 + (j[:, :, 0, 1] - (26 * Y + 7 * X)) ** 2, w) / 420)
+    assert l2 <= 6.6e-11
+    assert np.abs(v[:, :, 0] - (42 * X * X + 13 * Y * Y + 7 * X * Y)).max() < 1e-10

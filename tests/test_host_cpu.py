@@ -1,0 +1,171 @@
+"""CPU suite, part 2: the product's host logic (tree flattening into per-leaf affine index
+maps, size(prefix), node tree, error codes) against the oracle, and the C-ABI surface.
+No compute call needs a GPU here; on a machine without one the compute entry points must
+fail loudly with DFX_ERR_CUDA instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from cases import GRIDS, trees
+from dune_functions_b200 import _capi as capi
+from dune_functions_b200 import (YaspGrid, GlobalBasis, lagrange, lagrangeDG, power, composite, tree_array,
+                                 blockedInterleaved as BI, flatInterleaved as FI)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS_SRC = os.path.join(ROOT, "tests", "harness", "host_index_harness.cpp")
+HARNESS_SO = os.path.join(ROOT, "tests", "harness", "_build_harness.so")
+BASIS_SRC = os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_basis.cu")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    srcs = [HARNESS_SRC, BASIS_SRC, os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_internal.h")]
+    if not os.path.exists(HARNESS_SO) or any(os.path.getmtime(s) > os.path.getmtime(HARNESS_SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", HARNESS_SO,
+                               HARNESS_SRC, BASIS_SRC])
+    L = C.CDLL(HARNESS_SO)
+    L.harness_indices.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.POINTER(C.c_uint64)]
+    return L
+
+
+def lex_rank(dig, lens):
+    """flat container position = lexicographic rank of the multi-index among all indices"""
+    ne, nl, st = dig.shape
+    keys = np.full((ne * nl, st), -1, dtype=np.int64)
+    d = dig.reshape(-1, st).astype(np.int64)
+    ln = lens.reshape(-1)
+    for p in range(st):
+        keys[:, p] = np.where(p < ln, d[:, p], -1)
+    uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+    return inv.reshape(ne, nl)
+
+
+@pytest.mark.parametrize("gname", list(GRIDS))
+def test_flattened_index_maps_match_oracle(harness, gname):
+    grid = GRIDS[gname]
+    for name, tree in trees(grid.dim).items():
+        if "TH_" in name and grid.dim != 3:
+            continue
+        ob = orc.OracleBasis(grid, tree)
+        dig, lens = ob.indices()
+        st = ob.maxMultiIndexSize()
+        ne, nl = dig.shape[:2]
+        hd = np.zeros((ne, nl, st), dtype=np.uint64)
+        hf = np.zeros((ne, nl), dtype=np.uint64)
+        dim = C.c_uint64()
+        desc = grid.desc()
+        arr, n = tree_array(tree)
+        rc = harness.harness_indices(C.byref(desc), arr, n, hd.ctypes.data, st, hf.ctypes.data, C.byref(dim))
+        assert rc == 0, name
+        assert dim.value == ob.dimension(), name
+        assert (hd == dig).all(), f"{gname}/{name}: multi-index digits differ"
+        assert (hf.astype(np.int64) == lex_rank(dig, lens)).all(), f"{gname}/{name}: flat positions differ"
+        assert (hf == ob.flatIndices()).all(), name
+
+
+def test_partitioned_box_numbering_equals_local_grid(harness):
+    """a slab of a larger grid is numbered like a grid of the slab's size"""
+    tree = composite(power(lagrange(2), 3, BI()), lagrange(1))
+    whole = YaspGrid([3, 2, 8])
+    slab = whole.slab(1, 4)
+    assert list(slab.local_begin) == [0, 0, 2] and list(slab.local_n) == [3, 2, 2]
+    ref = orc.OracleBasis(YaspGrid([3, 2, 2]), tree)
+    dig, _ = ref.indices()
+    st = ref.maxMultiIndexSize()
+    hd = np.zeros_like(dig)
+    hf = np.zeros(dig.shape[:2], dtype=np.uint64)
+    dim = C.c_uint64()
+    desc = slab.desc()
+    arr, n = tree_array(tree)
+    assert harness.harness_indices(C.byref(desc), arr, n, hd.ctypes.data, st, hf.ctypes.data, C.byref(dim)) == 0
+    assert (hd == dig).all() and dim.value == ref.dimension()
+
+
+# ---- the shared library itself --------------------------------------------------------
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "dfx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfx_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/dfx.h but not exported"
+        assert name in capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert L.dfx_abi_version() == 1
+
+
+@pytest.mark.parametrize("gname", ["2d_3x2", "3d_3x4x5"])
+def test_global_basis_queries_match_oracle(gname):
+    grid = GRIDS[gname]
+    for name, tree in trees(grid.dim).items():
+        if "TH_" in name and grid.dim != 3:
+            continue
+        b = GlobalBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        assert b.dimension() == o.dimension()
+        assert b.maxNodeSize() == o.maxNodeSize()
+        assert b.maxMultiIndexSize() == o.maxMultiIndexSize()
+        assert b.minMultiIndexSize() == o.minMultiIndexSize()
+        assert b.numElements() == o.numElements()
+        assert b.numLeaves() == o.numLeaves()
+        assert b.numTreeNodes() == o.numTreeNodes()
+        for node in range(b.numTreeNodes()):
+            assert b.nodeInfo(node) == o.nodeInfo(node)
+        # size(prefix) for every prefix of a sample of multi-indices (basistest.hh:150-180)
+        dig, lens = o.indices(0, min(3, o.numElements()))
+        seen = set()
+        for e in range(dig.shape[0]):
+            for i in range(dig.shape[1]):
+                m = tuple(int(x) for x in dig[e, i, :lens[e, i]])
+                for p in range(len(m) + 1):
+                    if m[:p] not in seen:
+                        seen.add(m[:p])
+                        assert b.size(m[:p]) == o.size(m[:p]), (name, m[:p])
+        assert (b.localIndexSizes() == lens[0]).all()
+
+
+def test_error_codes():
+    g = YaspGrid([2, 2])
+    with pytest.raises(capi.RangeError):
+        GlobalBasis(g, lagrange(18))               # lagrangebasis.hh:795-796
+    with pytest.raises(capi.RangeError):
+        GlobalBasis(g, lagrange(-1))
+    with pytest.raises(capi.DfxError):
+        GlobalBasis(g, composite(lagrange(1), lagrange(2), FI()))   # composite has no interleaved strategy
+    with pytest.raises(capi.DfxError):
+        GlobalBasis(YaspGrid([2, 0]), lagrange(1))
+    with pytest.raises(capi.DfxError):
+        GlobalBasis(YaspGrid([2, 2], upper=[1.0, -1.0]), lagrange(1))
+    b = GlobalBasis(g, power(lagrange(1), 2, BI()))
+    with pytest.raises(capi.RangeError):
+        b.child(0, 5)
+    assert b.child(0, 1) == 2
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    b = GlobalBasis(YaspGrid([2, 2]), lagrange(2))
+    L = capi.lib()
+    buf = (C.c_double * b.dimension())()
+    f = capi.Function()
+    f.id, f.n_comp = capi.FN_GAUSSIAN, 1
+    rc = L.dfx_interpolate_host(b._h, 0, C.byref(f), buf, None)
+    assert rc == capi.DFX_ERR_CUDA
+    assert b"no CPU fallback" in L.dfx_last_error() or b"CUDA" in L.dfx_last_error()
+    xh = (C.c_double * 2)(0.5, 0.5)
+    out = (C.c_double * 4)()
+    assert L.dfx_evaluate_host(b._h, 0, buf, xh, 1, 0, 4, out, None) == capi.DFX_ERR_CUDA
+    idx = (C.c_uint32 * 36)()
+    assert L.dfx_indices_flat_host(b._h, 0, 4, idx) == capi.DFX_ERR_CUDA
