@@ -74,7 +74,7 @@ SIGNATURES = {
     "dfx_interpolate_from_values": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "dfx_evaluate": (C.c_int, [_vp, _i32, _vp, C.POINTER(C.c_double), _i32, _u64, _u64, _vp, _vp, _vp]),
     "dfx_evaluate_path": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), _i32, _i32]),
-    "dfx_set_eval_path": (None, [_i32]),
+    "dfx_set_kernel_path": (None, [_i32, _i32]),
     "dfx_interpolate_host": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp]),
     "dfx_evaluate_host": (C.c_int, [_vp, _i32, _vp, C.POINTER(C.c_double), _i32, _u64, _u64, _vp, _vp]),
     "dfx_indices_flat_host": (C.c_int, [_vp, _u64, _u64, _vp]),
@@ -84,6 +84,8 @@ SIGNATURES = {
     "dfx_halo_unpack": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "dfx_owned_ranges": (C.c_int, [_vp, _pu64, _pu64, _pu64, _i32, _pi32]),
 }
+
+OP_EVALUATE, OP_INTERPOLATE, OP_INDICES = 0, 1, 2
 
 _lib = None
 

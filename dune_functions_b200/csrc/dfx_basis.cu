@@ -344,6 +344,16 @@ int buildBasis(const dfx_grid_desc* gd, const dfx_tree_node* t, int n, int devic
         return fail(DFX_ERR_NOT_IMPLEMENTED, "index tree without an affine flat layout");
     D.leaves[l].posA = a; D.leaves[l].posB = r0;
   }
+  // per local index: leaf id and lattice multi-index alpha (i = sum alpha_j (k+1)^j)
+  b->localTab.resize(offset);
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const int k = D.layouts[D.leaves[l].layout].k;
+    for (int i = 0; i < D.leaves[l].nloc; ++i) {
+      int ii = i, a[3];
+      for (int j = 0; j < 3; ++j) { a[j] = ii % (k + 1); ii /= (k + 1); }
+      b->localTab[D.leaves[l].localOffset + i] = (unsigned)l | (a[0] << 5) | (a[1] << 10) | (a[2] << 15);
+    }
+  }
   *out = b.release();
   return DFX_OK;
 }

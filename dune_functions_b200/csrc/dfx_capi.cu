@@ -8,7 +8,9 @@ using namespace dfx;
 
 namespace {
 
-int g_forcedPath = -1;
+int g_forcedPath = -1;      // evaluate
+int g_interpPath = -1;      // interpolate
+int g_indicesPath = -1;     // indices
 
 int ensureDevice(const dfx_basis* b) {
   if (!b) return fail(DFX_ERR_INVALID, "null basis handle");
@@ -20,7 +22,17 @@ int ensureDevice(const dfx_basis* b) {
   }
   if (b->device < 0 || b->device >= n) return fail(DFX_ERR_CUDA, "device ordinal out of range");
   DFX_CUDA(cudaSetDevice(b->device));
+  if (!b->dLocalTab && !b->localTab.empty()) {
+    dfx_basis* mb = const_cast<dfx_basis*>(b);
+    DFX_CUDA(cudaMalloc(&mb->dLocalTab, b->localTab.size() * sizeof(unsigned)));
+    DFX_CUDA(cudaMemcpy(mb->dLocalTab, b->localTab.data(), b->localTab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   return DFX_OK;
+}
+
+bool fits32(const dfx_basis* b, uint64_t e0, uint64_t e1) {
+  const u64 ne = (u64)b->dev.grid.N[0] * b->dev.grid.N[1] * b->dev.grid.N[2];
+  return ne <= 0xffffffffull && (e1 - e0) * (u64)b->dev.nlocTotal <= 0xffffffffull;
 }
 
 int subtree(const dfx_basis* b, int node, int& firstLeaf, int& nLeaves) {
@@ -155,9 +167,11 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 
 void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
-  if (b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
+  if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
     cudaSetDevice(b->device);
     if (b->dShape) cudaFree(b->dShape);
+    if (b->dLocalTab) cudaFree(b->dLocalTab);
+    if (b->dSep) cudaFree(b->dSep);
     if (b->pinned) cudaFreeHost(b->pinned);
     for (int i = 0; i < 3; ++i) if (b->dScratch[i]) cudaFree(b->dScratch[i]);
     if (b->stream) cudaStreamDestroy((cudaStream_t)b->stream);
@@ -216,23 +230,27 @@ int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* ou
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_multi_u64");
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, true>(b, e0, e1, out, stride, (cudaStream_t)stream);
   return indicesMulti32(b, e0, e1, out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, int32_t stride, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, true>(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
   return indicesMulti64(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_flat_u64");
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, false>(b, e0, e1, out, 1, (cudaStream_t)stream);
   return indicesFlat32(b, e0, e1, out, (cudaStream_t)stream);
 }
 int dfx_indices_flat_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
   return indicesFlat64(b, e0, e1, (u64*)out, (cudaStream_t)stream);
 }
 
@@ -254,6 +272,10 @@ int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, dou
   if ((rc = subtree(b, node, fl, nl))) return rc;
   if ((rc = checkFunction(f, nl))) return rc;
   if (!coeff) return fail(DFX_ERR_INVALID, "null coefficient vector");
+  if (g_interpPath != 0 && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
+    g_interpMode = g_interpPath == 1 ? 0 : -1;
+    return interpolateFast(const_cast<dfx_basis*>(b), fl, nl, *f, coeff, mask, (cudaStream_t)stream);
+  }
   return interpolateRegistry(b, fl, nl, *f, coeff, mask, (cudaStream_t)stream);
 }
 
@@ -273,7 +295,11 @@ int dfx_interpolate_from_values(const dfx_basis* b, int32_t node, const double* 
 }
 
 // ---- evaluate ---------------------------------------------------------------------
-void dfx_set_eval_path(int32_t path) { g_forcedPath = path; }
+void dfx_set_kernel_path(int32_t op, int32_t path) {
+  if (op == DFX_OP_EVALUATE) g_forcedPath = path;
+  else if (op == DFX_OP_INTERPOLATE) g_interpPath = path;
+  else if (op == DFX_OP_INDICES) g_indicesPath = path;
+}
 
 int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host, int32_t n_q, int32_t want_jac) {
   if (!b || !xhat_host || n_q < 1) return -1;

@@ -1,8 +1,362 @@
+// dfx_eval_fast.cu — specialised evaluation kernels for tensor-product point sets.
+//
+// Path 1 (k_eval_reg): one thread per element, x-blocked (consecutive threads = consecutive
+// elements in x, so every coefficient load of a warp is a contiguous run inside one
+// index-set component); the (k+1)^d coefficients live in registers and are contracted
+// direction by direction (sum factorisation: d*(k+1)*m^d-ish FMAs instead of (k+1)^d*m^d);
+// the m^d results of the block's elements are staged in shared memory in output order and
+// leave the SM as ONE contiguous TMA bulk store (cp.async.bulk.global.shared::cta).
+//
+// Replaces LocalFunctionBase::bind + LocalFunction::operator() and the derivative's
+// operator() (discreteglobalbasisfunction.hh:124-148, :336-371, :583-627).
+#include <algorithm>
+#include <cstring>
+
+#include "dfx_device.cuh"
 #include "dfx_eval_fast.h"
 #include "dfx_launch.h"
+
 namespace dfx {
-int planFastEval(const dfx_basis*, int, int, const double*, int, bool, int, FastPlan&) { return 0; }
-int runFastEval(dfx_basis*, const FastPlan&, int, int, const double*, u64, u64, double*, double*, cudaStream_t) {
-  return fail(DFX_ERR_NOT_IMPLEMENTED, "no fast path");
+
+// ---------------------------------------------------------------------------
+// planner
+static bool tensorFactor(const double* xhat, int nq, int dim, int m, bool firstFastest, double x1[3][kMaxQ1]) {
+  int stride[3];
+  if (firstFastest) { stride[0] = 1; stride[1] = m; stride[2] = m * m; }
+  else { int s = 1; for (int j = dim - 1; j >= 0; --j) { stride[j] = s; s *= m; } }
+  for (int j = 0; j < dim; ++j)
+    for (int t = 0; t < m; ++t) x1[j][t] = xhat[(size_t)(t * stride[j]) * dim + j];
+  for (int q = 0; q < nq; ++q)
+    for (int j = 0; j < dim; ++j) {
+      const int t = (q / stride[j]) % m;
+      if (std::memcmp(&xhat[(size_t)q * dim + j], &x1[j][t], sizeof(double)) != 0) return false;
+    }
+  return true;
 }
+
+static bool regPathHas(int dim, int k, int m) {
+  return (dim == 2 || dim == 3) && (k == 1 || k == 2) && (m == 2 || m == 3);
 }
+
+int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
+                 FastPlan& plan) {
+  if (forced == 0) return 0;
+  const DevBasis& D = b->dev;
+  const int dim = D.grid.dim;
+  int m = 0;
+  for (int t = 1; t <= kMaxQ1; ++t) {
+    int p = 1; for (int j = 0; j < dim; ++j) p *= t;
+    if (p == nq) m = t;
+  }
+  if (m == 0) return 0;
+  double x1[3][kMaxQ1];
+  bool ff = true;
+  if (!tensorFactor(xhat, nq, dim, m, true, x1)) {
+    ff = false;
+    if (!tensorFactor(xhat, nq, dim, m, false, x1)) return 0;
+  }
+  // every leaf of the subtree must have the same order to share the 1-d tables
+  const int k = D.layouts[D.leaves[firstLeaf].layout].k;
+  for (int l = 0; l < nLeaves; ++l)
+    if (D.layouts[D.leaves[firstLeaf + l].layout].k != k) return 0;
+  if (k + 1 > kMaxN1) return 0;
+  int path = 0;
+  if (regPathHas(dim, k, m)) path = 1;
+  if (forced > 0 && forced != path) return 0;
+  if (path == 0) return 0;
+  plan.path = path; plan.dim = dim; plan.k = k; plan.m = m; plan.firstFastest = ff; plan.jac = wantJac; plan.nq = nq;
+  for (int j = 0; j < dim; ++j)
+    for (int t = 0; t < m; ++t)
+      for (int a = 0; a <= k; ++a) {
+        // LagrangeCubeLocalBasis: k = 1 uses (1-x, x); general k the product formula
+        if (k == 1) { plan.A[j][t][a] = a ? x1[j][t] : 1 - x1[j][t]; plan.Dm[j][t][a] = a ? 1.0 : -1.0; }
+        else { plan.A[j][t][a] = lagrangeP(k, a, x1[j][t]); plan.Dm[j][t][a] = lagrangeDP(k, a, x1[j][t]); }
+      }
+  return path;
+}
+
+// ---------------------------------------------------------------------------
+template <int N1, int M>
+struct Tables {
+  double A[3][M][N1];
+  double D[3][M][N1];
+};
+
+struct RegArgs {
+  int firstLeaf, nGroup;       // leaves [firstLeaf, firstLeaf+nGroup) share one layout
+  int compOffset, ncompTotal;  // where the group's range entries sit in the output
+  int qs[3];                   // stride of q_j in the point index
+  unsigned long long e0, ne;
+  FastDiv divN0, divN1;
+  int bulk;                    // 1: the block's output tile is contiguous and 16-byte aligned
+};
+
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// contiguous shared -> global copy by the TMA engine (SASS: UBLKCP)
+__device__ __forceinline__ void bulkStore(double* gdst, const double* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smemAddr(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulkStoreWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// contraction of one direction: out[q] = sum_a T[q][a] * in[a]
+template <int N1, int M>
+__device__ __forceinline__ void contract1(const double (&T)[M][N1], const double (&in)[N1], double (&out)[M]) {
+#pragma unroll
+  for (int q = 0; q < M; ++q) {
+    double s = T[q][0] * in[0];
+#pragma unroll
+    for (int a = 1; a < N1; ++a) s = fma(T[q][a], in[a], s);
+    out[q] = s;
+  }
+}
+
+// u[q0][q1][q2] = sum_a T0[q0][a0] T1[q1][a1] T2[q2][a2] c[a0][a1][a2]   (DIM = 3; DIM = 2 drops a2)
+template <int DIM, int N1, int M>
+__device__ __forceinline__ void sumFactor(const double (&T0)[M][N1], const double (&T1)[M][N1],
+                                          const double (&T2)[M][N1], const double* __restrict__ c,
+                                          double* __restrict__ u) {
+  constexpr int NZ = DIM == 3 ? N1 : 1;
+  constexpr int MZ = DIM == 3 ? M : 1;
+  // x: t1[q0][a1][a2]
+  double t1[M][N1][NZ];
+#pragma unroll
+  for (int a2 = 0; a2 < NZ; ++a2)
+#pragma unroll
+    for (int a1 = 0; a1 < N1; ++a1) {
+      double in[N1], out[M];
+#pragma unroll
+      for (int a0 = 0; a0 < N1; ++a0) in[a0] = c[a0 + N1 * (a1 + N1 * a2)];
+      contract1<N1, M>(T0, in, out);
+#pragma unroll
+      for (int q = 0; q < M; ++q) t1[q][a1][a2] = out[q];
+    }
+  // y: t2[q0][q1][a2]
+  double t2[M][M][NZ];
+#pragma unroll
+  for (int q0 = 0; q0 < M; ++q0)
+#pragma unroll
+    for (int a2 = 0; a2 < NZ; ++a2) {
+      double in[N1], out[M];
+#pragma unroll
+      for (int a1 = 0; a1 < N1; ++a1) in[a1] = t1[q0][a1][a2];
+      contract1<N1, M>(T1, in, out);
+#pragma unroll
+      for (int q = 0; q < M; ++q) t2[q0][q][a2] = out[q];
+    }
+  if (DIM == 2) {
+#pragma unroll
+    for (int q0 = 0; q0 < M; ++q0)
+#pragma unroll
+      for (int q1 = 0; q1 < M; ++q1) u[q0 + M * q1] = t2[q0][q1][0];
+    return;
+  }
+  // z
+#pragma unroll
+  for (int q0 = 0; q0 < M; ++q0)
+#pragma unroll
+    for (int q1 = 0; q1 < M; ++q1) {
+      double in[N1], out[M];
+#pragma unroll
+      for (int a2 = 0; a2 < NZ; ++a2) in[a2] = t2[q0][q1][a2];
+      contract1<N1, M>(T2, in, out);
+#pragma unroll
+      for (int q = 0; q < MZ; ++q) u[q0 + M * (q1 + M * q)] = out[q];
+    }
+}
+
+template <int DIM, int K, int M, bool JAC, int EPB>
+__global__ void __launch_bounds__(EPB)
+k_eval_reg(const __grid_constant__ DevBasis B, const __grid_constant__ Tables<K + 1, M> T,
+           const __grid_constant__ RegArgs R, const double* __restrict__ coeff, double* __restrict__ values,
+           double* __restrict__ jac) {
+  constexpr int N1 = K + 1;
+  constexpr int NLOC = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  constexpr int NQ = DIM == 3 ? M * M * M : M * M;
+  extern __shared__ __align__(128) double stage[];       // values tile [EPB][NQ][nGroup], then jac tile
+  const DevGrid& g = B.grid;
+  const int tid = threadIdx.x;
+  const u64 blk0 = (u64)blockIdx.x * EPB;
+  const u64 el = blk0 + tid;
+  const bool active = el < R.ne;
+  const u64 e = R.e0 + (active ? el : 0);
+  // element coordinates (x fastest)
+  int ec[3];
+  {
+    const unsigned e32 = (unsigned)e;       // numElements < 2^32 checked on the host
+    unsigned q, r;
+    R.divN0.divmod(e32, q, r);
+    ec[0] = (int)r;
+    unsigned q2;
+    R.divN1.divmod(q, q2, r);
+    ec[1] = (int)r; ec[2] = (int)q2;
+  }
+  const int nG = R.nGroup;
+  const int rowLen = NQ * nG;
+  double* vTile = stage;
+  double* jTile = stage + (size_t)EPB * rowLen;           // [EPB][NQ][nGroup][DIM]
+  double jinv[3] = {0, 0, 0};
+  if (JAC) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) jinv[d] = elementJacInv(g, d, g.off[d] + ec[d]);
+  }
+
+  for (int gI = 0; gI < nG; ++gI) {
+    const DevLeaf& leaf = B.leaves[R.firstLeaf + gI];
+    const DevLayout& L = B.layouts[leaf.layout];
+    double c[NLOC];
+    if (L.kind == DFX_NODE_LAGRANGE_DG) {
+      const u64 base = leaf.posA * (e * (u64)NLOC) + leaf.posB;
+#pragma unroll
+      for (int i = 0; i < NLOC; ++i) c[i] = __ldg(coeff + base + leaf.posA * (u64)i);
+    } else {
+#pragma unroll
+      for (int a2 = 0; a2 < (DIM == 3 ? N1 : 1); ++a2)
+#pragma unroll
+        for (int a1 = 0; a1 < N1; ++a1)
+#pragma unroll
+          for (int a0 = 0; a0 < N1; ++a0) {
+            // closed form of MCMGMapper::subIndex on the structured grid
+            constexpr int dummy = 0; (void)dummy;
+            const int s = ((a0 > 0 && a0 < K) ? 1 : 0) | ((a1 > 0 && a1 < K) ? 2 : 0) | ((DIM == 3 && a2 > 0 && a2 < K) ? 4 : 0);
+            const int c0 = ec[0] + (a0 == K ? 1 : 0);
+            const int c1 = ec[1] + (a1 == K ? 1 : 0);
+            const int c2 = ec[2] + ((DIM == 3 && a2 == K) ? 1 : 0);
+            // K <= 2 here: at most one interior node per direction, so the in-entity index is 0
+            const u64 ent = (u64)c0 + (u64)L.csize[s][0] * ((u64)c1 + (u64)L.csize[s][1] * (u64)c2);
+            const u64 j = L.compOffset[s] + ent * (u64)L.blk[s];
+            c[a0 + N1 * (a1 + N1 * a2)] = __ldg(coeff + leaf.posA * j + leaf.posB);
+          }
+    }
+    double u[NQ];
+    sumFactor<DIM, N1, M>(T.A[0], T.A[1], T.A[2], c, u);
+    if (values) {
+#pragma unroll
+      for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+        for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+          for (int q0 = 0; q0 < M; ++q0) {
+            const int q = q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2];
+            vTile[(size_t)tid * rowLen + q * nG + gI] = u[q0 + M * (q1 + M * q2)];
+          }
+    }
+    if (JAC) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        sumFactor<DIM, N1, M>(d == 0 ? T.D[0] : T.A[0], d == 1 ? T.D[1] : T.A[1], d == 2 ? T.D[2] : T.A[2], c, u);
+#pragma unroll
+        for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+          for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+            for (int q0 = 0; q0 < M; ++q0) {
+              const int q = q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2];
+              jTile[((size_t)tid * rowLen + q * nG + gI) * DIM + d] = u[q0 + M * (q1 + M * q2)] * jinv[d];
+            }
+      }
+    }
+  }
+
+  // ---- the block's results leave in output order ----
+  const u64 nAct = R.ne - blk0 < (u64)EPB ? R.ne - blk0 : (u64)EPB;
+  const bool full = nAct == (u64)EPB;
+  if (R.bulk && full) {
+    fenceProxyAsync();          // generic-proxy smem writes -> visible to the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      if (values) bulkStore(values + blk0 * (u64)rowLen, vTile, (unsigned)(EPB * rowLen * sizeof(double)));
+      if (JAC) bulkStore(jac + blk0 * (u64)rowLen * DIM, jTile, (unsigned)(EPB * rowLen * DIM * sizeof(double)));
+      bulkStoreWaitRead();      // shared memory must outlive the copy
+    }
+    return;
+  }
+  __syncthreads();
+  // partial tile, unaligned output or a sub-range of the range entries: cooperative stores
+  const int nT = R.ncompTotal, cOff = R.compOffset;
+  if (values) {
+    const u64 cnt = nAct * (u64)rowLen;
+    for (u64 i = tid; i < cnt; i += EPB) {
+      const u64 row = i / (u64)nG, gI = i - row * (u64)nG;       // row = el_local*NQ + q
+      values[(blk0 * (u64)NQ + row) * (u64)nT + cOff + gI] = vTile[i];
+    }
+  }
+  if (JAC) {
+    const u64 cnt = nAct * (u64)rowLen * DIM;
+    for (u64 i = tid; i < cnt; i += EPB) {
+      const u64 rg = i / DIM, d = i - rg * DIM;
+      const u64 row = rg / (u64)nG, gI = rg - row * (u64)nG;
+      jac[((blk0 * (u64)NQ + row) * (u64)nT + cOff + gI) * DIM + d] = jTile[i];
+    }
+  }
+}
+
+template <int DIM, int K, int M, bool JAC>
+static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const double* coeff, double* values,
+                     double* jac, cudaStream_t st) {
+  constexpr int EPB = JAC ? 64 : 128;
+  constexpr int NQ = DIM == 3 ? M * M * M : M * M;
+  Tables<K + 1, M> T;
+  for (int j = 0; j < 3; ++j)
+    for (int q = 0; q < M; ++q)
+      for (int a = 0; a <= K; ++a) { T.A[j][q][a] = plan.A[j][q][a]; T.D[j][q][a] = plan.Dm[j][q][a]; }
+  size_t smem = (size_t)EPB * NQ * R.nGroup * sizeof(double) * (JAC ? 1 + DIM : 1);
+  auto kern = k_eval_reg<DIM, K, M, JAC, EPB>;
+  if (smem > 200 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const u64 blocks = (R.ne + EPB - 1) / EPB;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  kern<<<(unsigned)blocks, EPB, smem, st>>>(b->dev, T, R, coeff, values, jac);
+  return postLaunch("k_eval_reg");
+}
+
+int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
+                double* values, double* jac, cudaStream_t st) {
+  if (e1 == e0) return DFX_OK;
+  const DevBasis& D = b->dev;
+  if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
+    return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
+  // runs of consecutive leaves that share a layout
+  int l = 0;
+  while (l < nLeaves) {
+    int r = l + 1;
+    while (r < nLeaves && D.leaves[firstLeaf + r].layout == D.leaves[firstLeaf + l].layout) ++r;
+    {
+      // bound the staging tile (<= 96 KB per block): long runs are cut into chunks of leaves
+      int nq = 1; for (int j = 0; j < plan.dim; ++j) nq *= plan.m;
+      const size_t perLeaf = (size_t)(plan.jac ? 64 : 128) * nq * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
+      const int maxG = (int)std::max<size_t>(1, (96 * 1024) / perLeaf);
+      if (r - l > maxG) r = l + maxG;
+    }
+    RegArgs R;
+    R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = l; R.ncompTotal = nLeaves;
+    const int m = plan.m, dim = plan.dim;
+    if (plan.firstFastest) { R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m; }
+    else { int s = 1; R.qs[0] = R.qs[1] = R.qs[2] = 0; for (int j = dim - 1; j >= 0; --j) { R.qs[j] = s; s *= m; } }
+    R.e0 = e0; R.ne = e1 - e0;
+    R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
+    const bool whole = R.nGroup == nLeaves;
+    const bool aligned = (!values || ((uintptr_t)values & 15) == 0) && (!jac || ((uintptr_t)jac & 15) == 0);
+    R.bulk = whole && aligned ? 1 : 0;
+    int rc = DFX_OK;
+#define DFX_REG(DIM_, K_, M_)                                                                      \
+  if (dim == DIM_ && plan.k == K_ && m == M_)                                                      \
+    rc = plan.jac ? launchReg<DIM_, K_, M_, true>(b, plan, R, coeff, values, jac, st)             \
+                  : launchReg<DIM_, K_, M_, false>(b, plan, R, coeff, values, jac, st);
+    DFX_REG(2, 1, 2) DFX_REG(2, 1, 3) DFX_REG(2, 2, 2) DFX_REG(2, 2, 3)
+    DFX_REG(3, 1, 2) DFX_REG(3, 1, 3) DFX_REG(3, 2, 2) DFX_REG(3, 2, 3)
+#undef DFX_REG
+    if (rc) return rc;
+    l = r;
+  }
+  return DFX_OK;
+}
+
+}  // namespace dfx

@@ -112,6 +112,9 @@ struct dfx_basis_impl {
   u64 dimension;
   int minDigits, maxDigits;
   // device scratch owned by the handle
+  std::vector<unsigned> localTab;                       // per local index: leaf | alpha (see k_indices_fast)
+  void* dLocalTab = nullptr;                            // uploaded on first use
+  void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f
   void* dShape = nullptr; size_t dShapeBytes = 0;       // shape tables of the last evaluate
   std::vector<double> lastXhat; int lastShapeNode = -1;
   void* pinned = nullptr; size_t pinnedBytes = 0;       // staging for *_host entry points

@@ -44,6 +44,11 @@ int interpolateFromValues(const dfx_basis* b, int firstLeaf, int nLeaves, const 
 int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* shape,
                 const double* dshape, const ShapeOffsets& so, int nq, u64 e0, u64 e1, double* values, double* jac,
                 cudaStream_t st);
+int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
+                    const uint8_t* mask, cudaStream_t st);
+extern int g_interpMode;
+template <class T, bool MULTI>
+int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st);
 int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
 
 }  // namespace dfx

@@ -208,11 +208,17 @@ int dfx_evaluate(const dfx_basis* b, int32_t subtree_node, const double* coeff,
                  double* out_values, double* out_jacobians, void* stream);
 /* which kernel family dfx_evaluate picks for this configuration:
  * 0 generic, 1 sum-factorised register kernel, 2 sum-factorised shared-memory
- * (TMA bulk) kernel, 3 dense FP64 tensor-core (DMMA) kernel.
- * dfx_set_eval_path forces one (-1 = automatic).                               */
+ * (TMA bulk) kernel, 3 dense FP64 tensor-core (DMMA) kernel.                   */
 int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xhat_host,
                       int32_t n_q, int32_t want_jacobians);
-void dfx_set_eval_path(int32_t path);
+/* force a kernel family (testing / profiling); path -1 = automatic.
+ * op DFX_OP_EVALUATE: paths as above; DFX_OP_INTERPOLATE: 0 generic per-DOF
+ * kernel, 1 structured kernel evaluating f at every node, 2 structured kernel
+ * with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast. */
+#define DFX_OP_EVALUATE 0
+#define DFX_OP_INTERPOLATE 1
+#define DFX_OP_INDICES 2
+void dfx_set_kernel_path(int32_t op, int32_t path);
 
 /* ---- host-buffer entry points (what a CPU caller of the reference uses) ----
  * Same semantics with HOST buffers; the copies are staged through pinned

@@ -28,7 +28,7 @@ def _gpu():
     assert torch.cuda.is_available()
     torch.cuda.set_device(0)
     yield
-    capi.lib().dfx_set_eval_path(-1)
+    capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
 
 
 def all_cases():
@@ -200,14 +200,14 @@ def random_coeff(n, seed=12345):
 
 def eval_both(grid, tree, pts, node=0, jac=True, path=-1):
     import torch
-    capi.lib().dfx_set_eval_path(path)
+    capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, path)
     b = dfx.makeBasis(grid, tree)
     o = orc.OracleBasis(grid, tree)
     c = random_coeff(b.dimension())
     f = dfx.makeDiscreteGlobalBasisFunction(b if node == 0 else _Sub(b, node), torch.from_numpy(c).cuda())
     v, j = f.evaluate(pts, jacobians=True) if jac else (f.evaluate(pts), None)
     vr, jr = o.evaluate(c, pts, node=node, jacobians=True) if jac else (o.evaluate(c, pts, node=node), None)
-    capi.lib().dfx_set_eval_path(-1)
+    capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
     return v.cpu().numpy(), (j.cpu().numpy() if jac else None), vr, jr
 
 
@@ -314,3 +314,110 @@ def test_derivative_of_q3_interpolant():
     l2 = np.sqrt(np.einsum("eq,q->", (j[:, :, 0, 0] - (84 * X + 7 * Y)) ** 2 + (j[:, :, 0, 1] - (26 * Y + 7 * X)) ** 2, w) / 420)
     assert l2 <= 6.6e-11
     assert np.abs(v[:, :, 0] - (42 * X * X + 13 * Y * Y + 7 * X * Y)).max() < 1e-10
+
+
+# ---- every kernel family gives the same answer ---------------------------------------------------
+@pytest.fixture
+def kernel_path():
+    def set_path(op, path):
+        capi.lib().dfx_set_kernel_path(op, path)
+    yield set_path
+    for op in (capi.OP_EVALUATE, capi.OP_INTERPOLATE, capi.OP_INDICES):
+        capi.lib().dfx_set_kernel_path(op, -1)
+
+
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_3x4x5"])
+def test_indices_kernel_families(kernel_path, gname, path):
+    import torch
+    kernel_path(capi.OP_INDICES, path)
+    grid = GRIDS[gname]
+    for name, tree in trees(grid.dim).items():
+        if "TH_" in name and grid.dim != 3:
+            continue
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        assert (b.indices().cpu().numpy().astype(np.uint64) == o.indices()[0]).all(), name
+        assert (b.flatIndices(dtype=torch.int64).cpu().numpy().astype(np.uint64) == o.flatIndices()).all(), name
+
+
+@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_3x4x5", "3d_2x1x3"])
+def test_interpolate_kernel_families(kernel_path, gname, path):
+    """generic per-DOF kernel, structured per-node kernel, separable-table kernel"""
+    kernel_path(capi.OP_INTERPOLATE, path)
+    grid = GRIDS[gname]
+    for name, tree in trees(grid.dim).items():
+        if "TH_" in name and grid.dim != 3:
+            continue
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        for fname, f in FUNCS.items():
+            x = b.newVector(-5.0)
+            dfx.interpolate(b, x, f)
+            ref = o.interpolate(f, coeff=np.full(o.dimension(), -5.0))
+            assert rel(x.cpu().numpy(), ref) <= TOL, (name, fname)
+            if fname in ("coord0", "const", "quadratic"):
+                assert (x.cpu().numpy() == ref).all(), (name, fname)
+
+
+def test_partitioned_interpolate_matches_global_run(kernel_path):
+    """a z-slab handle reproduces the serial run on the whole grid bit for bit, including the
+    interface plane whose last writer lives in the neighbouring slab (include/dfx.h, dfx_grid_desc)"""
+    whole = YaspGrid([4, 3, 8], upper=[1.0, 0.7, 1.3])
+    for tree in (lagrange(2), lagrange(3), lagrange(1), lagrangeDG(2)):
+        og = orc.OracleBasis(whole, tree)
+        ref = og.interpolate(dfx.coord(2))
+        gflat = og.flatIndices().reshape(8, 12, -1)
+        for path in (0, 1, 2):
+            kernel_path(capi.OP_INTERPOLATE, path)
+            for r in range(4):
+                slab = whole.slab(r, 4)
+                b = dfx.makeBasis(slab, tree)
+                x = dfx.interpolate(b, b.newVector(0.0), dfx.coord(2)).cpu().numpy()
+                lflat = b.flatIndices().cpu().numpy().reshape(2, 12, -1)
+                assert (x[lflat] == ref[gflat[2 * r:2 * r + 2].astype(np.int64)]).all()
+
+
+def test_halo_pack_unpack_and_owned_ranges():
+    """one-plane halo between z-slabs: pack the lower plane of slab r+1, unpack into the top
+    plane of slab r; owned ranges tile the global vector exactly once"""
+    import torch
+    whole = YaspGrid([3, 2, 6])
+    L = capi.lib()
+    for tree in (lagrange(2), power(lagrange(2), 3, BI()), composite(power(lagrange(2), 3, FL()), lagrange(1), FL()),
+                 lagrange(3), lagrangeDG(1)):
+        og = orc.OracleBasis(whole, tree)
+        gx = random_coeff(og.dimension())
+        gflat = og.flatIndices().reshape(6, 6, -1).astype(np.int64)
+        slabs = [dfx.makeBasis(whole.slab(r, 3), tree) for r in range(3)]
+        vecs = []
+        for r, b in enumerate(slabs):
+            lflat = b.flatIndices().cpu().numpy().reshape(2, 6, -1).astype(np.int64)
+            x = np.full(b.dimension(), np.nan)
+            x[lflat] = gx[gflat[2 * r:2 * r + 2]]
+            vecs.append(torch.from_numpy(x).cuda())
+        n = int(L.dfx_halo_size(slabs[0]._h))
+        for r in range(2):
+            top_before = vecs[r].clone()
+            buf = torch.zeros(max(n, 1), dtype=torch.float64, device="cuda")
+            capi.check(L.dfx_halo_pack(slabs[r + 1]._h, 0, C.c_void_p(vecs[r + 1].data_ptr()), C.c_void_p(buf.data_ptr()), None))
+            vecs[r].mul_(1.0)
+            # wipe the top plane, then restore it from the neighbour's buffer
+            scratch = vecs[r].clone()
+            capi.check(L.dfx_halo_unpack(slabs[r]._h, 1, C.c_void_p(torch.full_like(buf, -3.0).data_ptr()), C.c_void_p(scratch.data_ptr()), None))
+            assert ((scratch == -3.0).sum().item() == n)
+            capi.check(L.dfx_halo_unpack(slabs[r]._h, 1, C.c_void_p(buf.data_ptr()), C.c_void_p(scratch.data_ptr()), None))
+            assert torch.equal(scratch, top_before)
+        if all(True for _ in [0]) and tree.kind != capi.NODE_POWER:
+            # owned ranges: gather the slabs into the global vector
+            out = np.full(og.dimension(), np.nan)
+            for r, b in enumerate(slabs):
+                lb, cnt, gb = (C.c_uint64 * 64)(), (C.c_uint64 * 64)(), (C.c_uint64 * 64)()
+                nr = C.c_int32()
+                capi.check(L.dfx_owned_ranges(b._h, lb, cnt, gb, 64, C.byref(nr)))
+                xl = vecs[r].cpu().numpy()
+                for i in range(nr.value):
+                    assert np.isnan(out[gb[i]:gb[i] + cnt[i]]).all()
+                    out[gb[i]:gb[i] + cnt[i]] = xl[lb[i]:lb[i] + cnt[i]]
+            assert (out == gx).all()
