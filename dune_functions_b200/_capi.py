@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdfx.so")
+# DFX_LIB selects another build of the same library (tuning variants under lib/)
+LIB_PATH = os.environ.get("DFX_LIB") or os.path.join(HERE, "lib", "libdfx.so")
 
 DFX_MAX_DIM = 3
 DFX_MAX_DIGITS = 6

@@ -26,6 +26,8 @@ int ensureDevice(const dfx_basis* b) {
     dfx_basis* mb = const_cast<dfx_basis*>(b);
     DFX_CUDA(cudaMalloc(&mb->dLocalTab, b->localTab.size() * sizeof(unsigned)));
     DFX_CUDA(cudaMemcpy(mb->dLocalTab, b->localTab.data(), b->localTab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    DFX_CUDA(cudaMalloc(&mb->dDev, sizeof(DevBasis)));
+    DFX_CUDA(cudaMemcpy(mb->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice));
   }
   return DFX_OK;
 }
@@ -171,6 +173,7 @@ void dfx_basis_destroy(dfx_basis* b) {
     cudaSetDevice(b->device);
     if (b->dShape) cudaFree(b->dShape);
     if (b->dLocalTab) cudaFree(b->dLocalTab);
+    if (b->dDev) cudaFree(b->dDev);
     if (b->dSep) cudaFree(b->dSep);
     if (b->pinned) cudaFreeHost(b->pinned);
     for (int i = 0; i < 3; ++i) if (b->dScratch[i]) cudaFree(b->dScratch[i]);

@@ -59,47 +59,54 @@ __device__ __forceinline__ void localAlpha(int k, int i, int a[3]) {
 }
 
 // ---- registry of functions f (include/dfx.h, dfx_fn_id) ----------------------
+// Functor interface used by the interpolation kernels (also what a user-supplied device
+// functor implements): `common(x0,x1,x2)` computes the part shared by all range entries
+// (the transcendental), `comp(c, common, x0,x1,x2)` returns range entry c.  No arrays, so
+// everything stays in registers.
 struct RegistryFn {
   dfx_function f;
   int dim;
   __device__ __forceinline__ int ncomp() const { return f.n_comp; }
-  __device__ void operator()(const double* x, double* y) const {
+  __device__ __forceinline__ double norm2(double x0, double x1, double x2) const {
+    double s = __dmul_rn(x0, x0);                                   // x.two_norm2(): sum in index order
+    if (dim > 1) s = __dadd_rn(s, __dmul_rn(x1, x1));
+    if (dim > 2) s = __dadd_rn(s, __dmul_rn(x2, x2));
+    return s;
+  }
+  __device__ __forceinline__ double common(double x0, double x1, double x2) const {
     switch (f.id) {
-      case DFX_FN_CONSTANT:
-        for (int c = 0; c < f.n_comp; ++c) y[c] = f.p[c];
-        break;
-      case DFX_FN_GAUSSIAN: {
-        double s = 0;
-        for (int j = 0; j < dim; ++j) s = __dadd_rn(s, __dmul_rn(x[j], x[j]));   // x.two_norm2()
-        y[0] = exp(__dmul_rn(-f.p[0], s));
-        break; }
-      case DFX_FN_IDENTITY:
-        for (int c = 0; c < f.n_comp; ++c) y[c] = c < dim ? x[c] : 0.0;
-        break;
-      case DFX_FN_COORD: y[0] = x[(int)f.p[0]]; break;
+      case DFX_FN_GAUSSIAN:
+      case DFX_FN_GAUSSIAN_VEC:
+        return exp(__dmul_rn(-f.p[0], norm2(x0, x1, x2)));
       case DFX_FN_QUADRATIC: {
-        double xx[3] = {x[0], dim > 1 ? x[1] : 0.0, dim > 2 ? x[2] : 0.0};
+        const double xx[3] = {x0, dim > 1 ? x1 : 0.0, dim > 2 ? x2 : 0.0};
         double r = f.p[0];
+#pragma unroll
         for (int j = 0; j < 3; ++j) r = __dadd_rn(r, __dmul_rn(f.p[1 + j], xx[j]));
         int q = 4;
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
           for (int j = i; j < 3; ++j) { r = __dadd_rn(r, __dmul_rn(__dmul_rn(f.p[q], xx[i]), xx[j])); ++q; }
-        y[0] = r;
-        break; }
+        return r; }
       case DFX_FN_SINPROD: {
-        double r = 1;
-        for (int j = 0; j < dim; ++j) r = __dmul_rn(r, sin(__dmul_rn(f.p[0], x[j])));
-        y[0] = r;
-        break; }
-      case DFX_FN_GAUSSIAN_VEC: {
-        double s = 0;
-        for (int j = 0; j < dim; ++j) s = __dadd_rn(s, __dmul_rn(x[j], x[j]));
-        const double e = exp(__dmul_rn(-f.p[0], s));
-        for (int c = 0; c < f.n_comp; ++c) y[c] = __dmul_rn(c < dim ? x[c] : 1.0, e);
-        break; }
-      default:
-        for (int c = 0; c < f.n_comp; ++c) y[c] = 0.0;
+        double r = __dmul_rn(1.0, sin(__dmul_rn(f.p[0], x0)));
+        if (dim > 1) r = __dmul_rn(r, sin(__dmul_rn(f.p[0], x1)));
+        if (dim > 2) r = __dmul_rn(r, sin(__dmul_rn(f.p[0], x2)));
+        return r; }
+      case DFX_FN_COORD: {
+        const int j = (int)f.p[0];
+        return j == 0 ? x0 : (j == 1 ? x1 : x2); }
     }
+    return 0.0;
+  }
+  __device__ __forceinline__ double comp(int c, double cm, double x0, double x1, double x2) const {
+    switch (f.id) {
+      case DFX_FN_CONSTANT: return f.p[c];
+      case DFX_FN_IDENTITY: return c >= dim ? 0.0 : (c == 0 ? x0 : (c == 1 ? x1 : x2));
+      case DFX_FN_GAUSSIAN_VEC: return __dmul_rn(c >= dim ? 1.0 : (c == 0 ? x0 : (c == 1 ? x1 : x2)), cm);
+    }
+    return cm;
   }
 };
 

@@ -168,8 +168,14 @@ __device__ __forceinline__ void sumFactor(const double (&T0)[M][N1], const doubl
     }
 }
 
+// resident blocks per SM the register allocator is asked to allow (values-only kernels):
+// 6 x 128 threads = 24 warps at <= 80 registers, no spills for any instantiated (DIM, K, M)
+#ifndef DFX_EVAL_MINB
+#define DFX_EVAL_MINB 6
+#endif
+
 template <int DIM, int K, int M, bool JAC, int EPB>
-__global__ void __launch_bounds__(EPB)
+__global__ void __launch_bounds__(EPB, JAC ? 1 : DFX_EVAL_MINB)
 k_eval_reg(const __grid_constant__ DevBasis B, const __grid_constant__ Tables<K + 1, M> T,
            const __grid_constant__ RegArgs R, const double* __restrict__ coeff, double* __restrict__ values,
            double* __restrict__ jac) {

@@ -114,6 +114,7 @@ struct dfx_basis_impl {
   // device scratch owned by the handle
   std::vector<unsigned> localTab;                       // per local index: leaf | alpha (see k_indices_fast)
   void* dLocalTab = nullptr;                            // uploaded on first use
+  void* dDev = nullptr;                                 // device copy of `dev`
   void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f
   void* dShape = nullptr; size_t dShapeBytes = 0;       // shape tables of the last evaluate
   std::vector<double> lastXhat; int lastShapeNode = -1;

@@ -2,11 +2,12 @@
 //
 //   k_interp_rows      owner-writes interpolation of continuous Lagrange leaves.  The DOF
 //                      lattice has (k N_x + 1) x (k N_y + 1) x (k N_z + 1) points; a block takes
-//                      16 lattice rows (Y, Z fixed per row), 16 threads put the per-row index
-//                      bases into shared memory, then all threads stream (row, x-entity)
-//                      items: an item writes the row's vertex-type node and the k-1 edge-type
-//                      nodes right of it, so consecutive threads write consecutive addresses
-//                      in both index-set components the row touches.
+//                      32 lattice rows (Y, Z fixed per row) and first puts the per-row, per-leaf
+//                      flat-position bases into shared memory.  Each thread then owns fixed
+//                      x-entities (their x-direction factors / coordinates stay in registers)
+//                      and sweeps the rows: per row it writes the vertex-type node and the k-1
+//                      edge-type nodes right of it, so consecutive threads write consecutive
+//                      addresses in both index-set components the row touches.
 //   k_interp_cell      the same for element-local DOFs (LagrangeDG, Lagrange<0>).
 //   k_sep_tables       per-direction factor tables of a separable f (exp(-a|x|^2) =
 //                      prod_j exp(-a x_j^2), prod_j sin(w x_j), x_j, const): O(N) instead of
@@ -16,6 +17,8 @@
 //
 // Replaces the interpolate element loop (interpolate.hh:254-259 with :151-173) and
 // DefaultLocalView::bind -> PreBasis::indices (defaultlocalview.hh:95-101).
+#include <algorithm>
+
 #include "dfx_device.cuh"
 #include "dfx_launch.h"
 
@@ -27,7 +30,10 @@ struct RowArgs {
   int tabOff[3];           // separable mode: offset of direction j's table
   FastDiv divK;            // lattice coordinate -> (entity, node inside)
   FastDiv divLY;           // row index -> (Z, Y)
-  FastDiv divEnt;          // block item -> (row, x-entity)
+  int nActive;             // leaves of the subtree that live on this lattice
+  int leafId[DFX_MAX_LEAVES];     // their ids, range entries and in-entity position stride
+  int leafComp[DFX_MAX_LEAVES];
+  unsigned leafPosA[DFX_MAX_LEAVES];
 };
 
 // one direction of a lattice point: entity coordinate, in-entity node, owner element, alpha
@@ -80,29 +86,34 @@ k_sep_tables(const __grid_constant__ DevGrid g, const __grid_constant__ dfx_func
   tab[t] = sepFactor(f, j, nodeCoord(g, k, j, ie, a));
 }
 
-// per lattice row (Y, Z fixed): bases of the two index-set components it touches
-struct RowInfo {
-  u64 rowV, rowE;        // scalar index of entity 0's vertex-type / first edge-type node
-  double u1, u2;         // MODE 0: node coordinates x_1, x_2;  MODE 1: table factors t_y, t_z
-  int blkV, blkE;
-};
-constexpr int kRowsPerBlock = 16;
+// per lattice row (Y, Z fixed) and active leaf: flat position of x-entity 0's vertex-type
+// node / first edge-type node and the position stride between consecutive x-entities
+struct RowLeaf { u64 baseV, baseE; unsigned strideV, strideE; };
+struct RowCommon { double u1, u2; };   // MODE 0: node coordinates x_1, x_2;  MODE 1: factors t_y, t_z
+constexpr int kRowsPerBlock = 32;
+constexpr int kMaxHoist = 4;           // orders 1..4 keep the x-direction data in registers
 
-// MODE 0: f evaluated at every node; MODE 1: product of per-direction tables
-template <class F, int MODE>
+// MODE 0: f evaluated at every node; MODE 1: product of per-direction tables.
+// KT: compile-time order (0 = run-time order, nothing hoisted).  ONE: the subtree has a
+// single leaf on this lattice (the scalar case), its bases sit in slot 0.
+template <class F, int MODE, int KT, bool ONE>
 __global__ void __launch_bounds__(256)
 k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArgs A, const F f,
               const double* __restrict__ tab, double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
-  __shared__ RowInfo rows[kRowsPerBlock];
+  __shared__ RowCommon rowc[kRowsPerBlock];
+  __shared__ RowLeaf rowl[ONE ? 1 : DFX_MAX_LEAVES][kRowsPerBlock];
   const DevGrid& g = B.grid;
   const DevLayout& L = B.layouts[A.layoutId];
-  const int k = L.k;                          // >= 1
+  const int k = KT > 0 ? KT : L.k;            // >= 1
   const unsigned nRows = (unsigned)A.LX[1] * (unsigned)A.LX[2];
   const unsigned row0 = blockIdx.x * kRowsPerBlock;
   const unsigned nr = min((unsigned)kRowsPerBlock, nRows - row0);
-  if (threadIdx.x < nr) {
+  const int nAct = ONE ? 1 : A.nActive;
+  // ---- per-row setup by the first nr*nAct threads ----
+  for (unsigned w = threadIdx.x; w < nr * (unsigned)nAct; w += blockDim.x) {
+    const unsigned rI = w / (unsigned)nAct, lI = w - rI * (unsigned)nAct;
     unsigned Z, Y;
-    A.divLY.divmod(row0 + threadIdx.x, Z, Y);
+    A.divLY.divmod(row0 + rI, Z, Y);
     const Dir dy = latticeDir(g, A.divK, k, 1, (int)Y);
     const Dir dz = latticeDir(g, A.divK, k, 2, (int)Z);
     unsigned syz = 0;
@@ -110,47 +121,76 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
     if (g.dim > 1 && dy.inner) { syz |= 2u; fyz += (u64)(dy.inner - 1) * fs; fs *= (u64)(k - 1); }
     if (g.dim > 2 && dz.inner) { syz |= 4u; fyz += (u64)(dz.inner - 1) * fs; }
     const unsigned sV = syz, sE = syz | 1u;
-    RowInfo r;
-    r.blkV = L.blk[sV]; r.blkE = L.blk[sE];
-    r.rowV = L.compOffset[sV] + (u64)L.blk[sV] * ((u64)L.csize[sV][0] * ((u64)dy.c + (u64)L.csize[sV][1] * (u64)dz.c)) + fyz;
-    r.rowE = L.compOffset[sE] + (u64)L.blk[sE] * ((u64)L.csize[sE][0] * ((u64)dy.c + (u64)L.csize[sE][1] * (u64)dz.c)) + fyz * (u64)(k - 1);
-    if (MODE == 0) {
-      r.u1 = g.dim > 1 ? nodeCoord(g, k, 1, dy.ie, dy.a) : 0.0;
-      r.u2 = g.dim > 2 ? nodeCoord(g, k, 2, dz.ie, dz.a) : 0.0;
-    } else {
-      r.u1 = tab[A.tabOff[1] + (int)Y];
-      r.u2 = tab[A.tabOff[2] + (int)Z];
+    const u64 rowV = L.compOffset[sV] + (u64)L.blk[sV] * ((u64)L.csize[sV][0] * ((u64)dy.c + (u64)L.csize[sV][1] * (u64)dz.c)) + fyz;
+    const u64 rowE = L.compOffset[sE] + (u64)L.blk[sE] * ((u64)L.csize[sE][0] * ((u64)dy.c + (u64)L.csize[sE][1] * (u64)dz.c)) + fyz * (u64)(k - 1);
+    const DevLeaf& leaf = B.leaves[A.leafId[lI]];
+    RowLeaf rl;
+    rl.baseV = leaf.posA * rowV + leaf.posB;
+    rl.baseE = leaf.posA * rowE + leaf.posB;
+    rl.strideV = (unsigned)(leaf.posA * (u64)L.blk[sV]);
+    rl.strideE = (unsigned)(leaf.posA * (u64)L.blk[sE]);
+    rowl[lI][rI] = rl;
+    if (lI == 0) {
+      RowCommon rc;
+      if (MODE == 0) {
+        rc.u1 = g.dim > 1 ? nodeCoord(g, k, 1, dy.ie, dy.a) : 0.0;
+        rc.u2 = g.dim > 2 ? nodeCoord(g, k, 2, dz.ie, dz.a) : 0.0;
+      } else {
+        rc.u1 = __dmul_rn(tab[A.tabOff[1] + (int)Y], tab[A.tabOff[2] + (int)Z]);   // t_y * t_z
+        rc.u2 = 0.0;
+      }
+      rowc[rI] = rc;
     }
-    rows[threadIdx.x] = r;
   }
   __syncthreads();
   const bool scalar = MODE == 1 || f.ncomp() == 1;
-  const unsigned nEnt = (unsigned)g.N[0] + 1u;          // x-entities per row
-  const unsigned items = nr * nEnt;
-  for (unsigned w = threadIdx.x; w < items; w += blockDim.x) {
-    unsigned rI, c0;
-    A.divEnt.divmod(w, rI, c0);
-    const RowInfo r = rows[rI];
-    // this item's nodes: X = k c0 (vertex-type along x) and k c0 + a, a = 1..k-1
-    const int nNodes = c0 < (unsigned)g.N[0] ? k : 1;
-    for (int a = 0; a < nNodes; ++a) {
-      const u64 jdx = a == 0 ? r.rowV + (u64)r.blkV * (u64)c0 : r.rowE + (u64)r.blkE * (u64)c0 + (u64)(a - 1);
-      double y[DFX_MAX_LEAVES];
-      if (MODE == 0) {
-        int ie = g.off[0] + (int)c0, aa = a;
-        if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }      // last lattice plane: owner on the left
-        double x[3];
-        x[0] = nodeCoord(g, k, 0, ie, aa); x[1] = r.u1; x[2] = r.u2;
-        f(x, y);
-      } else {
-        // (t_x * t_y) * t_z: the order in which the reference's callable multiplies its factors
-        y[0] = __dmul_rn(__dmul_rn(tab[A.tabOff[0] + k * (int)c0 + a], r.u1), r.u2);
+  // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... and sweeps the rows ----
+  for (unsigned c0 = threadIdx.x; c0 <= (unsigned)g.N[0]; c0 += blockDim.x) {
+    const int nNodes = c0 < (unsigned)g.N[0] ? k : 1;     // the last entity is the closing vertex plane only
+    // x-direction data of this entity's nodes: X = k c0 + a, a = 0 (vertex-type) .. k-1
+    double hx[KT > 0 ? KT : 1];
+    if (KT > 0) {
+#pragma unroll
+      for (int a = 0; a < KT; ++a) {
+        if (a >= nNodes) { hx[a] = 0.0; continue; }
+        if (MODE == 0) {
+          int ie = g.off[0] + (int)c0, aa = a;
+          if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }    // last lattice plane: owner on the left
+          hx[a] = nodeCoord(g, k, 0, ie, aa);
+        } else {
+          hx[a] = tab[A.tabOff[0] + k * (int)c0 + a];
+        }
       }
-      for (int l = 0; l < A.nLeaves; ++l) {
-        const DevLeaf& leaf = B.leaves[A.firstLeaf + l];
-        if (leaf.layout != A.layoutId) continue;
-        const u64 p = leaf.posA * jdx + leaf.posB;
-        if (mask == nullptr || mask[p]) coeff[p] = scalar ? y[0] : y[l];
+    }
+#pragma unroll 2
+    for (unsigned rI = 0; rI < nr; ++rI) {
+      const RowCommon rc = rowc[rI];
+#pragma unroll
+      for (int a = 0; a < (KT > 0 ? KT : kMaxContinuousOrder); ++a) {
+        if (a >= nNodes) break;
+        double xa;
+        if (KT > 0) xa = hx[a];
+        else if (MODE == 0) {
+          int ie = g.off[0] + (int)c0, aa = a;
+          if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }
+          xa = nodeCoord(g, k, 0, ie, aa);
+        } else xa = tab[A.tabOff[0] + k * (int)c0 + a];
+        const double cm = MODE == 0 ? f.common(xa, rc.u1, rc.u2) : __dmul_rn(xa, rc.u1);
+        if (ONE) {
+          const RowLeaf rl = rowl[0][rI];
+          const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
+                               : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[0] * (u64)(a - 1);
+          if (mask == nullptr || mask[p])
+            coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[0], cm, xa, rc.u1, rc.u2);
+        } else {
+          for (int lI = 0; lI < nAct; ++lI) {
+            const RowLeaf rl = rowl[lI][rI];
+            const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
+                                 : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[lI] * (u64)(a - 1);
+            if (mask == nullptr || mask[p])
+              coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[lI], cm, xa, rc.u1, rc.u2);
+          }
+        }
       }
     }
   }
@@ -190,14 +230,13 @@ k_interp_cell(const __grid_constant__ DevBasis B, const __grid_constant__ CellAr
     if (MODE == 0) x[j] = nodeCoord(g, k, j, g.off[j] + ec[j], a[j]);
     else prod = __dmul_rn(prod, tab[A.tabOff[j] + ec[j] * (k + 1) + a[j]]);
   }
-  double y[DFX_MAX_LEAVES];
-  if (MODE == 0) f(x, y); else y[0] = prod;
+  const double cm = MODE == 0 ? f.common(x[0], x[1], x[2]) : prod;
   const bool scalar = MODE == 1 || f.ncomp() == 1;
   for (int l = 0; l < A.nLeaves; ++l) {
     const DevLeaf& leaf = B.leaves[A.firstLeaf + l];
     if (leaf.layout != A.layoutId) continue;
     const u64 p = leaf.posA * t + leaf.posB;
-    if (mask == nullptr || mask[p]) coeff[p] = scalar ? y[0] : y[l];
+    if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : l, cm, x[0], x[1], x[2]);
   }
 }
 
@@ -244,10 +283,31 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
     if (!cell) {
       const u64 nRows = (u64)A.LX[1] * A.LX[2];
       if (nRows > 0xffffffffull) return fail(DFX_ERR_RANGE, "lattice too large for one launch");
-      A.divLY = FastDiv((unsigned)A.LX[1]); A.divEnt = FastDiv((unsigned)g.N[0] + 1u);
+      A.divLY = FastDiv((unsigned)A.LX[1]);
+      A.nActive = 0;
+      for (int l = 0; l < nLeaves; ++l)
+        if (D.leaves[firstLeaf + l].layout == q) {
+          A.leafId[A.nActive] = firstLeaf + l; A.leafComp[A.nActive] = l;
+          A.leafPosA[A.nActive] = (unsigned)D.leaves[firstLeaf + l].posA;
+          ++A.nActive;
+        }
       const unsigned grid = (unsigned)((nRows + kRowsPerBlock - 1) / kRowsPerBlock);
-      if (sep) k_interp_rows<RegistryFn, 1><<<grid, 256, 0, st>>>(D, A, f, tab, coeff, mask);
-      else k_interp_rows<RegistryFn, 0><<<grid, 256, 0, st>>>(D, A, f, tab, coeff, mask);
+      // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
+      const unsigned nEnt = (unsigned)g.N[0] + 1u, chunks = (nEnt + 255) / 256;
+      const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
+#define DFX_ROWS2(KT_, ONE_)                                                                                 \
+  { if (sep) k_interp_rows<RegistryFn, 1, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask);      \
+    else k_interp_rows<RegistryFn, 0, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask); }
+#define DFX_ROWS(KT_) { if (A.nActive == 1) DFX_ROWS2(KT_, true) else DFX_ROWS2(KT_, false) }
+      switch (k) {
+        case 1: DFX_ROWS(1) break;
+        case 2: DFX_ROWS(2) break;
+        case 3: DFX_ROWS(3) break;
+        case 4: DFX_ROWS(4) break;
+        default: DFX_ROWS(0)
+      }
+#undef DFX_ROWS2
+#undef DFX_ROWS
       int rc = postLaunch("k_interp_rows");
       if (rc) return rc;
     } else {
@@ -269,52 +329,85 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
 }
 
 // ---------------------------------------------------------------------------
-// Index table: one thread per (element, local index); the host guarantees < 2^32 outputs.
+// Index table.  A thread keeps ONE local index li for its whole life, so everything that
+// depends on li only — leaf, lattice multi-index, index-set component, affine position map —
+// is folded once into (P0, S, cs0, cs1) and the per-element work is
+//     ent = ec0 + cs0 (ec1 + cs1 ec2);   out = P0 + S * ent
+// (for LagrangeDG cs = N, so ent is the element index).  Threads tid -> (element sub-slot,
+// li) with li fastest: the block's stores form one contiguous run of the table.
 struct IdxArgs {
-  u64 e0, total;
-  FastDiv divNloc, divN0, divN1;
-  int stride;
+  u64 e0, ne;
+  FastDiv divN0, divN1;
+  int stride;       // digits per multi-index (MULTI)
+  int lpb, m, iters;   // local indices per pass, elements in flight, iterations per block
 };
 
-// per local index: leaf (bits 0-4), alpha_0/1/2 (bits 5-9, 10-14, 15-19)
 template <class T, bool MULTI>
 __global__ void __launch_bounds__(256)
-k_indices_fast(const __grid_constant__ DevBasis B, const __grid_constant__ IdxArgs A,
+k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs A,
                const unsigned* __restrict__ localTab, T* __restrict__ out) {
-  const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
-  if (t >= A.total) return;
-  unsigned dq, li;
-  A.divNloc.divmod((unsigned)t, dq, li);
-  const unsigned e = (unsigned)A.e0 + dq;
-  int ec[3];
-  {
-    unsigned q, r, q2;
-    A.divN0.divmod(e, q, r); ec[0] = (int)r;
-    A.divN1.divmod(q, q2, r); ec[1] = (int)r; ec[2] = (int)q2;
-  }
-  const unsigned packed = __ldg(localTab + li);
-  const DevLeaf& leaf = B.leaves[packed & 31u];
-  const DevLayout& L = B.layouts[leaf.layout];
-  int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
-  const u64 j = layoutIndex(L, B.grid, ec, a, (int)li - leaf.localOffset);
-  if (MULTI) {
-    for (int p = 0; p < A.stride; ++p)
-      out[t * (u64)A.stride + p] = p < leaf.ndig ? (T)(leaf.digA[p] * j + leaf.digB[p]) : (T)0;
-  } else {
-    out[t] = (T)(leaf.posA * j + leaf.posB);
+  const DevGrid& g = Bp->grid;
+  const int nloc = Bp->nlocTotal;
+  const int sub = threadIdx.x / A.lpb, lane = threadIdx.x - sub * A.lpb;
+  const u64 blkEl0 = (u64)blockIdx.x * (u64)(A.m * A.iters);
+  for (int li = lane; li < nloc; li += A.lpb) {
+    const unsigned packed = __ldg(localTab + li);
+    const DevLeaf& leaf = Bp->leaves[packed & 31u];
+    const DevLayout& L = Bp->layouts[leaf.layout];
+    const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
+    const int zero[3] = {0, 0, 0};
+    // scalar index at element (0,0,0) and its stride per entity
+    const u64 jbase = layoutIndex(L, g, zero, a, li - leaf.localOffset);
+    unsigned s = 0;
+    if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << g.dim) - 1u;
+    else
+      for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
+    const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1];
+    const u64 blk = (u64)L.blk[s];
+    const u64 P0 = leaf.posA * jbase + leaf.posB;
+    const u64 S = leaf.posA * blk;
+    u64 dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
+    if (MULTI) {
+#pragma unroll
+      for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
+        dA[p] = p < leaf.ndig ? leaf.digA[p] * blk : 0;
+        dB[p] = p < leaf.ndig ? leaf.digA[p] * jbase + leaf.digB[p] : 0;
+      }
+    }
+    for (int it = 0; it < A.iters; ++it) {
+      const u64 el = blkEl0 + (u64)(it * A.m + sub);
+      if (el >= A.ne) break;
+      const unsigned e = (unsigned)(A.e0 + el);
+      unsigned q, ec0, ec1, ec2;
+      A.divN0.divmod(e, q, ec0);
+      A.divN1.divmod(q, ec2, ec1);
+      const unsigned ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+      const u64 o = el * (u64)nloc + (u64)li;
+      if (MULTI) {
+#pragma unroll
+        for (int p = 0; p < DFX_MAX_DIGITS; ++p)
+          if (p < A.stride) out[o * (u64)A.stride + p] = (T)(dB[p] + dA[p] * (u64)ent);
+      } else {
+        out[o] = (T)(P0 + S * (u64)ent);
+      }
+    }
   }
 }
 
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
   IdxArgs A;
-  A.e0 = e0; A.total = (e1 - e0) * (u64)b->dev.nlocTotal; A.stride = stride;
-  if (A.total == 0) return DFX_OK;
-  A.divNloc = FastDiv((unsigned)b->dev.nlocTotal);
+  A.e0 = e0; A.ne = e1 - e0; A.stride = stride;
+  if (A.ne == 0) return DFX_OK;
+  const int nloc = b->dev.nlocTotal;
+  A.lpb = std::min(nloc, 256);
+  A.m = std::max(1, 256 / A.lpb);
+  A.iters = 16;
   A.divN0 = FastDiv((unsigned)b->dev.grid.N[0]); A.divN1 = FastDiv((unsigned)b->dev.grid.N[1]);
-  const u64 blocks = (A.total + 255) / 256;
+  const u64 perBlock = (u64)A.m * A.iters;
+  const u64 blocks = (A.ne + perBlock - 1) / perBlock;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
-  k_indices_fast<T, MULTI><<<(unsigned)blocks, 256, 0, st>>>(b->dev, A, (const unsigned*)b->dLocalTab, out);
+  k_indices_fast<T, MULTI><<<(unsigned)blocks, A.lpb * A.m, 0, st>>>((const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out);
   return postLaunch("k_indices_fast");
 }
 

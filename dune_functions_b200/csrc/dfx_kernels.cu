@@ -138,15 +138,15 @@ k_interpolate(const __grid_constant__ DevBasis B, int layoutId, int firstLeaf, i
   const DevLayout& L = B.layouts[layoutId];
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L.dimension) return;
-  double x[3], y[DFX_MAX_LEAVES];
+  double x[3];
   nodePosition(B, L, t, x);
-  f(x, y);
+  const double cm = f.common(x[0], x[1], x[2]);
   const bool scalar = f.ncomp() == 1;
   for (int l = 0; l < nLeaves; ++l) {
     const DevLeaf& leaf = B.leaves[firstLeaf + l];
     if (leaf.layout != layoutId) continue;
     const u64 p = leaf.posA * t + leaf.posB;
-    if (mask == nullptr || mask[p]) coeff[p] = scalar ? y[0] : y[l];
+    if (mask == nullptr || mask[p]) coeff[p] = f.comp(scalar ? 0 : l, cm, x[0], x[1], x[2]);
   }
 }
 

@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Per-kernel timings (CUDA events, after warm-up) of the hot-path kernels on the BASELINE
+configs; prints one JSON line per measurement.  Development tool, not the bench contract.
+
+    python tools/microbench.py [--only c2,c3] [--reps 10]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import dune_functions_b200 as dfx  # noqa: E402
+from dune_functions_b200 import _capi as capi  # noqa: E402
+
+PEAK = 6543.4
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timeit(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def report(name, cfg, ms, best, nbytes, extra=None):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    line = {"kernel": name, "config": cfg, "ms_median": round(ms, 4), "ms_min": round(best, 4),
+            "alg_GB": round(nbytes / 1e9, 4), "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 4)}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else None
+    L = capi.lib()
+    torch.cuda.set_device(0)
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+
+    def want(c):
+        return only is None or c in only
+
+    # torch fill / copy as bandwidth references
+    if want("ref"):
+        n = 135005697
+        a = torch.empty(n, dtype=torch.float64, device="cuda")
+        b2 = torch.empty(n, dtype=torch.float64, device="cuda")
+        ms, best = timeit(lambda: a.fill_(1.0), args.reps)
+        report("torch.fill_", "135M doubles", ms, best, n * 8)
+        ms, best = timeit(lambda: b2.copy_(a), args.reps)
+        report("torch.copy_", "135M doubles", ms, best, 2 * n * 8)
+        del a, b2
+
+    for cfg, n, k in (("c2", [256, 256, 256], 2), ("c5", [512, 512, 512], 2), ("q1_256", [256, 256, 256], 1),
+                      ("q3_128", [128, 128, 128], 3)):
+        if not want(cfg):
+            continue
+        basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.lagrange(k))
+        x = basis.newVector(0.0)
+        nd = basis.dimension()
+        for mode, label in ((-1, "separable tables"), (1, "f at every node")):
+            L.dfx_set_kernel_path(capi.OP_INTERPOLATE, mode)
+            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0)), args.reps)
+            report("interpolate exp(-|x|^2) [" + label + "]", cfg, ms, best, nd * 8, {"dofs_per_s": nd / ms * 1e3})
+        L.dfx_set_kernel_path(capi.OP_INTERPOLATE, -1)
+        ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.quadratic(0.5, [1, 2, 3], [1, 2, 3, 4, 5, 6])), args.reps)
+        report("interpolate quadratic [f at every node]", cfg, ms, best, nd * 8, {"dofs_per_s": nd / ms * 1e3})
+        m = 3 if k <= 2 else k + 1
+        pts, _ = dfx.tensor_gauss(3, m)
+        ne = basis.numElements()
+        f = dfx.makeDiscreteGlobalBasisFunction(basis, x)
+        v = torch.empty((ne, len(pts), 1), dtype=torch.float64, device="cuda")
+        ms, best = timeit(lambda: f.evaluate(pts, out_values=v), args.reps)
+        report(f"evaluate values {m}^3", cfg, ms, best, nd * 8 + v.numel() * 8,
+               {"path": L.dfx_evaluate_path(basis._h, 0, pts.ctypes.data_as(C.POINTER(C.c_double)), len(pts), 0)})
+        if cfg in ("c2", "q1_256"):
+            j = torch.empty((ne, len(pts), 1, 3), dtype=torch.float64, device="cuda")
+            ms, best = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), args.reps)
+            report(f"evaluate values+jacobians {m}^3", cfg, ms, best, nd * 8 + v.numel() * 8 * 4)
+            del j
+        if cfg == "c2":
+            idx = torch.empty((ne, 27), dtype=torch.int32, device="cuda")
+            ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
+            report("indices flat u32", cfg, ms, best, idx.numel() * 4)
+            del idx
+        del basis, x, v, f
+        torch.cuda.empty_cache()
+
+    if want("c3"):
+        n = [128, 128, 128]
+        basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.taylorHood())
+        ne, nl = basis.numElements(), basis.maxNodeSize()
+        idx = torch.empty((ne, nl), dtype=torch.int32, device="cuda")
+        ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
+        report("indices flat u32 (Taylor-Hood 89/elem)", "c3", ms, best, idx.numel() * 4, {"indices_per_s": idx.numel() / ms * 1e3})
+        mi = torch.empty((ne, nl, 2), dtype=torch.int32, device="cuda")
+        ms, best = timeit(lambda: capi.check(L.dfx_indices_multi(basis._h, 0, ne, C.c_void_p(mi.data_ptr()), 2, st())), args.reps)
+        report("indices multi u32x2 (Taylor-Hood)", "c3", ms, best, mi.numel() * 4)
+        del idx, mi
+        x = basis.newVector(0.0)
+        vel, pre = dfx.subspaceBasis(basis, 0), dfx.subspaceBasis(basis, 1)
+
+        def interp():
+            dfx.interpolate(vel, x, dfx.identity(3))
+            dfx.interpolate(pre, x, dfx.gaussian(1.0))
+        ms, best = timeit(interp, args.reps)
+        report("interpolate velocity x + pressure exp", "c3", ms, best, basis.dimension() * 8)
+        pts, _ = dfx.tensor_gauss(3, 3)
+        fv = dfx.makeDiscreteGlobalBasisFunction(vel, x)
+        v = torch.empty((ne, 27, 3), dtype=torch.float64, device="cuda")
+        ms, best = timeit(lambda: fv.evaluate(pts, out_values=v), args.reps)
+        report("evaluate velocity values 3^3", "c3", ms, best, 3 * 257 ** 3 * 8 + v.numel() * 8)
+        del basis, x, v
+        torch.cuda.empty_cache()
+
+    if want("c4"):
+        n = [192, 192, 192]
+        basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.lagrangeDG(4))
+        x = basis.newVector(0.0)
+        nd, ne = basis.dimension(), basis.numElements()
+        for mode, label in ((-1, "separable tables"), (1, "f at every node")):
+            L.dfx_set_kernel_path(capi.OP_INTERPOLATE, mode)
+            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0)), args.reps)
+            report("interpolate DG4 exp(-|x|^2) [" + label + "]", "c4", ms, best, nd * 8)
+        L.dfx_set_kernel_path(capi.OP_INTERPOLATE, -1)
+        x.uniform_(-1, 1)
+        pts, _ = dfx.tensor_gauss(3, 5)
+        f = dfx.makeDiscreteGlobalBasisFunction(basis, x)
+        v = torch.empty((ne, 125, 1), dtype=torch.float64, device="cuda")
+        j = torch.empty((ne, 125, 1, 3), dtype=torch.float64, device="cuda")
+        path = L.dfx_evaluate_path(basis._h, 0, pts.ctypes.data_as(C.POINTER(C.c_double)), 125, 1)
+        ms, best = timeit(lambda: f.evaluate(pts, out_values=v), max(3, args.reps // 3), warm=1)
+        report("evaluate DG4 values 5^3", "c4", ms, best, nd * 8 + v.numel() * 8, {"path": path})
+        ms, best = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), max(3, args.reps // 3), warm=1)
+        report("evaluate DG4 values+jacobians 5^3", "c4", ms, best, nd * 8 + v.numel() * 8 * 4, {"path": path})
+
+
+if __name__ == "__main__":
+    main()
