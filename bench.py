@@ -275,9 +275,8 @@ def main():
     values = torch.empty((ne, nq, ncomp), dtype=torch.float64, device=dev)
     jac = torch.empty((ne, nq, ncomp, dim), dtype=torch.float64, device=dev) if wl["jac"] else None
     dgbf = dfx.makeDiscreteGlobalBasisFunction(basis, coeff)
-    halo_n = int(L.dfx_halo_size(basis._h)) if world > 1 else 0
-    send_buf = torch.empty(max(1, halo_n), dtype=torch.float64, device=dev)
-    recv_buf = torch.empty(max(1, halo_n), dtype=torch.float64, device=dev)
+    from dune_functions_b200.slab import HaloExchange
+    halo = HaloExchange(basis, rank, world, device=dev)
     index_table = None
     if args.workload == "c3":
         index_table = torch.empty((ne, basis.maxNodeSize()), dtype=torch.int32, device=dev)
@@ -305,19 +304,7 @@ def main():
             for node, fn in node_fns:
                 capi.check(L.dfx_interpolate(basis._h, node, C.byref(fn), C.c_void_p(coeff.data_ptr()), None, stream_ptr()))
         mark()
-        if world > 1 and halo_n > 0:
-            # the lower plane of my slab is the upper neighbour's... no: my bottom plane is the
-            # TOP plane of rank-1's slab; send it down, receive my top plane from rank+1
-            ops = []
-            if rank > 0:
-                capi.check(L.dfx_halo_pack(basis._h, 0, C.c_void_p(coeff.data_ptr()), C.c_void_p(send_buf.data_ptr()), stream_ptr()))
-                ops.append(dist.P2POp(dist.isend, send_buf, rank - 1))
-            if rank < world - 1:
-                ops.append(dist.P2POp(dist.irecv, recv_buf, rank + 1))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            if rank < world - 1:
-                capi.check(L.dfx_halo_unpack(basis._h, 1, C.c_void_p(recv_buf.data_ptr()), C.c_void_p(coeff.data_ptr()), stream_ptr()))
+        halo(coeff)          # N > 1: my top plane <- bottom plane of the slab above (NCCL send/recv)
         mark()
         dgbf.evaluate(pts, values=True, jacobians=wl["jac"], out_values=values, out_jacobians=jac)
         mark()

@@ -406,6 +406,36 @@ int dfx_indices_flat_host(const dfx_basis* cb, uint64_t e0, uint64_t e1, uint32_
   return DFX_OK;
 }
 
+int dfx_indices_multi_host(const dfx_basis* cb, uint64_t e0, uint64_t e1, uint64_t* out_host, int32_t stride) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if ((rc = checkRange(b, e0, e1))) return rc;
+  if (!out_host) return fail(DFX_ERR_INVALID, "null output");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t bytes = (e1 - e0) * (size_t)b->dev.nlocTotal * (size_t)stride * sizeof(uint64_t);
+  if (bytes == 0) return DFX_OK;
+  if ((rc = growScratch(b, 1, bytes))) return rc;
+  if ((rc = dfx_indices_multi_u64(b, e0, e1, (uint64_t*)b->dScratch[1], stride, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(out_host, b->dScratch[1], bytes, cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
+int dfx_interpolation_points_host(const dfx_basis* cb, double* out_xyz_host, int32_t* out_leaf_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!out_xyz_host || !out_leaf_host) return fail(DFX_ERR_INVALID, "null output");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension, dim = b->dev.grid.dim;
+  if ((rc = growScratch(b, 1, n * dim * sizeof(double)))) return rc;
+  if ((rc = growScratch(b, 2, n * sizeof(int32_t)))) return rc;
+  if ((rc = dfx_interpolation_points(b, (double*)b->dScratch[1], (int32_t*)b->dScratch[2], st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(out_xyz_host, b->dScratch[1], n * dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaMemcpyAsync(out_leaf_host, b->dScratch[2], n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
 // ---- slab partition helpers ------------------------------------------------------------
 int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint64_t* out_count, int32_t max_ranges,
                     int32_t* n) {

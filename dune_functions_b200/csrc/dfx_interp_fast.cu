@@ -144,55 +144,47 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
   }
   __syncthreads();
   const bool scalar = MODE == 1 || f.ncomp() == 1;
-  // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... and sweeps the rows ----
-  for (unsigned c0 = threadIdx.x; c0 <= (unsigned)g.N[0]; c0 += blockDim.x) {
-    const int nNodes = c0 < (unsigned)g.N[0] ? k : 1;     // the last entity is the closing vertex plane only
-    // x-direction data of this entity's nodes: X = k c0 + a, a = 0 (vertex-type) .. k-1
+  // x-direction datum of node a of x-entity c0: coordinate (MODE 0) or table factor (MODE 1)
+  auto xdata = [&](unsigned c0, int a) -> double {
+    if (MODE == 1) return tab[A.tabOff[0] + k * (int)c0 + a];
+    int ie = g.off[0] + (int)c0, aa = a;
+    if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }    // last lattice plane: owner on the left
+    return nodeCoord(g, k, 0, ie, aa);
+  };
+  // write node a of x-entity c0 in row rI for every active leaf
+  auto emit = [&](unsigned c0, unsigned rI, int a, double xa, const RowCommon& rc) {
+    const double cm = MODE == 0 ? f.common(xa, rc.u1, rc.u2) : __dmul_rn(xa, rc.u1);
+    for (int lI = 0; lI < (ONE ? 1 : nAct); ++lI) {
+      const RowLeaf rl = rowl[lI][rI];
+      const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
+                           : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[lI] * (u64)(a - 1);
+      if (mask == nullptr || mask[p])
+        coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[lI], cm, xa, rc.u1, rc.u2);
+    }
+  };
+  // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... < N_x and sweeps the rows ----
+  for (unsigned c0 = threadIdx.x; c0 < (unsigned)g.N[0]; c0 += blockDim.x) {
+    // nodes X = k c0 + a, a = 0 (vertex-type) .. k-1 (edge-type); their x-data stay in registers
     double hx[KT > 0 ? KT : 1];
     if (KT > 0) {
 #pragma unroll
-      for (int a = 0; a < KT; ++a) {
-        if (a >= nNodes) { hx[a] = 0.0; continue; }
-        if (MODE == 0) {
-          int ie = g.off[0] + (int)c0, aa = a;
-          if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }    // last lattice plane: owner on the left
-          hx[a] = nodeCoord(g, k, 0, ie, aa);
-        } else {
-          hx[a] = tab[A.tabOff[0] + k * (int)c0 + a];
-        }
-      }
+      for (int a = 0; a < KT; ++a) hx[a] = xdata(c0, a);
     }
-#pragma unroll 2
+#pragma unroll 4
     for (unsigned rI = 0; rI < nr; ++rI) {
       const RowCommon rc = rowc[rI];
+      if (KT > 0) {
 #pragma unroll
-      for (int a = 0; a < (KT > 0 ? KT : kMaxContinuousOrder); ++a) {
-        if (a >= nNodes) break;
-        double xa;
-        if (KT > 0) xa = hx[a];
-        else if (MODE == 0) {
-          int ie = g.off[0] + (int)c0, aa = a;
-          if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }
-          xa = nodeCoord(g, k, 0, ie, aa);
-        } else xa = tab[A.tabOff[0] + k * (int)c0 + a];
-        const double cm = MODE == 0 ? f.common(xa, rc.u1, rc.u2) : __dmul_rn(xa, rc.u1);
-        if (ONE) {
-          const RowLeaf rl = rowl[0][rI];
-          const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
-                               : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[0] * (u64)(a - 1);
-          if (mask == nullptr || mask[p])
-            coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[0], cm, xa, rc.u1, rc.u2);
-        } else {
-          for (int lI = 0; lI < nAct; ++lI) {
-            const RowLeaf rl = rowl[lI][rI];
-            const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
-                                 : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[lI] * (u64)(a - 1);
-            if (mask == nullptr || mask[p])
-              coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[lI], cm, xa, rc.u1, rc.u2);
-          }
-        }
+        for (int a = 0; a < KT; ++a) emit(c0, rI, a, hx[a], rc);
+      } else {
+        for (int a = 0; a < k; ++a) emit(c0, rI, a, xdata(c0, a), rc);
       }
     }
+  }
+  // ---- the closing vertex plane x-entity N_x: one node per row ----
+  if (threadIdx.x < nr) {
+    const unsigned rI = threadIdx.x;
+    emit((unsigned)g.N[0], rI, 0, xdata((unsigned)g.N[0], 0), rowc[rI]);
   }
 }
 
@@ -293,7 +285,7 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
         }
       const unsigned grid = (unsigned)((nRows + kRowsPerBlock - 1) / kRowsPerBlock);
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
-      const unsigned nEnt = (unsigned)g.N[0] + 1u, chunks = (nEnt + 255) / 256;
+      const unsigned nEnt = (unsigned)g.N[0], chunks = (nEnt + 255) / 256;
       const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
 #define DFX_ROWS2(KT_, ONE_)                                                                                 \
   { if (sep) k_interp_rows<RegistryFn, 1, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask);      \

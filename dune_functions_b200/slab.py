@@ -1,0 +1,109 @@
+"""z-slab partition of the element loop across ranks.
+
+One process per GPU; rank r owns the elements with z in [z_r, z_{r+1}) and a coefficient vector
+numbered over its own slab.  The only data that must travel is the lattice plane a slab shares
+with its upper neighbour ("halo"): the owner of that plane is the upper slab (the last writer
+in the reference's serial loop, interpolate.hh:254-259), so rank r receives its TOP plane from
+rank r+1 and sends its BOTTOM plane to rank r-1.
+
+Works with CUDA tensors over NCCL (pack/unpack kernels of the library) and with CPU tensors over
+gloo (contiguous ranges from dfx_halo_ranges) — the latter is what the CPU test-suite runs.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+
+MAX_RANGES = 256
+
+
+def halo_ranges(basis, side):
+    """[(flat begin, count)] of the lowest (side 0) / highest (side 1) lattice plane"""
+    b, c = (C.c_uint64 * MAX_RANGES)(), (C.c_uint64 * MAX_RANGES)()
+    n = C.c_int32()
+    capi.check(basis._lib.dfx_halo_ranges(basis._h, side, b, c, MAX_RANGES, C.byref(n)))
+    return [(int(b[i]), int(c[i])) for i in range(n.value)]
+
+
+def owned_ranges(basis):
+    """[(local flat begin, count, global flat begin)] of the DOFs this slab owns"""
+    lb, cnt, gb = (C.c_uint64 * MAX_RANGES)(), (C.c_uint64 * MAX_RANGES)(), (C.c_uint64 * MAX_RANGES)()
+    n = C.c_int32()
+    capi.check(basis._lib.dfx_owned_ranges(basis._h, lb, cnt, gb, MAX_RANGES, C.byref(n)))
+    return [(int(lb[i]), int(cnt[i]), int(gb[i])) for i in range(n.value)]
+
+
+def halo_size(basis):
+    return int(basis._lib.dfx_halo_size(basis._h))
+
+
+class HaloExchange:
+    """Reusable buffers + the send-down / receive-from-above step."""
+
+    def __init__(self, basis, rank, world, device=None, group=None):
+        self.basis, self.rank, self.world, self.group = basis, rank, world, group
+        self.n = halo_size(basis)
+        dev = device if device is not None else "cpu"
+        self.send = torch.empty(max(1, self.n), dtype=torch.float64, device=dev)
+        self.recv = torch.empty(max(1, self.n), dtype=torch.float64, device=dev)
+
+    def _pack(self, coeff, side, buf):
+        if coeff.is_cuda:
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            capi.check(self.basis._lib.dfx_halo_pack(self.basis._h, side, C.c_void_p(coeff.data_ptr()),
+                                                     C.c_void_p(buf.data_ptr()), st))
+        else:
+            o = 0
+            for b, c in halo_ranges(self.basis, side):
+                buf[o:o + c] = coeff[b:b + c]
+                o += c
+
+    def _unpack(self, coeff, side, buf):
+        if coeff.is_cuda:
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            capi.check(self.basis._lib.dfx_halo_unpack(self.basis._h, side, C.c_void_p(buf.data_ptr()),
+                                                       C.c_void_p(coeff.data_ptr()), st))
+        else:
+            o = 0
+            for b, c in halo_ranges(self.basis, side):
+                coeff[b:b + c] = buf[o:o + c]
+                o += c
+
+    def __call__(self, coeff):
+        """make the top plane of every slab equal to the bottom plane of the slab above it"""
+        if self.world == 1 or self.n == 0:
+            return coeff
+        ops = []
+        if self.rank > 0:
+            self._pack(coeff, 0, self.send)
+            ops.append(dist.P2POp(dist.isend, self.send, self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.irecv, self.recv, self.rank + 1, self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if self.rank < self.world - 1:
+            self._unpack(coeff, 1, self.recv)
+        return coeff
+
+
+def gather_global(basis, coeff, global_dimension, group=None):
+    """every rank gets the whole vector in GLOBAL flat order (result gather of DESIGN.md section 7)"""
+    world = dist.get_world_size(group)
+    ranges = owned_ranges(basis)
+    mine = torch.cat([coeff[lb:lb + c] for lb, c, _ in ranges]) if ranges else coeff[:0]
+    sizes = [None] * world
+    dist.all_gather_object(sizes, (ranges, mine.numel()), group=group)
+    pad = max(s[1] for s in sizes)
+    buf = torch.zeros(pad, dtype=coeff.dtype, device=coeff.device)
+    buf[:mine.numel()] = mine
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = torch.empty(global_dimension, dtype=coeff.dtype, device=coeff.device)
+    for (rng, _), part in zip(sizes, parts):
+        o = 0
+        for _, c, gb in rng:
+            out[gb:gb + c] = part[o:o + c]
+            o += c
+    return out

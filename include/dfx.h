@@ -232,6 +232,10 @@ int dfx_evaluate_host(const dfx_basis* b, int32_t subtree_node, const double* co
                       double* out_values_host, double* out_jacobians_host);
 int dfx_indices_flat_host(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
                           uint32_t* out_host);
+int dfx_indices_multi_host(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
+                           uint64_t* out_digits_host, int32_t stride);
+int dfx_interpolation_points_host(const dfx_basis* b, double* out_xyz_host /*[dimension][dim]*/,
+                                  int32_t* out_leaf_host /*[dimension]*/);
 
 /* ---- slab partition helpers (multi-GPU, one handle per rank) ---------------
  * When the local box spans the whole grid in every direction but the last,

@@ -1,0 +1,503 @@
+// dune_functions.hh — C++ façade that keeps the dune-functions names for the element-loop
+// path on top of the C ABI (include/dfx.h).  Host code written against the reference
+//
+//     using namespace Dune::Functions::BasisFactory;
+//     auto basis = makeBasis(gridView, composite(power<dim>(lagrange<2>(), flatLexicographic()),
+//                                                lagrange<1>(), flatLexicographic()));
+//     interpolate(subspaceBasis(basis, _0), x, f);
+//     auto u  = makeDiscreteGlobalBasisFunction<double>(basis, x);
+//     auto lf = localFunction(u);  lf.bind(element);  lf(xLocal);  derivative(lf)(xLocal);
+//     auto lv = basis.localView(); lv.bind(element);  lv.index(i);
+//
+// compiles against this header (plus the minimal Dune::YaspGrid / FieldVector stand-ins
+// below, since dune-grid / dune-common are not part of this repository) and computes on
+// the GPU.  Reference interfaces mirrored (dune-functions checkout):
+//   BasisFactory::makeBasis            functionspacebases/defaultglobalbasis.hh:205-209
+//   lagrange / lagrangeDG / power / composite / taylorHood
+//                                      lagrangebasis.hh:1006-1027, lagrangedgbasis.hh:150-170,
+//                                      powerbasis.hh:140-171, compositebasis.hh:420-445,
+//                                      taylorhoodbasis.hh:330-335
+//   index merging tags                 basistags.hh:192-225
+//   GlobalBasis / LocalView concepts   concepts.hh:222-273, defaultlocalview.hh:95-159
+//   interpolate                        interpolate.hh:204-302
+//   makeDiscreteGlobalBasisFunction    gridfunctions/discreteglobalbasisfunction.hh:457-478
+//   subspaceBasis                      subspacebasis.hh:147-157
+// Errors: non-zero dfx_status becomes Dune::RangeError / Dune::NotImplemented /
+// Dune::Exception, like the DUNE_THROW sites of the reference.  No CPU fallback: every
+// compute call goes through libdfx.so and fails if no device is present.
+#pragma once
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../dfx.h"
+
+namespace Dune {
+
+struct Exception : std::runtime_error { using std::runtime_error::runtime_error; };
+struct RangeError : Exception { using Exception::Exception; };
+struct NotImplemented : Exception { using Exception::Exception; };
+
+// ---- dune-common stand-ins -------------------------------------------------------------
+template <class K, int n>
+class FieldVector : public std::array<K, n> {
+ public:
+  FieldVector() { this->fill(K(0)); }
+  FieldVector(const K& v) { this->fill(v); }
+  FieldVector(std::initializer_list<K> l) { int i = 0; for (auto& v : l) (*this)[i++] = v; }
+  K two_norm2() const { K r = 0; for (auto& v : *this) r += v * v; return r; }
+  K two_norm() const { return std::sqrt(two_norm2()); }
+  static constexpr int dimension = n;
+};
+template <class K, int r, int c>
+using FieldMatrix = std::array<std::array<K, c>, r>;
+
+namespace Indices {
+template <std::size_t i> using index_constant = std::integral_constant<std::size_t, i>;
+inline constexpr index_constant<0> _0{};
+inline constexpr index_constant<1> _1{};
+inline constexpr index_constant<2> _2{};
+inline constexpr index_constant<3> _3{};
+}  // namespace Indices
+
+// ---- dune-grid stand-in: unrefined equidistant YaspGrid ---------------------------------
+template <int dim>
+class YaspGrid {
+ public:
+  static constexpr int dimension = dim;
+  using ctype = double;
+  struct Element {
+    std::size_t index;                     // position in elements(gridView), x fastest
+    std::array<int, dim> coord;
+  };
+  class LeafGridView {
+   public:
+    static constexpr int dimension = dim;
+    using Grid = YaspGrid;
+    explicit LeafGridView(const YaspGrid* g) : grid_(g) {}
+    const YaspGrid& grid() const { return *grid_; }
+    std::size_t size(int codim) const {
+      std::size_t r = 0;
+      for (unsigned s = 0; s < (1u << dim); ++s) {
+        if (__builtin_popcount(s) != dim - codim) continue;
+        std::size_t c = 1;
+        for (int j = 0; j < dim; ++j) c *= grid_->N_[j] + (((s >> j) & 1) ? 0 : 1);
+        r += c;
+      }
+      return r;
+    }
+    const YaspGrid* grid_;
+  };
+  YaspGrid(const FieldVector<double, dim>& L, const std::array<int, dim>& N) : L_(L), N_(N) { lower_.fill(0.0); }
+  YaspGrid(const FieldVector<double, dim>& lowerLeft, const FieldVector<double, dim>& upperRight,
+           const std::array<int, dim>& N) : L_(upperRight), N_(N) { for (int j = 0; j < dim; ++j) lower_[j] = lowerLeft[j]; }
+  LeafGridView leafGridView() const { return LeafGridView(this); }
+  std::size_t numElements() const { std::size_t n = 1; for (int j = 0; j < dim; ++j) n *= N_[j]; return n; }
+  Element element(std::size_t e) const {
+    Element el; el.index = e;
+    for (int j = 0; j < dim; ++j) { el.coord[j] = (int)(e % N_[j]); e /= N_[j]; }
+    return el;
+  }
+  FieldVector<double, dim> L_, lower_;
+  std::array<int, dim> N_;
+};
+
+// elements(gridView): the reference's range-based element loop
+template <int dim>
+class ElementRange {
+ public:
+  using Grid = YaspGrid<dim>;
+  struct iterator {
+    const Grid* g; std::size_t e;
+    typename Grid::Element operator*() const { return g->element(e); }
+    iterator& operator++() { ++e; return *this; }
+    bool operator!=(const iterator& o) const { return e != o.e; }
+  };
+  explicit ElementRange(const Grid* g) : g_(g) {}
+  iterator begin() const { return {g_, 0}; }
+  iterator end() const { return {g_, g_->numElements()}; }
+ private:
+  const Grid* g_;
+};
+template <class GV>
+ElementRange<GV::dimension> elements(const GV& gv) { return ElementRange<GV::dimension>(gv.grid_); }
+
+namespace Functions {
+
+namespace Impl {
+inline void check(int status) {
+  if (status == DFX_OK) return;
+  std::string msg = dfx_last_error();
+  if (status == DFX_ERR_RANGE) throw RangeError(msg);
+  if (status == DFX_ERR_NOT_IMPLEMENTED) throw NotImplemented(msg);
+  throw Exception(msg);
+}
+struct Handle {
+  dfx_basis* h = nullptr;
+  ~Handle() { if (h) dfx_basis_destroy(h); }
+};
+}  // namespace Impl
+
+// ---- BasisFactory: pre-basis factories lower to the POD tree descriptor -----------------
+namespace BasisFactory {
+
+struct FlatLexicographic { static constexpr int value = DFX_IMS_FLAT_LEXICOGRAPHIC; };
+struct FlatInterleaved { static constexpr int value = DFX_IMS_FLAT_INTERLEAVED; };
+struct BlockedLexicographic { static constexpr int value = DFX_IMS_BLOCKED_LEXICOGRAPHIC; };
+struct BlockedInterleaved { static constexpr int value = DFX_IMS_BLOCKED_INTERLEAVED; };
+inline FlatLexicographic flatLexicographic() { return {}; }
+inline FlatInterleaved flatInterleaved() { return {}; }
+inline BlockedLexicographic blockedLexicographic() { return {}; }
+inline BlockedInterleaved blockedInterleaved() { return {}; }
+
+struct PreBasisFactory { std::vector<dfx_tree_node> nodes; };
+
+template <int k> PreBasisFactory lagrange() { return {{{DFX_NODE_LAGRANGE, k, 0, DFX_IMS_NONE}}}; }
+inline PreBasisFactory lagrange(int k) { return {{{DFX_NODE_LAGRANGE, k, 0, DFX_IMS_NONE}}}; }
+template <int k> PreBasisFactory lagrangeDG() { return {{{DFX_NODE_LAGRANGE_DG, k, 0, DFX_IMS_NONE}}}; }
+inline PreBasisFactory lagrangeDG(int k) { return {{{DFX_NODE_LAGRANGE_DG, k, 0, DFX_IMS_NONE}}}; }
+inline PreBasisFactory taylorHood() { return {{{DFX_NODE_TAYLOR_HOOD, 0, 0, DFX_IMS_NONE}}}; }
+
+template <std::size_t C, class IMS = BlockedInterleaved>
+PreBasisFactory power(const PreBasisFactory& child, IMS = {}) {
+  PreBasisFactory f; f.nodes.push_back({DFX_NODE_POWER, 0, (int32_t)C, IMS::value});
+  f.nodes.insert(f.nodes.end(), child.nodes.begin(), child.nodes.end());
+  return f;
+}
+template <class IMS = BlockedInterleaved>
+PreBasisFactory power(const PreBasisFactory& child, std::size_t C, IMS = {}) {   // run-time exponent, dynamicpowerbasis.hh
+  PreBasisFactory f; f.nodes.push_back({DFX_NODE_POWER, 0, (int32_t)C, IMS::value});
+  f.nodes.insert(f.nodes.end(), child.nodes.begin(), child.nodes.end());
+  return f;
+}
+
+namespace Impl {
+template <class T> struct IsIMS : std::false_type {};
+template <> struct IsIMS<FlatLexicographic> : std::true_type {};
+template <> struct IsIMS<BlockedLexicographic> : std::true_type {};
+inline void collect(PreBasisFactory&, int&, int&) {}
+template <class A, class... R>
+void collect(PreBasisFactory& f, int& children, int& ims, const A& a, const R&... rest) {
+  if constexpr (IsIMS<A>::value) ims = A::value;
+  else { f.nodes.insert(f.nodes.end(), a.nodes.begin(), a.nodes.end()); ++children; }
+  collect(f, children, ims, rest...);
+}
+}  // namespace Impl
+
+// composite(child..., [ims]) — default BlockedLexicographic (compositebasis.hh:437-445)
+template <class... Args>
+PreBasisFactory composite(const Args&... args) {
+  PreBasisFactory f; f.nodes.push_back({DFX_NODE_COMPOSITE, 0, 0, DFX_IMS_BLOCKED_LEXICOGRAPHIC});
+  int children = 0, ims = DFX_IMS_BLOCKED_LEXICOGRAPHIC;
+  Impl::collect(f, children, ims, args...);
+  f.nodes[0].n_children = children; f.nodes[0].ims = ims;
+  return f;
+}
+
+}  // namespace BasisFactory
+
+// ---- multi-index: ReservedVector-like (defaultlocalview.hh:57-68) -----------------------
+class MultiIndex {
+ public:
+  std::size_t size() const { return n_; }
+  std::size_t operator[](std::size_t i) const { return d_[i]; }
+  operator std::size_t() const { return d_[0]; }     // flat bases: StaticMultiIndex<size_t,1> conversion
+  bool operator==(const MultiIndex& o) const { return n_ == o.n_ && std::equal(d_, d_ + n_, o.d_); }
+  bool operator<(const MultiIndex& o) const { return std::lexicographical_compare(d_, d_ + n_, o.d_, o.d_ + o.n_); }
+  std::size_t d_[DFX_MAX_DIGITS] = {0, 0, 0, 0, 0, 0};
+  std::size_t n_ = 0;
+};
+
+template <class GV> class DefaultGlobalBasis;
+
+// tree node handle (nodes.hh:130-209): size(), localIndex(i), child(i)
+template <class GV>
+class BasisNode {
+ public:
+  BasisNode(const DefaultGlobalBasis<GV>* b, int node) : basis_(b), node_(node) {
+    Impl::check(dfx_basis_node_info(b->handle(), node, &offset_, &size_, &firstLeaf_, &nLeaves_));
+  }
+  std::size_t size() const { return size_; }
+  std::size_t localIndex(std::size_t i) const { return offset_ + i; }
+  std::size_t treeIndex() const { return node_; }
+  BasisNode child(std::size_t i) const {
+    int c = dfx_basis_node_child(basis_->handle(), node_, (int)i);
+    if (c < 0) throw RangeError("no such child");
+    return BasisNode(basis_, c);
+  }
+  template <class... I> BasisNode child(std::size_t i, I... rest) const { return child(i).child(rest...); }
+  int id() const { return node_; }
+  int numLeaves() const { return nLeaves_; }
+ private:
+  const DefaultGlobalBasis<GV>* basis_;
+  int node_, offset_ = 0, size_ = 0, firstLeaf_ = 0, nLeaves_ = 0;
+};
+
+// ---- DefaultLocalView: bind + index served from the batched device table ----------------
+template <class GV>
+class DefaultLocalView {
+ public:
+  using GlobalBasis = DefaultGlobalBasis<GV>;
+  using Element = typename GV::Grid::Element;
+  using size_type = std::size_t;
+  using Tree = BasisNode<GV>;
+  static constexpr std::size_t window = 1 << 14;     // elements fetched per device call
+
+  explicit DefaultLocalView(const GlobalBasis& b) : basis_(&b), tree_(&b, 0) {
+    stride_ = dfx_basis_max_multi_index_size(b.handle());
+    nloc_ = dfx_basis_max_node_size(b.handle());
+    lens_.resize(nloc_);
+    Impl::check(dfx_basis_local_index_sizes(b.handle(), lens_.data()));
+  }
+  void bind(const Element& e) {
+    element_ = e; bound_ = true;
+    if (e.index < w0_ || e.index >= w1_) {
+      w0_ = e.index - e.index % window;
+      w1_ = std::min<std::size_t>(w0_ + window, dfx_basis_num_elements(basis_->handle()));
+      cache_.resize((w1_ - w0_) * nloc_ * stride_);
+      Impl::check(dfx_indices_multi_host(basis_->handle(), w0_, w1_, cache_.data(), stride_));
+    }
+  }
+  void unbind() { bound_ = false; }
+  bool bound() const { return bound_; }
+  const Element& element() const { return element_; }
+  const Tree& tree() const { return tree_; }
+  size_type size() const { return nloc_; }
+  size_type maxSize() const { return nloc_; }
+  MultiIndex index(size_type i) const {
+    MultiIndex m; m.n_ = lens_[i];
+    const uint64_t* p = &cache_[((element_.index - w0_) * nloc_ + i) * stride_];
+    for (std::size_t d = 0; d < m.n_; ++d) m.d_[d] = (std::size_t)p[d];
+    return m;
+  }
+  const GlobalBasis& globalBasis() const { return *basis_; }
+ private:
+  const GlobalBasis* basis_;
+  Tree tree_;
+  Element element_{};
+  bool bound_ = false;
+  int stride_ = 1, nloc_ = 0;
+  std::vector<uint8_t> lens_;
+  std::vector<uint64_t> cache_;
+  std::size_t w0_ = 0, w1_ = 0;
+};
+
+// ---- DefaultGlobalBasis (defaultglobalbasis.hh:51-191) -----------------------------------
+template <class GV>
+class DefaultGlobalBasis {
+ public:
+  using GridView = GV;
+  using LocalView = DefaultLocalView<GV>;
+  using size_type = std::size_t;
+  using SizePrefix = std::vector<std::size_t>;
+
+  DefaultGlobalBasis(const GV& gv, const BasisFactory::PreBasisFactory& f, int device = 0) : gv_(gv), h_(std::make_shared<Impl::Handle>()) {
+    constexpr int dim = GV::dimension;
+    dfx_grid_desc g{};
+    g.dim = dim;
+    for (int j = 0; j < 3; ++j) {
+      g.n_global[j] = g.local_n[j] = j < dim ? gv.grid().N_[j] : 1;
+      g.local_begin[j] = 0;
+      g.lower[j] = j < dim ? gv.grid().lower_[j] : 0.0;
+      g.upper[j] = j < dim ? gv.grid().L_[j] : 1.0;
+    }
+    Impl::check(dfx_basis_create(&g, f.nodes.data(), (int32_t)f.nodes.size(), device, &h_->h));
+  }
+  const GV& gridView() const { return gv_; }
+  size_type dimension() const { return dfx_basis_dimension(h_->h); }
+  size_type size() const { return dfx_basis_size(h_->h, nullptr, 0); }
+  template <class Prefix> size_type size(const Prefix& prefix) const {
+    std::vector<uint64_t> p(prefix.size());
+    for (std::size_t i = 0; i < p.size(); ++i) p[i] = prefix[i];
+    return dfx_basis_size(h_->h, p.data(), (int32_t)p.size());
+  }
+  LocalView localView() const { return LocalView(*this); }
+  const dfx_basis* handle() const { return h_->h; }
+  const DefaultGlobalBasis& rootBasis() const { return *this; }
+  int rootNode() const { return 0; }
+ private:
+  GV gv_;
+  std::shared_ptr<Impl::Handle> h_;
+};
+
+namespace BasisFactory {
+template <class GV>
+DefaultGlobalBasis<GV> makeBasis(const GV& gv, const PreBasisFactory& f) { return DefaultGlobalBasis<GV>(gv, f); }
+}  // namespace BasisFactory
+
+// the reference's convenience typedefs
+template <class GV, int k> struct LagrangeBasis : DefaultGlobalBasis<GV> {
+  explicit LagrangeBasis(const GV& gv) : DefaultGlobalBasis<GV>(gv, BasisFactory::lagrange<k>()) {}
+};
+template <class GV, int k> struct LagrangeDGBasis : DefaultGlobalBasis<GV> {
+  explicit LagrangeDGBasis(const GV& gv) : DefaultGlobalBasis<GV>(gv, BasisFactory::lagrangeDG<k>()) {}
+};
+template <class GV> struct TaylorHoodBasis : DefaultGlobalBasis<GV> {
+  explicit TaylorHoodBasis(const GV& gv) : DefaultGlobalBasis<GV>(gv, BasisFactory::taylorHood()) {}
+};
+
+// ---- SubspaceBasis (subspacebasis.hh:27-157) ----------------------------------------------
+template <class GV>
+class SubspaceBasis {
+ public:
+  using GridView = GV;
+  SubspaceBasis(const DefaultGlobalBasis<GV>& root, int node) : root_(&root), node_(node) {}
+  const DefaultGlobalBasis<GV>& rootBasis() const { return *root_; }
+  int rootNode() const { return node_; }
+  std::size_t dimension() const { return root_->dimension(); }     // the root's, :79-94
+  const GV& gridView() const { return root_->gridView(); }
+  const dfx_basis* handle() const { return root_->handle(); }
+ private:
+  const DefaultGlobalBasis<GV>* root_;
+  int node_;
+};
+template <class GV, class... I>
+SubspaceBasis<GV> subspaceBasis(const DefaultGlobalBasis<GV>& root, I... path) {
+  int node = 0;
+  for (std::size_t c : {(std::size_t)path...}) {
+    node = dfx_basis_node_child(root.handle(), node, (int)c);
+    if (node < 0) throw RangeError("subspaceBasis: no such child");
+  }
+  return SubspaceBasis<GV>(root, node);
+}
+
+// ---- functions: registry entries run on the device, any other callable at the nodes ------
+namespace Registry {
+struct Function { dfx_function f; };
+inline Function gaussian(double a = 1.0) { Function r{}; r.f.id = DFX_FN_GAUSSIAN; r.f.n_comp = 1; r.f.p[0] = a; return r; }
+inline Function identity(int n) { Function r{}; r.f.id = DFX_FN_IDENTITY; r.f.n_comp = n; return r; }
+inline Function coord(int j) { Function r{}; r.f.id = DFX_FN_COORD; r.f.n_comp = 1; r.f.p[0] = j; return r; }
+inline Function constant(double c) { Function r{}; r.f.id = DFX_FN_CONSTANT; r.f.n_comp = 1; r.f.p[0] = c; return r; }
+}  // namespace Registry
+
+namespace Impl {
+// flat view of a range value: scalar or anything indexable (HierarchicNodeToRangeMap + flatVectorView)
+template <class Y> double rangeEntry(const Y& y, int leaf, int nLeaves) {
+  if constexpr (std::is_arithmetic_v<Y>) { (void)leaf; (void)nLeaves; return (double)y; }
+  else return (double)y[leaf];
+}
+template <class C> double* coeffData(C& c, std::size_t n) {
+  using V = typename C::value_type;
+  static_assert(std::is_trivially_copyable_v<V>, "coefficient container must store plain values contiguously");
+  const std::size_t per = sizeof(V) / sizeof(double);
+  if (c.size() * per != n) c.resize((n + per - 1) / per);      // vector.resize(basis), interpolate.hh:235
+  return reinterpret_cast<double*>(c.data());
+}
+struct AllTrue {};
+}  // namespace Impl
+
+// interpolate(basis, coeff, f, bitVector) — interpolate.hh:204-282
+template <class B, class C, class F, class BV>
+void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
+  const dfx_basis* h = basis.handle();
+  const std::size_t n = dfx_basis_dimension(h);
+  double* x = Impl::coeffData(coeff, n);
+  const uint8_t* mask = nullptr;
+  std::vector<uint8_t> m;
+  if constexpr (!std::is_same_v<BV, Impl::AllTrue>) {
+    if (bv.size() != n) throw RangeError("bit vector size does not match basis");
+    m.resize(n);
+    for (std::size_t i = 0; i < n; ++i) m[i] = bv[i] ? 1 : 0;
+    mask = m.data();
+  }
+  if constexpr (std::is_same_v<F, Registry::Function>) {
+    Impl::check(dfx_interpolate_host(h, basis.rootNode(), &f.f, x, mask));
+  } else {
+    // arbitrary host callable: the device produces the node positions and the leaf of every
+    // coefficient (form (2) of include/dfx.h); f itself is the caller's CPU code
+    constexpr int dim = B::GridView::dimension;
+    std::vector<double> xyz(n * dim);
+    std::vector<int32_t> leaf(n);
+    Impl::check(dfx_interpolation_points_host(h, xyz.data(), leaf.data()));
+    int off, size, firstLeaf, nLeaves;
+    Impl::check(dfx_basis_node_info(h, basis.rootNode(), &off, &size, &firstLeaf, &nLeaves));
+    for (std::size_t p = 0; p < n; ++p) {
+      const int l = leaf[p] - firstLeaf;
+      if (l < 0 || l >= nLeaves || (mask && !mask[p])) continue;
+      FieldVector<double, dim> pos;
+      for (int j = 0; j < dim; ++j) pos[j] = xyz[p * dim + j];
+      x[p] = Impl::rangeEntry(f(pos), l, nLeaves);
+    }
+  }
+}
+template <class B, class C, class F>
+void interpolate(const B& basis, C&& coeff, const F& f) { interpolate(basis, coeff, f, Impl::AllTrue{}); }
+
+// ---- DiscreteGlobalBasisFunction ------------------------------------------------------------
+template <class R, class B, class C>
+class DiscreteGlobalBasisFunction {
+ public:
+  using GV = typename B::GridView;
+  static constexpr int dim = GV::dimension;
+  using Domain = FieldVector<double, dim>;
+  using Element = typename GV::Grid::Element;
+
+  // the basis is stored by value (rvalues are moved in, discreteglobalbasisfunction.hh:389-395);
+  // the coefficient vector is referenced like an lvalue passed to the reference
+  DiscreteGlobalBasisFunction(const B& basis, const C& coeff) : basis_(basis), coeff_(&coeff) {
+    if (coeff.size() * sizeof(typename C::value_type) != basis.dimension() * sizeof(double))
+      throw RangeError("coefficient vector size does not match basis");
+    int off, size, firstLeaf;
+    Impl::check(dfx_basis_node_info(basis.handle(), basis.rootNode(), &off, &size, &firstLeaf, &ncomp_));
+  }
+
+  // Batched form: values at the reference-element points `xhat` on ALL elements,
+  // out[e][q][comp]; jac[e][q][comp][dim] if requested.  This is the fast way to use the path.
+  void evaluateAll(const std::vector<Domain>& xhat, std::vector<double>& values, std::vector<double>* jac = nullptr) const {
+    const std::size_t ne = dfx_basis_num_elements(basis_.handle()), nq = xhat.size();
+    std::vector<double> pts(nq * dim);
+    for (std::size_t q = 0; q < nq; ++q) for (int j = 0; j < dim; ++j) pts[q * dim + j] = xhat[q][j];
+    values.resize(ne * nq * ncomp_);
+    if (jac) jac->resize(ne * nq * ncomp_ * dim);
+    Impl::check(dfx_evaluate_host(basis_.handle(), basis_.rootNode(), reinterpret_cast<const double*>(coeff_->data()),
+                                  pts.data(), (int32_t)nq, 0, ne, values.data(), jac ? jac->data() : nullptr));
+  }
+
+  // localFunction(f): bind(e) then operator()(xLocal) — discreteglobalbasisfunction.hh:124-148, :336-371.
+  // Each call evaluates one (element, point) pair on the device; use evaluateAll for loops.
+  class LocalFunction {
+   public:
+    explicit LocalFunction(const DiscreteGlobalBasisFunction& f, bool derivative = false) : f_(&f), derivative_(derivative) {}
+    void bind(const Element& e) { e_ = e; bound_ = true; }
+    void unbind() { bound_ = false; }
+    bool bound() const { return bound_; }
+    auto operator()(const Domain& x) const {
+      if (!bound_) throw Exception("local function is not bound");
+      std::vector<double> v(f_->ncomp_), j(f_->ncomp_ * dim);
+      Impl::check(dfx_evaluate_host(f_->basis_.handle(), f_->basis_.rootNode(),
+                                    reinterpret_cast<const double*>(f_->coeff_->data()), x.data(), 1, e_.index, e_.index + 1,
+                                    derivative_ ? nullptr : v.data(), derivative_ ? j.data() : nullptr));
+      return derivative_ ? j : v;       // flat range entries (values) or [comp][dim] (Jacobian)
+    }
+    friend LocalFunction derivative(const LocalFunction& lf) {
+      if (lf.derivative_) throw NotImplemented("derivative of derivative is not implemented");   // :630-633
+      return LocalFunction(*lf.f_, true);
+    }
+   private:
+    const DiscreteGlobalBasisFunction* f_;
+    Element e_{};
+    bool bound_ = false, derivative_;
+  };
+  friend LocalFunction localFunction(const DiscreteGlobalBasisFunction& f) { return LocalFunction(f); }
+  int numComponents() const { return ncomp_; }
+ private:
+  B basis_;
+  const C* coeff_;
+  int ncomp_ = 1;
+};
+
+template <class R, class B, class C>
+DiscreteGlobalBasisFunction<R, B, C> makeDiscreteGlobalBasisFunction(const B& basis, const C& coeff) {
+  return DiscreteGlobalBasisFunction<R, B, C>(basis, coeff);
+}
+
+}  // namespace Functions
+}  // namespace Dune

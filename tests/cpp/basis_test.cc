@@ -1,0 +1,153 @@
+// basis_test.cc — the reference's generic basis harness, restated against the façade:
+// checkBasis (dune/functions/functionspacebases/test/basistest.hh:692-713) with
+// checkLocalView (:275-383: size <= maxSize, every local index exactly once),
+// checkBasisIndices (:190-227: consecutive index tree from (0,...,0), size(prefix)
+// consistent, dimension() == number of indices), and the known answers of
+// lagrangebasistest.cc, lagrangedgbasistest.cc:31-66, taylorhoodbasistest.cc:35-146,
+// compositebasistest.cc:66-122, gridviewfunctionspacebasistest.cc:115-183.
+// Runs on the GPU through libdfx.so; exit code 0 = all checks passed.
+#include <cstdio>
+#include <map>
+#include <set>
+
+#include <dfx/dune_functions.hh>
+
+using namespace Dune;
+using namespace Dune::Functions;
+using namespace Dune::Functions::BasisFactory;
+
+static int failures = 0;
+#define CHECK(cond, what)                                                        \
+  do { if (!(cond)) { std::printf("FAILED %s (%s:%d)\n", what, __FILE__, __LINE__); ++failures; } } while (0)
+
+template <class Basis>
+void checkBasis(const Basis& basis, const char* name) {
+  auto localView = basis.localView();
+  std::set<MultiIndex> all;
+  for (const auto& e : elements(basis.gridView())) {
+    localView.bind(e);
+    CHECK(localView.size() <= localView.maxSize(), "localView.size() <= maxSize()");
+    std::set<MultiIndex> local;
+    for (std::size_t i = 0; i < localView.size(); ++i) local.insert(localView.index(i));
+    CHECK(local.size() == localView.size(), "each local index exactly once");
+    all.insert(local.begin(), local.end());
+  }
+  CHECK(all.size() == basis.dimension(), "dimension() == number of multi-indices");
+  // consecutive index tree + size(prefix)
+  std::map<std::vector<std::size_t>, std::set<std::size_t>> children;
+  for (const auto& m : all)
+    for (std::size_t p = 0; p < m.size(); ++p) {
+      std::vector<std::size_t> prefix(m.d_, m.d_ + p);
+      children[prefix].insert(m[p]);
+    }
+  for (const auto& [prefix, ch] : children) {
+    CHECK(*ch.begin() == 0 && *ch.rbegin() + 1 == ch.size(), "digits below a prefix are consecutive from 0");
+    CHECK(basis.size(prefix) == ch.size(), "size(prefix) consistent");
+  }
+  for (const auto& m : all) {
+    std::vector<std::size_t> full(m.d_, m.d_ + m.size());
+    CHECK(basis.size(full) == 0, "size(full multi-index) == 0");
+  }
+  std::printf("checkBasis %-34s dimension %8zu  %s\n", name, (std::size_t)basis.dimension(), failures ? "FAILED" : "ok");
+}
+
+// tensor Gauss rule with 3 points per direction on [0,1]^dim
+template <int dim>
+void gauss3(std::vector<FieldVector<double, dim>>& x, std::vector<double>& w) {
+  const double p[3] = {0.5 - 0.5 * std::sqrt(0.6), 0.5, 0.5 + 0.5 * std::sqrt(0.6)}, ww[3] = {5.0 / 18, 8.0 / 18, 5.0 / 18};
+  int n = 1; for (int j = 0; j < dim; ++j) n *= 3;
+  for (int q = 0; q < n; ++q) {
+    FieldVector<double, dim> pt; double wt = 1; int r = q;
+    for (int j = dim - 1; j >= 0; --j) { pt[j] = p[r % 3]; wt *= ww[r % 3]; r /= 3; }   // last coordinate fastest
+    x.push_back(pt); w.push_back(wt);
+  }
+}
+
+// gridviewfunctionspacebasistest.cc:115-183: the interpolant of x_0 integrates to 0.5
+template <class Basis>
+void checkIntegralOfX0(const Basis& basis, const char* name) {
+  constexpr int dim = Basis::GridView::dimension;
+  std::vector<double> x;
+  interpolate(basis, x, [](const FieldVector<double, dim>& p) { return p[0]; });
+  auto u = makeDiscreteGlobalBasisFunction<double>(basis, x);
+  std::vector<FieldVector<double, dim>> pts; std::vector<double> w, v;
+  gauss3<dim>(pts, w);
+  u.evaluateAll(pts, v);
+  const std::size_t ne = basis.gridView().grid().numElements();
+  double integral = 0;
+  for (std::size_t e = 0; e < ne; ++e)
+    for (std::size_t q = 0; q < pts.size(); ++q) integral += v[e * pts.size() + q] * w[q] / ne;
+  CHECK(std::abs(integral - 0.5) < 1e-10, "integral of interpolated x_0 == 0.5");
+  std::printf("integral   %-34s %.15f\n", name, integral);
+}
+
+int main() {
+  using Grid2 = YaspGrid<2>;
+  using Grid3 = YaspGrid<3>;
+  Grid2 grid2(FieldVector<double, 2>(1.0), {{10, 10}});
+  Grid3 grid3(FieldVector<double, 3>(1.0), {{3, 4, 2}});
+  auto gv2 = grid2.leafGridView();
+  auto gv3 = grid3.leafGridView();
+  try {
+    // lagrangebasistest.cc: orders 1..4, compile-time and run-time order
+    checkBasis(LagrangeBasis<Grid2::LeafGridView, 1>(gv2), "LagrangeBasis<1> 2d");
+    checkBasis(LagrangeBasis<Grid2::LeafGridView, 2>(gv2), "LagrangeBasis<2> 2d");
+    checkBasis(LagrangeBasis<Grid3::LeafGridView, 3>(gv3), "LagrangeBasis<3> 3d");
+    checkBasis(makeBasis(gv3, lagrange(4)), "lagrange(4) 3d");
+    checkBasis(makeBasis(gv2, lagrange<0>()), "lagrange<0> 2d");
+    // lagrangedgbasistest.cc:31-66
+    checkBasis(LagrangeDGBasis<Grid2::LeafGridView, 2>(gv2), "LagrangeDGBasis<2> 2d");
+    checkBasis(makeBasis(gv2, lagrangeDG(2)), "lagrangeDG(2) 2d");
+    // taylorhoodbasistest.cc:35-146
+    checkBasis(TaylorHoodBasis<Grid2::LeafGridView>(gv2), "TaylorHoodBasis 2d");
+    checkBasis(makeBasis(gv3, taylorHood()), "taylorHood() 3d");
+    // compositebasistest.cc:66-122 / makebasistest.cc:65-153: every merging strategy
+    checkBasis(makeBasis(gv2, composite(power<2>(lagrange<2>(), flatLexicographic()), lagrange<1>(), flatLexicographic())), "FL(FL) Taylor-Hood");
+    checkBasis(makeBasis(gv2, composite(power<2>(lagrange<2>(), flatInterleaved()), lagrange<1>(), blockedLexicographic())), "BL(FI) Taylor-Hood");
+    checkBasis(makeBasis(gv2, composite(power<2>(lagrange<2>(), blockedLexicographic()), lagrange<1>(), flatLexicographic())), "FL(BL) Taylor-Hood");
+    checkBasis(makeBasis(gv3, composite(power<3>(lagrange<2>(), blockedInterleaved()), lagrange<1>())), "BL(BI) Taylor-Hood 3d");
+    checkBasis(makeBasis(gv2, power<2>(composite(lagrange<1>(), lagrangeDG<1>(), blockedLexicographic()), blockedInterleaved())), "BI(BL(Q1,DG1))");
+    checkBasis(makeBasis(gv2, composite(power<2>(power<2>(lagrange<1>(), flatLexicographic()), blockedInterleaved()), lagrange<2>())), "BL(BI(FL(Q1)),Q2)");
+
+    checkIntegralOfX0(makeBasis(gv2, lagrange<0>()), "lagrange<0> 2d");
+    checkIntegralOfX0(LagrangeBasis<Grid2::LeafGridView, 3>(gv2), "LagrangeBasis<3> 2d");
+    checkIntegralOfX0(LagrangeBasis<Grid3::LeafGridView, 4>(gv3), "LagrangeBasis<4> 3d");
+    checkIntegralOfX0(LagrangeDGBasis<Grid3::LeafGridView, 2>(gv3), "LagrangeDGBasis<2> 3d");
+
+    // taylorhoodbasistest.cc:58-64: pressure DOFs addressed by indexSet.index(vertex) carry x_0
+    {
+      TaylorHoodBasis<Grid2::LeafGridView> th(gv2);
+      std::vector<double> x(th.dimension(), 0.0);
+      auto pressure = subspaceBasis(th, Indices::_1);
+      const std::size_t offset = 2 * 21 * 21;         // flat position of multi-index (1, j): after (0, *)
+      for (int vy = 0; vy <= 10; ++vy)
+        for (int vx = 0; vx <= 10; ++vx) x[offset + vx + 11 * vy] = vx / 10.0;
+      auto p = makeDiscreteGlobalBasisFunction<double>(pressure, x);
+      std::vector<FieldVector<double, 2>> pts; std::vector<double> w, v;
+      gauss3<2>(pts, w);
+      p.evaluateAll(pts, v);
+      double integral = 0;
+      for (std::size_t e = 0; e < 100; ++e) for (std::size_t q = 0; q < 9; ++q) integral += v[e * 9 + q] * w[q] / 100;
+      CHECK(std::abs(integral - 0.5) < 1e-10, "Taylor-Hood pressure integral == 0.5");
+    }
+    // error behaviour: RangeError for an unsupported order (lagrangebasis.hh:795-796)
+    bool threw = false;
+    try { makeBasis(gv3, lagrange(18)); } catch (const RangeError&) { threw = true; }
+    CHECK(threw, "order > 17 throws RangeError");
+    // derivative of derivative: NotImplemented (discreteglobalbasisfunction.hh:630-633)
+    {
+      LagrangeBasis<Grid2::LeafGridView, 2> b(gv2);
+      std::vector<double> x; interpolate(b, x, Registry::gaussian(1.0));
+      auto u = makeDiscreteGlobalBasisFunction<double>(b, x);
+      auto lf = localFunction(u);
+      threw = false;
+      try { derivative(derivative(lf)); } catch (const NotImplemented&) { threw = true; }
+      CHECK(threw, "second derivative throws NotImplemented");
+    }
+  } catch (const std::exception& e) {
+    std::printf("EXCEPTION %s\n", e.what());
+    return 2;
+  }
+  std::printf("%s\n", failures ? "basis_test FAILED" : "basis_test passed");
+  return failures ? 1 : 0;
+}
