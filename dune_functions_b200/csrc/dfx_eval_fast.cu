@@ -62,6 +62,8 @@ int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* x
   if (k + 1 > kMaxN1) return 0;
   int path = 0;
   if (regPathHas(dim, k, m)) path = 1;
+  else if (smemPathHas(dim, k, m)) path = 2;
+  if (forced == 2 && smemPathHas(dim, k, m)) path = 2;     // both apply for k = 2: testing / comparison
   if (forced > 0 && forced != path) return 0;
   if (path == 0) return 0;
   plan.path = path; plan.dim = dim; plan.k = k; plan.m = m; plan.firstFastest = ff; plan.jac = wantJac; plan.nq = nq;
@@ -326,6 +328,7 @@ static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st) {
   if (e1 == e0) return DFX_OK;
+  if (plan.path == 2) return runSmemEval(b, plan, firstLeaf, nLeaves, coeff, e0, e1, values, jac, st);
   const DevBasis& D = b->dev;
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
     return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");

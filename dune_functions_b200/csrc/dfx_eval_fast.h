@@ -27,6 +27,9 @@ struct FastPlan {
 // returns the path that will run (0 = generic) and fills `plan` when > 0
 int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
                  FastPlan& plan);
+bool smemPathHas(int dim, int k, int m);
+int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
+                double* values, double* jac, cudaStream_t st);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st);
 

@@ -93,7 +93,8 @@ def test_c3_taylor_hood_128_index_map_and_interpolation():
     exact = torch.stack([(e % 128 + 0.5) / 128, ((e // 128) % 128 + 0.5) / 128, (e // 16384 + 0.5) / 128], 1)
     assert float((v[:, 0, :] - exact).abs().max()) < 1e-13
     p = dfx.makeDiscreteGlobalBasisFunction(dfx.subspaceBasis(basis, 1), x).evaluate(centre)
-    assert float((p[:, 0, 0] - torch.exp(-(exact ** 2).sum(1))).abs().max()) < 2e-5   # Q1 interpolation error
+    # Q1 interpolation error at the cell centre: <= 3 h^2/8 max|f''| = 3/(8*128^2)*2 = 4.6e-5
+    assert float((p[:, 0, 0] - torch.exp(-(exact ** 2).sum(1))).abs().max()) < 6e-5
 
 
 def test_c4_lagrange_dg4_192_values_and_gradients():

@@ -421,3 +421,33 @@ def test_halo_pack_unpack_and_owned_ranges():
                     assert np.isnan(out[gb[i]:gb[i] + cnt[i]]).all()
                     out[gb[i]:gb[i] + cnt[i]] = xl[lb[i]:lb[i] + cnt[i]]
             assert (out == gx).all()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+@pytest.mark.parametrize("dm", [-1, 0, 1])
+@pytest.mark.parametrize("last_fastest", [True, False])
+def test_evaluate_shared_memory_path(kernel_path, k, dm, last_fastest):
+    """path 2 (one element per warp, sum factorisation through shared memory): every
+    instantiated (order, points-per-direction) pair, odd element counts, multi-leaf trees"""
+    m = k + 1 + dm
+    pts, _ = tensor_gauss(3, m, last_fastest)
+    for grid in (YaspGrid([3, 3, 5], upper=[1.0, 2.0, 0.5]), GRIDS["3d_2x1x3"]):
+        for tree in (lagrange(k), lagrangeDG(k), power(lagrange(k), 3, BI()),
+                     composite(power(lagrangeDG(k), 2, FL()), lagrange(k), BL())):
+            b = dfx.makeBasis(grid, tree)
+            import ctypes
+            kernel_path(capi.OP_EVALUATE, -1)
+            path = capi.lib().dfx_evaluate_path(b._h, 0, pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(pts), 1)
+            assert path == (1 if (k == 2 and m in (2, 3)) else 2)
+            kernel_path(capi.OP_EVALUATE, 2)
+            v, j, vr, jr = eval_both(grid, tree, pts, path=2)
+            assert rel(v, vr) <= TOL and rel(j, jr) <= TOL
+            # values only + element sub-range with an odd start
+            import torch
+            o = orc.OracleBasis(grid, tree)
+            c = random_coeff(b.dimension())
+            kernel_path(capi.OP_EVALUATE, 2)
+            f = dfx.makeDiscreteGlobalBasisFunction(b, torch.from_numpy(c).cuda())
+            ne = b.numElements()
+            got = f.evaluate(pts, elem_begin=1, elem_end=ne).cpu().numpy()
+            assert rel(got, o.evaluate(c, pts, e0=1, e1=ne)) <= TOL
