@@ -169,6 +169,7 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 
 void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
+  if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
   if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
     cudaSetDevice(b->device);
     if (b->dShape) cudaFree(b->dShape);
@@ -309,7 +310,10 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host,
   int fl, nl;
   if (subtree(b, node, fl, nl)) return -1;
   FastPlan plan;
-  return planFastEval(b, fl, nl, xhat_host, n_q, want_jac != 0, g_forcedPath, plan);
+  if (g_forcedPath == 3) return dmmaPathHas(b, fl, nl) ? 3 : 0;
+  const int path = planFastEval(b, fl, nl, xhat_host, n_q, want_jac != 0, g_forcedPath, plan);
+  if (path == 0 && g_forcedPath < 0 && dmmaPathHas(b, fl, nl)) return 3;
+  return path;
 }
 
 int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const double* xhat_host, int32_t n_q,
@@ -323,8 +327,11 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
   if (!out_values && !out_jac) return DFX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   FastPlan plan;
-  const int path = planFastEval(b, fl, nl, xhat_host, n_q, out_jac != nullptr, g_forcedPath, plan);
+  const int path = g_forcedPath == 3 ? 0 : planFastEval(b, fl, nl, xhat_host, n_q, out_jac != nullptr, g_forcedPath, plan);
   if (path > 0) return runFastEval(b, plan, fl, nl, coeff, e0, e1, out_values, out_jac, st);
+  // no tensor-product structure: dense contraction on the FP64 tensor cores when the element is big enough
+  if ((g_forcedPath == 3 || g_forcedPath < 0) && dmmaPathHas(b, fl, nl) && dfx_basis_num_elements(b) <= 0xffffffffull)
+    return runDmmaEval(b, node, fl, nl, xhat_host, n_q, coeff, e0, e1, out_values, out_jac, st);
   if (g_forcedPath > 0) return fail(DFX_ERR_NOT_IMPLEMENTED, "forced evaluation path does not apply to this configuration");
   ShapeOffsets so; const double *dS, *dDS;
   if ((rc = prepareShape(b, node, fl, nl, xhat_host, n_q, so, dS, dDS, st))) return rc;

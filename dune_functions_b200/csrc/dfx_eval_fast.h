@@ -28,6 +28,9 @@ struct FastPlan {
 int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
                  FastPlan& plan);
 bool smemPathHas(int dim, int k, int m);
+bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);
+int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, const double* coeff,
+                u64 e0, u64 e1, double* values, double* jac, cudaStream_t st);
 int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,

@@ -8,7 +8,8 @@
 //                      and sweeps the rows: per row it writes the vertex-type node and the k-1
 //                      edge-type nodes right of it, so consecutive threads write consecutive
 //                      addresses in both index-set components the row touches.
-//   k_interp_cell      the same for element-local DOFs (LagrangeDG, Lagrange<0>).
+//   k_interp_cell      element-local DOFs (LagrangeDG, Lagrange<0>): a warp sweeps consecutive
+//                      elements, each lane keeps fixed local indices; contiguous 256-byte stores.
 //   k_sep_tables       per-direction factor tables of a separable f (exp(-a|x|^2) =
 //                      prod_j exp(-a x_j^2), prod_j sin(w x_j), x_j, const): O(N) instead of
 //                      O(N^3) transcendental evaluations.
@@ -88,7 +89,7 @@ k_sep_tables(const __grid_constant__ DevGrid g, const __grid_constant__ dfx_func
 
 // per lattice row (Y, Z fixed) and active leaf: flat position of x-entity 0's vertex-type
 // node / first edge-type node and the position stride between consecutive x-entities
-struct RowLeaf { u64 baseV, baseE; unsigned strideV, strideE; };
+struct RowLeaf { u64 baseV, baseE; unsigned strideV, strideE, posA, comp; };
 struct RowCommon { double u1, u2; };   // MODE 0: node coordinates x_1, x_2;  MODE 1: factors t_y, t_z
 constexpr int kRowsPerBlock = 32;
 constexpr int kMaxHoist = 4;           // orders 1..4 keep the x-direction data in registers
@@ -129,6 +130,7 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
     rl.baseE = leaf.posA * rowE + leaf.posB;
     rl.strideV = (unsigned)(leaf.posA * (u64)L.blk[sV]);
     rl.strideE = (unsigned)(leaf.posA * (u64)L.blk[sE]);
+    rl.posA = (unsigned)leaf.posA; rl.comp = (unsigned)A.leafComp[lI];
     rowl[lI][rI] = rl;
     if (lI == 0) {
       RowCommon rc;
@@ -157,9 +159,9 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
     for (int lI = 0; lI < (ONE ? 1 : nAct); ++lI) {
       const RowLeaf rl = rowl[lI][rI];
       const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
-                           : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)A.leafPosA[lI] * (u64)(a - 1);
+                           : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)rl.posA * (u64)(a - 1);
       if (mask == nullptr || mask[p])
-        coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.leafComp[lI], cm, xa, rc.u1, rc.u2);
+        coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : (int)rl.comp, cm, xa, rc.u1, rc.u2);
     }
   };
   // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... < N_x and sweeps the rows ----
@@ -189,46 +191,75 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
 }
 
 struct CellArgs {
-  int layoutId, firstLeaf, nLeaves;
-  FastDiv divNloc, divN0, divN1, divK1;
-  u64 total;
+  int k, dim, nloc;              // direct copies: no indexed-constant loads in the kernel
+  int off[3];
+  FastDiv divN0, divN1, divK1;
+  u64 ne;                        // elements of the local box
   int tabOff[3];
+  int nActive;                   // leaves of the subtree on this lattice: position map + range entry
+  unsigned long long posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES];
+  int comp[DFX_MAX_LEAVES];
 };
 
+constexpr int kCellTask = 32;     // consecutive elements swept by one warp
+constexpr int kCellWarps = 8;
+
+// Element-local DOFs (LagrangeDG, Lagrange<0>): DOF index = element * nloc + i, so one element
+// is a contiguous run of nloc doubles.  A warp sweeps kCellTask consecutive elements; a lane
+// keeps one local index i = lane + 32 pass at a time (its lattice multi-index, the y/z data
+// of the current element row) and writes element after element: every store instruction of
+// the warp is one contiguous 256-byte run.
 template <class F, int MODE>
-__global__ void __launch_bounds__(256)
-k_interp_cell(const __grid_constant__ DevBasis B, const __grid_constant__ CellArgs A, const F f,
+__global__ void __launch_bounds__(kCellWarps * 32)
+k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArgs A, const F f,
               const double* __restrict__ tab, double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
-  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= A.total) return;
-  const DevGrid& g = B.grid;
-  const DevLayout& L = B.layouts[A.layoutId];
-  const int k = L.k;
-  unsigned e, i;                              // element; its DOFs are t itself: e*nloc + i
-  A.divNloc.divmod((unsigned)t, e, i);
-  int ec[3], a[3];
+  const int lane = threadIdx.x & 31;
+  const u64 task = (u64)blockIdx.x * kCellWarps + (threadIdx.x >> 5);
+  const u64 eBegin = task * kCellTask;
+  if (eBegin >= A.ne) return;
+  const unsigned nEl = (unsigned)((A.ne - eBegin) < (u64)kCellTask ? (A.ne - eBegin) : (u64)kCellTask);
+  const int k = A.k, k1 = k + 1, nloc = A.nloc;
+  const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
+  unsigned s0, s1, s2;                          // coordinates of the first element
   {
-    unsigned q, r, q2;
-    A.divN0.divmod(e, q, r); ec[0] = (int)r;
-    A.divN1.divmod(q, q2, r); ec[1] = (int)r; ec[2] = (int)q2;
-    A.divK1.divmod(i, q, r); a[0] = (int)r;
-    A.divK1.divmod(q, q2, r); a[1] = (int)r; a[2] = (int)q2;
+    unsigned q;
+    A.divN0.divmod((unsigned)eBegin, q, s0);
+    A.divN1.divmod(q, s2, s1);
   }
-  double x[3] = {0, 0, 0};
-  double prod = 1.0;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (j >= g.dim) continue;
-    if (MODE == 0) x[j] = nodeCoord(g, k, j, g.off[j] + ec[j], a[j]);
-    else prod = __dmul_rn(prod, tab[A.tabOff[j] + ec[j] * (k + 1) + a[j]]);
-  }
-  const double cm = MODE == 0 ? f.common(x[0], x[1], x[2]) : prod;
   const bool scalar = MODE == 1 || f.ncomp() == 1;
-  for (int l = 0; l < A.nLeaves; ++l) {
-    const DevLeaf& leaf = B.leaves[A.firstLeaf + l];
-    if (leaf.layout != A.layoutId) continue;
-    const u64 p = leaf.posA * t + leaf.posB;
-    if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : l, cm, x[0], x[1], x[2]);
+  for (int i = lane; i < nloc; i += 32) {
+    unsigned a0, a1, a2, q;
+    A.divK1.divmod((unsigned)i, q, a0);
+    A.divK1.divmod(q, a2, a1);
+    unsigned ec0 = s0, ec1 = s1, ec2 = s2;
+    bool newRow = true;
+    double yz = 1.0, x1 = 0.0, x2 = 0.0;      // MODE 1: t_y t_z of the row;  MODE 0: node coordinates
+    for (unsigned n = 0; n < nEl; ++n) {
+      if (newRow) {
+        if (MODE == 1) {
+          yz = __dmul_rn(A.dim > 1 ? tab[A.tabOff[1] + (int)(ec1 * k1 + a1)] : 1.0,
+                         A.dim > 2 ? tab[A.tabOff[2] + (int)(ec2 * k1 + a2)] : 1.0);
+        } else {
+          x1 = A.dim > 1 ? nodeCoord(g, k, 1, g.off[1] + (int)ec1, (int)a1) : 0.0;
+          x2 = A.dim > 2 ? nodeCoord(g, k, 2, g.off[2] + (int)ec2, (int)a2) : 0.0;
+        }
+        newRow = false;
+      }
+      double cm, x0 = 0.0;
+      if (MODE == 1) cm = __dmul_rn(tab[A.tabOff[0] + (int)(ec0 * k1 + a0)], yz);
+      else { x0 = nodeCoord(g, k, 0, g.off[0] + (int)ec0, (int)a0); cm = f.common(x0, x1, x2); }
+      const u64 t = (eBegin + n) * (u64)nloc + (u64)i;
+      if (A.nActive == 1) {
+        const u64 p = A.posA[0] * t + A.posB[0];
+        if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[0], cm, x0, x1, x2);
+      } else {
+        for (int l = 0; l < A.nActive; ++l) {
+          const u64 p = A.posA[l] * t + A.posB[l];
+          if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[l], cm, x0, x1, x2);
+        }
+      }
+      if (++ec0 >= N0) { ec0 = 0; newRow = true; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
+    }
   }
 }
 
@@ -304,15 +335,23 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       if (rc) return rc;
     } else {
       CellArgs C;
-      C.layoutId = q; C.firstLeaf = firstLeaf; C.nLeaves = nLeaves;
-      C.divNloc = FastDiv((unsigned)L.nloc); C.divN0 = FastDiv((unsigned)g.N[0]); C.divN1 = FastDiv((unsigned)g.N[1]);
+      C.k = k; C.dim = g.dim; C.nloc = L.nloc;
+      for (int j = 0; j < 3; ++j) C.off[j] = g.off[j];
+      C.nActive = 0;
+      for (int l = 0; l < nLeaves; ++l)
+        if (D.leaves[firstLeaf + l].layout == q) {
+          C.posA[C.nActive] = D.leaves[firstLeaf + l].posA; C.posB[C.nActive] = D.leaves[firstLeaf + l].posB;
+          C.comp[C.nActive] = l; ++C.nActive;
+        }
+      C.divN0 = FastDiv((unsigned)g.N[0]); C.divN1 = FastDiv((unsigned)g.N[1]);
       C.divK1 = FastDiv((unsigned)(k + 1));
-      C.total = L.dimension;
+      C.ne = (u64)g.N[0] * g.N[1] * g.N[2];
       for (int j = 0; j < 3; ++j) C.tabOff[j] = A.tabOff[j];
-      const u64 blocks = (C.total + 255) / 256;
+      const u64 tasks = (C.ne + kCellTask - 1) / kCellTask;
+      const u64 blocks = (tasks + kCellWarps - 1) / kCellWarps;
       if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
-      if (sep) k_interp_cell<RegistryFn, 1><<<(unsigned)blocks, 256, 0, st>>>(D, C, f, tab, coeff, mask);
-      else k_interp_cell<RegistryFn, 0><<<(unsigned)blocks, 256, 0, st>>>(D, C, f, tab, coeff, mask);
+      if (sep) k_interp_cell<RegistryFn, 1><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);
+      else k_interp_cell<RegistryFn, 0><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);
       int rc = postLaunch("k_interp_cell");
       if (rc) return rc;
     }
@@ -366,14 +405,19 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
         dB[p] = p < leaf.ndig ? leaf.digA[p] * jbase + leaf.digB[p] : 0;
       }
     }
-    for (int it = 0; it < A.iters; ++it) {
-      const u64 el = blkEl0 + (u64)(it * A.m + sub);
-      if (el >= A.ne) break;
-      const unsigned e = (unsigned)(A.e0 + el);
-      unsigned q, ec0, ec1, ec2;
-      A.divN0.divmod(e, q, ec0);
+    // walk this thread's elements el = blkEl0 + sub, + m, + 2m, ...: coordinates advance with carry
+    u64 el = blkEl0 + (u64)sub;
+    if (el >= A.ne) continue;
+    unsigned ec0, ec1, ec2;
+    {
+      unsigned q;
+      A.divN0.divmod((unsigned)(A.e0 + el), q, ec0);
       A.divN1.divmod(q, ec2, ec1);
-      const unsigned ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+    }
+    const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
+    unsigned rowBase = cs0 * (ec1 + cs1 * ec2);
+    for (int it = 0; it < A.iters && el < A.ne; ++it) {
+      const unsigned ent = ec0 + rowBase;
       const u64 o = el * (u64)nloc + (u64)li;
       if (MULTI) {
 #pragma unroll
@@ -381,6 +425,12 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
           if (p < A.stride) out[o * (u64)A.stride + p] = (T)(dB[p] + dA[p] * (u64)ent);
       } else {
         out[o] = (T)(P0 + S * (u64)ent);
+      }
+      el += (u64)A.m;
+      ec0 += (unsigned)A.m;
+      if (ec0 >= N0) {
+        do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
+        rowBase = cs0 * (ec1 + cs1 * ec2);
       }
     }
   }
@@ -394,7 +444,7 @@ int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStre
   const int nloc = b->dev.nlocTotal;
   A.lpb = std::min(nloc, 256);
   A.m = std::max(1, 256 / A.lpb);
-  A.iters = 16;
+  A.iters = 64;
   A.divN0 = FastDiv((unsigned)b->dev.grid.N[0]); A.divN1 = FastDiv((unsigned)b->dev.grid.N[1]);
   const u64 perBlock = (u64)A.m * A.iters;
   const u64 blocks = (A.ne + perBlock - 1) / perBlock;

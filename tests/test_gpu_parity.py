@@ -451,3 +451,40 @@ def test_evaluate_shared_memory_path(kernel_path, k, dm, last_fastest):
             ne = b.numElements()
             got = f.evaluate(pts, elem_begin=1, elem_end=ne).cpu().numpy()
             assert rel(got, o.evaluate(c, pts, e0=1, e1=ne)) <= TOL
+
+
+@pytest.mark.parametrize("gname", ["2d_10x10", "3d_3x4x5", "3d_2x1x3"])
+def test_evaluate_dense_tensor_core_path(kernel_path, gname):
+    """path 3 (FP64 mma.sync dense contraction): arbitrary points pick it automatically for
+    elements with >= 16 local DOFs; forced on tensor points it must agree as well"""
+    import ctypes
+    grid = GRIDS[gname]
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(0, 1, (7, grid.dim))
+    tp, _ = tensor_gauss(grid.dim, 3)
+    dim = grid.dim
+    big = [lagrange(3), lagrangeDG(3), lagrange(4), power(lagrange(3), 2, BI()),
+           composite(power(lagrangeDG(3), 2, FL()), lagrange(3), BL())]
+    if dim == 3:
+        big += [lagrange(2), lagrangeDG(4), taylorHood()]
+    for tree in big:
+        b = dfx.makeBasis(grid, tree)
+        kernel_path(capi.OP_EVALUATE, -1)
+        nodes = [0] if tree.kind != capi.NODE_TAYLOR_HOOD else [b.child(0, 0)]
+        for node in nodes:
+            expect = 3
+            got = capi.lib().dfx_evaluate_path(b._h, node, pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(pts), 1)
+            assert got == expect, (gname, got)
+            o = orc.OracleBasis(grid, tree)
+            c = random_coeff(b.dimension())
+            import torch
+            f = dfx.makeDiscreteGlobalBasisFunction(_Sub(b, node), torch.from_numpy(c).cuda())
+            for p, path in ((pts, -1), (tp, 3)):
+                kernel_path(capi.OP_EVALUATE, path)
+                v, j = f.evaluate(p, jacobians=True)
+                vr, jr = o.evaluate(c, p, node=node, jacobians=True)
+                assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL
+                v2 = f.evaluate(p, elem_begin=1, elem_end=b.numElements() - 1)
+                assert rel(v2.cpu().numpy(), o.evaluate(c, p, node=node, e0=1, e1=b.numElements() - 1)) <= TOL
+                j2 = f.evaluate(p, values=False, jacobians=True)
+                assert rel(j2.cpu().numpy(), jr) <= TOL

@@ -156,6 +156,16 @@ def main():
         report("evaluate DG4 values 5^3", "c4", ms, best, nd * 8 + v.numel() * 8, {"path": path})
         ms, best = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), max(3, args.reps // 3), warm=1)
         report("evaluate DG4 values+jacobians 5^3", "c4", ms, best, nd * 8 + v.numel() * 8 * 4, {"path": path})
+        # the same contraction done densely on the FP64 tensor cores (path 3) and by the generic kernel
+        L.dfx_set_kernel_path(capi.OP_EVALUATE, 3)
+        ms, best = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), 3, warm=1)
+        flops = 2.0 * 125 * 125 * 4 * ne
+        report("evaluate DG4 values+jacobians 5^3 [dense DMMA]", "c4", ms, best, nd * 8 + v.numel() * 8 * 4,
+               {"path": 3, "TFLOPs_fp64": flops / ms / 1e9})
+        ms, best = timeit(lambda: f.evaluate(pts, out_values=v), 3, warm=1)
+        report("evaluate DG4 values 5^3 [dense DMMA]", "c4", ms, best, nd * 8 + v.numel() * 8,
+               {"path": 3, "TFLOPs_fp64": 2.0 * 125 * 125 * ne / ms / 1e9})
+        L.dfx_set_kernel_path(capi.OP_EVALUATE, -1)
 
 
 if __name__ == "__main__":
