@@ -39,6 +39,7 @@ struct SmemArgs {
   u64 e0, ne;
   FastDiv divN0, divN1, divItems;     // divItems: item -> (pair slot, element in pair, leaf)
   int bulk;
+  int perm;                           // 1: contract direction 2 first (points ordered last-coordinate-fastest)
 };
 
 __device__ __forceinline__ unsigned smemAddr2(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -58,7 +59,7 @@ struct SmemLayout {
 };
 
 template <int N1, int M, bool JAC>
-__global__ void __launch_bounds__(kSmemWarps * 32, JAC ? 3 : 4)
+__global__ void __launch_bounds__(kSmemWarps * 32, 4)
 k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1, M> T,
             const __grid_constant__ SmemArgs R, const unsigned* __restrict__ localTab,
             const double* __restrict__ coeff, double* __restrict__ values, double* __restrict__ jac) {
@@ -93,12 +94,16 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
   const DevLeaf& leaf0 = Bp->leaves[R.firstLeaf];
   const DevLayout& L = Bp->layouts[leaf0.layout];
   u64 jbase[SETS];
-  unsigned blk[SETS], cs0[SETS], cs1[SETS];
+  unsigned blk[SETS], cs0[SETS], cs1[SETS], cpos[SETS];
 #pragma unroll
   for (int t = 0; t < SETS; ++t) {
     const int i = lane + 32 * t;
-    jbase[t] = 0; blk[t] = 0; cs0[t] = 0; cs1[t] = 0;
+    jbase[t] = 0; blk[t] = 0; cs0[t] = 0; cs1[t] = 0; cpos[t] = 0;
     if (i < NLOC) {
+      // perm: the coefficient of lattice node (a0, a1, a2) goes to cube position (a2, a1, a0), i.e. the
+      // kernel's first contraction runs over z.  The gather itself stays in local-index order (coalesced).
+      const int a0 = i % N1, a1 = (i / N1) % N1, a2 = i / (N1 * N1);
+      cpos[t] = R.perm ? (unsigned)(a2 + N1 * a1 + N1 * N1 * a0) : (unsigned)i;
       const unsigned packed = __ldg(localTab + leaf0.localOffset + i);
       const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
       const int zero[3] = {0, 0, 0};
@@ -159,9 +164,12 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
         jinv[1] = elementJacInv(g, 1, g.off[1] + (int)ec1);
         jinv[2] = elementJacInv(g, 2, g.off[2] + (int)ec2);
       }
+      // physical direction of the kernel's first / last contraction and its inverse-Jacobian entry
+      const int dFirst = R.perm ? 2 : 0, dLast = R.perm ? 0 : 2;
+      const double jFirst = R.perm ? jinv[2] : jinv[0], jLast = R.perm ? jinv[0] : jinv[2];
       __syncwarp();
 #pragma unroll
-      for (int t = 0; t < SETS; ++t) { const int i = lane + 32 * t; if (i < NLOC) cbuf[i] = cur[t]; }
+      for (int t = 0; t < SETS; ++t) { const int i = lane + 32 * t; if (i < NLOC) cbuf[cpos[t]] = cur[t]; }
       __syncwarp();
       // ---- stage x: pencil p = a1 + N1 a2 ----
       for (int p = lane; p < P1; p += 32) {
@@ -230,9 +238,10 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
             for (int a = 1; a < N1; ++a) {
               gz = fma(T.D[2][q2][a], in[a], gz); gx = fma(T.A[2][q2][a], inx[a], gx); gy = fma(T.A[2][q2][a], iny[a], gy);
             }
-            jst[o * 3 + 0] = gx * jinv[0];
+            // with permuted axes the first contracted direction is z: swap the x and z components back
+            jst[o * 3 + dFirst] = gx * jFirst;
             jst[o * 3 + 1] = gy * jinv[1];
-            jst[o * 3 + 2] = gz * jinv[2];
+            jst[o * 3 + dLast] = gz * jLast;
           }
         }
       }
@@ -290,9 +299,11 @@ static int launchSmem(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, con
                       double* jac, cudaStream_t st) {
   using Lay = SmemLayout<N1, M, JAC>;
   Tables3<N1, M> T;
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < 3; ++j) {
+    const int js = R.perm ? 2 - j : j;           // tables follow the contraction order
     for (int q = 0; q < M; ++q)
-      for (int a = 0; a < N1; ++a) { T.A[j][q][a] = plan.A[j][q][a]; T.D[j][q][a] = plan.Dm[j][q][a]; }
+      for (int a = 0; a < N1; ++a) { T.A[j][q][a] = plan.A[js][q][a]; T.D[j][q][a] = plan.Dm[js][q][a]; }
+  }
   const size_t smem = (size_t)kSmemWarps * (Lay::work + Lay::staging(R.nGroup)) * sizeof(double);
   if (smem > 220 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
   auto kern = k_eval_smem<N1, M, JAC>;
@@ -332,8 +343,11 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     }
     SmemArgs R;
     R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = l; R.ncompTotal = nLeaves;
-    if (plan.firstFastest) { R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m; }
-    else { R.qs[2] = 1; R.qs[1] = m; R.qs[0] = m * m; }
+    // the kernel's first contracted direction is the fastest output index: for points ordered
+    // last-coordinate-fastest the axes are permuted (z, y, x) instead of the output strides,
+    // so that the staging tile is always written with unit stride across the lanes
+    R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m;
+    R.perm = plan.firstFastest ? 0 : 1;
     R.e0 = e0; R.ne = e1 - e0;
     R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
     R.divItems = FastDiv(2u * (unsigned)R.nGroup);
