@@ -8,7 +8,7 @@ from .basis import (  # noqa: F401
     YaspGrid, makeBasis, GlobalBasis, lagrange, lagrangeDG, power, composite, taylorHood,
     flatLexicographic, flatInterleaved, blockedLexicographic, blockedInterleaved,
     subspaceBasis, SubspaceBasis, interpolate, interpolationPoints, interpolateFromValues,
-    makeDiscreteGlobalBasisFunction, DiscreteGlobalBasisFunction,
+    makeDiscreteGlobalBasisFunction, DiscreteGlobalBasisFunction, subEntityDOFs, boundaryDOFs,
     gaussian, identity, constant, coord, quadratic, sinprod, gaussian_vec, make_function,
     tensor_gauss, gauss_points_1d, tree_array,
 )

@@ -81,6 +81,9 @@ SIGNATURES = {
     "dfx_indices_flat_host": (C.c_int, [_vp, _u64, _u64, _vp]),
     "dfx_indices_multi_host": (C.c_int, [_vp, _u64, _u64, _vp, _i32]),
     "dfx_interpolation_points_host": (C.c_int, [_vp, _vp, _vp]),
+    "dfx_subentity_dofs": (C.c_int, [_vp, _i32, _i32, _i32, _pu8, _pi32, _pi32]),
+    "dfx_boundary_dofs": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "dfx_boundary_dofs_host": (C.c_int, [_vp, _i32, _vp]),
     "dfx_halo_ranges": (C.c_int, [_vp, _i32, _pu64, _pu64, _i32, _pi32]),
     "dfx_halo_size": (_u64, [_vp]),
     "dfx_halo_pack": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),

@@ -354,6 +354,34 @@ def interpolateFromValues(basis, coeff, values, mask=None):
     return coeff
 
 
+def subEntityDOFs(basis, subEntityIndex, subEntityCodim):
+    """subEntityDOFs(localView, subEntityIndex, subEntityCodim) — subentitydofs.hh:71-95, 182-190.
+    Returns (contained local indices in the reference's order, dofIsContained flags); on a cube
+    grid they are the same for every element.  An intersection is (indexInInside, 1)."""
+    root, node = _root_and_node(basis)
+    nloc = root.maxNodeSize()
+    flags = (C.c_uint8 * nloc)()
+    lst = (C.c_int32 * nloc)()
+    n = C.c_int32()
+    capi.check(root._lib.dfx_subentity_dofs(root._h, node, subEntityIndex, subEntityCodim, flags, lst, C.byref(n)))
+    return [int(lst[i]) for i in range(n.value)], np.frombuffer(flags, dtype=np.uint8).astype(bool)
+
+
+def boundaryDOFs(basis, mask=None):
+    """forEachBoundaryDOF(basis, [&](auto&& index){ mask[index] = true; }) — boundarydofs.hh:110-128.
+    mask: uint8/bool CUDA tensor of dimension() entries in flat container order (created zeroed
+    when omitted); entries that are not boundary DOFs of the (sub-space) basis keep their value."""
+    import torch
+    root, node = _root_and_node(basis)
+    if mask is None:
+        mask = torch.zeros(root.dimension(), dtype=torch.uint8, device=f"cuda:{root.device}")
+    if mask.numel() != root.dimension():
+        raise capi.RangeError("mask size does not match basis.dimension()")
+    m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    capi.check(root._lib.dfx_boundary_dofs(root._h, node, _ptr(m), _stream()))
+    return mask
+
+
 class DiscreteGlobalBasisFunction:
     """makeDiscreteGlobalBasisFunction<R>(basis, coeff) — discreteglobalbasisfunction.hh:281-478.
 

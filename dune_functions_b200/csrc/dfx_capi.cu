@@ -443,6 +443,80 @@ int dfx_interpolation_points_host(const dfx_basis* cb, double* out_xyz_host, int
   return DFX_OK;
 }
 
+// ---- boundary DOFs ---------------------------------------------------------------------
+// state of reference-cube sub-entity (index, codim) per direction: 0 lower end, 1 upper end,
+// 2 extended (dune-geometry cube numbering)
+static bool subEntityState(int dim, int index, int codim, int st[3]) {
+  st[0] = st[1] = st[2] = 2;
+  if (codim < 0 || codim > dim || index < 0) return false;
+  if (codim == 0) return index == 0;
+  if (codim == dim) { if (index >= (1 << dim)) return false; for (int j = 0; j < dim; ++j) st[j] = (index >> j) & 1; return true; }
+  if (codim == 1) { if (index >= 2 * dim) return false; st[index / 2] = index % 2; return true; }
+  // dim == 3, codim == 2: edges 0-3 z-directed, 4,5 / 8,9 y-directed at z = 0 / 1, 6,7 / 10,11 x-directed
+  if (index >= 12) return false;
+  if (index < 4) { st[0] = index & 1; st[1] = (index >> 1) & 1; return true; }
+  const int r = (index - 4) & 3;
+  st[2] = (index - 4) >> 2;
+  if (r < 2) st[0] = r; else st[1] = r - 2;
+  return true;
+}
+
+int dfx_subentity_dofs(const dfx_basis* b, int32_t node, int32_t sub_entity_index, int32_t sub_entity_codim,
+                       uint8_t* contained_host, int32_t* out_local_host, int32_t* n) {
+  if (!b || !n) return fail(DFX_ERR_INVALID, "null argument");
+  int fl, nl, rc;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  const DevBasis& D = b->dev;
+  const int dim = D.grid.dim;
+  int st[3];
+  if (!subEntityState(dim, sub_entity_index, sub_entity_codim, st))
+    return fail(DFX_ERR_RANGE, "no such sub-entity of the reference cube");
+  if (contained_host) std::memset(contained_host, 0, (size_t)D.nlocTotal);
+  int cnt = 0;
+  for (int l = fl; l < fl + nl; ++l) {
+    const DevLeaf& leaf = D.leaves[l];
+    const int k = D.layouts[leaf.layout].k;
+    for (int i = 0; i < leaf.nloc; ++i) {
+      bool in = true;
+      int ii = i;
+      for (int j = 0; j < dim; ++j) {
+        const int a = ii % (k + 1); ii /= (k + 1);
+        const int sd = k == 0 ? 2 : (a == 0 ? 0 : (a == k ? 1 : 2));     // where the DOF's own sub-entity sits
+        if (st[j] != 2 && sd != st[j]) in = false;
+      }
+      if (!in) continue;
+      if (contained_host) contained_host[leaf.localOffset + i] = 1;
+      if (out_local_host) out_local_host[cnt] = leaf.localOffset + i;
+      ++cnt;
+    }
+  }
+  *n = cnt;
+  return DFX_OK;
+}
+
+int dfx_boundary_dofs(const dfx_basis* b, int32_t node, uint8_t* mask, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if (!mask) return fail(DFX_ERR_INVALID, "null mask");
+  return boundaryDofs(b, fl, nl, mask, (cudaStream_t)stream);
+}
+
+int dfx_boundary_dofs_host(const dfx_basis* cb, int32_t node, uint8_t* mask_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!mask_host) return fail(DFX_ERR_INVALID, "null mask");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  if ((rc = growScratch(b, 1, n))) return rc;
+  uint8_t* dM = (uint8_t*)b->dScratch[1];
+  DFX_CUDA(cudaMemcpyAsync(dM, mask_host, n, cudaMemcpyHostToDevice, st));   // other bytes keep their value
+  if ((rc = dfx_boundary_dofs(b, node, dM, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(mask_host, dM, n, cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
 // ---- slab partition helpers ------------------------------------------------------------
 int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint64_t* out_count, int32_t max_ranges,
                     int32_t* n) {

@@ -281,6 +281,74 @@ int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* co
 }
 
 // ---------------------------------------------------------------------------
+// Boundary DOFs: forEachBoundaryDOF (boundarydofs.hh:110-128) + SubEntityDOFs::bind
+// (subentitydofs.hh:71-95) in closed form.  A DOF is visited by the reference iff it is
+// attached to a sub-entity of a boundary facet, i.e. iff in some direction its entity is
+// pinned to a lattice plane (not extended) that is the first or last plane of the GLOBAL
+// grid.  DG leaves use the same local keys (LagrangeNode, lagrangedgbasis.hh:37-38), so
+// the element's own nodes on a boundary facet count; order 0 has one interior key -> none.
+// One thread per scalar DOF of one layout; only boundary DOFs write.
+__global__ void __launch_bounds__(256)
+k_boundary(const __grid_constant__ DevBasis B, int layoutId, int firstLeaf, int nLeaves, uint8_t* __restrict__ mask) {
+  const DevLayout& L = B.layouts[layoutId];
+  const DevGrid& g = B.grid;
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.dimension) return;
+  const int k = L.k;
+  if (k == 0) return;
+  bool bnd = false;
+  if (L.kind == DFX_NODE_LAGRANGE_DG) {
+    const u64 e = t / (u64)L.nloc;
+    int a[3];
+    localAlpha(k, (int)(t - e * (u64)L.nloc), a);
+    int ie[3];
+    ie[0] = (int)(e % (u64)g.N[0]) + g.off[0];
+    const u64 r = e / (u64)g.N[0];
+    ie[1] = (int)(r % (u64)g.N[1]) + g.off[1];
+    ie[2] = (int)(r / (u64)g.N[1]) + g.off[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < g.dim) bnd = bnd || (a[j] == 0 && ie[j] == 0) || (a[j] == k && ie[j] == g.G[j] - 1);
+  } else {
+    int s = L.order[0];
+    for (int q = 1; q < L.ncomp; ++q)
+      if (t >= L.compOffset[L.order[q]]) s = L.order[q];
+    const u64 ent = (t - L.compOffset[s]) / (u64)L.blk[s];
+    int c[3];
+    c[0] = (int)(ent % (u64)L.csize[s][0]);
+    const u64 r2 = ent / (u64)L.csize[s][0];
+    c[1] = (int)(r2 % (u64)L.csize[s][1]);
+    c[2] = (int)(r2 / (u64)L.csize[s][1]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= g.dim || ((s >> j) & 1)) continue;
+      const int gc = g.off[j] + c[j];
+      bnd = bnd || gc == 0 || gc == g.G[j];
+    }
+  }
+  if (!bnd) return;
+  for (int l = 0; l < nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[firstLeaf + l];
+    if (leaf.layout == layoutId) mask[leaf.posA * t + leaf.posB] = 1;
+  }
+}
+
+int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, cudaStream_t st) {
+  for (int q = 0; q < b->dev.nLayouts; ++q) {
+    bool used = false;
+    for (int l = 0; l < nLeaves; ++l) used = used || b->dev.leaves[firstLeaf + l].layout == q;
+    if (!used || b->dev.layouts[q].k == 0) continue;
+    const u64 n = b->dev.layouts[q].dimension;
+    const u64 blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
+    k_boundary<<<(unsigned)blocks, 256, 0, st>>>(b->dev, q, firstLeaf, nLeaves, mask);
+    int rc = postLaunch("k_boundary");
+    if (rc) return rc;
+  }
+  return DFX_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Halo: the lowest (side 0) / highest (side 1) lattice plane in the last direction.
 // Buffer order: leaves in tree order, per leaf the index-set components that lie in
 // the plane (shift bit of the last direction clear) in layout order.

@@ -49,6 +49,7 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
 extern int g_interpMode;
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st);
+int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, cudaStream_t st);
 int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
 
 }  // namespace dfx

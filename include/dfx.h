@@ -237,6 +237,25 @@ int dfx_indices_multi_host(const dfx_basis* b, uint64_t elem_begin, uint64_t ele
 int dfx_interpolation_points_host(const dfx_basis* b, double* out_xyz_host /*[dimension][dim]*/,
                                   int32_t* out_leaf_host /*[dimension]*/);
 
+/* ---- boundary DOFs (Dirichlet set-up) ---------------------------------------
+ * SubEntityDOFs::bind(localView, subEntityIndex, subEntityCodim), subentitydofs.hh:71-95:
+ * local indices (below subtree_node) of the DOFs attached to sub-entity
+ * (sub_entity_index, sub_entity_codim) of the reference cube or to one of its
+ * sub-sub-entities.  On a cube grid the answer is the same for every element, so this
+ * is host bookkeeping.  contained_host[max_node_size] receives dofIsContained_ (may be
+ * NULL), out_local_host[max_node_size] the contained local indices in the reference's
+ * order (may be NULL), *n their number.  An intersection is (indexInInside, 1).       */
+int dfx_subentity_dofs(const dfx_basis* b, int32_t subtree_node, int32_t sub_entity_index,
+                       int32_t sub_entity_codim, uint8_t* contained_host,
+                       int32_t* out_local_host, int32_t* n);
+/* forEachBoundaryDOF(basis, [&](auto&& index){ mask[index] = 1; }), boundarydofs.hh:110-128
+ * (usage: examples/poisson-pq2.cc:272-276, stokes-taylorhood.cc:419-438 with a sub-space
+ * basis = subtree_node): sets mask[flat position] = 1 for every DOF of the subtree that is
+ * attached to a sub-entity of a boundary intersection of the GLOBAL grid; all other mask
+ * bytes are left untouched.  mask has dimension() bytes.                               */
+int dfx_boundary_dofs(const dfx_basis* b, int32_t subtree_node, uint8_t* mask, void* stream);
+int dfx_boundary_dofs_host(const dfx_basis* b, int32_t subtree_node, uint8_t* mask_host);
+
 /* ---- slab partition helpers (multi-GPU, one handle per rank) ---------------
  * When the local box spans the whole grid in every direction but the last,
  * the DOFs of one z-layer of every Yasp index-set component are contiguous.

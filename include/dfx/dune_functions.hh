@@ -22,6 +22,9 @@
 //   interpolate                        interpolate.hh:204-302
 //   makeDiscreteGlobalBasisFunction    gridfunctions/discreteglobalbasisfunction.hh:457-478
 //   subspaceBasis                      subspacebasis.hh:147-157
+//   SubspaceLocalView                  subspacelocalview.hh:32-153
+//   subEntityDOFs / SubEntityDOFs      subentitydofs.hh:45-236
+//   forEachBoundaryDOF                 boundarydofs.hh:39-127
 // Errors: non-zero dfx_status becomes Dune::RangeError / Dune::NotImplemented /
 // Dune::Exception, like the DUNE_THROW sites of the reference.  No CPU fallback: every
 // compute call goes through libdfx.so and fails if no device is present.
@@ -129,6 +132,28 @@ class ElementRange {
 };
 template <class GV>
 ElementRange<GV::dimension> elements(const GV& gv) { return ElementRange<GV::dimension>(gv.grid_); }
+
+// intersections(gridView, element): the 2*dim facets of a Yasp element in indexInInside order
+// (facet 2*dir + side); boundary() = facet lies on the boundary of the grid
+template <int dim>
+struct YaspIntersection {
+  int face; bool onBoundary;
+  int indexInInside() const { return face; }
+  bool boundary() const { return onBoundary; }
+};
+template <class GV>
+std::vector<YaspIntersection<GV::dimension>> intersections(const GV& gv, const typename GV::Grid::Element& e) {
+  constexpr int dim = GV::dimension;
+  std::vector<YaspIntersection<dim>> r;
+  for (int f = 0; f < 2 * dim; ++f)
+    r.push_back({f, (f % 2 == 0) ? e.coord[f / 2] == 0 : e.coord[f / 2] == gv.grid().N_[f / 2] - 1});
+  return r;
+}
+template <class GV>
+bool hasBoundaryIntersections(const GV& gv, const typename GV::Grid::Element& e) {
+  for (const auto& i : intersections(gv, e)) if (i.boundary()) return true;
+  return false;
+}
 
 namespace Functions {
 
@@ -246,6 +271,7 @@ template <class GV>
 class DefaultLocalView {
  public:
   using GlobalBasis = DefaultGlobalBasis<GV>;
+  using GridView = GV;
   using Element = typename GV::Grid::Element;
   using size_type = std::size_t;
   using Tree = BasisNode<GV>;
@@ -279,6 +305,8 @@ class DefaultLocalView {
     return m;
   }
   const GlobalBasis& globalBasis() const { return *basis_; }
+  const dfx_basis* handle() const { return basis_->handle(); }
+  int subtreeNode() const { return 0; }
  private:
   const GlobalBasis* basis_;
   Tree tree_;
@@ -345,10 +373,39 @@ template <class GV> struct TaylorHoodBasis : DefaultGlobalBasis<GV> {
 };
 
 // ---- SubspaceBasis (subspacebasis.hh:27-157) ----------------------------------------------
+// SubspaceLocalView (subspacelocalview.hh:32-153): the root's local view and indices,
+// tree() = the child at the prefix path, size()/index() forward to the root
+template <class GV>
+class SubspaceLocalView {
+ public:
+  using RootLocalView = DefaultLocalView<GV>;
+  using GridView = GV;
+  using Element = typename RootLocalView::Element;
+  using Tree = BasisNode<GV>;
+  SubspaceLocalView(const DefaultGlobalBasis<GV>& root, int node) : rootLocalView_(root), tree_(&root, node), node_(node) {}
+  void bind(const Element& e) { rootLocalView_.bind(e); }
+  void unbind() { rootLocalView_.unbind(); }
+  bool bound() const { return rootLocalView_.bound(); }
+  const Element& element() const { return rootLocalView_.element(); }
+  const Tree& tree() const { return tree_; }
+  std::size_t size() const { return rootLocalView_.size(); }
+  std::size_t maxSize() const { return rootLocalView_.maxSize(); }
+  MultiIndex index(std::size_t i) const { return rootLocalView_.index(i); }
+  const RootLocalView& rootLocalView() const { return rootLocalView_; }
+  const dfx_basis* handle() const { return rootLocalView_.handle(); }
+  int subtreeNode() const { return node_; }
+ private:
+  RootLocalView rootLocalView_;
+  Tree tree_;
+  int node_;
+};
+
 template <class GV>
 class SubspaceBasis {
  public:
   using GridView = GV;
+  using LocalView = SubspaceLocalView<GV>;
+  LocalView localView() const { return LocalView(*root_, node_); }
   SubspaceBasis(const DefaultGlobalBasis<GV>& root, int node) : root_(&root), node_(node) {}
   const DefaultGlobalBasis<GV>& rootBasis() const { return *root_; }
   int rootNode() const { return node_; }
@@ -430,6 +487,86 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
 }
 template <class B, class C, class F>
 void interpolate(const B& basis, C&& coeff, const F& f) { interpolate(basis, coeff, f, Impl::AllTrue{}); }
+
+// ---- SubEntityDOFs (subentitydofs.hh:45-236) ------------------------------------------------
+// Range of the local indices of the DOFs attached to a sub-entity (or its sub-sub-entities)
+// of the element a local view is bound to, plus contains(localIndex).
+template <class GV>
+class SubEntityDOFs {
+ public:
+  template <class LocalView>
+  SubEntityDOFs& bind(const LocalView& localView, std::size_t subEntityIndex, std::size_t subEntityCodim) {
+    const int nloc = (int)localView.size();
+    std::vector<uint8_t> flags(nloc);
+    std::vector<int32_t> list(nloc);
+    int32_t n = 0;
+    Impl::check(dfx_subentity_dofs(localView.handle(), localView.subtreeNode(), (int32_t)subEntityIndex,
+                                   (int32_t)subEntityCodim, flags.data(), list.data(), &n));
+    containedDOFs_.assign(list.begin(), list.begin() + n);
+    dofIsContained_.assign(flags.begin(), flags.end());
+    return *this;
+  }
+  template <class LocalView, int dim>
+  SubEntityDOFs& bind(const LocalView& localView, const YaspIntersection<dim>& intersection) {
+    return bind(localView, intersection.indexInInside(), 1);
+  }
+  auto begin() const { return containedDOFs_.cbegin(); }
+  auto end() const { return containedDOFs_.cend(); }
+  std::size_t size() const { return containedDOFs_.size(); }
+  std::size_t operator[](std::size_t i) const { return containedDOFs_[i]; }
+  bool contains(std::size_t localIndex) const { return dofIsContained_[localIndex]; }
+ private:
+  std::vector<std::size_t> containedDOFs_;
+  std::vector<bool> dofIsContained_;
+};
+template <class T>
+auto subEntityDOFs(const T&) { return SubEntityDOFs<typename T::GridView>{}; }
+template <class LocalView>
+auto subEntityDOFs(const LocalView& localView, std::size_t subEntityIndex, std::size_t subEntityCodim) {
+  SubEntityDOFs<typename LocalView::GridView> s;
+  s.bind(localView, subEntityIndex, subEntityCodim);
+  return s;
+}
+
+// ---- forEachBoundaryDOF (boundarydofs.hh:39-127) ---------------------------------------------
+// The three callback signatures of the reference: f(localIndex, localView, intersection),
+// f(localIndex, localView), f(globalMultiIndex).  Same visiting order as the reference (a DOF
+// may be visited several times).  The element loop runs on the host over the boundary
+// elements; bind/index are served from the device index table.  For large grids use
+// markBoundaryDOFs below, which does the whole loop in one kernel.
+template <class Basis, class F>
+void forEachBoundaryDOF(const Basis& basis, F&& f) {
+  using GV = typename Basis::GridView;
+  using LV = typename Basis::LocalView;
+  auto localView = basis.localView();
+  SubEntityDOFs<GV> seDOFs;
+  const auto& gridView = basis.gridView();
+  for (const auto& element : elements(gridView)) {
+    if (!hasBoundaryIntersections(gridView, element)) continue;
+    localView.bind(element);
+    for (const auto& intersection : intersections(gridView, element)) {
+      if (!intersection.boundary()) continue;
+      for (auto localIndex : seDOFs.bind(localView, intersection)) {
+        if constexpr (std::is_invocable_v<F, std::size_t, const LV&, decltype(intersection)>) f(localIndex, localView, intersection);
+        else if constexpr (std::is_invocable_v<F, std::size_t, const LV&>) f(localIndex, localView);
+        else f(localView.index(localIndex));
+      }
+    }
+  }
+}
+
+// Not in the reference: the loop above with the callback `bitVector[index] = true`, done on the
+// device in closed form (dfx_boundary_dofs).  bitVector is in flat container order like the
+// coefficient vector; entries that are not boundary DOFs of the (sub-space) basis are kept.
+template <class Basis, class BV>
+void markBoundaryDOFs(const Basis& basis, BV& bitVector) {
+  const std::size_t n = dfx_basis_dimension(basis.handle());
+  if (bitVector.size() != n) bitVector.resize(n);
+  std::vector<uint8_t> m(n);
+  for (std::size_t i = 0; i < n; ++i) m[i] = bitVector[i] ? 1 : 0;
+  Impl::check(dfx_boundary_dofs_host(basis.handle(), basis.rootNode(), m.data()));
+  for (std::size_t i = 0; i < n; ++i) if (m[i]) bitVector[i] = true;
+}
 
 // ---- DiscreteGlobalBasisFunction ------------------------------------------------------------
 template <class R, class B, class C>

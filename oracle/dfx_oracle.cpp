@@ -170,6 +170,26 @@ static int refCubeSubEntityNumber(int dim, int codim, const int st[MAXDIM]) {
   assert(false); return -1;
 }
 
+// [EXT dune-geometry] ReferenceElement::subEntities(i, c, cc).contains(ii): is the codim-cc
+// sub-entity ii a sub-(sub-)entity of the codim-c sub-entity i?  In state notation: wherever
+// the outer entity is pinned to an end, the inner one is pinned to the same end.
+static int refCubeSize(int dim, int codim) {
+  if (codim == 0) return 1;
+  if (codim == dim) return 1 << dim;
+  if (dim == 2) return 4;
+  return codim == 1 ? 6 : 12;
+}
+static bool refCubeSubEntityContains(int dim, int i, int c, int ii, int cc) {
+  if (cc < c) return false;
+  if (i < 0 || i >= refCubeSize(dim, c) || ii < 0 || ii >= refCubeSize(dim, cc)) return false;
+  int so[MAXDIM], si[MAXDIM];
+  refCubeSubEntity(dim, c, i, so);
+  refCubeSubEntity(dim, cc, ii, si);
+  for (int j = 0; j < dim; ++j)
+    if (so[j] != 2 && si[j] != so[j]) return false;
+  return true;
+}
+
 // IndexSet::subIndex(e, i, codim)  [EXT YaspEntity::subCompressedIndex]
 static size_type yaspSubIndex(const Grid& g, const int ec[MAXDIM], int i, int codim) {
   int st[MAXDIM]; refCubeSubEntity(g.dim, codim, i, st);
@@ -855,6 +875,66 @@ void orc_evaluate(void* h, int32_t subtreeNode, const double* coeff, const doubl
       }
     }
   });
+}
+
+// SubEntityDOFs::bind(localView, subEntityIndex, subEntityCodim) — subentitydofs.hh:71-95.
+// On a cube-only grid the result is the same for every element.  contained[localSize]
+// (dofIsContained_), list[] = containedDOFs_ in push_back order; returns their number.
+int32_t orc_subentity_dofs(void* h, int32_t subtreeNode, int32_t subEntityIndex, int32_t subEntityCodim,
+                           uint8_t* contained, int32_t* list) {
+  auto* b = (orc::Basis*)h;
+  const int dim = b->grid.dim;
+  const auto& nd = b->nodes[subtreeNode];
+  int32_t n = 0;
+  for (size_t i = 0; i < b->localSize(); ++i) contained[i] = 0;          // dofIsContained_.assign(size, false)
+  for (int l = 0; l < nd[3]; ++l) {                                      // forEachLeafNode(localView.tree())
+    const orc::LeafNode& leaf = b->leaves[nd[2] + l];
+    const orc::LagrangeCubeFE& fe = *leaf.fe;
+    for (int i = 0; i < fe.size(); ++i) {
+      const orc::LocalKey& key = fe.keys[i];
+      if (orc::refCubeSubEntityContains(dim, subEntityIndex, subEntityCodim, key.subEntity, key.codim)) {
+        if (list) list[n] = leaf.offset + i;                             // node.localIndex(i)
+        ++n;
+        contained[leaf.offset + i] = 1;
+      }
+    }
+  }
+  return n;
+}
+
+// forEachBoundaryDOF(basis, [&](auto&& index){ mask[index] = 1; }) — boundarydofs.hh:110-128.
+// Boundary = boundary of the GLOBAL grid (intersection.boundary(); processor boundaries of a
+// slab are not boundary intersections).  Intersections of a Yasp element are visited in
+// indexInInside order 0..2*dim-1 (face 2*dir + side)  [EXT].  Returns the number of callback
+// invocations (a DOF may be visited several times, as the reference documents).
+uint64_t orc_boundary_dofs(void* h, int32_t subtreeNode, uint8_t* mask) {
+  auto* b = (orc::Basis*)h;
+  if (b->maxDigits > 1) b->buildPositions();
+  const orc::Grid& g = b->grid;
+  const int dim = g.dim;
+  std::vector<orc::MultiIndex> idx;
+  std::vector<uint8_t> contained(b->localSize());
+  std::vector<int32_t> list(b->localSize());
+  uint64_t visits = 0;
+  for (size_t e = 0; e < g.numElements(); ++e) {
+    int ec[3]; g.elementCoords(e, ec);
+    bool hasBoundaryIntersections = false;
+    for (int j = 0; j < dim; ++j)
+      hasBoundaryIntersections = hasBoundaryIntersections || g.off[j] + ec[j] == 0 || g.off[j] + ec[j] == g.G[j] - 1;
+    if (!hasBoundaryIntersections) continue;
+    b->bind(e, idx);
+    for (int face = 0; face < 2 * dim; ++face) {                          // intersections(gridView, element)
+      const int dir = face / 2, side = face % 2;
+      const bool boundary = side == 0 ? g.off[dir] + ec[dir] == 0 : g.off[dir] + ec[dir] == g.G[dir] - 1;
+      if (!boundary) continue;
+      const int32_t n = orc_subentity_dofs(h, subtreeNode, face, 1, contained.data(), list.data());
+      for (int32_t q = 0; q < n; ++q) {
+        mask[b->flat(idx[list[q]])] = 1;                                  // f(localView.index(localIndex))
+        ++visits;
+      }
+    }
+  }
+  return visits;
 }
 
 int32_t orc_max_threads(void) {

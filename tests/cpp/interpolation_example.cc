@@ -59,19 +59,41 @@ int main() {
     }
     CHECK(err < 1e-13, "velocity interpolant of f(x) = x is exact");
 
-    // masked interpolation: only boundary DOFs of the P2 basis take new values (interpolate.hh:278-282)
-    std::vector<char> isBoundary(p2basis.dimension(), 0);
+    // boundary mask + masked interpolation, examples/interpolation.cc:99-122: mark the velocity
+    // boundary DOFs of the Taylor-Hood basis, then interpolate f2 into the marked entries only
+    std::vector<char> isBoundary(taylorHoodBasis.dimension(), 0);
+    std::size_t visits = 0;
+    Functions::forEachBoundaryDOF(Functions::subspaceBasis(taylorHoodBasis, _0), [&](auto&& index) {
+      isBoundary[index] = true;
+      ++visits;
+    });
+    std::vector<char> isBoundaryDev(taylorHoodBasis.dimension(), 0);
+    Functions::markBoundaryDOFs(Functions::subspaceBasis(taylorHoodBasis, _0), isBoundaryDev);
+    CHECK(isBoundary == isBoundaryDev, "forEachBoundaryDOF loop and the device mask kernel agree");
+    const std::size_t n2 = 129 * 129;
+    std::size_t nbv = 0, nbp = 0;
+    for (std::size_t i = 0; i < isBoundary.size(); ++i) (i < 2 * n2 ? nbv : nbp) += isBoundary[i];
+    CHECK(nbv == 2 * 4 * 128 && nbp == 0, "2 x 512 velocity boundary DOFs, no pressure DOF");
+    CHECK(visits == 4 * 64 * 3 * 2, "one visit per (boundary facet, facet DOF, component)");
+    std::vector<double> x3(taylorHoodBasis.dimension(), -1.0);
+    interpolate(Functions::subspaceBasis(taylorHoodBasis, _0), x3, f2, isBoundary);
+    bool ok = true;
+    for (std::size_t i = 0; i < x3.size(); ++i) ok = ok && (isBoundary[i] ? x3[i] == x2[i] : x3[i] == -1.0);
+    CHECK(ok, "masked interpolation touches exactly the marked DOFs");
+
+    // the other two callback signatures (boundarydofs.hh:39-96) and SubEntityDOFs::contains
     {
-      std::vector<double> mark(p2basis.dimension(), 0.0);
-      interpolate(p2basis, mark, [](const FieldVector<double, 2>& x) {
-        return (x[0] < 1e-12 || x[0] > 1 - 1e-12 || x[1] < 1e-12 || x[1] > 1 - 1e-12) ? 1.0 : 0.0; });
-      for (std::size_t i = 0; i < mark.size(); ++i) isBoundary[i] = mark[i] > 0.5;
+      std::size_t n3 = 0, n2arg = 0; bool inside = true;
+      Functions::forEachBoundaryDOF(p2basis, [&](auto&& localIndex, const auto& localView, const auto& intersection) {
+        ++n3;
+        inside = inside && intersection.boundary() &&
+                 Functions::subEntityDOFs(localView, intersection.indexInInside(), 1).contains(localIndex);
+      });
+      Functions::forEachBoundaryDOF(p2basis, [&](auto&& localIndex, const auto& localView) {
+        n2arg += localView.index(localIndex).size();
+      });
+      CHECK(n3 == 4 * 64 * 3 && n2arg == n3 && inside, "three- and two-argument callbacks");
     }
-    std::vector<double> x3(p2basis.dimension(), -1.0);
-    interpolate(p2basis, x3, Functions::Registry::constant(7.0), isBoundary);
-    std::size_t nb = 0; bool ok = true;
-    for (std::size_t i = 0; i < x3.size(); ++i) { nb += isBoundary[i]; ok = ok && x3[i] == (isBoundary[i] ? 7.0 : -1.0); }
-    CHECK(ok && nb == 4 * 128, "masked interpolation touches exactly the 512 boundary DOFs");
 
     // local function idiom: bind + evaluate + derivative on one element
     auto u = Functions::makeDiscreteGlobalBasisFunction<double>(p2basis, x1);

@@ -38,6 +38,10 @@ def lib():
         L.orc_interpolate.argtypes = [vp, i32, C.POINTER(capi.Function), vp, vp, i32]
         L.orc_evaluate.argtypes = [vp, i32, vp, vp, i32, u64, u64, vp, vp, i32]
         L.orc_max_threads.restype = i32
+        L.orc_subentity_dofs.restype = i32
+        L.orc_subentity_dofs.argtypes = [vp, i32, i32, i32, vp, vp]
+        L.orc_boundary_dofs.restype = u64
+        L.orc_boundary_dofs.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 
@@ -122,3 +126,17 @@ class OracleBasis:
         if values and jacobians:
             return v, j
         return v if values else j
+
+    def subEntityDOFs(self, subEntityIndex, subEntityCodim, node=0):
+        nl = self.maxNodeSize()
+        flags = np.zeros(nl, dtype=np.uint8)
+        lst = np.zeros(nl, dtype=np.int32)
+        n = lib().orc_subentity_dofs(self._h, node, subEntityIndex, subEntityCodim, flags.ctypes.data, lst.ctypes.data)
+        return lst[:n].tolist(), flags.astype(bool)
+
+    def boundaryDOFs(self, node=0, mask=None):
+        """(mask, number of callback invocations) of forEachBoundaryDOF"""
+        if mask is None:
+            mask = np.zeros(self.dimension(), dtype=np.uint8)
+        visits = lib().orc_boundary_dofs(self._h, node, mask.ctypes.data)
+        return mask, int(visits)
