@@ -1,4 +1,5 @@
 // dfx_capi.cu — the extern "C" boundary declared in include/dfx.h.
+#include <algorithm>
 #include <cstring>
 
 #include "dfx_eval_fast.h"
@@ -11,6 +12,7 @@ namespace {
 int g_forcedPath = -1;      // evaluate
 int g_interpPath = -1;      // interpolate
 int g_indicesPath = -1;     // indices
+int g_hostBandKiB = -1;     // result bytes per band of dfx_evaluate_host (-1: 192 MiB)
 
 int ensureDevice(const dfx_basis* b) {
   if (!b) return fail(DFX_ERR_INVALID, "null basis handle");
@@ -170,6 +172,7 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
   if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
+  if (b->evStream[0]) { cudaSetDevice(b->device); cudaStreamDestroy((cudaStream_t)b->evStream[0]); }
   if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
     cudaSetDevice(b->device);
     if (b->dShape) cudaFree(b->dShape);
@@ -303,6 +306,7 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   if (op == DFX_OP_EVALUATE) g_forcedPath = path;
   else if (op == DFX_OP_INTERPOLATE) g_interpPath = path;
   else if (op == DFX_OP_INDICES) g_indicesPath = path;
+  else if (op == DFX_OP_HOST_BAND_KIB) g_hostBandKiB = path;
 }
 
 int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host, int32_t n_q, int32_t want_jac) {
@@ -363,6 +367,61 @@ int dfx_interpolate_host(const dfx_basis* cb, int32_t node, const dfx_function* 
   return DFX_OK;
 }
 
+// Flat-position ranges [begin, end) of the coefficients that the elements of the z-layers
+// [zlo, zhi) (z = last grid direction) gather, merged into disjoint sorted intervals.  Every
+// index-set component is lexicographic with z slowest, so a band of layers is one index range
+// per (leaf, component); interleaved leaves (posA > 1) contribute the hull of their stride.
+typedef std::vector<std::pair<u64, u64>> Intervals;
+static void normalise(Intervals& v) {
+  std::sort(v.begin(), v.end());
+  Intervals out;
+  for (auto& r : v) {
+    if (r.first >= r.second) continue;
+    if (!out.empty() && r.first <= out.back().second) out.back().second = std::max(out.back().second, r.second);
+    else out.push_back(r);
+  }
+  v.swap(out);
+}
+static Intervals layerBandRanges(const dfx_basis* b, int fl, int nl, u64 zlo, u64 zhi) {
+  const DevBasis& D = b->dev;
+  const int dz = D.grid.dim - 1;
+  Intervals out;
+  for (int l = fl; l < fl + nl; ++l) {
+    const DevLeaf& leaf = D.leaves[l];
+    const DevLayout& L = D.layouts[leaf.layout];
+    for (int q = 0; q < L.ncomp; ++q) {
+      const int s = L.order[q];
+      const u64 plane = L.compCount[s] / (u64)L.csize[s][dz];
+      const u64 top = ((s >> dz) & 1) ? zhi : zhi + 1;               // pinned components own the plane above too
+      const u64 j0 = L.compOffset[s] + plane * zlo, j1 = L.compOffset[s] + plane * top;
+      if (j1 > j0) out.push_back({leaf.posA * j0 + leaf.posB, leaf.posA * (j1 - 1) + leaf.posB + 1});
+    }
+  }
+  normalise(out);
+  return out;
+}
+// a minus b (both normalised)
+static Intervals subtract(const Intervals& a, const Intervals& b) {
+  Intervals out;
+  size_t k = 0;
+  for (auto r : a) {
+    while (k < b.size() && b[k].second <= r.first) ++k;
+    size_t m = k;
+    u64 cur = r.first;
+    while (m < b.size() && b[m].first < r.second) {
+      if (b[m].first > cur) out.push_back({cur, b[m].first});
+      cur = std::max(cur, b[m].second);
+      ++m;
+    }
+    if (cur < r.second) out.push_back({cur, r.second});
+  }
+  return out;
+}
+
+// Pipelined: the element range is cut into bands of z-layers; an input stream brings over the
+// coefficients each band needs (only what earlier bands have not brought yet) while the work
+// stream evaluates the previous band and sends its results back, so both PCIe directions are
+// busy at once and the device never holds more than one band of results.
 int dfx_evaluate_host(const dfx_basis* cb, int32_t node, const double* coeff_host, const double* xhat_host,
                       int32_t n_q, uint64_t e0, uint64_t e1, double* out_values_host, double* out_jac_host) {
   dfx_basis* b = const_cast<dfx_basis*>(cb);
@@ -371,30 +430,66 @@ int dfx_evaluate_host(const dfx_basis* cb, int32_t node, const double* coeff_hos
   if ((rc = subtree(b, node, fl, nl))) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (!coeff_host || !xhat_host || n_q < 1) return fail(DFX_ERR_INVALID, "null argument");
+  if (e0 == e1 || (!out_values_host && !out_jac_host)) return DFX_OK;
   cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  if (!b->evStream[0]) {
+    cudaStream_t s;
+    DFX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    b->evStream[0] = (void*)s;
+  }
+  cudaStream_t sin = (cudaStream_t)b->evStream[0];
   const size_t n = b->dimension;
   const int dim = b->dev.grid.dim;
   if ((rc = growScratch(b, 0, n * sizeof(double)))) return rc;
   double* dC = (double*)b->dScratch[0];
-  DFX_CUDA(cudaMemcpyAsync(dC, coeff_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
-  // element chunks bound the device scratch (<= 1 GiB of values per chunk)
   const size_t perElemV = (size_t)n_q * nl * sizeof(double);
   const size_t perElemJ = perElemV * dim;
-  u64 chunk = std::max<u64>(1, (1ull << 30) / perElemV);
-  chunk = std::min<u64>(chunk, std::max<u64>(1, e1 - e0));
-  if (out_values_host && (rc = growScratch(b, 1, chunk * perElemV))) return rc;
-  if (out_jac_host && (rc = growScratch(b, 2, chunk * perElemJ))) return rc;
+  const size_t perElem = (out_values_host ? perElemV : 0) + (out_jac_host ? perElemJ : 0);
+  // bands of whole z-layers, about 192 MiB of results each
+  u64 layer = 1;
+  for (int j = 0; j + 1 < dim; ++j) layer *= (u64)b->dev.grid.N[j];
+  const u64 bandBytes = g_hostBandKiB > 0 ? (u64)g_hostBandKiB << 10 : 192ull << 20;
+  u64 chunk = std::max<u64>(1, bandBytes / perElem);
+  chunk = std::max<u64>(layer, chunk / layer * layer);
+  const u64 bandMax = std::min<u64>(chunk, e1 - e0);
+  if (out_values_host && (rc = growScratch(b, 1, bandMax * perElemV))) return rc;
+  if (out_jac_host && (rc = growScratch(b, 2, bandMax * perElemJ))) return rc;
   double* dV = out_values_host ? (double*)b->dScratch[1] : nullptr;
   double* dJ = out_jac_host ? (double*)b->dScratch[2] : nullptr;
-  for (u64 c0 = e0; c0 < e1; c0 += chunk) {
-    const u64 c1 = std::min<u64>(e1, c0 + chunk);
-    if ((rc = dfx_evaluate(b, node, dC, xhat_host, n_q, c0, c1, dV, dJ, st))) return rc;
-    if (dV) DFX_CUDA(cudaMemcpyAsync((char*)out_values_host + (c0 - e0) * perElemV, dV, (c1 - c0) * perElemV,
-                                     cudaMemcpyDeviceToHost, st));
-    if (dJ) DFX_CUDA(cudaMemcpyAsync((char*)out_jac_host + (c0 - e0) * perElemJ, dJ, (c1 - c0) * perElemJ,
-                                     cudaMemcpyDeviceToHost, st));
+  // with the test knob set, poison the coefficient scratch (NaN) so that a band that gathers
+  // something it did not bring over cannot pass unnoticed
+  if (g_hostBandKiB > 0) DFX_CUDA(cudaMemsetAsync(dC, 0xFF, n * sizeof(double), sin));
+  Intervals have;
+  std::vector<cudaEvent_t> events;
+  auto cleanup = [&]() { for (auto ev : events) cudaEventDestroy(ev); };
+  // band boundaries on multiples of `chunk` so that a band is whole layers except at the ends
+  for (u64 c0 = e0; c0 < e1;) {
+    const u64 c1 = std::min<u64>(e1, (c0 / chunk + 1) * chunk);
+    Intervals need = subtract(layerBandRanges(b, fl, nl, c0 / layer, (c1 - 1) / layer + 1), have);
+    for (auto& r : need) {
+      cudaError_t e = cudaMemcpyAsync(dC + r.first, coeff_host + r.first, (r.second - r.first) * sizeof(double),
+                                      cudaMemcpyHostToDevice, sin);
+      if (e != cudaSuccess) { cleanup(); return cudaFail(e, "cudaMemcpyAsync(coefficients)"); }
+      have.push_back(r);
+    }
+    normalise(have);
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cleanup(); return fail(DFX_ERR_CUDA, "cudaEventCreate"); }
+    events.push_back(ev);
+    cudaEventRecord(ev, sin);
+    cudaStreamWaitEvent(st, ev, 0);
+    if ((rc = dfx_evaluate(b, node, dC, xhat_host, n_q, c0, c1, dV, dJ, st))) { cudaStreamSynchronize(sin); cleanup(); return rc; }
+    cudaError_t e = cudaSuccess;
+    if (dV) e = cudaMemcpyAsync((char*)out_values_host + (c0 - e0) * perElemV, dV, (c1 - c0) * perElemV, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && dJ)
+      e = cudaMemcpyAsync((char*)out_jac_host + (c0 - e0) * perElemJ, dJ, (c1 - c0) * perElemJ, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { cudaStreamSynchronize(sin); cleanup(); return cudaFail(e, "cudaMemcpyAsync(results)"); }
+    c0 = c1;
   }
-  DFX_CUDA(cudaStreamSynchronize(st));
+  cudaError_t e1s = cudaStreamSynchronize(sin), e2s = cudaStreamSynchronize(st);
+  cleanup();
+  if (e1s != cudaSuccess) return cudaFail(e1s, "cudaStreamSynchronize");
+  if (e2s != cudaSuccess) return cudaFail(e2s, "cudaStreamSynchronize");
   return DFX_OK;
 }
 

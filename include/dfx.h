@@ -214,16 +214,21 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
 /* force a kernel family (testing / profiling); path -1 = automatic.
  * op DFX_OP_EVALUATE: paths as above; DFX_OP_INTERPOLATE: 0 generic per-DOF
  * kernel, 1 structured kernel evaluating f at every node, 2 structured kernel
- * with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast. */
+ * with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast;
+ * DFX_OP_HOST_BAND_KIB: `path` = KiB of results per pipeline band of dfx_evaluate_host
+ * (-1 = default 192 MiB).                                                          */
 #define DFX_OP_EVALUATE 0
 #define DFX_OP_INTERPOLATE 1
 #define DFX_OP_INDICES 2
+#define DFX_OP_HOST_BAND_KIB 3
 void dfx_set_kernel_path(int32_t op, int32_t path);
 
 /* ---- host-buffer entry points (what a CPU caller of the reference uses) ----
- * Same semantics with HOST buffers; the copies are staged through pinned
- * memory on the handle's stream and the call returns when the result is in
- * the host buffer.                                                            */
+ * Same semantics with HOST buffers (pinned buffers make the copies asynchronous);
+ * the call returns when the result is in the host buffer.  dfx_evaluate_host is
+ * pipelined over bands of z-layers: the coefficients a band needs travel to the
+ * device on one stream while the previous band is evaluated and its results
+ * travel back on another, so both PCIe directions are busy at once.           */
 int dfx_interpolate_host(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
                          double* coeff_host, const uint8_t* mask_host);
 int dfx_evaluate_host(const dfx_basis* b, int32_t subtree_node, const double* coeff_host,

@@ -268,6 +268,36 @@ def test_evaluate_host_entry_point():
     assert rel(v, vr) <= TOL and rel(j, jr) <= TOL
 
 
+@pytest.mark.parametrize("gname,tname", [("3d_3x4x5", "lagrange2"), ("3d_3x4x5", "taylorHood"), ("3d_3x4x5", "TH_FL(FI)"),
+                                         ("3d_3x4x5", "TH_BL(BI)"), ("3d_3x4x5", "lagrangeDG2"), ("3d_2x1x3", "lagrange3"),
+                                         ("3d_3x4x5", "nested_FL_FI_BL"), ("2d_10x10", "power3_q2_BI"),
+                                         ("2d_10x10", "lagrange1"), ("1d_5", "lagrange4")])
+@pytest.mark.parametrize("band_kib", [1, 7, 64])
+def test_evaluate_host_pipeline_bands(gname, tname, band_kib):
+    """many small bands: every band must find the coefficients it gathers on the device
+    (contiguous and interleaved layouts, sub-ranges that start and end inside a layer)"""
+    grid = GRIDS[gname]
+    tree = trees(grid.dim)[tname]
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    c = random_coeff(b.dimension())
+    d = grid.dim
+    pts, _ = tensor_gauss(d, 2)
+    nq, nc, ne = len(pts), b.numLeaves(), b.numElements()
+    L = capi.lib()
+    L.dfx_set_kernel_path(capi.OP_HOST_BAND_KIB, band_kib)
+    try:
+        for e0, e1 in ((0, ne), (1, ne - 1), (ne // 2, ne // 2 + 1)):
+            v = np.full((e1 - e0, nq, nc), np.nan)
+            j = np.full((e1 - e0, nq, nc, d), np.nan)
+            capi.check(L.dfx_evaluate_host(b._h, 0, c.ctypes.data, pts.ctypes.data_as(C.POINTER(C.c_double)), nq,
+                                           e0, e1, v.ctypes.data, j.ctypes.data))
+            vr, jr = o.evaluate(c, pts, jacobians=True, e0=e0, e1=e1)
+            assert rel(v, vr) <= TOL and rel(j, jr) <= TOL
+    finally:
+        L.dfx_set_kernel_path(capi.OP_HOST_BAND_KIB, -1)
+
+
 # ---- the reference's known answers, now through the GPU path ------------------------------------
 @pytest.mark.parametrize("tree", [lagrange(0), lagrange(1), lagrange(2), lagrange(3), lagrange(4),
                                   lagrangeDG(1), lagrangeDG(2), lagrangeDG(3)])
