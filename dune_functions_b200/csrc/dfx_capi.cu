@@ -172,6 +172,7 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
   if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
+  if (b->dJinv) { cudaSetDevice(b->device); cudaFree(b->dJinv); }
   if (b->evStream[0]) { cudaSetDevice(b->device); cudaStreamDestroy((cudaStream_t)b->evStream[0]); }
   if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
     cudaSetDevice(b->device);
@@ -307,6 +308,7 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_INTERPOLATE) g_interpPath = path;
   else if (op == DFX_OP_INDICES) g_indicesPath = path;
   else if (op == DFX_OP_HOST_BAND_KIB) g_hostBandKiB = path;
+  else if (op == DFX_OP_SMEM_GRADIENT) g_smemGrad = path;
 }
 
 int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host, int32_t n_q, int32_t want_jac) {

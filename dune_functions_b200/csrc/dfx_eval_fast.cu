@@ -10,6 +10,7 @@
 // Replaces LocalFunctionBase::bind + LocalFunction::operator() and the derivative's
 // operator() (discreteglobalbasisfunction.hh:124-148, :336-371, :583-627).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "dfx_device.cuh"
@@ -74,6 +75,30 @@ int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* x
         if (k == 1) { plan.A[j][t][a] = a ? x1[j][t] : 1 - x1[j][t]; plan.Dm[j][t][a] = a ? 1.0 : -1.0; }
         else { plan.A[j][t][a] = lagrangeP(k, a, x1[j][t]); plan.Dm[j][t][a] = lagrangeDP(k, a, x1[j][t]); }
       }
+  // collocation derivative matrices (barycentric form)
+  plan.colloc = true;
+  for (int j = 0; j < dim; ++j) {
+    double w[kMaxQ1];
+    for (int q = 0; q < m; ++q) {
+      w[q] = 1.0;
+      for (int r = 0; r < m; ++r)
+        if (r != q) {
+          const double d = x1[j][q] - x1[j][r];
+          if (std::abs(d) < 1e-9) plan.colloc = false;
+          w[q] *= d;
+        }
+    }
+    if (!plan.colloc) break;
+    for (int q = 0; q < m; ++q) {
+      double diag = 0.0;
+      for (int r = 0; r < m; ++r) {
+        if (r == q) continue;
+        plan.Cm[j][q][r] = (w[q] / w[r]) / (x1[j][q] - x1[j][r]);
+        diag += 1.0 / (x1[j][q] - x1[j][r]);
+      }
+      plan.Cm[j][q][q] = diag;
+    }
+  }
   return path;
 }
 

@@ -21,6 +21,10 @@ struct FastPlan {
   // 1-d tables A[q][a] = l_a(x_q), Dm[q][a] = l_a'(x_q) per direction
   double A[3][kMaxQ1][kMaxN1];
   double Dm[3][kMaxQ1][kMaxN1];
+  // collocation derivative on the points, Cm[q][r] = l_r'(x_q) with l_r the Lagrange polynomials
+  // through the m points of the direction; valid (colloc) when the points are distinct
+  double Cm[3][kMaxQ1][kMaxQ1];
+  bool colloc = false;
   std::vector<double> xhat;   // the points (dense DMMA path builds its table from them)
 };
 
@@ -28,6 +32,7 @@ struct FastPlan {
 int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
                  FastPlan& plan);
 bool smemPathHas(int dim, int k, int m);
+extern int g_smemGrad;
 bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);
 int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, const double* coeff,
                 u64 e0, u64 e1, double* values, double* jac, cudaStream_t st);

@@ -8,7 +8,12 @@
 //   stage y: t1[q0][a1][a2]  -> t2[q1][q0][a2] (+ t2y, and t2x from d1)
 //   stage z: t2[q1][q0][a2]  -> u[q0][q1][q2], du/dx, du/dy, du/dz
 // 9 x (k+1) m^3-ish FMAs per element with gradients instead of 4 (k+1)^3 m^3 for the dense
-// contraction (DG4 at 5^3: 5 625 vs 62 500).  Buffers are laid out so that lane p reads
+// contraction (DG4 at 5^3: 5 625 vs 62 500).  When there are at least k+1 distinct points per
+// direction (GRAD == 2) the gradient is taken from the point values instead: u restricted to
+// a grid line is a polynomial of degree k, so its derivative at the m >= k+1 points is the
+// collocation derivative C[q][r] = l_r'(x_q) (l_r: Lagrange polynomials through the points)
+// applied to the values on that line — 6 contractions (3 750 FMAs) and no derivative
+// intermediates in shared memory, which is what bounds this kernel.  Buffers are laid out so that lane p reads
 // N1*p + a (odd stride: conflict free) and writes q*P + p (unit stride).  Only __syncwarp
 // separates the stages.  The coefficients of the NEXT (element, leaf) item are fetched into
 // registers while the current one is contracted.  A warp handles PAIRS of consecutive
@@ -30,24 +35,28 @@ namespace dfx {
 template <int N1, int M>
 struct Tables3 {
   double A[3][M][N1];
-  double D[3][M][N1];
+  double D[3][M][N1];     // GRAD == 1: l_a'(x_q);  GRAD == 2: unused
+  double C[3][M][M];      // GRAD == 2: collocation derivative on the points
 };
 
 struct SmemArgs {
   int firstLeaf, nGroup, compOffset, ncompTotal;
-  int qs[3];
   u64 e0, ne;
   FastDiv divN0, divN1, divItems;     // divItems: item -> (pair slot, element in pair, leaf)
   int bulk;
+  int isDG;                           // element-local DOFs: scalar index = e * NLOC + i
   int perm;                           // 1: contract direction 2 first (points ordered last-coordinate-fastest)
 };
 
 __device__ __forceinline__ unsigned smemAddr2(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 constexpr int kSmemWarps = 4;
+int g_smemGrad = -1;        // 1 forces the differentiated-table gradients (testing / comparison)
 
-template <int N1, int M, bool JAC>
+// GRAD: 0 values only, 1 gradients by differentiated tables, 2 gradients by collocation
+template <int N1, int M, int GRAD>
 struct SmemLayout {
+  static constexpr bool JAC = GRAD == 1;                          // derivative intermediates t1/t2
   static constexpr int NLOC = N1 * N1 * N1;
   static constexpr int NQ = M * M * M;
   static constexpr int P1 = N1 * N1, P2 = N1 * M, P3 = M * M;     // pencils per stage
@@ -55,22 +64,24 @@ struct SmemLayout {
   static constexpr int W2raw = (JAC ? 3 : 1) * M * P2;            // t2 (+ t2x, t2y)
   static constexpr int W2 = W2raw > NLOC ? W2raw : NLOC;          // c aliases the t2 region
   static constexpr int work = (W1 + W2 + 1) & ~1;                 // doubles per warp (even: 16-byte tiles)
-  static int staging(int nG) { return 2 * NQ * nG * (JAC ? 4 : 1); }
+  static int staging(int nG) { return 2 * NQ * nG * (GRAD ? 4 : 1); }
 };
 
-template <int N1, int M, bool JAC>
-__global__ void __launch_bounds__(kSmemWarps * 32, 4)
+template <int N1, int M, int GRAD>
+__global__ void __launch_bounds__(kSmemWarps * 32, GRAD == 1 ? 4 : (GRAD == 2 ? 5 : 6))
 k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1, M> T,
             const __grid_constant__ SmemArgs R, const unsigned* __restrict__ localTab,
-            const double* __restrict__ coeff, double* __restrict__ values, double* __restrict__ jac) {
-  using Lay = SmemLayout<N1, M, JAC>;
+            const double* __restrict__ jinvTab, const double* __restrict__ coeff, double* __restrict__ values, double* __restrict__ jac) {
+  using Lay = SmemLayout<N1, M, GRAD>;
+  constexpr bool JAC = GRAD == 1;            // differentiated tables through every stage
+  constexpr bool OUTJ = GRAD != 0;           // Jacobians are produced
   constexpr int NLOC = Lay::NLOC, NQ = Lay::NQ, P1 = Lay::P1, P2 = Lay::P2, P3 = Lay::P3;
   constexpr int SETS = (NLOC + 31) / 32;
   extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nG = R.nGroup;
   const int stageLen = 2 * NQ * nG;                       // values of the pair
-  const int perWarp = Lay::work + stageLen * (JAC ? 4 : 1);
+  const int perWarp = Lay::work + stageLen * (OUTJ ? 4 : 1);
   double* t1 = smem + (size_t)warp * perWarp;
   double* d1 = t1 + M * P1;
   double* t2 = t1 + Lay::W1;
@@ -84,10 +95,8 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
   const u64 nPairs = (R.ne + 1) / 2;
   const u64 warpId = (u64)blockIdx.x * kSmemWarps + warp, nWarps = (u64)gridDim.x * kSmemWarps;
   if (warpId >= nPairs) return;
-  // this warp's pairs: warpId, warpId + nWarps, ...; its items: (pair slot, element, leaf)
-  const u64 myPairs = (nPairs - warpId + nWarps - 1) / nWarps;
-  const unsigned itemsPerPair = 2u * (unsigned)nG;
-  const u64 nItems = myPairs * itemsPerPair;
+  // this warp's pairs: warpId, warpId + nWarps, ...; its items: (pair, element in pair, leaf),
+  // walked with counters (no divisions in the loop)
 
   // per-lane gather constants of the local indices lane, lane+32, ... (same for every leaf of
   // the group: they share the layout): scalar index j = jbase + blk * lex(ec; cs0, cs1)
@@ -116,53 +125,61 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
     }
   }
 
-  // item n of this warp -> element (relative to e0), element-in-pair, leaf; false past the end
-  auto locate = [&](u64 n, u64& el, int& eI, int& gI) -> bool {
-    if (n >= nItems) return false;
-    const u64 slot = n / itemsPerPair;
-    const unsigned rem = (unsigned)(n - slot * itemsPerPair);
-    eI = (int)(rem / (unsigned)nG); gI = (int)(rem - (unsigned)eI * (unsigned)nG);
-    el = (warpId + slot * nWarps) * 2 + (u64)eI;
-    return el < R.ne;
+  // next item after (pr, e_, g_): leaves of the group, then the second element, then the next pair
+  auto advance = [&](u64& pr, int& e_, int& g_) {
+    if (++g_ < nG) return;
+    g_ = 0;
+    if (e_ == 0 && pr * 2 + 1 < R.ne) { e_ = 1; return; }
+    e_ = 0; pr += nWarps;
   };
   // gather of one item into registers (LocalFunctionBase::bind, :140-147)
-  auto fetch = [&](u64 el, int gI, double (&c)[SETS]) {
+  auto fetch = [&](u64 el, int gI, double (&c)[SETS], unsigned (&ec)[3]) {
     const unsigned e = (unsigned)(R.e0 + el);
-    unsigned q, ec0, ec1, ec2;
-    R.divN0.divmod(e, q, ec0);
-    R.divN1.divmod(q, ec2, ec1);
+    unsigned q;
+    R.divN0.divmod(e, q, ec[0]);
+    R.divN1.divmod(q, ec[2], ec[1]);
     const DevLeaf& leaf = Bp->leaves[R.firstLeaf + gI];
     const u64 posA = leaf.posA, posB = leaf.posB;
+    if (R.isDG) {
+      const double* src = coeff + posA * ((u64)e * (u64)NLOC) + posB;
+#pragma unroll
+      for (int t = 0; t < SETS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < NLOC) c[t] = __ldg(src + posA * (u64)i);
+      }
+      return;
+    }
 #pragma unroll
     for (int t = 0; t < SETS; ++t) {
       const int i = lane + 32 * t;
       if (i < NLOC) {
-        const unsigned ent = ec0 + cs0[t] * (ec1 + cs1[t] * ec2);
+        const unsigned ent = ec[0] + cs0[t] * (ec[1] + cs1[t] * ec[2]);
         c[t] = __ldg(coeff + posA * (jbase[t] + (u64)blk[t] * (u64)ent) + posB);
       }
     }
   };
 
   double cur[SETS], nxt[SETS];
-  u64 el = 0, elN = 0; int eI = 0, gI = 0, eIN = 0, gIN = 0;
-  bool have = locate(0, el, eI, gI);
-  if (have) fetch(el, gI, cur);
+  unsigned ec[3], ecN[3];
+  u64 pair = warpId, pairN;
+  int eI = 0, gI = 0, eIN, gIN;
+  fetch(pair * 2, 0, cur, ec);
   bool pendingStore = false;               // lane 0: a bulk store of the staging tile is in flight
   const int nT = R.ncompTotal, cOff = R.compOffset;
 
-  for (u64 n = 0; n < nItems; ++n) {
-    const bool haveN = locate(n + 1, elN, eIN, gIN);
-    if (haveN) fetch(elN, gIN, nxt);       // in flight while this item is contracted
-    if (have) {
+  while (true) {
+    const u64 el = pair * 2 + (u64)eI;
+    pairN = pair; eIN = eI; gIN = gI;
+    advance(pairN, eIN, gIN);
+    const bool haveN = pairN < nPairs;
+    if (haveN) fetch(pairN * 2 + (u64)eIN, gIN, nxt, ecN);       // in flight while this item is contracted
+    {
       double jinv[3] = {0, 0, 0};
-      if (JAC) {
-        const unsigned e = (unsigned)(R.e0 + el);
-        unsigned q, ec0, ec1, ec2;
-        R.divN0.divmod(e, q, ec0);
-        R.divN1.divmod(q, ec2, ec1);
-        jinv[0] = elementJacInv(g, 0, g.off[0] + (int)ec0);
-        jinv[1] = elementJacInv(g, 1, g.off[1] + (int)ec1);
-        jinv[2] = elementJacInv(g, 2, g.off[2] + (int)ec2);
+      if (OUTJ) {
+        // AxisAlignedCubeGeometry::jacobianInverse per direction, tabulated once per handle
+        jinv[0] = __ldg(jinvTab + ec[0]);
+        jinv[1] = __ldg(jinvTab + g.N[0] + ec[1]);
+        jinv[2] = __ldg(jinvTab + g.N[0] + g.N[1] + ec[2]);
       }
       // physical direction of the kernel's first / last contraction and its inverse-Jacobian entry
       const int dFirst = R.perm ? 2 : 0, dLast = R.perm ? 0 : 2;
@@ -219,19 +236,19 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
       __syncwarp();
       // ---- stage z: pencil p = q0 + M q1; t2[q1][a2 + N1 q0] = t2[N1 p + a2] ----
       for (int p = lane; p < P3; p += 32) {
-        const int q1 = p / M, q0 = p - q1 * M;
         const int base = N1 * p;
         double in[N1], inx[N1], iny[N1];
 #pragma unroll
         for (int a = 0; a < N1; ++a) { in[a] = t2[base + a]; if (JAC) { inx[a] = t2x[base + a]; iny[a] = t2y[base + a]; } }
+        double u[M];
 #pragma unroll
         for (int q2 = 0; q2 < M; ++q2) {
           double s = T.A[2][q2][0] * in[0];
 #pragma unroll
           for (int a = 1; a < N1; ++a) s = fma(T.A[2][q2][a], in[a], s);
-          const int qi = q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2];
-          const int o = (eI * NQ + qi) * nG + gI;
+          const int o = (eI * NQ + p + q2 * P3) * nG + gI;      // point q0 + M (q1 + M q2)
           vst[o] = s;
+          u[q2] = s;
           if (JAC) {
             double gz = T.D[2][q2][0] * in[0], gx = T.A[2][q2][0] * inx[0], gy = T.A[2][q2][0] * iny[0];
 #pragma unroll
@@ -242,6 +259,48 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
             jst[o * 3 + dFirst] = gx * jFirst;
             jst[o * 3 + 1] = gy * jinv[1];
             jst[o * 3 + dLast] = gz * jLast;
+          }
+        }
+        if (GRAD == 2) {
+          // derivative along the last contracted direction: this lane holds the whole line
+#pragma unroll
+          for (int q2 = 0; q2 < M; ++q2) {
+            double gz = T.C[2][q2][0] * u[0];
+#pragma unroll
+            for (int r = 1; r < M; ++r) gz = fma(T.C[2][q2][r], u[r], gz);
+            jst[((eI * NQ + p + q2 * P3) * nG + gI) * 3 + dLast] = gz * jLast;
+          }
+        }
+      }
+      if (GRAD == 2) {
+        __syncwarp();
+        // ---- lines along the first direction: pencil p = q1 + M q2, points r + M p ----
+        for (int p = lane; p < P3; p += 32) {
+          const int o0 = (eI * NQ + M * p) * nG + gI;
+          double u[M];
+#pragma unroll
+          for (int r = 0; r < M; ++r) u[r] = vst[o0 + r * nG];
+#pragma unroll
+          for (int q0 = 0; q0 < M; ++q0) {
+            double gx = T.C[0][q0][0] * u[0];
+#pragma unroll
+            for (int r = 1; r < M; ++r) gx = fma(T.C[0][q0][r], u[r], gx);
+            jst[(o0 + q0 * nG) * 3 + dFirst] = gx * jFirst;
+          }
+        }
+        // ---- lines along the middle direction: pencil p = q0 + M q2, points q0 + M r + M^2 q2 ----
+        for (int p = lane; p < P3; p += 32) {
+          const int q2 = p / M, q0 = p - q2 * M;
+          const int o0 = (eI * NQ + q0 + P3 * q2) * nG + gI;
+          double u[M];
+#pragma unroll
+          for (int r = 0; r < M; ++r) u[r] = vst[o0 + r * M * nG];
+#pragma unroll
+          for (int q1 = 0; q1 < M; ++q1) {
+            double gy = T.C[1][q1][0] * u[0];
+#pragma unroll
+            for (int r = 1; r < M; ++r) gy = fma(T.C[1][q1][r], u[r], gy);
+            jst[(o0 + q1 * M * nG) * 3 + 1] = gy * jinv[1];
           }
         }
       }
@@ -257,7 +316,7 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
             if (values)
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(values + el0 * (u64)(NQ * nG)),
                            "r"(smemAddr2(vst)), "r"((unsigned)(stageLen * sizeof(double))) : "memory");
-            if (JAC)
+            if (OUTJ)
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(jac + el0 * (u64)(NQ * nG) * 3),
                            "r"(smemAddr2(jst)), "r"((unsigned)(stageLen * 3 * sizeof(double))) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -270,7 +329,7 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
               const int row = i / nG, c = i - row * nG;                 // row = eI*NQ + q
               values[(el0 * (u64)NQ + (u64)row) * (u64)nT + cOff + c] = vst[i];
             }
-          if (JAC)
+          if (OUTJ)
             for (int i = lane; i < nEl * NQ * nG * 3; i += 32) {
               const int rg = i / 3, d = i - rg * 3;
               const int row = rg / nG, c = rg - row * nG;
@@ -280,13 +339,35 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
         }
       }
     }
+    if (!haveN) break;
     // rotate the prefetched item in
-    have = haveN; el = elN; eI = eIN; gI = gIN;
+    pair = pairN; eI = eIN; gI = gIN;
 #pragma unroll
     for (int t = 0; t < SETS; ++t) cur[t] = nxt[t];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ec[j] = ecN[j];
   }
   // shared memory must outlive the last bulk store's read
   if (lane == 0 && pendingStore) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// diag(J^-1) per direction and element coordinate, [N0 | N1 | N2] (elementJacInv of the local box)
+__global__ void k_jinv_table(const __grid_constant__ DevGrid g, double* __restrict__ tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n01 = g.N[0] + g.N[1];
+  if (t >= n01 + g.N[2]) return;
+  const int j = t >= n01 ? 2 : (t >= g.N[0] ? 1 : 0);
+  const int i = t - (j == 2 ? n01 : (j == 1 ? g.N[0] : 0));
+  tab[t] = j < g.dim ? elementJacInv(g, j, g.off[j] + i) : 1.0;
+}
+
+int ensureJinvTable(dfx_basis* b, cudaStream_t st) {
+  if (b->dJinv) return DFX_OK;
+  const DevGrid& g = b->dev.grid;
+  const int n = g.N[0] + g.N[1] + g.N[2];
+  DFX_CUDA(cudaMalloc(&b->dJinv, (size_t)n * sizeof(double)));
+  k_jinv_table<<<(n + 255) / 256, 256, 0, st>>>(g, (double*)b->dJinv);
+  return postLaunch("k_jinv_table");
 }
 
 bool smemPathHas(int dim, int k, int m) {
@@ -294,19 +375,21 @@ bool smemPathHas(int dim, int k, int m) {
   return dim == 3 && n1 >= 3 && n1 <= 6 && m >= n1 - 1 && m <= n1 + 1 && m >= 2;
 }
 
-template <int N1, int M, bool JAC>
+template <int N1, int M, int GRAD>
 static int launchSmem(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, const double* coeff, double* values,
                       double* jac, cudaStream_t st) {
-  using Lay = SmemLayout<N1, M, JAC>;
+  using Lay = SmemLayout<N1, M, GRAD>;
   Tables3<N1, M> T;
   for (int j = 0; j < 3; ++j) {
     const int js = R.perm ? 2 - j : j;           // tables follow the contraction order
-    for (int q = 0; q < M; ++q)
+    for (int q = 0; q < M; ++q) {
       for (int a = 0; a < N1; ++a) { T.A[j][q][a] = plan.A[js][q][a]; T.D[j][q][a] = plan.Dm[js][q][a]; }
+      for (int r = 0; r < M; ++r) T.C[j][q][r] = plan.Cm[js][q][r];
+    }
   }
   const size_t smem = (size_t)kSmemWarps * (Lay::work + Lay::staging(R.nGroup)) * sizeof(double);
   if (smem > 220 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
-  auto kern = k_eval_smem<N1, M, JAC>;
+  auto kern = k_eval_smem<N1, M, GRAD>;
   static thread_local size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -320,7 +403,7 @@ static int launchSmem(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, con
   const u64 want = (pairs + kSmemWarps - 1) / kSmemWarps;
   const u64 blocks = std::min<u64>(want, (u64)std::max(1, perSM) * (u64)std::max(1, sms));
   kern<<<(unsigned)blocks, kSmemWarps * 32, smem, st>>>((const DevBasis*)b->dDev, T, R, (const unsigned*)b->dLocalTab,
-                                                         coeff, values, jac);
+                                                         (const double*)b->dJinv, coeff, values, jac);
   return postLaunch("k_eval_smem");
 }
 
@@ -331,6 +414,7 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
     return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
   const int n1 = plan.k + 1, m = plan.m;
+  if (plan.jac) { int rc = ensureJinvTable(b, st); if (rc) return rc; }
   int l = 0;
   while (l < nLeaves) {
     int r = l + 1;
@@ -346,8 +430,8 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     // the kernel's first contracted direction is the fastest output index: for points ordered
     // last-coordinate-fastest the axes are permuted (z, y, x) instead of the output strides,
     // so that the staging tile is always written with unit stride across the lanes
-    R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m;
     R.perm = plan.firstFastest ? 0 : 1;
+    R.isDG = D.layouts[D.leaves[firstLeaf + l].layout].kind == DFX_NODE_LAGRANGE_DG ? 1 : 0;
     R.e0 = e0; R.ne = e1 - e0;
     R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
     R.divItems = FastDiv(2u * (unsigned)R.nGroup);
@@ -357,8 +441,10 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     int rc = DFX_ERR_NOT_IMPLEMENTED;
 #define DFX_SMEM(N1_, M_)                                                                    \
   if (n1 == N1_ && m == M_)                                                                  \
-    rc = plan.jac ? launchSmem<N1_, M_, true>(b, plan, R, coeff, values, jac, st)           \
-                  : launchSmem<N1_, M_, false>(b, plan, R, coeff, values, jac, st);
+    rc = !plan.jac ? launchSmem<N1_, M_, 0>(b, plan, R, coeff, values, jac, st)             \
+         : (M_ >= N1_ && plan.colloc && g_smemGrad != 1)                                     \
+             ? launchSmem<N1_, M_, (M_ >= N1_ ? 2 : 1)>(b, plan, R, coeff, values, jac, st)  \
+             : launchSmem<N1_, M_, 1>(b, plan, R, coeff, values, jac, st);
     DFX_SMEM(3, 2) DFX_SMEM(3, 3) DFX_SMEM(3, 4)
     DFX_SMEM(4, 3) DFX_SMEM(4, 4) DFX_SMEM(4, 5)
     DFX_SMEM(5, 4) DFX_SMEM(5, 5) DFX_SMEM(5, 6)

@@ -205,11 +205,13 @@ constexpr int kCellTask = 32;     // consecutive elements swept by one warp
 constexpr int kCellWarps = 8;
 
 // Element-local DOFs (LagrangeDG, Lagrange<0>): DOF index = element * nloc + i, so one element
-// is a contiguous run of nloc doubles.  A warp sweeps kCellTask consecutive elements; a lane
-// keeps one local index i = lane + 32 pass at a time (its lattice multi-index, the y/z data
-// of the current element row) and writes element after element: every store instruction of
-// the warp is one contiguous 256-byte run.
-template <class F, int MODE>
+// is a contiguous run of nloc doubles.  A warp sweeps kCellTask consecutive elements and
+// writes each of them completely before moving on (lane i writes local indices i, i + 32,
+// ...), so a warp's stores walk through memory strictly forward in 256-byte runs.  The
+// per-lane data of up to NP local indices (lattice multi-index, reference coordinate, the
+// y/z factors or coordinates of the current element row) stay in registers; NP = 0 is the
+// run-time variant for elements with more than 32 * 8 DOFs (one local index at a time).
+template <class F, int MODE, int NP>
 __global__ void __launch_bounds__(kCellWarps * 32)
 k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArgs A, const F f,
               const double* __restrict__ tab, double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
@@ -227,6 +229,69 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
     A.divN1.divmod(q, s2, s1);
   }
   const bool scalar = MODE == 1 || f.ncomp() == 1;
+  // one DOF: common part cm, node (x0, x1, x2), scalar DOF index t -> every active leaf
+  auto emit = [&](u64 t, double cm, double x0, double x1, double x2) {
+    if (A.nActive == 1) {
+      const u64 p = A.posA[0] * t + A.posB[0];
+      if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[0], cm, x0, x1, x2);
+    } else {
+      for (int l = 0; l < A.nActive; ++l) {
+        const u64 p = A.posA[l] * t + A.posB[l];
+        if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[l], cm, x0, x1, x2);
+      }
+    }
+  };
+  if (NP > 0) {
+    constexpr int NR = NP > 0 ? NP : 1;
+    unsigned a0[NR], a1[NR], a2[NR];
+    double xh0[NR];                             // MODE 0: reference coordinate alpha_0 / k of the node
+    double u1[NR], u2[NR];                      // MODE 1: (t_y t_z, -); MODE 0: node coordinates x_1, x_2 of the row
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      const unsigned i = (unsigned)(lane + 32 * t);
+      unsigned q;
+      A.divK1.divmod(i < (unsigned)nloc ? i : 0u, q, a0[t]);
+      A.divK1.divmod(q, a2[t], a1[t]);
+      xh0[t] = k == 0 ? 0.5 : __ddiv_rn(__dmul_rn(1.0, (double)a0[t]), (double)k);
+      u1[t] = 1.0; u2[t] = 0.0;
+    }
+    unsigned ec0 = s0, ec1 = s1, ec2 = s2;
+    bool newRow = true;
+    for (unsigned n = 0; n < nEl; ++n) {
+      if (newRow) {
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          if (MODE == 1) {
+            u1[t] = __dmul_rn(A.dim > 1 ? tab[A.tabOff[1] + (int)(ec1 * k1 + a1[t])] : 1.0,
+                              A.dim > 2 ? tab[A.tabOff[2] + (int)(ec2 * k1 + a2[t])] : 1.0);
+          } else {
+            u1[t] = A.dim > 1 ? nodeCoord(g, k, 1, g.off[1] + (int)ec1, (int)a1[t]) : 0.0;
+            u2[t] = A.dim > 2 ? nodeCoord(g, k, 2, g.off[2] + (int)ec2, (int)a2[t]) : 0.0;
+          }
+        }
+        newRow = false;
+      }
+      const u64 tBase = (eBegin + n) * (u64)nloc + (u64)lane;
+      if (MODE == 1) {
+        const double* tx = tab + A.tabOff[0] + (int)(ec0 * k1);
+#pragma unroll
+        for (int t = 0; t < NP; ++t)
+          if (lane + 32 * t < nloc) emit(tBase + 32 * t, __dmul_rn(tx[a0[t]], u1[t]), 0.0, 0.0, 0.0);
+      } else {
+        // elementGlobal(g, 0, ie, xhat) with the element's end points hoisted out of the pass loop
+        const double lo = gridCoordinate(g, 0, g.off[0] + (int)ec0), up = gridCoordinate(g, 0, g.off[0] + (int)ec0 + 1);
+        const double d = __dsub_rn(up, lo);
+#pragma unroll
+        for (int t = 0; t < NP; ++t)
+          if (lane + 32 * t < nloc) {
+            const double x0 = __dadd_rn(lo, __dmul_rn(xh0[t], d));
+            emit(tBase + 32 * t, f.common(x0, u1[t], u2[t]), x0, u1[t], u2[t]);
+          }
+      }
+      if (++ec0 >= N0) { ec0 = 0; newRow = true; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
+    }
+    return;
+  }
   for (int i = lane; i < nloc; i += 32) {
     unsigned a0, a1, a2, q;
     A.divK1.divmod((unsigned)i, q, a0);
@@ -248,16 +313,7 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
       double cm, x0 = 0.0;
       if (MODE == 1) cm = __dmul_rn(tab[A.tabOff[0] + (int)(ec0 * k1 + a0)], yz);
       else { x0 = nodeCoord(g, k, 0, g.off[0] + (int)ec0, (int)a0); cm = f.common(x0, x1, x2); }
-      const u64 t = (eBegin + n) * (u64)nloc + (u64)i;
-      if (A.nActive == 1) {
-        const u64 p = A.posA[0] * t + A.posB[0];
-        if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[0], cm, x0, x1, x2);
-      } else {
-        for (int l = 0; l < A.nActive; ++l) {
-          const u64 p = A.posA[l] * t + A.posB[l];
-          if (mask == nullptr || mask[p]) coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : A.comp[l], cm, x0, x1, x2);
-        }
-      }
+      emit((eBegin + n) * (u64)nloc + (u64)i, cm, x0, x1, x2);
       if (++ec0 >= N0) { ec0 = 0; newRow = true; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
     }
   }
@@ -350,8 +406,18 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       const u64 tasks = (C.ne + kCellTask - 1) / kCellTask;
       const u64 blocks = (tasks + kCellWarps - 1) / kCellWarps;
       if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
-      if (sep) k_interp_cell<RegistryFn, 1><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);
-      else k_interp_cell<RegistryFn, 0><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);
+      const int passes = (L.nloc + 31) / 32;
+#define DFX_CELL(NP_)                                                                                              \
+  {                                                                                                                \
+    if (sep) k_interp_cell<RegistryFn, 1, NP_><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask); \
+    else k_interp_cell<RegistryFn, 0, NP_><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);     \
+  }
+      if (passes <= 1) DFX_CELL(1)
+      else if (passes <= 2) DFX_CELL(2)
+      else if (passes <= 4) DFX_CELL(4)
+      else if (passes <= 8) DFX_CELL(8)
+      else DFX_CELL(0)
+#undef DFX_CELL
       int rc = postLaunch("k_interp_cell");
       if (rc) return rc;
     }
@@ -395,18 +461,21 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
       for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
     const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1];
     const u64 blk = (u64)L.blk[s];
-    const u64 P0 = leaf.posA * jbase + leaf.posB;
-    const u64 S = leaf.posA * blk;
-    u64 dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
+    // all per-entry arithmetic runs in the output type: for 32-bit tables the true values fit
+    // (checked by the caller), so wrapping 32-bit multiply-adds give the same bits as 64-bit ones
+    const T P0 = (T)(leaf.posA * jbase + leaf.posB);
+    const T S = (T)(leaf.posA * blk);
+    T dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
     if (MULTI) {
 #pragma unroll
       for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
-        dA[p] = p < leaf.ndig ? leaf.digA[p] * blk : 0;
-        dB[p] = p < leaf.ndig ? leaf.digA[p] * jbase + leaf.digB[p] : 0;
+        dA[p] = p < leaf.ndig ? (T)(leaf.digA[p] * blk) : (T)0;
+        dB[p] = p < leaf.ndig ? (T)(leaf.digA[p] * jbase + leaf.digB[p]) : (T)0;
       }
     }
-    // walk this thread's elements el = blkEl0 + sub, + m, + 2m, ...: coordinates advance with carry
-    u64 el = blkEl0 + (u64)sub;
+    // walk this thread's elements el = blkEl0 + sub, + m, + 2m, ...: coordinates advance with carry,
+    // the value and the output pointer advance by constant steps between carries
+    const u64 el = blkEl0 + (u64)sub;
     if (el >= A.ne) continue;
     unsigned ec0, ec1, ec2;
     {
@@ -415,22 +484,35 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
       A.divN1.divmod(q, ec2, ec1);
     }
     const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
-    unsigned rowBase = cs0 * (ec1 + cs1 * ec2);
-    for (int it = 0; it < A.iters && el < A.ne; ++it) {
-      const unsigned ent = ec0 + rowBase;
-      const u64 o = el * (u64)nloc + (u64)li;
-      if (MULTI) {
+    const unsigned m = (unsigned)A.m;
+    const u64 left = (A.ne - el + m - 1) / m;
+    const int nIt = left < (u64)A.iters ? (int)left : A.iters;
+    unsigned ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+    if (MULTI) {
+      T* po = out + (el * (u64)nloc + (u64)li) * (u64)A.stride;
+      const size_t step = (size_t)m * nloc * A.stride;
+      for (int it = 0; it < nIt; ++it) {
 #pragma unroll
         for (int p = 0; p < DFX_MAX_DIGITS; ++p)
-          if (p < A.stride) out[o * (u64)A.stride + p] = (T)(dB[p] + dA[p] * (u64)ent);
-      } else {
-        out[o] = (T)(P0 + S * (u64)ent);
+          if (p < A.stride) po[p] = (T)(dB[p] + dA[p] * (T)ent);
+        po += step; ec0 += m; ent += m;
+        if (ec0 >= N0) {
+          do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
+          ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+        }
       }
-      el += (u64)A.m;
-      ec0 += (unsigned)A.m;
-      if (ec0 >= N0) {
-        do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
-        rowBase = cs0 * (ec1 + cs1 * ec2);
+    } else {
+      T* po = out + (el * (u64)nloc + (u64)li);
+      const size_t step = (size_t)m * nloc;
+      T v = (T)(P0 + S * (T)ent);
+      const T dv = (T)(S * (T)m);
+      for (int it = 0; it < nIt; ++it) {
+        *po = v;
+        po += step; ec0 += m; v += dv;
+        if (ec0 >= N0) {
+          do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
+          v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
+        }
       }
     }
   }

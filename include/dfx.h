@@ -216,11 +216,15 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
  * kernel, 1 structured kernel evaluating f at every node, 2 structured kernel
  * with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast;
  * DFX_OP_HOST_BAND_KIB: `path` = KiB of results per pipeline band of dfx_evaluate_host
- * (-1 = default 192 MiB).                                                          */
+ * (-1 = default 192 MiB); DFX_OP_SMEM_GRADIENT: how the shared-memory evaluation kernel
+ * forms gradients: 1 = differentiated shape tables in every stage, -1 = automatic
+ * (collocation derivative of the point values when every direction has at least
+ * order+1 distinct points).                                                        */
 #define DFX_OP_EVALUATE 0
 #define DFX_OP_INTERPOLATE 1
 #define DFX_OP_INDICES 2
 #define DFX_OP_HOST_BAND_KIB 3
+#define DFX_OP_SMEM_GRADIENT 4
 void dfx_set_kernel_path(int32_t op, int32_t path);
 
 /* ---- host-buffer entry points (what a CPU caller of the reference uses) ----

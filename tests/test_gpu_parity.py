@@ -352,7 +352,7 @@ def kernel_path():
     def set_path(op, path):
         capi.lib().dfx_set_kernel_path(op, path)
     yield set_path
-    for op in (capi.OP_EVALUATE, capi.OP_INTERPOLATE, capi.OP_INDICES):
+    for op in (capi.OP_EVALUATE, capi.OP_INTERPOLATE, capi.OP_INDICES, capi.OP_SMEM_GRADIENT):
         capi.lib().dfx_set_kernel_path(op, -1)
 
 
@@ -470,8 +470,13 @@ def test_evaluate_shared_memory_path(kernel_path, k, dm, last_fastest):
             path = capi.lib().dfx_evaluate_path(b._h, 0, pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(pts), 1)
             assert path == (1 if (k == 2 and m in (2, 3)) else 2)
             kernel_path(capi.OP_EVALUATE, 2)
-            v, j, vr, jr = eval_both(grid, tree, pts, path=2)
-            assert rel(v, vr) <= TOL and rel(j, jr) <= TOL
+            # gradients by collocation of the point values (automatic when m >= k + 1) and by
+            # differentiated shape tables in every stage
+            for grad_mode in (-1, 1):
+                kernel_path(capi.OP_SMEM_GRADIENT, grad_mode)
+                v, j, vr, jr = eval_both(grid, tree, pts, path=2)
+                assert rel(v, vr) <= TOL and rel(j, jr) <= TOL, grad_mode
+            kernel_path(capi.OP_SMEM_GRADIENT, -1)
             # values only + element sub-range with an odd start
             import torch
             o = orc.OracleBasis(grid, tree)
