@@ -614,6 +614,83 @@ int dfx_boundary_dofs_host(const dfx_basis* cb, int32_t node, uint8_t* mask_host
   return DFX_OK;
 }
 
+// ---- element-loop callers ------------------------------------------------------------------
+int dfx_matrix_pattern(const dfx_basis* cb, uint64_t* row_ptr, uint32_t* col_idx, uint64_t* nnz_host, void* stream) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr) return fail(DFX_ERR_INVALID, "null row_ptr");
+  return matrixPattern(b, (u64*)row_ptr, col_idx, (u64*)nnz_host, (cudaStream_t)stream);
+}
+
+int dfx_assemble_laplace(const dfx_basis* cb, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                         const dfx_function* f, double* rhs, void* stream) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr || !col_idx) return fail(DFX_ERR_INVALID, "null pattern");
+  if (rhs && (rc = checkFunction(f, 1))) return rc;
+  return assembleLaplace(b, (const u64*)row_ptr, col_idx, values, f, rhs, (cudaStream_t)stream);
+}
+
+int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, const double* values,
+               const double* x, double* y, int32_t subtract, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr || !col_idx || !values || !x || !y) return fail(DFX_ERR_INVALID, "null argument");
+  return csrMv(b->dimension, (const u64*)row_ptr, col_idx, values, x, y, subtract != 0, (cudaStream_t)stream);
+}
+
+int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                        const uint8_t* dirichlet, const double* x, double* rhs, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr || !col_idx || !values || !dirichlet || !x || !rhs) return fail(DFX_ERR_INVALID, "null argument");
+  return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream);
+}
+
+int dfx_matrix_pattern_host(const dfx_basis* cb, uint64_t* row_ptr_host, uint32_t* col_idx_host, uint64_t* nnz_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr_host) return fail(DFX_ERR_INVALID, "null row_ptr");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  if ((rc = growScratch(b, 1, (n + 1) * sizeof(u64)))) return rc;
+  u64* dRow = (u64*)b->dScratch[1];
+  u64 nnz = 0;
+  if ((rc = matrixPattern(b, dRow, nullptr, &nnz, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(row_ptr_host, dRow, (n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (col_idx_host && nnz) {
+    if ((rc = growScratch(b, 2, nnz * sizeof(uint32_t)))) return rc;
+    if ((rc = matrixPattern(b, dRow, (uint32_t*)b->dScratch[2], nullptr, st))) return rc;
+    DFX_CUDA(cudaMemcpyAsync(col_idx_host, b->dScratch[2], nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  DFX_CUDA(cudaStreamSynchronize(st));
+  if (nnz_host) *nnz_host = nnz;
+  return DFX_OK;
+}
+
+int dfx_assemble_laplace_host(const dfx_basis* cb, const uint64_t* row_ptr_host, const uint32_t* col_idx_host,
+                              double* values_host, const dfx_function* f, double* rhs_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr_host || !col_idx_host) return fail(DFX_ERR_INVALID, "null pattern");
+  if (rhs_host && (rc = checkFunction(f, 1))) return rc;
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  const u64 nnz = row_ptr_host[n];
+  if ((rc = growScratch(b, 1, (n + 1) * sizeof(u64)))) return rc;
+  if ((rc = growScratch(b, 2, std::max<size_t>(1, nnz) * sizeof(uint32_t)))) return rc;
+  if ((rc = growScratch(b, 0, (std::max<size_t>(1, nnz) + n) * sizeof(double)))) return rc;
+  u64* dRow = (u64*)b->dScratch[1];
+  uint32_t* dCol = (uint32_t*)b->dScratch[2];
+  double* dVal = (double*)b->dScratch[0];
+  double* dRhs = dVal + std::max<size_t>(1, nnz);
+  DFX_CUDA(cudaMemcpyAsync(dRow, row_ptr_host, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+  DFX_CUDA(cudaMemcpyAsync(dCol, col_idx_host, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if ((rc = assembleLaplace(b, dRow, dCol, values_host ? dVal : nullptr, f, rhs_host ? dRhs : nullptr, st))) return rc;
+  if (values_host) DFX_CUDA(cudaMemcpyAsync(values_host, dVal, nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (rhs_host) DFX_CUDA(cudaMemcpyAsync(rhs_host, dRhs, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
 // ---- slab partition helpers ------------------------------------------------------------
 int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint64_t* out_count, int32_t max_ranges,
                     int32_t* n) {

@@ -50,6 +50,13 @@ extern int g_interpMode;
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st);
 int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, cudaStream_t st);
+int matrixPattern(dfx_basis* b, u64* rowPtr, uint32_t* col, u64* nnzHost, cudaStream_t st);
+int assembleLaplace(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double* values, const dfx_function* f,
+                    double* rhs, cudaStream_t st);
+int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, const double* x, double* y, bool subtract,
+          cudaStream_t st);
+int dirichletRows(u64 n, const u64* rowPtr, const uint32_t* col, double* values, const uint8_t* dirichlet, const double* x,
+                  double* rhs, cudaStream_t st);
 int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
 
 }  // namespace dfx

@@ -265,6 +265,35 @@ int dfx_subentity_dofs(const dfx_basis* b, int32_t subtree_node, int32_t sub_ent
 int dfx_boundary_dofs(const dfx_basis* b, int32_t subtree_node, uint8_t* mask, void* stream);
 int dfx_boundary_dofs_host(const dfx_basis* b, int32_t subtree_node, uint8_t* mask_host);
 
+/* ---- element-loop callers: sparse operator set-up ---------------------------
+ * What examples/poisson-pq2.cc builds on top of a global basis, on the device.  Rows and
+ * columns are flat container positions; all pointers are device pointers.
+ *
+ * dfx_matrix_pattern — getOccupationPattern (poisson-pq2.cc:137-174) + MatrixIndexSet::
+ * exportIdx: CSR pattern of every pair of DOFs that share an element, ascending columns per
+ * row.  Call once with col_idx == NULL to get row_ptr[dimension()+1] (and the number of
+ * non-zeros in *nnz_host, may be NULL), allocate, call again to fill col_idx[nnz].      */
+int dfx_matrix_pattern(const dfx_basis* b, uint64_t* row_ptr, uint32_t* col_idx, uint64_t* nnz_host, void* stream);
+/* assembleLaplaceMatrix (poisson-pq2.cc:176-255, getLocalMatrix :35-87, getVolumeTerm :91-134)
+ * for a single-leaf (scalar) basis: values[nnz] in the order of the pattern and rhs[dimension()]
+ * for the volume term f (registry function); either output may be NULL.                     */
+int dfx_assemble_laplace(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                         const dfx_function* volume_term_host, double* rhs, void* stream);
+/* BCRSMatrix::mv (subtract == 0: y = A x) / mmv (subtract != 0: y -= A x), rows = dimension() */
+int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, const double* values,
+               const double* x, double* y, int32_t subtract, void* stream);
+/* symmetric incorporation of Dirichlet values (poisson-pq2.cc:356-386): rhs -= A x (x holds the
+ * Dirichlet values, zero elsewhere), then Dirichlet rows and columns become those of the identity
+ * and rhs[i] = x[i] on them.  dirichlet: mask bytes as produced by dfx_boundary_dofs.          */
+int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                        const uint8_t* dirichlet, const double* x, double* rhs, void* stream);
+
+/* host-buffer forms of the two set-up calls (what a CPU caller of the example uses): same
+ * semantics with HOST arrays; col_idx_host == NULL returns row_ptr and *nnz only.          */
+int dfx_matrix_pattern_host(const dfx_basis* b, uint64_t* row_ptr_host, uint32_t* col_idx_host, uint64_t* nnz_host);
+int dfx_assemble_laplace_host(const dfx_basis* b, const uint64_t* row_ptr_host, const uint32_t* col_idx_host,
+                              double* values_host, const dfx_function* volume_term_host, double* rhs_host);
+
 /* ---- slab partition helpers (multi-GPU, one handle per rank) ---------------
  * When the local box spans the whole grid in every direction but the last,
  * the DOFs of one z-layer of every Yasp index-set component are contiguous.

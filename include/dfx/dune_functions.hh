@@ -432,6 +432,7 @@ struct Function { dfx_function f; };
 inline Function gaussian(double a = 1.0) { Function r{}; r.f.id = DFX_FN_GAUSSIAN; r.f.n_comp = 1; r.f.p[0] = a; return r; }
 inline Function identity(int n) { Function r{}; r.f.id = DFX_FN_IDENTITY; r.f.n_comp = n; return r; }
 inline Function coord(int j) { Function r{}; r.f.id = DFX_FN_COORD; r.f.n_comp = 1; r.f.p[0] = j; return r; }
+inline Function sinprod(double w) { Function r{}; r.f.id = DFX_FN_SINPROD; r.f.n_comp = 1; r.f.p[0] = w; return r; }
 inline Function constant(double c) { Function r{}; r.f.id = DFX_FN_CONSTANT; r.f.n_comp = 1; r.f.p[0] = c; return r; }
 }  // namespace Registry
 

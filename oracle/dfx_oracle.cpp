@@ -937,6 +937,200 @@ uint64_t orc_boundary_dofs(void* h, int32_t subtreeNode, uint8_t* mask) {
   return visits;
 }
 
+// ===========================================================================
+// SURVEY.md section 8(f) row 2 — the element-loop CALLERS of examples/poisson-pq2.cc, restated:
+// getOccupationPattern (:137-174), getLocalMatrix (:35-87), getVolumeTerm (:91-134),
+// assembleLaplaceMatrix (:176-255), the symmetric Dirichlet treatment (:356-386).
+}  // extern "C"
+
+namespace orc {
+
+// [EXT dune-geometry] QuadratureRules<double,dim>::rule(cube, order): tensor product of the
+// Gauss-Legendre rule with m = order/2 + 1 points on [0,1], last coordinate fastest.
+static void gaussLegendre01(int m, std::vector<double>& x, std::vector<double>& w) {
+  x.resize(m); w.resize(m);
+  for (int i = 0; i < m; ++i) {
+    long double z = std::cos(3.14159265358979323846264338327950288L * (i + 0.75L) / (m + 0.5L));
+    long double pp = 0;
+    for (int it = 0; it < 100; ++it) {
+      long double p1 = 1, p2 = 0;
+      for (int j = 1; j <= m; ++j) { long double p3 = p2; p2 = p1; p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j; }
+      pp = m * (z * p1 - p2) / (z * z - 1);
+      long double dz = p1 / pp;
+      z -= dz;
+      if (std::fabs((double)dz) < 1e-19) break;
+    }
+    x[m - 1 - i] = (double)(0.5L * (1 + z));
+    w[m - 1 - i] = (double)(1 / ((1 - z * z) * pp * pp));
+  }
+}
+struct QuadratureRule { int n; std::vector<double> pos, weight; };
+static QuadratureRule quadratureRule(int dim, int order) {
+  const int m = order / 2 + 1;
+  std::vector<double> x, w; gaussLegendre01(m, x, w);
+  QuadratureRule q; q.n = (int)ipow(m, dim);
+  q.pos.resize((size_t)q.n * dim); q.weight.resize(q.n);
+  for (int p = 0; p < q.n; ++p) {
+    int r = p; double wt = 1;
+    for (int j = dim - 1; j >= 0; --j) { int i = r % m; r /= m; q.pos[(size_t)p * dim + j] = x[i]; wt *= w[i]; }
+    q.weight[p] = wt;
+  }
+  return q;
+}
+
+// element geometry pieces  [EXT AxisAlignedCubeGeometry]
+static void elementGeometry(const Grid& g, const int ec[3], double lower[3], double upper[3], double jacInv[3], double& integrationElement) {
+  integrationElement = 1;
+  for (int j = 0; j < g.dim; ++j) {
+    lower[j] = g.coordinate(j, g.off[j] + ec[j]);
+    upper[j] = g.coordinate(j, g.off[j] + ec[j] + 1);
+    jacInv[j] = 1.0 / (upper[j] - lower[j]);
+    integrationElement *= upper[j] - lower[j];
+  }
+}
+
+// getLocalMatrix, poisson-pq2.cc:35-87
+static void getLocalMatrix(const Basis& b, size_t e, std::vector<double>& elementMatrix) {
+  const Grid& g = b.grid; const int dim = g.dim;
+  const LagrangeCubeFE& fe = *b.leaves[0].fe;
+  const int n = fe.size();
+  elementMatrix.assign((size_t)n * n, 0.0);
+  int ec[3]; g.elementCoords(e, ec);
+  double lower[3], upper[3], jacInv[3], integrationElement;
+  elementGeometry(g, ec, lower, upper, jacInv, integrationElement);
+  const int order = 2 * (dim * fe.k - 1);                  // localBasis().order() == k
+  const QuadratureRule quad = quadratureRule(dim, order < 0 ? 0 : order);
+  std::vector<double> referenceJacobians((size_t)n * dim), jacobians((size_t)n * dim);
+  for (int pt = 0; pt < quad.n; ++pt) {
+    const double* quadPos = &quad.pos[(size_t)pt * dim];
+    fe.evaluateJacobian(quadPos, referenceJacobians.data());
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < dim; ++j) jacobians[(size_t)i * dim + j] = referenceJacobians[(size_t)i * dim + j] * jacInv[j];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double dot = 0;
+        for (int d = 0; d < dim; ++d) dot += jacobians[(size_t)i * dim + d] * jacobians[(size_t)j * dim + d];
+        elementMatrix[(size_t)i * n + j] += dot * quad.weight[pt] * integrationElement;
+      }
+  }
+}
+
+// getVolumeTerm, poisson-pq2.cc:91-134 with localVolumeTerm = f o geometry.global
+static void getVolumeTerm(const Basis& b, size_t e, const dfx_function& f, std::vector<double>& localRhs) {
+  const Grid& g = b.grid; const int dim = g.dim;
+  const LagrangeCubeFE& fe = *b.leaves[0].fe;
+  const int n = fe.size();
+  localRhs.assign(n, 0.0);
+  int ec[3]; g.elementCoords(e, ec);
+  double lower[3], upper[3], jacInv[3], integrationElement;
+  elementGeometry(g, ec, lower, upper, jacInv, integrationElement);
+  const QuadratureRule quad = quadratureRule(dim, dim * fe.k);
+  std::vector<double> shapeFunctionValues(n);
+  for (int pt = 0; pt < quad.n; ++pt) {
+    const double* quadPos = &quad.pos[(size_t)pt * dim];
+    double x[3] = {0, 0, 0}, y[DFX_MAX_LEAVES];
+    for (int j = 0; j < dim; ++j) x[j] = lower[j] + quadPos[j] * (upper[j] - lower[j]);
+    evalFunction(f, dim, x, y);
+    const double functionValue = y[0];
+    fe.evaluateFunction(quadPos, shapeFunctionValues.data());
+    for (int i = 0; i < n; ++i) localRhs[i] += shapeFunctionValues[i] * functionValue * quad.weight[pt] * integrationElement;
+  }
+}
+
+}  // namespace orc
+
+extern "C" {
+
+// getOccupationPattern (poisson-pq2.cc:137-174) + MatrixIndexSet::exportIdx: CSR pattern with
+// ascending column indices; rows and columns are flat container positions.  row_ptr has
+// dimension+1 entries; col_idx may be NULL (sizes only).  Returns the number of non-zeros.
+uint64_t orc_occupation_pattern(void* h, uint64_t* row_ptr, uint32_t* col_idx) {
+  auto* b = (orc::Basis*)h;
+  if (b->maxDigits > 1) b->buildPositions();
+  const size_t n = b->pre->dimension();
+  std::vector<std::vector<uint32_t>> nb(n);
+  std::vector<orc::MultiIndex> idx;
+  for (size_t e = 0; e < b->grid.numElements(); ++e) {
+    b->bind(e, idx);
+    for (size_t i = 0; i < idx.size(); ++i)
+      for (size_t j = 0; j < idx.size(); ++j) nb[b->flat(idx[i])].push_back((uint32_t)b->flat(idx[j]));   // nb.add(iIdx, jIdx)
+  }
+  uint64_t nnz = 0;
+  for (size_t r = 0; r < n; ++r) {
+    std::sort(nb[r].begin(), nb[r].end());
+    nb[r].erase(std::unique(nb[r].begin(), nb[r].end()), nb[r].end());
+    row_ptr[r] = nnz;
+    if (col_idx) std::copy(nb[r].begin(), nb[r].end(), col_idx + nnz);
+    nnz += nb[r].size();
+  }
+  row_ptr[n] = nnz;
+  return nnz;
+}
+
+// assembleLaplaceMatrix (poisson-pq2.cc:176-255) for a single-leaf (scalar) basis: values in
+// the order of the given CSR pattern, rhs for the volume term f; either may be NULL.
+int32_t orc_assemble_laplace(void* h, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                             const dfx_function* f, double* rhs) {
+  auto* b = (orc::Basis*)h;
+  if (b->leaves.size() != 1) return 1;
+  const size_t n = b->pre->dimension();
+  if (values) std::fill(values, values + row_ptr[n], 0.0);                // matrix = 0
+  if (rhs) std::fill(rhs, rhs + n, 0.0);                                  // rhs = 0
+  std::vector<orc::MultiIndex> idx;
+  std::vector<double> elementMatrix, localRhs;
+  for (size_t e = 0; e < b->grid.numElements(); ++e) {
+    b->bind(e, idx);
+    const size_t nl = idx.size();
+    if (values) {
+      orc::getLocalMatrix(*b, e, elementMatrix);
+      for (size_t i = 0; i < nl; ++i) {
+        const size_t row = idx[i][0];
+        for (size_t j = 0; j < nl; ++j) {
+          const uint32_t col = (uint32_t)idx[j][0];
+          const uint32_t* lo = col_idx + row_ptr[row];
+          const uint32_t* hi = col_idx + row_ptr[row + 1];
+          const uint32_t* it = std::lower_bound(lo, hi, col);
+          values[it - col_idx] += elementMatrix[i * nl + j];              // matrix[row][col] += elementMatrix[i][j]
+        }
+      }
+    }
+    if (rhs && f) {
+      orc::getVolumeTerm(*b, e, *f, localRhs);
+      for (size_t i = 0; i < nl; ++i) rhs[idx[i][0]] += localRhs[i];
+    }
+  }
+  return 0;
+}
+
+// Symmetric incorporation of Dirichlet values (poisson-pq2.cc:356-386): rhs -= A x (x holds the
+// Dirichlet values, zero elsewhere), Dirichlet rows/columns -> identity, rhs[i] = x[i] there.
+void orc_dirichlet(uint64_t n, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
+                   const uint8_t* dirichlet, const double* x, double* rhs) {
+  for (uint64_t i = 0; i < n; ++i) {                                      // stiffnessMatrix.mmv(x, rhs)
+    double s = rhs[i];
+    for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) s -= values[p] * x[col_idx[p]];
+    rhs[i] = s;
+  }
+  for (uint64_t i = 0; i < n; ++i) {
+    if (dirichlet[i]) {
+      rhs[i] = x[i];
+      for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) values[p] = (col_idx[p] == i) ? 1.0 : 0.0;
+    } else {
+      for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) if (dirichlet[col_idx[p]]) values[p] = 0.0;
+    }
+  }
+}
+
+// y = A x (BCRSMatrix::mv), row sums in storage order
+void orc_csr_mv(uint64_t n, const uint64_t* row_ptr, const uint32_t* col_idx, const double* values,
+                const double* x, double* y) {
+  for (uint64_t i = 0; i < n; ++i) {
+    double s = 0;
+    for (uint64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) s += values[p] * x[col_idx[p]];
+    y[i] = s;
+  }
+}
+
 int32_t orc_max_threads(void) {
   unsigned n = std::thread::hardware_concurrency();
   return n ? (int32_t)n : 1;

@@ -42,6 +42,12 @@ def lib():
         L.orc_subentity_dofs.argtypes = [vp, i32, i32, i32, vp, vp]
         L.orc_boundary_dofs.restype = u64
         L.orc_boundary_dofs.argtypes = [vp, i32, vp]
+        L.orc_occupation_pattern.restype = u64
+        L.orc_occupation_pattern.argtypes = [vp, vp, vp]
+        L.orc_assemble_laplace.restype = i32
+        L.orc_assemble_laplace.argtypes = [vp, vp, vp, vp, C.POINTER(capi.Function), vp]
+        L.orc_dirichlet.argtypes = [u64, vp, vp, vp, vp, vp, vp]
+        L.orc_csr_mv.argtypes = [u64, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -140,3 +146,36 @@ class OracleBasis:
             mask = np.zeros(self.dimension(), dtype=np.uint8)
         visits = lib().orc_boundary_dofs(self._h, node, mask.ctypes.data)
         return mask, int(visits)
+
+    # ---- examples/poisson-pq2.cc restated ----
+    def occupationPattern(self):
+        n = self.dimension()
+        row_ptr = np.zeros(n + 1, dtype=np.uint64)
+        nnz = lib().orc_occupation_pattern(self._h, row_ptr.ctypes.data, None)
+        col = np.zeros(nnz, dtype=np.uint32)
+        lib().orc_occupation_pattern(self._h, row_ptr.ctypes.data, col.ctypes.data)
+        return row_ptr, col
+
+    def assembleLaplace(self, f=None, pattern=None):
+        row_ptr, col = pattern if pattern is not None else self.occupationPattern()
+        values = np.zeros(len(col))
+        rhs = np.zeros(self.dimension()) if f is not None else None
+        rc = lib().orc_assemble_laplace(self._h, row_ptr.ctypes.data, col.ctypes.data, values.ctypes.data,
+                                        C.byref(f) if f is not None else None, None if rhs is None else rhs.ctypes.data)
+        if rc:
+            raise ValueError("oracle: the Laplace assembler needs a single-leaf basis")
+        return (row_ptr, col, values), rhs
+
+
+def oracle_dirichlet(csr, dirichlet, x, rhs):
+    row_ptr, col, values = csr
+    d = np.ascontiguousarray(dirichlet, dtype=np.uint8)
+    lib().orc_dirichlet(len(row_ptr) - 1, row_ptr.ctypes.data, col.ctypes.data, values.ctypes.data, d.ctypes.data,
+                        x.ctypes.data, rhs.ctypes.data)
+
+
+def oracle_mv(csr, x):
+    row_ptr, col, values = csr
+    y = np.zeros(len(row_ptr) - 1)
+    lib().orc_csr_mv(len(row_ptr) - 1, row_ptr.ctypes.data, col.ctypes.data, values.ctypes.data, x.ctypes.data, y.ctypes.data)
+    return y

@@ -167,6 +167,31 @@ def main():
                {"path": 3, "TFLOPs_fp64": 2.0 * 125 * 125 * ne / ms / 1e9})
         L.dfx_set_kernel_path(capi.OP_EVALUATE, -1)
 
+    # the element-loop callers (examples/poisson-pq2.cc): pattern, Laplace assembly, SpMV, boundary mask
+    if want("ops"):
+        for cfg, n, k in (("ops_q2_96", [96, 96, 96], 2), ("ops_q1_256", [256, 256, 256], 1)):
+            basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.lagrange(k))
+            nd = basis.dimension()
+            pat = dfx.getOccupationPattern(basis)
+            nnz = pat[1].numel()
+            ms, best = timeit(lambda: dfx.getOccupationPattern(basis), max(2, args.reps // 3), warm=1)
+            report("occupation pattern (CSR, sorted)", cfg, ms, best, nnz * 4 + (nd + 1) * 8 * 2, {"nnz": nnz, "rows": nd})
+            A, rhs = dfx.assembleLaplaceMatrix(basis, dfx.gaussian(1.0), pattern=pat)
+            ms, best = timeit(lambda: dfx.assembleLaplaceMatrix(basis, None, pattern=pat), max(2, args.reps // 3), warm=1)
+            report("Laplace matrix values (owner-computes rows)", cfg, ms, best, nnz * 12 + (nd + 1) * 8, {"nnz_per_s": nnz / ms * 1e3})
+            ms, best = timeit(lambda: dfx.assembleLaplaceMatrix(basis, dfx.gaussian(1.0), pattern=pat), max(2, args.reps // 3), warm=1)
+            report("Laplace matrix + load vector", cfg, ms, best, nnz * 12 + (nd + 1) * 8 + nd * 8)
+            x = basis.newVector(0.0).uniform_(-1, 1)
+            y = torch.empty_like(x)
+            ms, best = timeit(lambda: A.mv(x, y), args.reps)
+            report("SpMV y = A x (CSR, warp per row)", cfg, ms, best, nnz * 12 + (nd + 1) * 8 + 2 * nd * 8,
+                   {"GFLOPs": 2.0 * nnz / ms / 1e6})
+            mask = torch.zeros(nd, dtype=torch.uint8, device="cuda")
+            ms, best = timeit(lambda: dfx.boundaryDOFs(basis, mask), args.reps)
+            report("boundary DOF mask", cfg, ms, best, nd, {"dofs_per_s": nd / ms * 1e3})
+            del basis, A, rhs, x, y, pat, mask
+            torch.cuda.empty_cache()
+
 
 if __name__ == "__main__":
     main()
