@@ -270,7 +270,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     bind_to_gpu_numa_node(physical_gpu_index(local_rank))
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner out of the one-JSON-line stdout
         dist.init_process_group("nccl", device_id=dev)
     L = capi.lib()

@@ -615,6 +615,21 @@ int dfx_boundary_dofs_host(const dfx_basis* cb, int32_t node, uint8_t* mask_host
 }
 
 // ---- element-loop callers ------------------------------------------------------------------
+// typical number of entries of a matrix row of this basis (interior node: every leaf's DOFs of a
+// 2^dim element box, about half of it on average), used to pick the SpMV lane grouping
+static int meanRowLength(const dfx_basis* b) {
+  const DevBasis& D = b->dev;
+  double len = 0;
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const DevLayout& L = D.layouts[D.leaves[l].layout];
+    const bool cell = L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0;
+    double n = 1;
+    for (int j = 0; j < D.grid.dim; ++j) n *= cell ? (L.k + 1) : (1.5 * L.k + 1);
+    len += n;
+  }
+  return (int)len;
+}
+
 int dfx_matrix_pattern(const dfx_basis* cb, uint64_t* row_ptr, uint32_t* col_idx, uint64_t* nnz_host, void* stream) {
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
@@ -635,14 +650,14 @@ int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_
                const double* x, double* y, int32_t subtract, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx || !values || !x || !y) return fail(DFX_ERR_INVALID, "null argument");
-  return csrMv(b->dimension, (const u64*)row_ptr, col_idx, values, x, y, subtract != 0, (cudaStream_t)stream);
+  return csrMv(b->dimension, (const u64*)row_ptr, col_idx, values, x, y, subtract != 0, (cudaStream_t)stream, meanRowLength(b));
 }
 
 int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
                         const uint8_t* dirichlet, const double* x, double* rhs, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx || !values || !dirichlet || !x || !rhs) return fail(DFX_ERR_INVALID, "null argument");
-  return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream);
+  return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream, meanRowLength(b));
 }
 
 int dfx_matrix_pattern_host(const dfx_basis* cb, uint64_t* row_ptr_host, uint32_t* col_idx_host, uint64_t* nnz_host) {

@@ -211,7 +211,9 @@ constexpr int kCellWarps = 8;
 // per-lane data of up to NP local indices (lattice multi-index, reference coordinate, the
 // y/z factors or coordinates of the current element row) stay in registers; NP = 0 is the
 // run-time variant for elements with more than 32 * 8 DOFs (one local index at a time).
-template <class F, int MODE, int NP>
+// SIMPLE: one leaf on the lattice with unit position stride and no mask — the store address
+// is a running pointer (the scalar case of every BASELINE config).
+template <class F, int MODE, int NP, bool SIMPLE>
 __global__ void __launch_bounds__(kCellWarps * 32)
 k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArgs A, const F f,
               const double* __restrict__ tab, double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
@@ -272,7 +274,13 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
         newRow = false;
       }
       const u64 tBase = (eBegin + n) * (u64)nloc + (u64)lane;
-      if (MODE == 1) {
+      if (MODE == 1 && SIMPLE) {
+        const double* tx = tab + A.tabOff[0] + (int)(ec0 * k1);
+        double* po = coeff + A.posB[0] + tBase;
+#pragma unroll
+        for (int t = 0; t < NP; ++t)
+          if (lane + 32 * t < nloc) po[32 * t] = __dmul_rn(tx[a0[t]], u1[t]);
+      } else if (MODE == 1) {
         const double* tx = tab + A.tabOff[0] + (int)(ec0 * k1);
 #pragma unroll
         for (int t = 0; t < NP; ++t)
@@ -407,10 +415,12 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       const u64 blocks = (tasks + kCellWarps - 1) / kCellWarps;
       if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
       const int passes = (L.nloc + 31) / 32;
+      const bool simple = sep && C.nActive == 1 && C.posA[0] == 1 && mask == nullptr;
 #define DFX_CELL(NP_)                                                                                              \
   {                                                                                                                \
-    if (sep) k_interp_cell<RegistryFn, 1, NP_><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask); \
-    else k_interp_cell<RegistryFn, 0, NP_><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);     \
+    if (simple) k_interp_cell<RegistryFn, 1, NP_, true><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);       \
+    else if (sep) k_interp_cell<RegistryFn, 1, NP_, false><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);   \
+    else k_interp_cell<RegistryFn, 0, NP_, false><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);             \
   }
       if (passes <= 1) DFX_CELL(1)
       else if (passes <= 2) DFX_CELL(2)

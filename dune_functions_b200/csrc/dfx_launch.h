@@ -54,9 +54,9 @@ int matrixPattern(dfx_basis* b, u64* rowPtr, uint32_t* col, u64* nnzHost, cudaSt
 int assembleLaplace(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double* values, const dfx_function* f,
                     double* rhs, cudaStream_t st);
 int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, const double* x, double* y, bool subtract,
-          cudaStream_t st);
+          cudaStream_t st, int meanRow);
 int dirichletRows(u64 n, const u64* rowPtr, const uint32_t* col, double* values, const uint8_t* dirichlet, const double* x,
-                  double* rhs, cudaStream_t st);
+                  double* rhs, cudaStream_t st, int meanRow);
 int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
 
 }  // namespace dfx

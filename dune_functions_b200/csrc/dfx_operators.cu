@@ -304,20 +304,24 @@ k_volume_rows(const DevBasis* __restrict__ Bp, const __grid_constant__ LaplaceAr
   if (lane == 0) rhs[A.posA * t + A.posB] = total;
 }
 
-// y = A x (SUB = false) or y -= A x (SUB = true); one warp per row
-template <bool SUB>
+// y = A x (SUB = false) or y -= A x (SUB = true).  LPR lanes share one row (CSR-vector): LPR is
+// picked from the mean row length so that short rows (Q1: 27 entries) do not idle most of a warp;
+// the reduction tree inside the lane group is fixed, so results do not depend on the launch.
+template <bool SUB, int LPR>
 __global__ void __launch_bounds__(256)
 k_csr_mv(u64 n, const u64* __restrict__ rowPtr, const uint32_t* __restrict__ col, const double* __restrict__ values,
          const double* __restrict__ x, double* __restrict__ y) {
-  const u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const u64 p0 = rowPtr[row], p1 = rowPtr[row + 1];
+  const u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x & (LPR - 1);
+  const bool active = row < n;
   double s = 0.0;
-  for (u64 p = p0 + lane; p < p1; p += 32) s += values[p] * __ldg(x + col[p]);
+  if (active) {
+    const u64 p0 = rowPtr[row], p1 = rowPtr[row + 1];
+    for (u64 p = p0 + lane; p < p1; p += LPR) s += values[p] * __ldg(x + col[p]);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) y[row] = SUB ? y[row] - s : s;
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (active && lane == 0) y[row] = SUB ? y[row] - s : s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -516,19 +520,25 @@ int assembleLaplace(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double
 }
 
 int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, const double* x, double* y, bool subtract,
-          cudaStream_t st) {
+          cudaStream_t st, int meanRow) {
   if (n == 0) return DFX_OK;
-  const u64 blocks = (n * 32 + 255) / 256;
+  const int lpr = meanRow > 48 ? 32 : (meanRow > 24 ? 16 : (meanRow > 12 ? 8 : 4));
+  const u64 blocks = (n * (u64)lpr + 255) / 256;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "matrix too large for one launch");
-  if (subtract) k_csr_mv<true><<<(unsigned)blocks, 256, 0, st>>>(n, rowPtr, col, values, x, y);
-  else k_csr_mv<false><<<(unsigned)blocks, 256, 0, st>>>(n, rowPtr, col, values, x, y);
+#define DFX_MV(LPR_)                                                                                   \
+  if (lpr == LPR_) {                                                                                   \
+    if (subtract) k_csr_mv<true, LPR_><<<(unsigned)blocks, 256, 0, st>>>(n, rowPtr, col, values, x, y); \
+    else k_csr_mv<false, LPR_><<<(unsigned)blocks, 256, 0, st>>>(n, rowPtr, col, values, x, y);         \
+  }
+  DFX_MV(4) DFX_MV(8) DFX_MV(16) DFX_MV(32)
+#undef DFX_MV
   return postLaunch("k_csr_mv");
 }
 
 int dirichletRows(u64 n, const u64* rowPtr, const uint32_t* col, double* values, const uint8_t* dirichlet, const double* x,
-                  double* rhs, cudaStream_t st) {
+                  double* rhs, cudaStream_t st, int meanRow) {
   if (n == 0) return DFX_OK;
-  int rc = csrMv(n, rowPtr, col, values, x, rhs, true, st);       // stiffnessMatrix.mmv(x, rhs)
+  int rc = csrMv(n, rowPtr, col, values, x, rhs, true, st, meanRow);       // stiffnessMatrix.mmv(x, rhs)
   if (rc) return rc;
   const u64 blocks = (n * 32 + 255) / 256;
   k_dirichlet<<<(unsigned)blocks, 256, 0, st>>>(n, rowPtr, col, values, dirichlet, x, rhs);
