@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: interface-plane exchange over NVLink peer memory (P2P stores + on-stream counters) or NCCL send/recv")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -295,8 +297,9 @@ def main():
     values = torch.empty((ne, nq, ncomp), dtype=torch.float64, device=dev)
     jac = torch.empty((ne, nq, ncomp, dim), dtype=torch.float64, device=dev) if wl["jac"] else None
     dgbf = dfx.makeDiscreteGlobalBasisFunction(basis, coeff)
-    from dune_functions_b200.slab import HaloExchange
+    from dune_functions_b200.slab import HaloExchange, PeerHaloExchange
     halo = HaloExchange(basis, rank, world, device=dev)
+    peer = PeerHaloExchange(basis, rank, world) if (world > 1 and args.halo == "peer") else None
     index_table = None
     if args.workload == "c3":
         index_table = torch.empty((ne, basis.maxNodeSize()), dtype=torch.int32, device=dev)
@@ -338,7 +341,20 @@ def main():
             for node, fn in node_fns:
                 capi.check(L.dfx_interpolate(basis._h, node, C.byref(fn), C.c_void_p(coeff.data_ptr()), None, stream_ptr()))
         mark()
-        if world > 1:
+        if world > 1 and peer is not None:
+            # push my bottom plane into the lower neighbour's buffer right away, evaluate everything that
+            # does not need the interface plane, then take the upper neighbour's plane (by now it has
+            # usually arrived: the wait is a counter check on the stream) and finish with the top layer
+            st = stream_ptr()
+            peer.step += 1
+            if rank > 0:
+                capi.check(L.dfx_halo_push(basis._h, peer._link, C.c_void_p(coeff.data_ptr()), peer.step, st))
+            evaluate_range(0, split)
+            if rank < world - 1:
+                capi.check(L.dfx_halo_pull(basis._h, peer._link, C.c_void_p(coeff.data_ptr()), peer.step, st))
+            mark()
+            evaluate_range(split, ne)
+        elif world > 1:
             main = torch.cuda.current_stream()
             comm_stream.wait_stream(main)
             with torch.cuda.stream(comm_stream):
@@ -437,7 +453,8 @@ def main():
             "eval_points_per_s": world * ne * nq / t_eval if t_eval > 0 else None,
             "ms": {"interpolate": t_interp * 1e3, "evaluate": t_eval * 1e3, "indices": t_index * 1e3,
                    "evaluate_interior_overlapped_with_halo_exchange": t_halo * 1e3 if world > 1 else None,
-                   "halo_bytes_per_rank": int(halo.n * 8) if world > 1 else 0},
+                   "halo_bytes_per_rank": int(halo.n * 8) if world > 1 else 0,
+                   "halo_transport": (args.halo if world > 1 else None)},
             "roofline": {"bound": "hbm", "kernel": "evaluate (DiscreteGlobalBasisFunction at Gauss points)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes": eval_bytes,
@@ -463,6 +480,13 @@ def main():
             if t1:
                 line["cpu_baseline"]["single_thread_dofs_per_s"] = ob.dimension() / t1
         print(json.dumps(line))
+    if peer is not None:
+        err = peer.error()
+        if err:
+            print(f"rank {rank}: halo link wait timed out at step {err}", file=sys.stderr)
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -94,6 +94,14 @@ SIGNATURES = {
     "dfx_halo_size": (_u64, [_vp]),
     "dfx_halo_pack": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "dfx_halo_unpack": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "dfx_halo_link_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "dfx_halo_link_destroy": (None, [_vp]),
+    "dfx_halo_link_export": (C.c_int, [_vp, _vp]),
+    "dfx_halo_link_block": (_vp, [_vp]),
+    "dfx_halo_link_attach": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "dfx_halo_link_error": (_u64, [_vp]),
+    "dfx_halo_push": (C.c_int, [_vp, _vp, _vp, _u64, _vp]),
+    "dfx_halo_pull": (C.c_int, [_vp, _vp, _vp, _u64, _vp]),
     "dfx_owned_ranges": (C.c_int, [_vp, _pu64, _pu64, _pu64, _i32, _pi32]),
 }
 

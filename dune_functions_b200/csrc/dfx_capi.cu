@@ -784,4 +784,77 @@ int dfx_owned_ranges(const dfx_basis* b, uint64_t* local_begin, uint64_t* count,
   return DFX_OK;
 }
 
+// ---- peer-memory halo link ------------------------------------------------------------------
+int dfx_halo_link_create(const dfx_basis* b, dfx_halo_link** out) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!out) return fail(DFX_ERR_INVALID, "null argument");
+  auto* l = new dfx_halo_link();
+  l->device = b->device;
+  l->n = haloCount(b);
+  size_t bytes; haloLinkBytes(l->n, bytes);
+  cudaError_t e = cudaMalloc((void**)&l->local, bytes);
+  if (e != cudaSuccess) { delete l; return cudaFail(e, "cudaMalloc(halo link)"); }
+  e = cudaMemset(l->local, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(l->local); delete l; return cudaFail(e, "cudaMemset(halo link)"); }
+  *out = l;
+  return DFX_OK;
+}
+
+void dfx_halo_link_destroy(dfx_halo_link* l) {
+  if (!l) return;
+  cudaSetDevice(l->device);
+  if (l->lower && l->lowerIpc) cudaIpcCloseMemHandle(l->lower);
+  if (l->upper && l->upperIpc) cudaIpcCloseMemHandle(l->upper);
+  if (l->local) cudaFree(l->local);
+  delete l;
+}
+
+int dfx_halo_link_export(dfx_halo_link* l, uint8_t ipc_handle_out[64]) {
+  if (!l || !ipc_handle_out) return fail(DFX_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  DFX_CUDA(cudaSetDevice(l->device));
+  cudaIpcMemHandle_t h;
+  DFX_CUDA(cudaIpcGetMemHandle(&h, l->local));
+  std::memcpy(ipc_handle_out, &h, 64);
+  return DFX_OK;
+}
+
+void* dfx_halo_link_block(dfx_halo_link* l) { return l ? l->local : nullptr; }
+
+int dfx_halo_link_attach(dfx_halo_link* l, int32_t which, const uint8_t* ipc_handle, void* raw_block) {
+  if (!l || (which != 0 && which != 1) || (!ipc_handle && !raw_block)) return fail(DFX_ERR_INVALID, "bad halo link attachment");
+  DFX_CUDA(cudaSetDevice(l->device));
+  void* p = raw_block;
+  if (ipc_handle) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    DFX_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  if (which == 0) { l->lower = (double*)p; l->lowerIpc = ipc_handle != nullptr; }
+  else { l->upper = (double*)p; l->upperIpc = ipc_handle != nullptr; }
+  return DFX_OK;
+}
+
+uint64_t dfx_halo_link_error(dfx_halo_link* l) {
+  if (!l) return 0;
+  cudaSetDevice(l->device);
+  unsigned long long v = 0;
+  cudaMemcpy(&v, reinterpret_cast<unsigned long long*>(l->local + 2 * l->n) + 2, sizeof(v), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+int dfx_halo_push(const dfx_basis* b, dfx_halo_link* l, const double* coeff, uint64_t step, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!l || !coeff || step == 0) return fail(DFX_ERR_INVALID, "bad argument");
+  if (l->n != haloCount(b)) return fail(DFX_ERR_INVALID, "halo link belongs to another basis");
+  return haloPush(b, l, coeff, step, (cudaStream_t)stream);
+}
+
+int dfx_halo_pull(const dfx_basis* b, dfx_halo_link* l, double* coeff, uint64_t step, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!l || !coeff || step == 0) return fail(DFX_ERR_INVALID, "bad argument");
+  if (l->n != haloCount(b)) return fail(DFX_ERR_INVALID, "halo link belongs to another basis");
+  return haloPull(b, l, coeff, step, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -140,6 +140,18 @@ u64 preSize(const dfx_basis_impl* b, const u64* prefix, int len);
 double lagrangeP(int k, int i, double x);
 double lagrangeDP(int k, int i, double x);
 
+// peer-memory halo link (dfx_kernels.cu): block layout [buf 0 | buf 1 | arrival | consumed | error]
+struct dfx_halo_link_impl {
+  int device = 0;
+  u64 n = 0;                       // doubles per plane buffer
+  double* local = nullptr;         // this rank's block (receives from the upper neighbour)
+  double* lower = nullptr;         // lower neighbour's block (we push into it)
+  double* upper = nullptr;         // upper neighbour's block (we acknowledge into it)
+  bool lowerIpc = false, upperIpc = false;
+};
+int haloLinkBytes(u64 n, size_t& bytes);
+
 }  // namespace dfx
 
 struct dfx_basis : dfx::dfx_basis_impl {};
+struct dfx_halo_link : dfx::dfx_halo_link_impl {};

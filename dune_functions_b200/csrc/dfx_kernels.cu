@@ -392,3 +392,55 @@ int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf
 }
 
 }  // namespace dfx
+
+// ---------------------------------------------------------------------------
+// Peer-memory halo link (multi-GPU, one process per GPU): the sender packs its bottom lattice
+// plane STRAIGHT INTO the lower neighbour's receive buffer over NVLink (P2P stores from the pack
+// kernel) and then raises an arrival counter there; the receiver spins on its own counter,
+// unpacks, and acknowledges by writing the consumed counter in the sender's block.  No
+// rendezvous, no host involvement, two receive buffers so that a sender may run one step ahead.
+// Block layout (doubles): [buf 0 | buf 1 | arrival (u64) | consumed (u64) | error (u64)].
+namespace dfx {
+
+__device__ __forceinline__ unsigned long long* linkFlag(double* block, u64 n, int which) {
+  return reinterpret_cast<unsigned long long*>(block + 2 * n) + which;
+}
+
+// wait until *flag >= want (written by a peer GPU); gives up after ~4 s and records an error
+__global__ void k_link_wait(double* block, u64 n, int which, unsigned long long want) {
+  volatile unsigned long long* flag = linkFlag(block, n, which);
+  const long long t0 = clock64();
+  while (*flag < want) {
+    __nanosleep(200);
+    if (clock64() - t0 > 8000000000ll) { *linkFlag(block, n, 2) = want; return; }
+  }
+}
+__global__ void k_link_set(double* block, u64 n, int which, unsigned long long value) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(linkFlag(block, n, which)) = value;
+  __threadfence_system();
+}
+
+int haloLinkBytes(u64 n, size_t& bytes) { bytes = (2 * n + 4) * sizeof(double); return DFX_OK; }
+
+int haloPush(const dfx_basis* b, dfx_halo_link_impl* l, const double* coeff, u64 step, cudaStream_t st) {
+  if (!l->lower) return fail(DFX_ERR_INVALID, "halo link: no lower neighbour attached");
+  // the buffer of parity step % 2 is free once the neighbour has consumed step - 2 (its acknowledgement lands in MY block)
+  if (step > 2) { k_link_wait<<<1, 1, 0, st>>>(l->local, l->n, 1, step - 2); int rc = postLaunch("k_link_wait"); if (rc) return rc; }
+  int rc = haloCopy(b, 0, true, const_cast<double*>(coeff), l->lower + (step & 1) * l->n, l->n, st);
+  if (rc) return rc;
+  k_link_set<<<1, 1, 0, st>>>(l->lower, l->n, 0, step);
+  return postLaunch("k_link_set");
+}
+
+int haloPull(const dfx_basis* b, dfx_halo_link_impl* l, double* coeff, u64 step, cudaStream_t st) {
+  if (!l->upper) return fail(DFX_ERR_INVALID, "halo link: no upper neighbour attached");
+  k_link_wait<<<1, 1, 0, st>>>(l->local, l->n, 0, step);
+  int rc = postLaunch("k_link_wait"); if (rc) return rc;
+  rc = haloCopy(b, 1, false, coeff, l->local + (step & 1) * l->n, l->n, st);
+  if (rc) return rc;
+  k_link_set<<<1, 1, 0, st>>>(l->upper, l->n, 1, step);
+  return postLaunch("k_link_set");
+}
+
+}  // namespace dfx

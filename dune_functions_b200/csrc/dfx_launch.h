@@ -57,6 +57,8 @@ int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, c
           cudaStream_t st, int meanRow);
 int dirichletRows(u64 n, const u64* rowPtr, const uint32_t* col, double* values, const uint8_t* dirichlet, const double* x,
                   double* rhs, cudaStream_t st, int meanRow);
+int haloPush(const dfx_basis* b, dfx_halo_link_impl* l, const double* coeff, u64 step, cudaStream_t st);
+int haloPull(const dfx_basis* b, dfx_halo_link_impl* l, double* coeff, u64 step, cudaStream_t st);
 int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf, u64 total, cudaStream_t st);
 
 }  // namespace dfx

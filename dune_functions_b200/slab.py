@@ -88,6 +88,57 @@ class HaloExchange:
         return coeff
 
 
+class PeerHaloExchange:
+    """The same step as HaloExchange over NVLink peer memory instead of NCCL send/recv: every rank
+    owns a receive block; the upper neighbour's pack kernel stores the plane straight into it and
+    raises a counter, the receiver waits for the counter ON THE STREAM (no rendezvous, no host
+    synchronisation), unpacks and acknowledges (dfx_halo_link_*, dfx_halo_push / dfx_halo_pull).
+    Set-up exchanges the CUDA IPC handles of the blocks through torch.distributed once."""
+
+    def __init__(self, basis, rank, world, group=None):
+        self.basis, self.rank, self.world = basis, rank, world
+        self.n = halo_size(basis)
+        self.step = 0
+        self._link = None
+        if world == 1 or self.n == 0:
+            return
+        L = basis._lib
+        link = C.c_void_p()
+        capi.check(L.dfx_halo_link_create(basis._h, C.byref(link)))
+        self._link = link
+        handle = (C.c_uint8 * 64)()
+        capi.check(L.dfx_halo_link_export(link, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        if rank > 0:
+            h = (C.c_uint8 * 64).from_buffer_copy(handles[rank - 1])
+            capi.check(L.dfx_halo_link_attach(link, 0, h, None))
+        if rank < world - 1:
+            h = (C.c_uint8 * 64).from_buffer_copy(handles[rank + 1])
+            capi.check(L.dfx_halo_link_attach(link, 1, h, None))
+        dist.barrier(group=group)
+
+    def __call__(self, coeff):
+        if self._link is None:
+            return coeff
+        self.step += 1
+        L = self.basis._lib
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.rank > 0:
+            capi.check(L.dfx_halo_push(self.basis._h, self._link, C.c_void_p(coeff.data_ptr()), self.step, st))
+        if self.rank < self.world - 1:
+            capi.check(L.dfx_halo_pull(self.basis._h, self._link, C.c_void_p(coeff.data_ptr()), self.step, st))
+        return coeff
+
+    def error(self):
+        return 0 if self._link is None else int(self.basis._lib.dfx_halo_link_error(self._link))
+
+    def close(self):
+        if self._link is not None:
+            self.basis._lib.dfx_halo_link_destroy(self._link)
+            self._link = None
+
+
 def gather_global(basis, coeff, global_dimension, group=None):
     """every rank gets the whole vector in GLOBAL flat order (result gather of DESIGN.md section 7)"""
     world = dist.get_world_size(group)

@@ -314,6 +314,26 @@ int dfx_halo_unpack(const dfx_basis* b, int32_t side, const double* buf, double*
 int dfx_owned_ranges(const dfx_basis* b, uint64_t* local_begin_host, uint64_t* count_host,
                      uint64_t* global_begin_host, int32_t max_ranges, int32_t* n);
 
+/* ---- peer-memory halo link (one process per GPU, NVLink) -------------------------
+ * The sender packs its bottom lattice plane straight into the lower neighbour's receive buffer
+ * (P2P stores from the pack kernel) and raises an arrival counter there; the receiver waits on its
+ * own counter on the stream, unpacks into its top plane and acknowledges into the sender's block.
+ * No rendezvous and no host synchronisation; two receive buffers let a sender run a step ahead.
+ * Set-up: every rank creates a link (allocates its receive block), exports the 64-byte CUDA IPC
+ * handle, and attaches the handles of its lower (`which` = 0) and upper (`which` = 1) neighbours;
+ * inside one process a raw device pointer (dfx_halo_link_block) can be attached instead.
+ * `step` counts exchanges from 1 and must be the same on both sides of a link.              */
+typedef struct dfx_halo_link dfx_halo_link;
+int   dfx_halo_link_create(const dfx_basis* b, dfx_halo_link** out);
+void  dfx_halo_link_destroy(dfx_halo_link* l);
+int   dfx_halo_link_export(dfx_halo_link* l, uint8_t ipc_handle_out[64]);
+void* dfx_halo_link_block(dfx_halo_link* l);
+int   dfx_halo_link_attach(dfx_halo_link* l, int32_t which, const uint8_t* ipc_handle, void* raw_block);
+/* 0 if no wait of this link has timed out so far, else the step that did                  */
+uint64_t dfx_halo_link_error(dfx_halo_link* l);
+int dfx_halo_push(const dfx_basis* b, dfx_halo_link* l, const double* coeff, uint64_t step, void* stream);
+int dfx_halo_pull(const dfx_basis* b, dfx_halo_link* l, double* coeff, uint64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,6 +298,39 @@ def test_evaluate_host_pipeline_bands(gname, tname, band_kib):
         L.dfx_set_kernel_path(capi.OP_HOST_BAND_KIB, -1)
 
 
+def test_peer_memory_halo_link_between_two_slabs():
+    """dfx_halo_link_* / dfx_halo_push / dfx_halo_pull with both slabs on one GPU (raw-pointer
+    attachment instead of CUDA IPC): the upper slab's bottom plane lands in the lower slab's top
+    plane, step after step, through both receive buffers, without any host synchronisation."""
+    import torch
+    whole = YaspGrid([3, 2, 6], upper=[1.0, 0.5, 2.0])
+    L = capi.lib()
+    for tree in (lagrange(2), trees(3)["TH_FL(FI)"], lagrange(3)):
+        b0, b1 = dfx.makeBasis(whole.slab(0, 2), tree), dfx.makeBasis(whole.slab(1, 2), tree)
+        l0, l1 = C.c_void_p(), C.c_void_p()
+        capi.check(L.dfx_halo_link_create(b0._h, C.byref(l0)))
+        capi.check(L.dfx_halo_link_create(b1._h, C.byref(l1)))
+        capi.check(L.dfx_halo_link_attach(l1, 0, None, L.dfx_halo_link_block(l0)))     # slab 1 pushes into slab 0
+        capi.check(L.dfx_halo_link_attach(l0, 1, None, L.dfx_halo_link_block(l1)))     # slab 0 acknowledges into slab 1
+        n = int(L.dfx_halo_size(b0._h))
+        assert n == int(L.dfx_halo_size(b1._h)) and n > 0
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        c0 = torch.full((b0.dimension(),), float("nan"), dtype=torch.float64, device="cuda")
+        top, bottom = torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda")
+        for step in range(1, 6):
+            c1 = torch.from_numpy(random_coeff(b1.dimension(), seed=step)).cuda()
+            capi.check(L.dfx_halo_push(b1._h, l1, C.c_void_p(c1.data_ptr()), step, st))
+            capi.check(L.dfx_halo_pull(b0._h, l0, C.c_void_p(c0.data_ptr()), step, st))
+            capi.check(L.dfx_halo_pack(b0._h, 1, C.c_void_p(c0.data_ptr()), C.c_void_p(top.data_ptr()), st))
+            capi.check(L.dfx_halo_pack(b1._h, 0, C.c_void_p(c1.data_ptr()), C.c_void_p(bottom.data_ptr()), st))
+            assert torch.equal(top, bottom), step
+        assert L.dfx_halo_link_error(l0) == 0 and L.dfx_halo_link_error(l1) == 0
+        # everything but the top plane of slab 0 is untouched
+        assert int(torch.isnan(c0).sum()) == b0.dimension() - n
+        L.dfx_halo_link_destroy(l0)
+        L.dfx_halo_link_destroy(l1)
+
+
 # ---- the reference's known answers, now through the GPU path ------------------------------------
 @pytest.mark.parametrize("tree", [lagrange(0), lagrange(1), lagrange(2), lagrange(3), lagrange(4),
                                   lagrangeDG(1), lagrangeDG(2), lagrangeDG(3)])
