@@ -381,8 +381,10 @@ def main():
     for _ in range(warmup):
         step(False)
     barrier()
+    # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     launches0 = L.dfx_kernel_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -391,7 +393,8 @@ def main():
     stop.record()
     barrier()
     sampler.stop_flag.set()
-    sampler.join()
+    if rank == 0:
+        sampler.join()
     launches = int(L.dfx_kernel_launch_count() - launches0)
     t_ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     parts = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) if v else 0.0 for k, v in ev.items()}
