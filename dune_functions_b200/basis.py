@@ -190,6 +190,12 @@ def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _check_range(begin, end, n):
+    """the element range check of the ABI (DFX_ERR_RANGE), done before any buffer is sized from it"""
+    if not (0 <= begin <= end <= n):
+        raise capi.RangeError(f"element range [{begin}, {end}) outside the local box of {n} elements")
+
+
 def _stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -265,6 +271,7 @@ class GlobalBasis:
         import torch
         ne_all = self.numElements()
         elem_end = ne_all if elem_end is None else elem_end
+        _check_range(elem_begin, elem_end, ne_all)
         ne = elem_end - elem_begin
         stride = self.maxMultiIndexSize()
         dtype = dtype or torch.int32
@@ -278,6 +285,7 @@ class GlobalBasis:
         import torch
         ne_all = self.numElements()
         elem_end = ne_all if elem_end is None else elem_end
+        _check_range(elem_begin, elem_end, ne_all)
         ne = elem_end - elem_begin
         dtype = dtype or torch.int32
         out = torch.empty((ne, self.maxNodeSize()), dtype=dtype, device=f"cuda:{self.device}")
@@ -408,6 +416,7 @@ class DiscreteGlobalBasisFunction:
         nq = xh.shape[0]
         ne_all = root.numElements()
         elem_end = ne_all if elem_end is None else elem_end
+        _check_range(elem_begin, elem_end, ne_all)
         ne = elem_end - elem_begin
         nc = self.nComp()
         dev = f"cuda:{root.device}"

@@ -660,6 +660,14 @@ int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint3
   return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream, meanRowLength(b));
 }
 
+int dfx_apply_laplace(const dfx_basis* cb, const double* x, double* y, const uint8_t* dirichlet, double* scratch,
+                      void* stream) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!x || !y || !scratch) return fail(DFX_ERR_INVALID, "null argument");
+  return applyLaplace(b, x, y, dirichlet, scratch, (cudaStream_t)stream);
+}
+
 int dfx_matrix_pattern_host(const dfx_basis* cb, uint64_t* row_ptr_host, uint32_t* col_idx_host, uint64_t* nnz_host) {
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;

@@ -86,3 +86,26 @@ def applyDirichlet(matrix, dirichletNodes, x, rhs):
     capi.check(b._lib.dfx_apply_dirichlet(b._h, _ptr(matrix.row_ptr), _ptr(matrix.col_idx), _ptr(matrix.values), _ptr(m),
                                           _ptr(x), _ptr(rhs), _stream()))
     return matrix, rhs
+
+
+class LaplaceOperator:
+    """The Laplace stiffness matrix of assembleLaplaceMatrix as a matrix-free operator
+    (dfx_apply_laplace): mv(x) = A x without ever storing A.  With dirichletNodes the operator is the
+    symmetrically modified matrix of poisson-pq2.cc:356-386 (identity on those rows and columns)."""
+
+    def __init__(self, basis, dirichletNodes=None):
+        import torch
+        self.basis = basis
+        self.mask = None
+        if dirichletNodes is not None:
+            self.mask = dirichletNodes.view(torch.uint8) if dirichletNodes.dtype == torch.bool else dirichletNodes
+        self.scratch = torch.empty(basis.maxNodeSize() * basis.numElements() + basis.dimension(), dtype=torch.float64,
+                                   device=f"cuda:{basis.device}")
+
+    def mv(self, x, y=None):
+        import torch
+        if y is None:
+            y = torch.empty_like(x)
+        b = self.basis
+        capi.check(b._lib.dfx_apply_laplace(b._h, _ptr(x), _ptr(y), _ptr(self.mask), _ptr(self.scratch), _stream()))
+        return y

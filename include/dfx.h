@@ -288,6 +288,15 @@ int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_
 int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
                         const uint8_t* dirichlet, const double* x, double* rhs, void* stream);
 
+/* y = A x with the same Laplace stiffness matrix, never assembled (matrix-free): per element
+ * gather, sum-factorised gradients at (order+1)^dim Gauss points, scale, transposed contraction;
+ * every DOF then sums its element contributions in ascending element order (deterministic).
+ * Continuous Lagrange order 1 or 2 in 2-d / 3-d.  dirichlet (may be NULL): mask bytes as produced by
+ * dfx_boundary_dofs — those rows and columns behave like the identity, i.e. the result equals the
+ * product with the matrix after dfx_apply_dirichlet.  `scratch` holds max_node_size() *
+ * num_elements() + dimension() doubles.                                                      */
+int dfx_apply_laplace(const dfx_basis* b, const double* x, double* y, const uint8_t* dirichlet, double* scratch,
+                      void* stream);
 /* host-buffer forms of the two set-up calls (what a CPU caller of the example uses): same
  * semantics with HOST arrays; col_idx_host == NULL returns row_ptr and *nnz only.          */
 int dfx_matrix_pattern_host(const dfx_basis* b, uint64_t* row_ptr_host, uint32_t* col_idx_host, uint64_t* nnz_host);

@@ -331,6 +331,49 @@ def test_peer_memory_halo_link_between_two_slabs():
         L.dfx_halo_link_destroy(l1)
 
 
+@pytest.mark.parametrize("tree,n", [(lagrange(17), [2, 1, 1]), (lagrange(17), [2, 3]), (lagrange(11), [1, 2, 2]),
+                                    (lagrangeDG(12), [2, 1, 2]), (lagrangeDG(12), [3])])
+def test_maximum_orders_indices_and_nodes(tree, n):
+    """the largest orders the reference admits (LagrangeFaceDOFPermutation::maxOrder3d = 17,
+    lagrangebasis.hh:579, :795-796): index table bit-exact, interpolated coordinates bit-exact"""
+    grid = YaspGrid(n)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    assert b.dimension() == o.dimension()
+    assert np.array_equal(b.indices().cpu().numpy()[:, :, 0].astype(np.uint64), o.indices()[0][:, :, 0])
+    for j in range(len(n)):
+        x = b.newVector(0.0)
+        dfx.interpolate(b, x, dfx.coord(j))
+        assert np.array_equal(x.cpu().numpy(), o.interpolate(dfx.coord(j)))
+    got = dfx.boundaryDOFs(b).cpu().numpy()
+    assert np.array_equal(got, o.boundaryDOFs()[0])
+
+
+def test_empty_and_ragged_element_ranges():
+    """zero-length ranges are no-ops, sub-ranges that start and end inside a row give the same
+    entries as the full table; out-of-range requests raise"""
+    import torch
+    grid, tree = GRIDS["3d_3x4x5"], trees(3)["taylorHood"]
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    ne = b.numElements()
+    full = b.flatIndices().cpu().numpy()
+    assert b.flatIndices(7, 7).shape[0] == 0 and b.indices(ne, ne).shape[0] == 0
+    for e0, e1 in ((1, 2), (5, 23), (ne - 1, ne)):
+        assert np.array_equal(b.flatIndices(e0, e1).cpu().numpy(), full[e0:e1])
+        assert np.array_equal(b.indices(e0, e1).cpu().numpy().astype(np.uint64), o.indices(e0, e1)[0])
+    c = torch.from_numpy(random_coeff(b.dimension())).cuda()
+    f = dfx.makeDiscreteGlobalBasisFunction(b, c)
+    pts, _ = tensor_gauss(3, 3)
+    assert f.evaluate(pts, elem_begin=4, elem_end=4).shape[0] == 0
+    v = f.evaluate(pts, elem_begin=5, elem_end=23).cpu().numpy()
+    assert rel(v, o.evaluate(c.cpu().numpy(), pts, e0=5, e1=23)) <= TOL
+    with pytest.raises(capi.RangeError):
+        b.flatIndices(0, ne + 1)
+    with pytest.raises(capi.RangeError):
+        f.evaluate(pts, elem_begin=3, elem_end=2)
+
+
 # ---- the reference's known answers, now through the GPU path ------------------------------------
 @pytest.mark.parametrize("tree", [lagrange(0), lagrange(1), lagrange(2), lagrange(3), lagrange(4),
                                   lagrangeDG(1), lagrangeDG(2), lagrangeDG(3)])

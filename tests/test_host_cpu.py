@@ -169,3 +169,17 @@ def test_compute_without_gpu_fails_loudly():
     assert L.dfx_evaluate_host(b._h, 0, buf, xh, 1, 0, 4, out, None) == capi.DFX_ERR_CUDA
     idx = (C.c_uint32 * 36)()
     assert L.dfx_indices_flat_host(b._h, 0, 4, idx) == capi.DFX_ERR_CUDA
+    # the newer entry points: boundary mask, operator set-up, peer link
+    mask = (C.c_uint8 * b.dimension())()
+    assert L.dfx_boundary_dofs_host(b._h, 0, mask) == capi.DFX_ERR_CUDA
+    row_ptr = (C.c_uint64 * (b.dimension() + 1))()
+    nnz = C.c_uint64()
+    assert L.dfx_matrix_pattern_host(b._h, row_ptr, None, C.byref(nnz)) == capi.DFX_ERR_CUDA
+    col = (C.c_uint32 * 4)()
+    assert L.dfx_assemble_laplace_host(b._h, row_ptr, col, buf, C.byref(f), buf) == capi.DFX_ERR_CUDA
+    link = C.c_void_p()
+    assert L.dfx_halo_link_create(b._h, C.byref(link)) == capi.DFX_ERR_CUDA
+    # host bookkeeping still works without a device
+    n = C.c_int32()
+    lst = (C.c_int32 * b.maxNodeSize())()
+    assert L.dfx_subentity_dofs(b._h, 0, 1, 1, None, lst, C.byref(n)) == capi.DFX_OK and n.value == 3

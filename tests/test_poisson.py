@@ -177,6 +177,49 @@ def test_unsupported_operator_inputs_raise():
         dfx.getOccupationPattern(b)                      # (2*6+1)^3 = 2197 columns per vertex row
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("gname", ["2d_3x2", "2d_10x10", "3d_3x4x5", "3d_2x1x3", "3d_1x1x1"])
+@pytest.mark.parametrize("k", [1, 2])
+def test_matrix_free_laplace_equals_the_assembled_matrix(gname, k):
+    """dfx_apply_laplace (never assembled, 3^d Gauss points) against the CSR product with the matrix
+    of dfx_assemble_laplace and against the oracle's matrix, with and without Dirichlet rows"""
+    import torch
+    grid = GRIDS[gname]
+    b = dfx.makeBasis(grid, lagrange(k))
+    ob = orc.OracleBasis(grid, lagrange(k))
+    A, _ = dfx.assembleLaplaceMatrix(b)
+    csr, _ = ob.assembleLaplace()
+    xr = np.random.default_rng(11).uniform(-1, 1, b.dimension())
+    x = torch.from_numpy(xr).cuda()
+    y = dfx.LaplaceOperator(b).mv(x).cpu().numpy()
+    assert rel(y, orc.oracle_mv(csr, xr)) <= TOL
+    assert rel(y, A.mv(x).cpu().numpy()) <= TOL
+    # Dirichlet rows/columns: same as the product with the modified matrix
+    dn = dfx.boundaryDOFs(b)
+    rhs = torch.zeros_like(x)
+    dfx.applyDirichlet(A, dn, torch.zeros_like(x), rhs)
+    ym = dfx.LaplaceOperator(b, dn).mv(x).cpu().numpy()
+    assert rel(ym, A.mv(x).cpu().numpy()) <= TOL
+
+
+@pytest.mark.gpu
+def test_matrix_free_laplace_slab_and_unsupported():
+    import torch
+    from dune_functions_b200 import _capi as capi
+    whole = YaspGrid([3, 2, 6], upper=[1.0, 0.5, 2.0])
+    mine = whole.slab(1, 3)
+    b = dfx.makeBasis(mine, lagrange(2))
+    ob = orc.OracleBasis(mine, lagrange(2))
+    csr, _ = ob.assembleLaplace()
+    xr = np.random.default_rng(3).uniform(-1, 1, b.dimension())
+    y = dfx.LaplaceOperator(b).mv(torch.from_numpy(xr).cuda()).cpu().numpy()
+    assert rel(y, orc.oracle_mv(csr, xr)) <= TOL
+    for tree in (lagrange(3), lagrangeDG(1), dfx.taylorHood()):
+        bb = dfx.makeBasis(YaspGrid([2, 2, 2]), tree)
+        with pytest.raises(capi.NotImplementedDfx):
+            dfx.LaplaceOperator(bb).mv(bb.newVector(1.0))
+
+
 def conjugate_gradient(A, rhs, x, tol=1e-12, maxit=2000):
     """plain CG on the device: A.mv is the library's SpMV, the vector updates are torch"""
     r = rhs - A.mv(x)
@@ -213,8 +256,13 @@ def test_poisson_problem_end_to_end(k, n, tol):
     x = b.newVector(0.0)
     dfx.interpolate(b, x, constant(0.0), mask=dn)
     dfx.applyDirichlet(A, dn, x, rhs)
+    x_mf = x.clone()
     its = conjugate_gradient(A, rhs, x)
     assert its < 2000
+    if k <= 2:
+        # the same solve without a matrix: CG on the matrix-free operator
+        its_mf = conjugate_gradient(dfx.LaplaceOperator(b, dn), rhs, x_mf)
+        assert its_mf < 2000 and float((x_mf - x).abs().max()) < 1e-9
     exact = b.newVector(0.0)
     dfx.interpolate(b, exact, sinprod(np.pi))
     assert float((x - exact).abs().max()) < tol

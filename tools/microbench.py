@@ -186,11 +186,32 @@ def main():
             ms, best = timeit(lambda: A.mv(x, y), args.reps)
             report("SpMV y = A x (CSR, warp per row)", cfg, ms, best, nnz * 12 + (nd + 1) * 8 + 2 * nd * 8,
                    {"GFLOPs": 2.0 * nnz / ms / 1e6})
+            op = dfx.LaplaceOperator(basis)
+            ne_ = basis.numElements()
+            nl_ = basis.maxNodeSize()
+            ms, best = timeit(lambda: op.mv(x, y), args.reps)
+            report("matrix-free Laplace y = A x", cfg, ms, best, 2 * nd * 8 + 2 * ne_ * nl_ * 8,
+                   {"dofs_per_s": nd / ms * 1e3, "alg_bytes_note": "x + y + element-local scratch written and read once"})
+            del op
             mask = torch.zeros(nd, dtype=torch.uint8, device="cuda")
             ms, best = timeit(lambda: dfx.boundaryDOFs(basis, mask), args.reps)
             report("boundary DOF mask", cfg, ms, best, nd, {"dofs_per_s": nd / ms * 1e3})
             del basis, A, rhs, x, y, pat, mask
             torch.cuda.empty_cache()
+        # matrix-free only: the size of BASELINE config 2 (no assembled matrix would fit)
+        basis = dfx.makeBasis(dfx.YaspGrid([256, 256, 256]), dfx.lagrange(2))
+        nd, ne_, nl_ = basis.dimension(), basis.numElements(), basis.maxNodeSize()
+        x = basis.newVector(0.0).uniform_(-1, 1)
+        y = torch.empty_like(x)
+        op = dfx.LaplaceOperator(basis)
+        ms, best = timeit(lambda: op.mv(x, y), args.reps)
+        report("matrix-free Laplace y = A x", "ops_q2_256", ms, best, 2 * nd * 8 + 2 * ne_ * nl_ * 8, {"dofs_per_s": nd / ms * 1e3})
+        dn = dfx.boundaryDOFs(basis)
+        opd = dfx.LaplaceOperator(basis, dn)
+        ms, best = timeit(lambda: opd.mv(x, y), args.reps)
+        report("matrix-free Laplace with Dirichlet rows", "ops_q2_256", ms, best, 2 * nd * 8 + 2 * ne_ * nl_ * 8 + 2 * nd)
+        del basis, x, y, op, opd, dn
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
