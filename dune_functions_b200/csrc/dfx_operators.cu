@@ -110,6 +110,59 @@ __device__ __forceinline__ u64 boxIndex(const DevLayout& L, const DevGrid& g, co
   return layoutIndex(L, g, c, a, 0);
 }
 
+// ---- a single continuous leaf: the columns of a row in ASCENDING index order, in closed form ----
+// The scalar index is compOffset[s'] + blk[s'] * lex(entity) + in-entity offset with the components
+// ordered by compOffset, so the sorted columns are: for every component s' (in L.order) the
+// entities of the element box in lexicographic order (x fastest; W_j = ne_j entities along an
+// extended direction, ne_j + 1 lattice planes along a pinned one), each with its blk in-entity nodes.
+struct BoxRank {
+  unsigned prefix[9];      // prefix[q] = number of columns in components L.order[0..q)
+  unsigned W[8][3];        // entities of the box per direction, per component (indexed by position q)
+};
+__device__ __forceinline__ void boxRankInit(const DevLayout& L, const DevGrid& g, const int lo[3], const int hi[3], BoxRank& R) {
+  unsigned run = 0;
+  for (int q = 0; q < L.ncomp; ++q) {
+    const int s = L.order[q];
+    unsigned n = (unsigned)L.blk[s];
+    for (int j = 0; j < 3; ++j) {
+      const unsigned ne = j < g.dim ? (unsigned)(hi[j] - lo[j] + 1) : 1u;
+      R.W[q][j] = j >= g.dim ? 1u : (((s >> j) & 1) ? ne : ne + 1u);
+      n *= R.W[q][j];
+    }
+    R.prefix[q] = run;
+    run += n;
+  }
+  R.prefix[L.ncomp] = run;
+}
+// the v-th smallest column of the row
+__device__ __forceinline__ u64 boxColumn(const DevLayout& L, const int lo[3], const BoxRank& R, unsigned v) {
+  int q = 0;
+  while (q + 1 < L.ncomp && v >= R.prefix[q + 1]) ++q;
+  const int s = L.order[q];
+  unsigned r = v - R.prefix[q];
+  const unsigned blk = (unsigned)L.blk[s];
+  const unsigned fr = r % blk; r /= blk;
+  const unsigned e0 = r % R.W[q][0]; r /= R.W[q][0];
+  const unsigned e1 = r % R.W[q][1]; r /= R.W[q][1];
+  const u64 ent = (u64)(lo[0] + (int)e0) + (u64)L.csize[s][0] * ((u64)(lo[1] + (int)e1) + (u64)L.csize[s][1] * (u64)(lo[2] + (int)r));
+  return L.compOffset[s] + ent * (u64)blk + fr;
+}
+// rank of lattice node alpha of element e (inside the box) among the row's columns
+__device__ __forceinline__ unsigned boxRankOf(const DevLayout& L, const int lo[3], const BoxRank& R, const int e[3], const int a[3]) {
+  const int k = L.k;
+  int s = 0, c[3];
+  unsigned fr = 0, frs = 1;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (a[j] > 0 && a[j] < k) { s |= 1 << j; c[j] = e[j]; fr += (unsigned)(a[j] - 1) * frs; frs *= (unsigned)(k - 1); }
+    else c[j] = e[j] + (a[j] == k ? 1 : 0);
+  }
+  int q = 0;
+  while (q + 1 < L.ncomp && L.order[q] != s) ++q;
+  const unsigned ent = (unsigned)(c[0] - lo[0]) + R.W[q][0] * ((unsigned)(c[1] - lo[1]) + R.W[q][1] * (unsigned)(c[2] - lo[2]));
+  return R.prefix[q] + ent * (unsigned)L.blk[s] + fr;
+}
+
 // in-warp bitonic sort of n <= kMaxRowLen keys in shared memory (padded with 0xffffffff)
 __device__ __forceinline__ void warpSort(unsigned* key, int n, int lane) {
   int p2 = 32;
@@ -153,6 +206,15 @@ k_pattern(const DevBasis* __restrict__ Bp, int layoutId, u64* __restrict__ len, 
     if (lane == 0)
       for (int l = 0; l < B.nLeaves; ++l)
         if (B.leaves[l].layout == layoutId) len[B.leaves[l].posA * t + B.leaves[l].posB] = total;
+    return;
+  }
+  if (B.nLeaves == 1 && L.kind == DFX_NODE_LAGRANGE && L.k >= 1 && B.leaves[0].posA == 1) {
+    // single continuous leaf: emit the columns in rank order, no sort
+    BoxRank R;
+    boxRankInit(L, g, lo, hi, R);
+    const u64 row = t + B.leaves[0].posB;
+    uint32_t* dst = col + rowPtr[row];
+    for (unsigned v = lane; v < total; v += 32) dst[v] = (uint32_t)(boxColumn(L, lo, R, v) + B.leaves[0].posB);
     return;
   }
   unsigned* key = keys[warp];
@@ -212,6 +274,9 @@ k_laplace_rows(const DevBasis* __restrict__ Bp, const __grid_constant__ LaplaceA
   for (int v = lane; v < rowLen; v += 32) a[v] = 0.0;
   __syncwarp();
   const int k = L.k, n = A.nloc;
+  const bool ranked = L.kind == DFX_NODE_LAGRANGE && k >= 1;
+  BoxRank BR;
+  if (ranked) boxRankInit(L, g, lo, hi, BR);
   // ascending element index = the order in which the reference's element loop adds to this row
   for (int e2 = lo[2]; e2 <= hi[2]; ++e2)
     for (int e1 = lo[1]; e1 <= hi[1]; ++e1)
@@ -238,8 +303,9 @@ k_laplace_rows(const DevBasis* __restrict__ Bp, const __grid_constant__ LaplaceA
         for (int jl = lane; jl < n; jl += 32) {
           int aj[3];
           localAlpha(k, jl, aj);
-          const uint32_t c = (uint32_t)(A.posA * layoutIndex(L, g, e, aj, jl) + A.posB);
-          const u64 pos = findColumn(col, p0, p1, c);
+          u64 pos;
+          if (ranked) pos = p0 + boxRankOf(L, lo, BR, e, aj);          // closed-form position in the sorted row
+          else pos = findColumn(col, p0, p1, (uint32_t)(A.posA * layoutIndex(L, g, e, aj, jl) + A.posB));
           double s = 0.0;
           for (int d = 0; d < g.dim; ++d) s += coef[d] * K[((size_t)d * n + iLoc) * n + jl];
           a[pos - p0] += s;                 // distinct jl -> distinct columns: no two lanes meet
