@@ -272,9 +272,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     bind_to_gpu_numa_node(physical_gpu_index(local_rank))
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner out of the one-JSON-line stdout
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the first communicator comes up; stdout must
+        # carry exactly one JSON line, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     L = capi.lib()
 
     ng = global_grid(wl, world)
@@ -299,7 +310,22 @@ def main():
     dgbf = dfx.makeDiscreteGlobalBasisFunction(basis, coeff)
     from dune_functions_b200.slab import HaloExchange, PeerHaloExchange
     halo = HaloExchange(basis, rank, world, device=dev)
-    peer = PeerHaloExchange(basis, rank, world) if (world > 1 and args.halo == "peer") else None
+    peer, halo_note = None, args.halo
+    if world > 1 and args.halo == "peer":
+        # every rank must get its link (CUDA IPC between the processes of this node); otherwise all
+        # ranks take the NCCL transport together and the JSON line says so
+        ok = 1
+        try:
+            peer = PeerHaloExchange(basis, rank, world)
+        except Exception as exc:          # noqa: BLE001
+            ok, peer = 0, None
+            print(f"rank {rank}: peer-memory halo link unavailable ({exc}); using NCCL", file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer, halo_note = None, "nccl (peer link unavailable)"
     index_table = None
     if args.workload == "c3":
         index_table = torch.empty((ne, basis.maxNodeSize()), dtype=torch.int32, device=dev)
@@ -457,7 +483,7 @@ def main():
             "ms": {"interpolate": t_interp * 1e3, "evaluate": t_eval * 1e3, "indices": t_index * 1e3,
                    "evaluate_interior_overlapped_with_halo_exchange": t_halo * 1e3 if world > 1 else None,
                    "halo_bytes_per_rank": int(halo.n * 8) if world > 1 else 0,
-                   "halo_transport": (args.halo if world > 1 else None)},
+                   "halo_transport": (halo_note if world > 1 else None)},
             "roofline": {"bound": "hbm", "kernel": "evaluate (DiscreteGlobalBasisFunction at Gauss points)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes": eval_bytes,

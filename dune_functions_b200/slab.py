@@ -104,19 +104,33 @@ class PeerHaloExchange:
             return
         L = basis._lib
         link = C.c_void_p()
-        capi.check(L.dfx_halo_link_create(basis._h, C.byref(link)))
-        self._link = link
+        err = None
         handle = (C.c_uint8 * 64)()
-        capi.check(L.dfx_halo_link_export(link, handle))
+        try:
+            capi.check(L.dfx_halo_link_create(basis._h, C.byref(link)))
+            self._link = link
+            capi.check(L.dfx_halo_link_export(link, handle))
+        except capi.DfxError as exc:
+            err = exc
+        # the collectives below are entered by every rank, whatever happened locally
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        if rank > 0:
-            h = (C.c_uint8 * 64).from_buffer_copy(handles[rank - 1])
-            capi.check(L.dfx_halo_link_attach(link, 0, h, None))
-        if rank < world - 1:
-            h = (C.c_uint8 * 64).from_buffer_copy(handles[rank + 1])
-            capi.check(L.dfx_halo_link_attach(link, 1, h, None))
+        dist.all_gather_object(handles, None if err else bytes(handle), group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                if rank > 0:
+                    h = (C.c_uint8 * 64).from_buffer_copy(handles[rank - 1])
+                    capi.check(L.dfx_halo_link_attach(link, 0, h, None))
+                if rank < world - 1:
+                    h = (C.c_uint8 * 64).from_buffer_copy(handles[rank + 1])
+                    capi.check(L.dfx_halo_link_attach(link, 1, h, None))
+            except capi.DfxError as exc:
+                err = exc
+        elif err is None:
+            err = capi.DfxError("a neighbouring rank could not create its halo link")
         dist.barrier(group=group)
+        if err is not None:
+            self.close()
+            raise err
 
     def __call__(self, coeff):
         if self._link is None:
