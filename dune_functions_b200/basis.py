@@ -333,7 +333,9 @@ def interpolate(basis, coeff, f, mask=None):
     """interpolate(basis, coeff, f[, bitVector]) — interpolate.hh:204-302.
 
     coeff: float64 CUDA tensor of basis.dimension() entries (flat container order),
-    f: a dfx_function from the registry (gaussian(), identity(n), ...),
+    f: a dfx_function from the registry (gaussian(), identity(n), ...) or a
+       DiscreteGlobalBasisFunction over any basis on the same grid (a grid function: its local
+       function is evaluated at the interpolation nodes, gridviewfunction.hh:68-75),
     mask: optional uint8/bool CUDA tensor in the same order."""
     root, node = _root_and_node(basis)
     if coeff.numel() != root.dimension():
@@ -342,6 +344,10 @@ def interpolate(basis, coeff, f, mask=None):
     if mask is not None:
         import torch
         m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    if isinstance(f, DiscreteGlobalBasisFunction):
+        capi.check(root._lib.dfx_interpolate_dgbf(root._h, node, f.root._h, f.node, _ptr(f.coeff), _ptr(coeff), _ptr(m),
+                                                  None, 0, _stream()))
+        return coeff
     capi.check(root._lib.dfx_interpolate(root._h, node, C.byref(f), _ptr(coeff), _ptr(m), _stream()))
     return coeff
 

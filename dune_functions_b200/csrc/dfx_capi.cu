@@ -173,6 +173,7 @@ void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
   if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
   if (b->dJinv) { cudaSetDevice(b->device); cudaFree(b->dJinv); }
+  if (b->dNodal) { cudaSetDevice(b->device); cudaFree(b->dNodal); }
   if (b->evStream[0]) { cudaSetDevice(b->device); cudaStreamDestroy((cudaStream_t)b->evStream[0]); }
   if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
     cudaSetDevice(b->device);
@@ -300,6 +301,104 @@ int dfx_interpolate_from_values(const dfx_basis* b, int32_t node, const double* 
   if ((rc = subtree(b, node, fl, nl))) return rc;
   if (!values || !coeff) return fail(DFX_ERR_INVALID, "null argument");
   return interpolateFromValues(b, fl, nl, values, coeff, mask, (cudaStream_t)stream);
+}
+
+// ---- interpolate a DiscreteGlobalBasisFunction into another basis ---------------------------
+int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const double* xhat_host, int32_t n_q,
+                 uint64_t e0, uint64_t e1, double* out_values, double* out_jac, void* stream);
+
+static bool sameGrid(const dfx_basis* a, const dfx_basis* b) {
+  const dfx_grid_desc &x = a->gridDesc, &y = b->gridDesc;
+  if (x.dim != y.dim) return false;
+  for (int j = 0; j < x.dim; ++j)
+    if (x.n_global[j] != y.n_global[j] || x.local_begin[j] != y.local_begin[j] || x.local_n[j] != y.local_n[j] ||
+        x.lower[j] != y.lower[j] || x.upper[j] != y.upper[j]) return false;
+  return true;
+}
+
+int dfx_interpolate_dgbf(const dfx_basis* target, int32_t target_node, const dfx_basis* source, int32_t source_node,
+                         const double* source_coeff, double* target_coeff, const uint8_t* mask, double* scratch,
+                         uint64_t scratch_doubles, void* stream) {
+  int rc = ensureDevice(target); if (rc) return rc;
+  if (!source || !source_coeff || !target_coeff) return fail(DFX_ERR_INVALID, "null argument");
+  if (source->device != target->device) return fail(DFX_ERR_INVALID, "source and target basis live on different devices");
+  if ((rc = ensureDevice(source))) return rc;
+  if (!sameGrid(target, source)) return fail(DFX_ERR_RANGE, "source and target basis are not defined on the same grid box");
+  int flT, nlT, flS, nlS;
+  if ((rc = subtree(target, target_node, flT, nlT))) return rc;
+  if ((rc = subtree(source, source_node, flS, nlS))) return rc;
+  if (nlS != 1 && nlS != nlT) return fail(DFX_ERR_RANGE, "range of the grid function does not match the leaves of the (sub)tree");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevBasis& T = target->dev;
+  const int dim = T.grid.dim;
+  const u64 ne = dfx_basis_num_elements(target);
+  u64 layer = 1;
+  for (int j = 0; j + 1 < dim; ++j) layer *= (u64)T.grid.N[j];
+  int maxNloc = 1;
+  for (int l = 0; l < nlT; ++l) maxNloc = std::max(maxNloc, T.layouts[T.leaves[flT + l].layout].nloc);
+  const u64 perElem = (u64)maxNloc * (u64)nlS;
+  double* buf = scratch;
+  u64 cap = scratch_doubles;
+  if (!buf) {
+    // no caller scratch: a band buffer owned by the target handle (<= 1 GiB, kept across calls)
+    dfx_basis* t = const_cast<dfx_basis*>(target);
+    cap = std::min<u64>(ne * perElem, std::max<u64>(layer * perElem, (1ull << 30) / sizeof(double)));
+    if (t->dNodalBytes < cap * sizeof(double)) {
+      if (t->dNodal) cudaFree(t->dNodal);
+      t->dNodal = nullptr; t->dNodalBytes = 0;
+      DFX_CUDA(cudaMalloc(&t->dNodal, cap * sizeof(double)));
+      t->dNodalBytes = cap * sizeof(double);
+    }
+    buf = (double*)t->dNodal;
+  }
+  if (cap < layer * perElem) return fail(DFX_ERR_RANGE, "scratch smaller than one z-layer of nodal values");
+  const u64 band = std::min<u64>(ne, (cap / perElem) / layer * layer);
+  rc = DFX_OK;
+  for (int q = 0; q < T.nLayouts && !rc; ++q) {
+    bool used = false;
+    for (int l = 0; l < nlT; ++l) used = used || T.leaves[flT + l].layout == q;
+    if (!used) continue;
+    const DevLayout& L = T.layouts[q];
+    // local interpolation nodes of this layout: alpha / k (element centre for k = 0), local index order
+    std::vector<double> xhat((size_t)L.nloc * dim);
+    for (int i = 0; i < L.nloc; ++i) {
+      int ii = i;
+      for (int j = 0; j < dim; ++j) {
+        const int a = ii % (L.k + 1); ii /= (L.k + 1);
+        xhat[(size_t)i * dim + j] = L.k == 0 ? 0.5 : (1.0 * a) / L.k;
+      }
+    }
+    for (u64 e0 = 0; e0 < ne && !rc; e0 += band) {
+      const u64 e1 = std::min<u64>(ne, e0 + band);
+      rc = dfx_evaluate(source, source_node, source_coeff, xhat.data(), L.nloc, e0, e1, buf, nullptr, st);
+      if (!rc) rc = scatterNodes(target, q, flT, nlT, nlS, e0, e1, buf, target_coeff, mask, st);
+    }
+  }
+  return rc;
+}
+
+int dfx_interpolate_dgbf_host(const dfx_basis* target, int32_t target_node, const dfx_basis* source, int32_t source_node,
+                              const double* source_coeff_host, double* target_coeff_host, const uint8_t* mask_host) {
+  dfx_basis* t = const_cast<dfx_basis*>(target);
+  int rc = ensureDevice(t); if (rc) return rc;
+  if (!source || !source_coeff_host || !target_coeff_host) return fail(DFX_ERR_INVALID, "null argument");
+  cudaStream_t st; if ((rc = privateStream(t, st))) return rc;
+  const size_t nT = t->dimension, nS = source->dimension;
+  if ((rc = growScratch(t, 0, (nT + nS) * sizeof(double)))) return rc;
+  double* dT = (double*)t->dScratch[0];
+  double* dS = dT + nT;
+  uint8_t* dM = nullptr;
+  DFX_CUDA(cudaMemcpyAsync(dT, target_coeff_host, nT * sizeof(double), cudaMemcpyHostToDevice, st));   // untouched entries keep their value
+  DFX_CUDA(cudaMemcpyAsync(dS, source_coeff_host, nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mask_host) {
+    if ((rc = growScratch(t, 1, nT))) return rc;
+    dM = (uint8_t*)t->dScratch[1];
+    DFX_CUDA(cudaMemcpyAsync(dM, mask_host, nT, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = dfx_interpolate_dgbf(target, target_node, source, source_node, dS, dT, dM, nullptr, 0, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(target_coeff_host, dT, nT * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
 }
 
 // ---- evaluate ---------------------------------------------------------------------

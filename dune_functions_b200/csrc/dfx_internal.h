@@ -117,6 +117,7 @@ struct dfx_basis_impl {
   void* dDev = nullptr;                                 // device copy of `dev`
   void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f
   void* dShape = nullptr; size_t dShapeBytes = 0;       // shape tables of the last evaluate
+  void* dNodal = nullptr; size_t dNodalBytes = 0;       // nodal values of a grid function (dfx_interpolate_dgbf)
   void* dJinv = nullptr;                                // diag(J^-1) per direction and element coordinate
   void* dDense = nullptr; size_t dDenseBytes = 0;       // dense table of the DMMA path
   std::vector<double> denseXhat; int dDenseNode = -1, dDenseCols = 0, dDenseVal = 0;

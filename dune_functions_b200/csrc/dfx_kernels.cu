@@ -220,6 +220,110 @@ int interpolateFromValues(const dfx_basis* b, int firstLeaf, int nLeaves, const 
 }
 
 // ---------------------------------------------------------------------------
+// interpolate(basis, coeff, gridFunction) for a grid function that is evaluated element by
+// element (a DiscreteGlobalBasisFunction of another basis): `vals[(e - e0)][i][c]` holds the
+// function at local interpolation node i of element e (range entry c).  One thread per
+// (element, local node): it writes iff its element is the LAST one of [e0, e1) — in grid-view
+// iteration order — that contains the node, i.e. unless the node sits on an upper face whose
+// neighbour is also in the range; later bands overwrite earlier ones like the reference's loop.
+struct ScatterArgs {
+  int layoutId, firstLeaf, nLeaves, ncompVals;
+  int tileLog2;                        // a block handles 2^tileLog2 consecutive elements
+  u64 e0, e1;
+  FastDiv divN0, divN1, divK1;
+};
+
+// A block stages the nodal values of a tile of consecutive elements in shared memory (coalesced
+// read of `vals`, which is element-major) and then walks (local node, element) with the element
+// fastest, so that the lanes of a warp write consecutive entities of one index-set component.
+__global__ void __launch_bounds__(256)
+k_scatter_nodes(const __grid_constant__ DevBasis B, const __grid_constant__ ScatterArgs A,
+                const double* __restrict__ vals, double* __restrict__ coeff, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) double tile[];
+  // the layout's per-component tables are indexed by a per-lane shift mask: shared memory, not
+  // the (serialising) indexed-constant path
+  __shared__ u64 sOff[8];
+  __shared__ unsigned sCs0[8], sCs1[8], sBlk[8];
+  const DevLayout& L = B.layouts[A.layoutId];
+  const DevGrid& g = B.grid;
+  if (threadIdx.x < 8) {
+    sOff[threadIdx.x] = L.compOffset[threadIdx.x];
+    sCs0[threadIdx.x] = (unsigned)L.csize[threadIdx.x][0];
+    sCs1[threadIdx.x] = (unsigned)L.csize[threadIdx.x][1];
+    sBlk[threadIdx.x] = (unsigned)L.blk[threadIdx.x];
+  }
+  const unsigned tileEl = 1u << A.tileLog2;
+  const u64 elBase = (u64)blockIdx.x * tileEl;                 // relative to e0
+  const u64 nEl = A.e1 - A.e0;
+  const unsigned cnt = (unsigned)(nEl - elBase < (u64)tileEl ? nEl - elBase : (u64)tileEl);
+  const unsigned perEl = (unsigned)L.nloc * (unsigned)A.ncompVals;
+  const double* src = vals + elBase * (u64)perEl;
+  for (unsigned w = threadIdx.x; w < cnt * perEl; w += blockDim.x) tile[w] = src[w];
+  __syncthreads();
+  const int k = L.k;
+  const unsigned last = (unsigned)A.e1;
+  const unsigned work = (unsigned)L.nloc << A.tileLog2;
+  for (unsigned w = threadIdx.x; w < work; w += blockDim.x) {
+    const unsigned elLoc = w & (tileEl - 1u), i = w >> A.tileLog2;
+    if (elLoc >= cnt) continue;
+    const unsigned e = (unsigned)(A.e0 + elBase) + elLoc;
+    unsigned q, ec0, ec1, ec2;
+    A.divN0.divmod(e, q, ec0);
+    A.divN1.divmod(q, ec2, ec1);
+    u64 jdx;
+    if (L.kind == DFX_NODE_LAGRANGE && k > 0) {
+      unsigned a0, a1, a2, r;
+      A.divK1.divmod(i, r, a0);
+      A.divK1.divmod(r, a2, a1);
+      // the element one step up in direction j: inside [e0, e1)?  then it writes this node, not us
+      if ((int)a0 == k && ec0 + 1 < (unsigned)g.N[0] && e + 1 < last) continue;
+      if (g.dim > 1 && (int)a1 == k && ec1 + 1 < (unsigned)g.N[1] && e + (unsigned)g.N[0] < last) continue;
+      if (g.dim > 2 && (int)a2 == k && ec2 + 1 < (unsigned)g.N[2] && (u64)e + (u64)g.N[0] * (u64)g.N[1] < (u64)last) continue;
+      unsigned s = 0, fr = 0, frs = 1;
+      unsigned c0 = ec0, c1 = ec1, c2 = ec2;
+      if (a0 > 0 && (int)a0 < k) { s |= 1u; fr += (a0 - 1) * frs; frs *= (unsigned)(k - 1); } else c0 += (int)a0 == k ? 1u : 0u;
+      if (a1 > 0 && (int)a1 < k) { s |= 2u; fr += (a1 - 1) * frs; frs *= (unsigned)(k - 1); } else c1 += (int)a1 == k ? 1u : 0u;
+      if (a2 > 0 && (int)a2 < k) { s |= 4u; fr += (a2 - 1) * frs; } else c2 += (int)a2 == k ? 1u : 0u;
+      const u64 ent = (u64)c0 + (u64)sCs0[s] * ((u64)c1 + (u64)sCs1[s] * (u64)c2);
+      jdx = sOff[s] + ent * (u64)sBlk[s] + fr;
+    } else {
+      const u64 ei = (u64)ec0 + (u64)g.N[0] * ((u64)ec1 + (u64)g.N[1] * (u64)ec2);
+      jdx = ei * (u64)L.nloc + i;               // element-local DOFs (LagrangeDG, Lagrange<0>)
+    }
+    const double* v = tile + (elLoc * (unsigned)L.nloc + i) * (unsigned)A.ncompVals;
+    for (int l = 0; l < A.nLeaves; ++l) {
+      const DevLeaf& leaf = B.leaves[A.firstLeaf + l];
+      if (leaf.layout != A.layoutId) continue;
+      const u64 p = leaf.posA * jdx + leaf.posB;
+      if (mask == nullptr || mask[p]) coeff[p] = v[A.ncompVals == 1 ? 0 : l];
+    }
+  }
+}
+
+int scatterNodes(const dfx_basis* b, int layoutId, int firstLeaf, int nLeaves, int ncompVals, u64 e0, u64 e1,
+                 const double* vals, double* coeff, const uint8_t* mask, cudaStream_t st) {
+  const DevLayout& L = b->dev.layouts[layoutId];
+  if (e1 == e0) return DFX_OK;
+  if (e1 > 0xffffffffull) return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
+  // tile: as many elements (a power of two, <= 64) as fit 40 KB of shared memory
+  const size_t perEl = (size_t)L.nloc * ncompVals * sizeof(double);
+  int tl = 6;
+  while (tl > 0 && (perEl << tl) > 40 * 1024) --tl;
+  const size_t smem = perEl << tl;
+  if (smem > 200 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "element too large for the scatter tile");
+  if (smem > 48 * 1024) DFX_CUDA(cudaFuncSetAttribute(k_scatter_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const u64 blocks = ((e1 - e0) + (1ull << tl) - 1) >> tl;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  ScatterArgs A;
+  A.layoutId = layoutId; A.firstLeaf = firstLeaf; A.nLeaves = nLeaves; A.ncompVals = ncompVals; A.e0 = e0; A.e1 = e1;
+  A.tileLog2 = tl;
+  A.divN0 = FastDiv((unsigned)b->dev.grid.N[0]); A.divN1 = FastDiv((unsigned)b->dev.grid.N[1]);
+  A.divK1 = FastDiv((unsigned)(L.k + 1));
+  k_scatter_nodes<<<(unsigned)blocks, 256, smem, st>>>(b->dev, A, vals, coeff, mask);
+  return postLaunch("k_scatter_nodes");
+}
+
+// ---------------------------------------------------------------------------
 // Generic evaluation: one thread per (element, point); shape tables
 // shape[layout][q][i], dshape[layout][q][i][dim] precomputed on the host exactly as
 // LagrangeCubeLocalBasis::evaluateFunction / evaluateJacobian produce them.

@@ -193,6 +193,22 @@ int dfx_interpolation_points(const dfx_basis* b, double* out_xyz /*[dimension][d
 int dfx_interpolate_from_values(const dfx_basis* b, int32_t subtree_node, const double* values,
                                 double* coeff, const uint8_t* mask, void* stream);
 
+/* interpolate(targetBasis, coeff, gridFunction) where the grid function is a
+ * DiscreteGlobalBasisFunction over `source` (any basis on the SAME grid box): makeGridViewFunction
+ * hands grid functions through (gridfunctions/gridviewfunction.hh:68-75), so interpolateLocal
+ * (interpolate.hh:151-173) evaluates localFunction(f) at the target's local interpolation nodes,
+ * element by element — the first variant of checkInterpolationConsistency
+ * (gridfunctions/test/discreteglobalbasisfunctiontest.cc:49-77).  Leaf l below target_node takes
+ * range entry l of f (= leaf l below source_node); a one-leaf source is broadcast.
+ * `scratch` (device, may be NULL = allocated per call): scratch_doubles doubles; the element
+ * loop runs in bands that fit it (at least one z-layer: layer elements * max target n_loc *
+ * source leaves).                                                                       */
+int dfx_interpolate_dgbf(const dfx_basis* target, int32_t target_node, const dfx_basis* source, int32_t source_node,
+                         const double* source_coeff, double* target_coeff, const uint8_t* mask,
+                         double* scratch, uint64_t scratch_doubles, void* stream);
+int dfx_interpolate_dgbf_host(const dfx_basis* target, int32_t target_node, const dfx_basis* source, int32_t source_node,
+                              const double* source_coeff_host, double* target_coeff_host, const uint8_t* mask_host);
+
 /* ---- DiscreteGlobalBasisFunction local evaluation --------------------------
  * Replaces LocalFunctionBase::bind (discreteglobalbasisfunction.hh:124-148),
  * LocalFunction::operator() (:336-371) and

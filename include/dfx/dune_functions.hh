@@ -436,7 +436,11 @@ inline Function sinprod(double w) { Function r{}; r.f.id = DFX_FN_SINPROD; r.f.n
 inline Function constant(double c) { Function r{}; r.f.id = DFX_FN_CONSTANT; r.f.n_comp = 1; r.f.p[0] = c; return r; }
 }  // namespace Registry
 
+template <class R, class B, class C> class DiscreteGlobalBasisFunction;
+
 namespace Impl {
+template <class T> struct IsDiscreteGlobalBasisFunction : std::false_type {};
+template <class R, class B, class C> struct IsDiscreteGlobalBasisFunction<DiscreteGlobalBasisFunction<R, B, C>> : std::true_type {};
 // flat view of a range value: scalar or anything indexable (HierarchicNodeToRangeMap + flatVectorView)
 template <class Y> double rangeEntry(const Y& y, int leaf, int nLeaves) {
   if constexpr (std::is_arithmetic_v<Y>) { (void)leaf; (void)nLeaves; return (double)y; }
@@ -468,6 +472,11 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
   }
   if constexpr (std::is_same_v<F, Registry::Function>) {
     Impl::check(dfx_interpolate_host(h, basis.rootNode(), &f.f, x, mask));
+  } else if constexpr (Impl::IsDiscreteGlobalBasisFunction<F>::value) {
+    // a grid function: its local function is evaluated at the interpolation nodes, element by
+    // element (gridviewfunction.hh:68-75; discreteglobalbasisfunctiontest.cc:49-77)
+    Impl::check(dfx_interpolate_dgbf_host(h, basis.rootNode(), f.basis().handle(), f.basis().rootNode(),
+                                          f.coefficientData(), x, mask));
   } else {
     // arbitrary host callable: the device produces the node positions and the leaf of every
     // coefficient (form (2) of include/dfx.h); f itself is the caller's CPU code
@@ -626,6 +635,8 @@ class DiscreteGlobalBasisFunction {
   };
   friend LocalFunction localFunction(const DiscreteGlobalBasisFunction& f) { return LocalFunction(f); }
   int numComponents() const { return ncomp_; }
+  const B& basis() const { return basis_; }
+  const double* coefficientData() const { return reinterpret_cast<const double*>(coeff_->data()); }
  private:
   B basis_;
   const C* coeff_;

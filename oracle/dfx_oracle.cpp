@@ -822,6 +822,54 @@ void orc_interpolate(void* h, int32_t subtreeNode, const dfx_function* f, double
   });
 }
 
+// interpolate(targetBasis, coeff, f) where f is a DiscreteGlobalBasisFunction over another basis
+// on the same grid: makeGridViewFunction hands a grid function through unchanged
+// (gridviewfunction.hh:68-75), so interpolateLocal (interpolate.hh:151-173) evaluates
+// localFunction(f) at the target's local interpolation nodes — no global search.  This is the
+// first variant of checkInterpolationConsistency (discreteglobalbasisfunctiontest.cc:49-77).
+int32_t orc_interpolate_dgbf(void* hTarget, int32_t targetNode, void* hSource, int32_t sourceNode,
+                             const double* sourceCoeff, double* coeff, const uint8_t* mask) {
+  auto* bt = (orc::Basis*)hTarget;
+  auto* bs = (orc::Basis*)hSource;
+  if (bt->maxDigits > 1) bt->buildPositions();
+  if (bs->maxDigits > 1) bs->buildPositions();
+  const orc::Grid& g = bt->grid;
+  const int dim = g.dim;
+  const auto& nt = bt->nodes[targetNode];
+  const auto& ns = bs->nodes[sourceNode];
+  const int nLeavesT = nt[3], nLeavesS = ns[3];
+  if (nLeavesS != 1 && nLeavesS != nLeavesT) return 1;
+  if (bs->grid.numElements() != g.numElements()) return 2;
+  std::vector<orc::MultiIndex> idxT, idxS;
+  std::vector<double> localDoFs(bs->localSize()), shapeValues;
+  for (size_t e = 0; e < g.numElements(); ++e) {               // for (const auto& e : elements(gridView))
+    bt->bind(e, idxT);                                          // localView.bind(e)
+    bs->bind(e, idxS);                                          // localF.bind(e): gather of the source's local DOFs
+    for (int i = 0; i < ns[1]; ++i) localDoFs[ns[0] + i] = sourceCoeff[bs->flat(idxS[ns[0] + i])];
+    for (int l = 0; l < nLeavesT; ++l) {                        // forEachLeafNode of the target tree
+      const orc::LeafNode& leaf = bt->leaves[nt[2] + l];
+      const orc::LagrangeCubeFE& fe = *leaf.fe;
+      std::vector<double> interpolationCoefficients(fe.size());
+      const orc::LeafNode& src = bs->leaves[ns[2] + (nLeavesS == 1 ? 0 : l)];   // range entry of this leaf
+      for (int i = 0; i < fe.size(); ++i) {
+        double xhat[3];
+        fe.node(i, xhat);
+        shapeValues.resize(src.fe->size());
+        src.fe->evaluateFunction(xhat, shapeValues.data());    // LocalFunction::operator()(xhat), :336-371
+        double v = 0;
+        for (int a = 0; a < src.fe->size(); ++a) v += localDoFs[src.offset + a] * shapeValues[a];
+        interpolationCoefficients[i] = v;
+      }
+      for (int i = 0; i < fe.size(); ++i) {
+        size_t p = bt->flat(idxT[leaf.offset + i]);
+        if (!mask || mask[p]) coeff[p] = interpolationCoefficients[i];
+      }
+    }
+  }
+  (void)dim;
+  return 0;
+}
+
 // DiscreteGlobalBasisFunction local evaluation at points xhat[nq][dim] on elements
 // [e0,e1): values [ne][nq][ncomp], jacobians [ne][nq][ncomp][dim] (either may be NULL)
 // discreteglobalbasisfunction.hh:124-148 (bind/gather), :336-371 (values), :583-627 (jacobians)

@@ -130,6 +130,30 @@ int main() {
       for (std::size_t e = 0; e < 100; ++e) for (std::size_t q = 0; q < 9; ++q) integral += v[e * 9 + q] * w[q] / 100;
       CHECK(std::abs(integral - 0.5) < 1e-10, "Taylor-Hood pressure integral == 0.5");
     }
+    // checkInterpolationConsistency (gridfunctions/test/discreteglobalbasisfunctiontest.cc:49-77):
+    // interpolating the discrete function of a coefficient vector returns the vector, both through
+    // its local function (grid function) and through a lambda that forces evaluation at the nodes
+    {
+      auto basis = makeBasis(gv2, power<2>(lagrange<2>(), blockedInterleaved()));
+      std::vector<double> x;
+      interpolate(basis, x, [](const FieldVector<double, 2>& p) { return FieldVector<double, 2>{p[1], p[0]}; });
+      auto f = makeDiscreteGlobalBasisFunction<FieldVector<double, 2>>(basis, x);
+      std::vector<double> y;
+      interpolate(basis, y, f);
+      double diff = 0;
+      for (std::size_t i = 0; i < x.size(); ++i) diff = std::max(diff, std::abs(x[i] - y[i]));
+      CHECK(y.size() == x.size() && diff < 1e-10, "interpolation of a DiscreteGlobalBasisFunction reproduces its coefficients");
+      // Q2 function into the Q1 basis of the same grid: the vertex values
+      LagrangeBasis<Grid2::LeafGridView, 2> q2(gv2);
+      LagrangeBasis<Grid2::LeafGridView, 1> q1(gv2);
+      std::vector<double> c2, c1, c1ref;
+      interpolate(q2, c2, Registry::gaussian(1.0));
+      interpolate(q1, c1ref, Registry::gaussian(1.0));
+      interpolate(q1, c1, makeDiscreteGlobalBasisFunction<double>(q2, c2));
+      diff = 0;
+      for (std::size_t i = 0; i < c1.size(); ++i) diff = std::max(diff, std::abs(c1[i] - c1ref[i]));
+      CHECK(diff < 1e-14, "Q2 discrete function interpolated into Q1 = nodal values");
+    }
     // error behaviour: RangeError for an unsupported order (lagrangebasis.hh:795-796)
     bool threw = false;
     try { makeBasis(gv3, lagrange(18)); } catch (const RangeError&) { threw = true; }

@@ -42,6 +42,8 @@ def lib():
         L.orc_subentity_dofs.argtypes = [vp, i32, i32, i32, vp, vp]
         L.orc_boundary_dofs.restype = u64
         L.orc_boundary_dofs.argtypes = [vp, i32, vp]
+        L.orc_interpolate_dgbf.restype = i32
+        L.orc_interpolate_dgbf.argtypes = [vp, i32, vp, i32, vp, vp, vp]
         L.orc_occupation_pattern.restype = u64
         L.orc_occupation_pattern.argtypes = [vp, vp, vp]
         L.orc_assemble_laplace.restype = i32
@@ -146,6 +148,18 @@ class OracleBasis:
             mask = np.zeros(self.dimension(), dtype=np.uint8)
         visits = lib().orc_boundary_dofs(self._h, node, mask.ctypes.data)
         return mask, int(visits)
+
+    def interpolateGridFunction(self, source, sourceCoeff, coeff=None, mask=None, node=0, sourceNode=0):
+        """interpolate(self, coeff, makeDiscreteGlobalBasisFunction(source, sourceCoeff))"""
+        if coeff is None:
+            coeff = np.zeros(self.dimension())
+        sc = np.ascontiguousarray(sourceCoeff, dtype=np.float64)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        rc = lib().orc_interpolate_dgbf(self._h, node, source._h, sourceNode, sc.ctypes.data, coeff.ctypes.data,
+                                        None if m is None else m.ctypes.data)
+        if rc:
+            raise ValueError(f"oracle: grid-function interpolation failed ({rc})")
+        return coeff
 
     # ---- examples/poisson-pq2.cc restated ----
     def occupationPattern(self):

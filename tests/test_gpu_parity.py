@@ -298,6 +298,76 @@ def test_evaluate_host_pipeline_bands(gname, tname, band_kib):
         L.dfx_set_kernel_path(capi.OP_HOST_BAND_KIB, -1)
 
 
+# ---- interpolate(basis, coeff, gridFunction) -----------------------------------------------------
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_3x4x5", "3d_2x1x3"])
+def test_interpolation_consistency_of_discrete_functions(gname):
+    """checkInterpolationConsistency, discreteglobalbasisfunctiontest.cc:49-77: interpolating
+    makeDiscreteGlobalBasisFunction(basis, x) into the same basis returns x (the reference asks
+    for 1e-10; a nodal basis reproduces its own coefficients to rounding)"""
+    import torch
+    grid = GRIDS[gname]
+    for tname, tree in trees(grid.dim).items():
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        x = random_coeff(b.dimension())
+        xt = torch.from_numpy(x).cuda()
+        y = b.newVector(float("nan"))
+        dfx.interpolate(b, y, dfx.makeDiscreteGlobalBasisFunction(b, xt))
+        got = y.cpu().numpy()
+        assert np.abs(got - x).max() <= 1e-10, tname
+        assert rel(got, o.interpolateGridFunction(o, x)) <= TOL, tname
+
+
+@pytest.mark.parametrize("src,dst", [("lagrange2", "lagrange1"), ("lagrange1", "lagrange2"), ("lagrange3", "lagrangeDG2"),
+                                     ("lagrangeDG1", "lagrange2"), ("lagrange2", "lagrange0"), ("lagrange4", "lagrange3"),
+                                     ("power3_q2_BI", "power3_dg1_FL"), ("lagrange2", "power3_q2_BI")])
+def test_interpolate_grid_function_between_bases(src, dst):
+    """a discrete function of one basis interpolated into another basis on the same grid (restriction,
+    injection, DG <-> continuous: last element in iteration order wins on shared nodes), small bands"""
+    import torch
+    grid = GRIDS["3d_3x4x5"]
+    ts, td = trees(3)[src], trees(3)[dst]
+    bs, bd = dfx.makeBasis(grid, ts), dfx.makeBasis(grid, td)
+    os_, od = orc.OracleBasis(grid, ts), orc.OracleBasis(grid, td)
+    xs = random_coeff(bs.dimension())
+    f = dfx.makeDiscreteGlobalBasisFunction(bs, torch.from_numpy(xs).cuda())
+    y = bd.newVector(-7.0)
+    dfx.interpolate(bd, y, f)
+    exp = od.interpolateGridFunction(os_, xs, coeff=np.full(od.dimension(), -7.0))
+    assert rel(y.cpu().numpy(), exp) <= TOL
+    # element loop in bands of one z-layer (the smallest scratch the entry point accepts) and a mask
+    L = capi.lib()
+    layer = 3 * 4
+    nl = max(od.nodeInfo(0)["size"], 1)
+    ncomp = os_.numLeaves()
+    scratch = torch.empty(layer * bd.maxNodeSize() * ncomp, dtype=torch.float64, device="cuda")
+    mask = (np.arange(bd.dimension()) % 3 != 1).astype(np.uint8)
+    y2 = bd.newVector(-7.0)
+    capi.check(L.dfx_interpolate_dgbf(bd._h, 0, bs._h, 0, C.c_void_p(f.coeff.data_ptr()), C.c_void_p(y2.data_ptr()),
+                                      C.c_void_p(torch.from_numpy(mask).cuda().data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                      scratch.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    exp2 = od.interpolateGridFunction(os_, xs, coeff=np.full(od.dimension(), -7.0), mask=mask)
+    assert rel(y2.cpu().numpy(), exp2) <= TOL
+    del nl
+    # host entry point
+    yh = np.full(bd.dimension(), -7.0)
+    capi.check(L.dfx_interpolate_dgbf_host(bd._h, 0, bs._h, 0, xs.ctypes.data, yh.ctypes.data, None))
+    assert rel(yh, exp) <= TOL
+
+
+def test_interpolate_grid_function_errors():
+    import torch
+    b3 = dfx.makeBasis(GRIDS["3d_3x4x5"], lagrange(1))
+    other = dfx.makeBasis(GRIDS["3d_2x1x3"], lagrange(1))
+    f = dfx.makeDiscreteGlobalBasisFunction(other, other.newVector(1.0))
+    with pytest.raises(capi.RangeError):
+        dfx.interpolate(b3, b3.newVector(0.0), f)                       # different grids
+    th = dfx.makeBasis(GRIDS["3d_3x4x5"], taylorHood())
+    fv = dfx.makeDiscreteGlobalBasisFunction(dfx.subspaceBasis(th, 0), th.newVector(1.0))
+    with pytest.raises(capi.RangeError):
+        dfx.interpolate(dfx.makeBasis(GRIDS["3d_3x4x5"], power(lagrange(1), 2, BI())), torch.zeros(2 * 4 * 5 * 6, dtype=torch.float64, device="cuda"), fv)
+
+
 def test_peer_memory_halo_link_between_two_slabs():
     """dfx_halo_link_* / dfx_halo_push / dfx_halo_pull with both slabs on one GPU (raw-pointer
     attachment instead of CUDA IPC): the upper slab's bottom plane lands in the lower slab's top

@@ -102,6 +102,12 @@ def main():
             report(f"evaluate values+jacobians {m}^3", cfg, ms, best, nd * 8 + v.numel() * 8 * 4)
             del j
         if cfg == "c2":
+            # interpolate(basis, y, makeDiscreteGlobalBasisFunction(basis, x)): evaluate at the nodes + owner scatter
+            y2 = basis.newVector(0.0)
+            ms, best = timeit(lambda: dfx.interpolate(basis, y2, f), max(2, args.reps // 2), warm=1)
+            report("interpolate a DiscreteGlobalBasisFunction (Q2 -> Q2)", cfg, ms, best, 2 * nd * 8 + 2 * ne * 27 * 8,
+                   {"dofs_per_s": nd / ms * 1e3})
+            del y2
             idx = torch.empty((ne, 27), dtype=torch.int32, device="cuda")
             ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
             report("indices flat u32", cfg, ms, best, idx.numel() * 4)
