@@ -264,10 +264,9 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   }
 }
 
-template <int DIM, int K, int M, bool JAC>
-static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const double* coeff, double* values,
-                     double* jac, cudaStream_t st) {
-  constexpr int EPB = JAC ? 64 : 128;
+template <int DIM, int K, int M, bool JAC, int EPB>
+static int launchRegE(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const double* coeff, double* values,
+                      double* jac, cudaStream_t st) {
   constexpr int NQ = DIM == 3 ? M * M * M : M * M;
   Tables<K + 1, M> T;
   for (int j = 0; j < 3; ++j)
@@ -288,6 +287,16 @@ static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const
   return postLaunch("k_eval_reg");
 }
 
+// elements per block: 128 (values) / 64 (with Jacobians); vector-valued groups of a values-only
+// evaluation take 32 so that the staging tile (EPB x points x leaves) leaves room for >= 10 blocks per SM
+template <int DIM, int K, int M, bool JAC>
+static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const double* coeff, double* values,
+                     double* jac, cudaStream_t st) {
+  if (JAC) return launchRegE<DIM, K, M, JAC, 64>(b, plan, R, coeff, values, jac, st);
+  if (R.nGroup >= 2) return launchRegE<DIM, K, M, JAC, 32>(b, plan, R, coeff, values, jac, st);
+  return launchRegE<DIM, K, M, JAC, 128>(b, plan, R, coeff, values, jac, st);
+}
+
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st) {
   if (e1 == e0) return DFX_OK;
@@ -303,7 +312,7 @@ int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     {
       // bound the staging tile (<= 96 KB per block): long runs are cut into chunks of leaves
       int nq = 1; for (int j = 0; j < plan.dim; ++j) nq *= plan.m;
-      const size_t perLeaf = (size_t)(plan.jac ? 64 : 128) * nq * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
+      const size_t perLeaf = (size_t)(plan.jac ? 64 : 32) * nq * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
       const int maxG = (int)std::max<size_t>(1, (96 * 1024) / perLeaf);
       if (r - l > maxG) r = l + maxG;
     }
