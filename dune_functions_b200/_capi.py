@@ -76,6 +76,8 @@ SIGNATURES = {
     "dfx_interpolate_dgbf": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "dfx_interpolate_dgbf_host": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dfx_evaluate": (C.c_int, [_vp, _i32, _vp, C.POINTER(C.c_double), _i32, _u64, _u64, _vp, _vp, _vp]),
+    "dfx_evaluate_global": (C.c_int, [_vp, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "dfx_evaluate_global_host": (C.c_int, [_vp, _i32, _vp, _vp, _u64, _vp, _vp, _vp]),
     "dfx_evaluate_path": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), _i32, _i32]),
     "dfx_set_kernel_path": (None, [_i32, _i32]),
     "dfx_interpolate_host": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp]),

@@ -440,6 +440,28 @@ class DiscreteGlobalBasisFunction:
         return v if values else j
 
 
+def _evaluate_global(self, x, values=True, jacobians=False, return_elements=False):
+    """operator()(x) for world coordinates x [n, dim] (CUDA tensor or array):
+    values [n, n_comp], jacobians [n, n_comp, dim]; NaN (and element -1) where no element of the
+    local box contains the point — discreteglobalbasisfunction.hh:402-410."""
+    import torch
+    root = self.root
+    dev = f"cuda:{root.device}"
+    xs = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+    xs = xs.to(device=dev, dtype=torch.float64).reshape(-1, root.grid.dim).contiguous()
+    n, nc = xs.shape[0], self.nComp()
+    v = torch.empty((n, nc), dtype=torch.float64, device=dev) if values else None
+    j = torch.empty((n, nc, root.grid.dim), dtype=torch.float64, device=dev) if jacobians else None
+    el = torch.empty(n, dtype=torch.int32, device=dev) if return_elements else None
+    capi.check(root._lib.dfx_evaluate_global(root._h, self.node, _ptr(self.coeff), _ptr(xs), n, _ptr(v), _ptr(j), _ptr(el),
+                                             _stream()))
+    out = tuple(t for t in (v, j, el) if t is not None)
+    return out[0] if len(out) == 1 else out
+
+
+DiscreteGlobalBasisFunction.evaluateGlobal = _evaluate_global
+
+
 def makeDiscreteGlobalBasisFunction(basis, coeff):
     return DiscreteGlobalBasisFunction(basis, coeff)
 

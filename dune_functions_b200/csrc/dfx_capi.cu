@@ -443,6 +443,17 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
   return evalGeneric(b, fl, nl, coeff, dS, dDS, so, n_q, e0, e1, out_values, out_jac, st);
 }
 
+int dfx_evaluate_global(const dfx_basis* b, int32_t node, const double* coeff, const double* x, uint64_t n_points,
+                        double* out_values, double* out_jac, int32_t* out_element, void* stream) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if (!coeff || (!x && n_points)) return fail(DFX_ERR_INVALID, "null argument");
+  if (!out_values && !out_jac) return fail(DFX_ERR_INVALID, "no output requested");
+  if (dfx_basis_num_elements(b) > 0x7fffffffull) return fail(DFX_ERR_RANGE, "more than 2^31 elements in one box");
+  return evalGlobal(b, fl, nl, coeff, x, n_points, out_values, out_jac, out_element, (cudaStream_t)stream);
+}
+
 // ---- host-buffer entry points -------------------------------------------------------
 int dfx_interpolate_host(const dfx_basis* cb, int32_t node, const dfx_function* f, double* coeff_host,
                          const uint8_t* mask_host) {
@@ -591,6 +602,38 @@ int dfx_evaluate_host(const dfx_basis* cb, int32_t node, const double* coeff_hos
   cleanup();
   if (e1s != cudaSuccess) return cudaFail(e1s, "cudaStreamSynchronize");
   if (e2s != cudaSuccess) return cudaFail(e2s, "cudaStreamSynchronize");
+  return DFX_OK;
+}
+
+int dfx_evaluate_global_host(const dfx_basis* cb, int32_t node, const double* coeff_host, const double* x_host,
+                             uint64_t n_points, double* out_values_host, double* out_jac_host, int32_t* out_element_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  int fl, nl;
+  if ((rc = subtree(b, node, fl, nl))) return rc;
+  if (!coeff_host || (!x_host && n_points)) return fail(DFX_ERR_INVALID, "null argument");
+  if (!out_values_host && !out_jac_host) return fail(DFX_ERR_INVALID, "no output requested");
+  if (n_points == 0) return DFX_OK;
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension, dim = b->dev.grid.dim;
+  // the coefficient vector stays on the device between calls with the same host pointer and content
+  // version is unknown, so it is sent every time; points and results share one scratch block
+  if ((rc = growScratch(b, 0, n * sizeof(double)))) return rc;
+  const size_t perPoint = dim + (size_t)nl * (1 + dim);
+  if ((rc = growScratch(b, 1, n_points * perPoint * sizeof(double)))) return rc;
+  if ((rc = growScratch(b, 2, n_points * sizeof(int32_t)))) return rc;
+  double* dC = (double*)b->dScratch[0];
+  double* dX = (double*)b->dScratch[1];
+  double* dV = dX + n_points * dim;
+  double* dJ = dV + n_points * (size_t)nl;
+  int32_t* dE = (int32_t*)b->dScratch[2];
+  DFX_CUDA(cudaMemcpyAsync(dC, coeff_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  DFX_CUDA(cudaMemcpyAsync(dX, x_host, n_points * dim * sizeof(double), cudaMemcpyHostToDevice, st));
+  if ((rc = dfx_evaluate_global(b, node, dC, dX, n_points, out_values_host ? dV : nullptr, out_jac_host ? dJ : nullptr, dE, st))) return rc;
+  if (out_values_host) DFX_CUDA(cudaMemcpyAsync(out_values_host, dV, n_points * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out_jac_host) DFX_CUDA(cudaMemcpyAsync(out_jac_host, dJ, n_points * (size_t)nl * dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out_element_host) DFX_CUDA(cudaMemcpyAsync(out_element_host, dE, n_points * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
   return DFX_OK;
 }
 

@@ -453,6 +453,118 @@ int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, 
 }
 
 // ---------------------------------------------------------------------------
+// DiscreteGlobalBasisFunction::operator()(x) for world coordinates
+// (discreteglobalbasisfunction.hh:402-410) and its derivative (:637-650).  The reference finds
+// the element with a HierarchicSearch (first element in iteration order whose reference cube
+// contains geometry.local(x) up to 64 eps); on the structured grid that is, per direction, the
+// lowest element whose tolerant interval contains x — a closed form around floor((x - lower)/h).
+// One thread per point; shape functions are formed on the fly from the 1-d Lagrange values, the
+// sum runs over i ascending with phi_i = ((1 * l_{a0}(x0)) * l_{a1}(x1)) * l_{a2}(x2) like
+// LagrangeCubeLocalBasis::evaluateFunction.
+__device__ __forceinline__ int locateDirection(const DevGrid& g, int j, double x, double& local, double& jinv) {
+  const double tol = 64 * 2.220446049250313e-16;
+  int i0 = (int)floor((x - g.lower[j]) / g.h[j]);
+  const int first = g.off[j], lastEl = g.off[j] + g.N[j] - 1;
+  i0 = i0 < first ? first : (i0 > lastEl ? lastEl : i0);
+  for (int i = (i0 > first ? i0 - 1 : i0); i <= (i0 < lastEl ? i0 + 1 : i0); ++i) {
+    const double lo = gridCoordinate(g, j, i), up = gridCoordinate(g, j, i + 1);
+    const double l = __ddiv_rn(__dsub_rn(x, lo), __dsub_rn(up, lo));
+    if (l >= -tol && l <= 1 + tol) { local = l; jinv = __ddiv_rn(1.0, __dsub_rn(up, lo)); return i - first; }
+  }
+  return -1;
+}
+
+// l_i(x) and l_i'(x) on the nodes m/k, the reference's product formulas (k >= 2)
+__device__ __forceinline__ double lagrange1d(int k, int i, double x) {
+  double r = 1.0;
+  for (int j = 0; j <= k; ++j) if (j != i) r = __dmul_rn(r, __ddiv_rn(__dsub_rn(__dmul_rn((double)k, x), (double)j), (double)(i - j)));
+  return r;
+}
+__device__ __forceinline__ double dlagrange1d(int k, int i, double x) {
+  double result = 0.0;
+  for (int j = 0; j <= k; ++j) if (j != i) {
+    double prod = __ddiv_rn(__dmul_rn((double)k, 1.0), (double)(i - j));
+    for (int l = 0; l <= k; ++l) if (l != i && l != j) prod = __dmul_rn(prod, __ddiv_rn(__dsub_rn(__dmul_rn((double)k, x), (double)l), (double)(i - l)));
+    result = __dadd_rn(result, prod);
+  }
+  return result;
+}
+
+template <bool VAL, bool JAC>
+__global__ void __launch_bounds__(128)
+k_eval_global(const __grid_constant__ DevBasis B, int firstLeaf, int nLeaves, const double* __restrict__ coeff,
+              const double* __restrict__ x, u64 nPoints, double* __restrict__ values, double* __restrict__ jac,
+              int* __restrict__ elementOut) {
+  const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nPoints) return;
+  const DevGrid& g = B.grid;
+  int ec[3] = {0, 0, 0};
+  double xl[3] = {0, 0, 0}, jinv[3] = {1, 1, 1};
+  bool found = true;
+  for (int j = 0; j < g.dim; ++j) {
+    ec[j] = locateDirection(g, j, x[p * g.dim + j], xl[j], jinv[j]);
+    found = found && ec[j] >= 0;
+  }
+  if (elementOut) elementOut[p] = found ? (int)((u64)ec[0] + (u64)g.N[0] * ((u64)ec[1] + (u64)g.N[1] * (u64)ec[2])) : -1;
+  if (!found) {
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    for (int l = 0; l < nLeaves; ++l) {
+      if (VAL) values[p * (u64)nLeaves + l] = nanv;
+      if (JAC) for (int d = 0; d < g.dim; ++d) jac[(p * (u64)nLeaves + l) * g.dim + d] = nanv;
+    }
+    return;
+  }
+  double lv[3][kMaxContinuousOrder + 1], ld[3][kMaxContinuousOrder + 1];
+  int kPrev = -1;
+  for (int l = 0; l < nLeaves; ++l) {
+    const DevLeaf& leaf = B.leaves[firstLeaf + l];
+    const DevLayout& L = B.layouts[leaf.layout];
+    const int k = L.k;
+    if (k != kPrev) {
+      for (int j = 0; j < g.dim; ++j)
+        for (int a = 0; a <= k; ++a) {
+          if (k == 0) { lv[j][a] = 1.0; ld[j][a] = 0.0; }
+          else if (k == 1) { lv[j][a] = a ? xl[j] : __dsub_rn(1.0, xl[j]); ld[j][a] = a ? 1.0 : -1.0; }
+          else { lv[j][a] = lagrange1d(k, a, xl[j]); if (JAC) ld[j][a] = dlagrange1d(k, a, xl[j]); }
+        }
+      kPrev = k;
+    }
+    double v = 0.0, rj[3] = {0, 0, 0};
+    for (int i = 0; i < L.nloc; ++i) {
+      int a[3];
+      localAlpha(k, i, a);
+      const u64 jdx = layoutIndex(L, g, ec, a, i);
+      const double c = coeff[leaf.posA * jdx + leaf.posB];
+      if (VAL) {
+        double phi = 1.0;
+        for (int j = 0; j < g.dim; ++j) phi = __dmul_rn(phi, lv[j][a[j]]);
+        v = __dadd_rn(v, __dmul_rn(c, phi));
+      }
+      if (JAC)
+        for (int d = 0; d < g.dim; ++d) {
+          double dphi = k == 1 ? ld[d][a[d]] : 1.0;
+          if (k == 1) { for (int j = 0; j < g.dim; ++j) if (j != d) dphi = __dmul_rn(dphi, lv[j][a[j]]); }
+          else for (int j = 0; j < g.dim; ++j) dphi = __dmul_rn(dphi, j == d ? ld[j][a[j]] : lv[j][a[j]]);
+          rj[d] = __dadd_rn(rj[d], __dmul_rn(c, dphi));
+        }
+    }
+    if (VAL) values[p * (u64)nLeaves + l] = v;
+    if (JAC) for (int d = 0; d < g.dim; ++d) jac[(p * (u64)nLeaves + l) * g.dim + d] = __dmul_rn(rj[d], jinv[d]);
+  }
+}
+
+int evalGlobal(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* x, u64 nPoints,
+               double* values, double* jac, int* elementOut, cudaStream_t st) {
+  if (nPoints == 0) return DFX_OK;
+  const u64 blocks = (nPoints + 127) / 128;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "too many points for one launch");
+  if (values && jac) k_eval_global<true, true><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, x, nPoints, values, jac, elementOut);
+  else if (jac) k_eval_global<false, true><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, x, nPoints, values, jac, elementOut);
+  else k_eval_global<true, false><<<(unsigned)blocks, 128, 0, st>>>(b->dev, firstLeaf, nLeaves, coeff, x, nPoints, values, jac, elementOut);
+  return postLaunch("k_eval_global");
+}
+
+// ---------------------------------------------------------------------------
 // Halo: the lowest (side 0) / highest (side 1) lattice plane in the last direction.
 // Buffer order: leaves in tree order, per leaf the index-set components that lie in
 // the plane (shift bit of the last direction clear) in layout order.

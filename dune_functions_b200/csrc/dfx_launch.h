@@ -41,6 +41,8 @@ int interpolateRegistry(const dfx_basis* b, int firstLeaf, int nLeaves, const df
 int interpolationPoints(const dfx_basis* b, double* xyz, int* leafOut, cudaStream_t st);
 int interpolateFromValues(const dfx_basis* b, int firstLeaf, int nLeaves, const double* values, double* coeff,
                           const uint8_t* mask, cudaStream_t st);
+int evalGlobal(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* x, u64 nPoints,
+               double* values, double* jac, int* elementOut, cudaStream_t st);
 int scatterNodes(const dfx_basis* b, int layoutId, int firstLeaf, int nLeaves, int ncompVals, u64 e0, u64 e1,
                  const double* vals, double* coeff, const uint8_t* mask, cudaStream_t st);
 int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* shape,

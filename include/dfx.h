@@ -222,6 +222,19 @@ int dfx_evaluate(const dfx_basis* b, int32_t subtree_node, const double* coeff,
                  const double* xhat_host, int32_t n_q,
                  uint64_t elem_begin, uint64_t elem_end,
                  double* out_values, double* out_jacobians, void* stream);
+/* DiscreteGlobalBasisFunction::operator()(x) and its derivative for points in WORLD coordinates
+ * (discreteglobalbasisfunction.hh:402-410, :637-650).  The reference locates the element with a
+ * HierarchicSearch ("very slow" by its own comment); on the structured grid the element is a
+ * closed form: per direction the lowest element whose interval contains x up to 64 eps (the first
+ * match of the reference's search), then the local function is evaluated at geometry.local(x).
+ *   x[p*dim + j]                         n_points world coordinates (device)
+ *   out_values[p*n_comp + c]             (may be NULL)
+ *   out_jacobians[(p*n_comp + c)*dim+j]  (may be NULL)
+ *   out_element[p]                       element index in the local box, -1 if no element of the
+ *                                        local box contains the point (results NaN; the reference
+ *                                        throws GridError) — may be NULL                          */
+int dfx_evaluate_global(const dfx_basis* b, int32_t subtree_node, const double* coeff, const double* x,
+                        uint64_t n_points, double* out_values, double* out_jacobians, int32_t* out_element, void* stream);
 /* which kernel family dfx_evaluate picks for this configuration:
  * 0 generic, 1 sum-factorised register kernel, 2 sum-factorised shared-memory
  * (TMA bulk) kernel, 3 dense FP64 tensor-core (DMMA) kernel.                   */
@@ -255,6 +268,9 @@ int dfx_evaluate_host(const dfx_basis* b, int32_t subtree_node, const double* co
                       const double* xhat_host, int32_t n_q,
                       uint64_t elem_begin, uint64_t elem_end,
                       double* out_values_host, double* out_jacobians_host);
+int dfx_evaluate_global_host(const dfx_basis* b, int32_t subtree_node, const double* coeff_host, const double* x_host,
+                             uint64_t n_points, double* out_values_host, double* out_jacobians_host,
+                             int32_t* out_element_host);
 int dfx_indices_flat_host(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,
                           uint32_t* out_host);
 int dfx_indices_multi_host(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_end,

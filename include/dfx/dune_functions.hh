@@ -596,6 +596,26 @@ class DiscreteGlobalBasisFunction {
     Impl::check(dfx_basis_node_info(basis.handle(), basis.rootNode(), &off, &size, &firstLeaf, &ncomp_));
   }
 
+  // operator()(x) for WORLD coordinates (discreteglobalbasisfunction.hh:402-410): the element is
+  // located in closed form on the device; a point outside the grid throws like the reference's
+  // HierarchicSearch.  One device call per point — use evaluateGlobal for many points.
+  std::vector<double> operator()(const Domain& x) const {
+    std::vector<double> v;
+    evaluateGlobal(std::vector<Domain>{x}, v);
+    return v;
+  }
+  void evaluateGlobal(const std::vector<Domain>& x, std::vector<double>& values, std::vector<double>* jac = nullptr) const {
+    const std::size_t n = x.size();
+    std::vector<double> pts(n * dim);
+    for (std::size_t p = 0; p < n; ++p) for (int j = 0; j < dim; ++j) pts[p * dim + j] = x[p][j];
+    values.resize(n * ncomp_);
+    if (jac) jac->resize(n * ncomp_ * dim);
+    std::vector<int32_t> el(n);
+    Impl::check(dfx_evaluate_global_host(basis_.handle(), basis_.rootNode(), reinterpret_cast<const double*>(coeff_->data()),
+                                         pts.data(), n, values.data(), jac ? jac->data() : nullptr, el.data()));
+    for (std::size_t p = 0; p < n; ++p) if (el[p] < 0) throw Exception("GridError: coordinates are outside of the grid");
+  }
+
   // Batched form: values at the reference-element points `xhat` on ALL elements,
   // out[e][q][comp]; jac[e][q][comp][dim] if requested.  This is the fast way to use the path.
   void evaluateAll(const std::vector<Domain>& xhat, std::vector<double>& values, std::vector<double>* jac = nullptr) const {

@@ -1179,6 +1179,71 @@ void orc_csr_mv(uint64_t n, const uint64_t* row_ptr, const uint32_t* col_idx, co
   }
 }
 
+// DiscreteGlobalBasisFunction::operator()(x) with x in world coordinates
+// (discreteglobalbasisfunction.hh:402-410): HierarchicSearch::findEntity, local function bound to
+// that element, evaluation at geometry.local(x); derivative likewise (:637-650).
+// [EXT dune-grid HierarchicSearch on a one-level grid]: the first element in iteration order with
+// referenceElement.checkInside(geometry.local(x)); [EXT dune-geometry] checkInside of the cube:
+// every coordinate in [-tol, 1 + tol], tol = 64 eps.  [EXT AxisAlignedCubeGeometry::local]
+// (x - lower) / (upper - lower).  A point no element contains gets element -1 and NaN results
+// (the reference throws GridError).
+void orc_evaluate_global(void* h, int32_t subtreeNode, const double* coeff, const double* x, uint64_t nPoints,
+                         double* values, double* jacobians, int64_t* elementOut) {
+  auto* b = (orc::Basis*)h;
+  if (b->maxDigits > 1) b->buildPositions();
+  const orc::Grid& g = b->grid;
+  const int dim = g.dim;
+  const auto& nd = b->nodes[subtreeNode];
+  const int firstLeaf = nd[2], nLeaves = nd[3];
+  const double tol = 64 * 2.220446049250313e-16;
+  std::vector<orc::MultiIndex> idx;
+  std::vector<double> localDoFs(b->localSize()), shapeValues, shapeJacobians;
+  for (uint64_t p = 0; p < nPoints; ++p) {
+    const double* xp = x + p * dim;
+    int64_t found = -1;
+    double local[3] = {0, 0, 0}, jacInv[3] = {1, 1, 1};
+    for (size_t e = 0; e < g.numElements() && found < 0; ++e) {       // findEntity: linear search over level 0
+      int ec[3]; g.elementCoords(e, ec);
+      bool inside = true;
+      double l[3] = {0, 0, 0}, ji[3] = {1, 1, 1};
+      for (int j = 0; j < dim; ++j) {
+        const double lo = g.coordinate(j, g.off[j] + ec[j]), up = g.coordinate(j, g.off[j] + ec[j] + 1);
+        l[j] = (xp[j] - lo) / (up - lo);
+        ji[j] = 1.0 / (up - lo);
+        inside = inside && l[j] >= -tol && l[j] <= 1 + tol;
+      }
+      if (inside) { found = (int64_t)e; for (int j = 0; j < 3; ++j) { local[j] = l[j]; jacInv[j] = ji[j]; } }
+    }
+    if (elementOut) elementOut[p] = found;
+    if (found < 0) {
+      if (values) for (int l = 0; l < nLeaves; ++l) values[p * nLeaves + l] = std::nan("");
+      if (jacobians) for (int q = 0; q < nLeaves * dim; ++q) jacobians[p * nLeaves * dim + q] = std::nan("");
+      continue;
+    }
+    b->bind((size_t)found, idx);
+    for (int i = 0; i < nd[1]; ++i) localDoFs[nd[0] + i] = coeff[b->flat(idx[nd[0] + i])];
+    for (int l = 0; l < nLeaves; ++l) {
+      const orc::LeafNode& leaf = b->leaves[firstLeaf + l];
+      const orc::LagrangeCubeFE& fe = *leaf.fe;
+      if (values) {
+        shapeValues.resize(fe.size());
+        fe.evaluateFunction(local, shapeValues.data());
+        double v = 0;
+        for (int i = 0; i < fe.size(); ++i) v += localDoFs[leaf.offset + i] * shapeValues[i];
+        values[p * nLeaves + l] = v;
+      }
+      if (jacobians) {
+        shapeJacobians.resize((size_t)fe.size() * dim);
+        fe.evaluateJacobian(local, shapeJacobians.data());
+        double refJac[3] = {0, 0, 0};
+        for (int i = 0; i < fe.size(); ++i)
+          for (int j = 0; j < dim; ++j) refJac[j] += localDoFs[leaf.offset + i] * shapeJacobians[(size_t)i * dim + j];
+        for (int j = 0; j < dim; ++j) jacobians[(p * nLeaves + l) * dim + j] = refJac[j] * jacInv[j];
+      }
+    }
+  }
+}
+
 int32_t orc_max_threads(void) {
   unsigned n = std::thread::hardware_concurrency();
   return n ? (int32_t)n : 1;

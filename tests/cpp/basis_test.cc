@@ -143,6 +143,16 @@ int main() {
       double diff = 0;
       for (std::size_t i = 0; i < x.size(); ++i) diff = std::max(diff, std::abs(x[i] - y[i]));
       CHECK(y.size() == x.size() && diff < 1e-10, "interpolation of a DiscreteGlobalBasisFunction reproduces its coefficients");
+      // "By wrapping into a lambda, we force interpolate to use the global evaluation of f" (:58-59)
+      auto fGlobal = [&](const FieldVector<double, 2>& p) { return f(p); };
+      std::vector<double> yg;
+      interpolate(basis, yg, fGlobal);
+      diff = 0;
+      for (std::size_t i = 0; i < x.size(); ++i) diff = std::max(diff, std::abs(x[i] - yg[i]));
+      CHECK(yg.size() == x.size() && diff < 1e-10, "interpolation through the global evaluation reproduces the coefficients");
+      bool outside = false;
+      try { f(FieldVector<double, 2>{1.5, 0.5}); } catch (const Exception&) { outside = true; }
+      CHECK(outside, "evaluation outside of the grid throws");
       // Q2 function into the Q1 basis of the same grid: the vertex values
       LagrangeBasis<Grid2::LeafGridView, 2> q2(gv2);
       LagrangeBasis<Grid2::LeafGridView, 1> q1(gv2);

@@ -44,6 +44,7 @@ def lib():
         L.orc_boundary_dofs.argtypes = [vp, i32, vp]
         L.orc_interpolate_dgbf.restype = i32
         L.orc_interpolate_dgbf.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+        L.orc_evaluate_global.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
         L.orc_occupation_pattern.restype = u64
         L.orc_occupation_pattern.argtypes = [vp, vp, vp]
         L.orc_assemble_laplace.restype = i32
@@ -160,6 +161,20 @@ class OracleBasis:
         if rc:
             raise ValueError(f"oracle: grid-function interpolation failed ({rc})")
         return coeff
+
+    def evaluateGlobal(self, coeff, x, node=0, jacobians=False):
+        """DiscreteGlobalBasisFunction::operator()(x) at world coordinates x [n, dim]:
+        (values [n, ncomp], jacobians [n, ncomp, dim] or None, element [n])"""
+        xs = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, self.grid.dim))
+        n = xs.shape[0]
+        nc = self.nodeInfo(node)["n_leaves"]
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        v = np.zeros((n, nc))
+        j = np.zeros((n, nc, self.grid.dim)) if jacobians else None
+        el = np.zeros(n, dtype=np.int64)
+        lib().orc_evaluate_global(self._h, node, coeff.ctypes.data, xs.ctypes.data, n, v.ctypes.data,
+                                  None if j is None else j.ctypes.data, el.ctypes.data)
+        return v, j, el
 
     # ---- examples/poisson-pq2.cc restated ----
     def occupationPattern(self):

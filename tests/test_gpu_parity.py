@@ -368,6 +368,74 @@ def test_interpolate_grid_function_errors():
         dfx.interpolate(dfx.makeBasis(GRIDS["3d_3x4x5"], power(lagrange(1), 2, BI())), torch.zeros(2 * 4 * 5 * 6, dtype=torch.float64, device="cuda"), fv)
 
 
+# ---- evaluation at world coordinates ----------------------------------------------------------------
+@pytest.mark.parametrize("grid,tree", list(all_cases()))
+def test_evaluate_at_world_coordinates(grid, tree):
+    """DiscreteGlobalBasisFunction::operator()(x) (discreteglobalbasisfunction.hh:402-410): random points,
+    points on element faces / vertices / the domain boundary (first element of the search wins, which
+    matters for DG), points outside (element -1, NaN)"""
+    import torch
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    d = grid.dim
+    lo = np.array(grid.lower if grid.lower is not None else [0.0] * d)
+    up = np.array(grid.upper if grid.upper is not None else [1.0] * d)
+    rng = np.random.default_rng(17)
+    pts = [lo + (up - lo) * rng.uniform(0, 1, (40, d))]
+    # lattice points of the grid (faces, edges, vertices incl. the boundary) and just beside them
+    nodes = np.stack(np.meshgrid(*[lo[j] + (up[j] - lo[j]) * np.arange(grid.n[j] + 1) / grid.n[j] for j in range(d)],
+                                 indexing="ij"), -1).reshape(-1, d)
+    pts += [nodes, nodes + 1e-15, nodes - 1e-15]
+    pts.append(np.array([up + 0.25 * (up - lo), lo - 1e-3 * (up - lo)]))        # outside
+    x = np.concatenate(pts)
+    c = random_coeff(b.dimension())
+    f = dfx.makeDiscreteGlobalBasisFunction(b, torch.from_numpy(c).cuda())
+    v, j, el = f.evaluateGlobal(x, jacobians=True, return_elements=True)
+    vr, jr, er = o.evaluateGlobal(c, x, jacobians=True)
+    assert np.array_equal(el.cpu().numpy().astype(np.int64), er)
+    assert (er[-2:] == -1).all() and (er[:40] >= 0).all()
+    inside = er >= 0
+    assert np.isnan(v.cpu().numpy()[~inside]).all() and np.isnan(j.cpu().numpy()[~inside]).all()
+    assert rel(v.cpu().numpy()[inside], vr[inside]) <= TOL
+    assert rel(j.cpu().numpy()[inside], jr[inside]) <= 1e-11      # sums of k^2-sized terms for the higher orders
+
+
+def test_interpolation_consistency_through_world_coordinates():
+    """second variant of checkInterpolationConsistency (discreteglobalbasisfunctiontest.cc:58-76): a
+    lambda forces interpolate to use the GLOBAL evaluation of the discrete function; here the node
+    positions come from dfx_interpolation_points and the values from dfx_evaluate_global"""
+    import torch
+    for gname, tname in (("2d_10x10", "lagrange1"), ("2d_3x2", "power2_q1_FI"), ("3d_3x4x5", "lagrange2"),
+                         ("3d_2x1x3", "taylorHood"), ("3d_3x4x5", "lagrange3")):
+        grid = GRIDS[gname]
+        tree = trees(grid.dim)[tname]
+        b = dfx.makeBasis(grid, tree)
+        x = torch.from_numpy(random_coeff(b.dimension())).cuda()
+        f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+        xyz, leaf = dfx.interpolationPoints(b)
+        vals = f.evaluateGlobal(xyz)                              # [n, n_leaves]
+        nodal = vals.gather(1, leaf.long().unsqueeze(1)).squeeze(1).contiguous()
+        y = b.newVector(float("nan"))
+        dfx.interpolateFromValues(b, y, nodal)
+        assert float((y - x).abs().max()) <= 1e-10, (gname, tname)
+
+
+def test_evaluate_at_world_coordinates_on_a_slab():
+    import torch
+    whole = YaspGrid([3, 2, 6], upper=[1.0, 0.5, 2.0])
+    mine = whole.slab(1, 3)
+    b = dfx.makeBasis(mine, lagrange(2))
+    o = orc.OracleBasis(mine, lagrange(2))
+    c = random_coeff(b.dimension())
+    x = np.array([[0.3, 0.2, 0.9], [0.3, 0.2, 0.1], [0.5, 0.25, 2.0 / 3], [0.5, 0.25, 4.0 / 3], [0.1, 0.1, 1.9]])
+    f = dfx.makeDiscreteGlobalBasisFunction(b, torch.from_numpy(c).cuda())
+    v, el = f.evaluateGlobal(x, return_elements=True)
+    vr, _, er = o.evaluateGlobal(c, x)
+    assert np.array_equal(el.cpu().numpy().astype(np.int64), er) and er[1] == -1 and er[4] == -1 and er[0] >= 0
+    ok = er >= 0
+    assert rel(v.cpu().numpy()[ok], vr[ok]) <= TOL
+
+
 def test_peer_memory_halo_link_between_two_slabs():
     """dfx_halo_link_* / dfx_halo_push / dfx_halo_pull with both slabs on one GPU (raw-pointer
     attachment instead of CUDA IPC): the upper slab's bottom plane lands in the lower slab's top
