@@ -235,6 +235,7 @@ static int checkRange(const dfx_basis* b, uint64_t e0, uint64_t e1) {
 }
 
 int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, int32_t stride, void* stream) {
+  DFX_RANGE("dfx_indices_multi");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
@@ -243,6 +244,7 @@ int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* ou
   return indicesMulti32(b, e0, e1, out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, int32_t stride, void* stream) {
+  DFX_RANGE("dfx_indices_multi_u64");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
@@ -250,6 +252,7 @@ int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t
   return indicesMulti64(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, void* stream) {
+  DFX_RANGE("dfx_indices_flat");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_flat_u64");
@@ -257,6 +260,7 @@ int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out
   return indicesFlat32(b, e0, e1, out, (cudaStream_t)stream);
 }
 int dfx_indices_flat_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, void* stream) {
+  DFX_RANGE("dfx_indices_flat_u64");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
@@ -276,6 +280,7 @@ static int checkFunction(const dfx_function* f, int nLeaves) {
 
 int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
                     void* stream) {
+  DFX_RANGE("dfx_interpolate");
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
   if ((rc = subtree(b, node, fl, nl))) return rc;
@@ -296,6 +301,7 @@ int dfx_interpolation_points(const dfx_basis* b, double* out_xyz, int32_t* out_l
 
 int dfx_interpolate_from_values(const dfx_basis* b, int32_t node, const double* values, double* coeff,
                                 const uint8_t* mask, void* stream) {
+  DFX_RANGE("dfx_interpolate_from_values");
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
   if ((rc = subtree(b, node, fl, nl))) return rc;
@@ -319,6 +325,7 @@ static bool sameGrid(const dfx_basis* a, const dfx_basis* b) {
 int dfx_interpolate_dgbf(const dfx_basis* target, int32_t target_node, const dfx_basis* source, int32_t source_node,
                          const double* source_coeff, double* target_coeff, const uint8_t* mask, double* scratch,
                          uint64_t scratch_doubles, void* stream) {
+  DFX_RANGE("dfx_interpolate_dgbf");
   int rc = ensureDevice(target); if (rc) return rc;
   if (!source || !source_coeff || !target_coeff) return fail(DFX_ERR_INVALID, "null argument");
   if (source->device != target->device) return fail(DFX_ERR_INVALID, "source and target basis live on different devices");
@@ -423,6 +430,7 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host,
 
 int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const double* xhat_host, int32_t n_q,
                  uint64_t e0, uint64_t e1, double* out_values, double* out_jac, void* stream) {
+  DFX_RANGE("dfx_evaluate");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
@@ -445,6 +453,7 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
 
 int dfx_evaluate_global(const dfx_basis* b, int32_t node, const double* coeff, const double* x, uint64_t n_points,
                         double* out_values, double* out_jac, int32_t* out_element, void* stream) {
+  DFX_RANGE("dfx_evaluate_global");
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
   if ((rc = subtree(b, node, fl, nl))) return rc;
@@ -457,6 +466,7 @@ int dfx_evaluate_global(const dfx_basis* b, int32_t node, const double* coeff, c
 // ---- host-buffer entry points -------------------------------------------------------
 int dfx_interpolate_host(const dfx_basis* cb, int32_t node, const dfx_function* f, double* coeff_host,
                          const uint8_t* mask_host) {
+  DFX_RANGE("dfx_interpolate_host");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   if (!coeff_host) return fail(DFX_ERR_INVALID, "null coefficient vector");
@@ -536,6 +546,7 @@ static Intervals subtract(const Intervals& a, const Intervals& b) {
 // busy at once and the device never holds more than one band of results.
 int dfx_evaluate_host(const dfx_basis* cb, int32_t node, const double* coeff_host, const double* xhat_host,
                       int32_t n_q, uint64_t e0, uint64_t e1, double* out_values_host, double* out_jac_host) {
+  DFX_RANGE("dfx_evaluate_host");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
@@ -734,6 +745,7 @@ int dfx_subentity_dofs(const dfx_basis* b, int32_t node, int32_t sub_entity_inde
 }
 
 int dfx_boundary_dofs(const dfx_basis* b, int32_t node, uint8_t* mask, void* stream) {
+  DFX_RANGE("dfx_boundary_dofs");
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
   if ((rc = subtree(b, node, fl, nl))) return rc;
@@ -773,6 +785,7 @@ static int meanRowLength(const dfx_basis* b) {
 }
 
 int dfx_matrix_pattern(const dfx_basis* cb, uint64_t* row_ptr, uint32_t* col_idx, uint64_t* nnz_host, void* stream) {
+  DFX_RANGE("dfx_matrix_pattern");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr) return fail(DFX_ERR_INVALID, "null row_ptr");
@@ -781,6 +794,7 @@ int dfx_matrix_pattern(const dfx_basis* cb, uint64_t* row_ptr, uint32_t* col_idx
 
 int dfx_assemble_laplace(const dfx_basis* cb, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
                          const dfx_function* f, double* rhs, void* stream) {
+  DFX_RANGE("dfx_assemble_laplace");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx) return fail(DFX_ERR_INVALID, "null pattern");
@@ -790,6 +804,7 @@ int dfx_assemble_laplace(const dfx_basis* cb, const uint64_t* row_ptr, const uin
 
 int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, const double* values,
                const double* x, double* y, int32_t subtract, void* stream) {
+  DFX_RANGE("dfx_csr_mv");
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx || !values || !x || !y) return fail(DFX_ERR_INVALID, "null argument");
   return csrMv(b->dimension, (const u64*)row_ptr, col_idx, values, x, y, subtract != 0, (cudaStream_t)stream, meanRowLength(b));
@@ -797,6 +812,7 @@ int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_
 
 int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
                         const uint8_t* dirichlet, const double* x, double* rhs, void* stream) {
+  DFX_RANGE("dfx_apply_dirichlet");
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx || !values || !dirichlet || !x || !rhs) return fail(DFX_ERR_INVALID, "null argument");
   return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream, meanRowLength(b));
@@ -804,6 +820,7 @@ int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint3
 
 int dfx_apply_laplace(const dfx_basis* cb, const double* x, double* y, const uint8_t* dirichlet, double* scratch,
                       void* stream) {
+  DFX_RANGE("dfx_apply_laplace");
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   if (!x || !y || !scratch) return fail(DFX_ERR_INVALID, "null argument");
@@ -885,10 +902,12 @@ int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint6
 uint64_t dfx_halo_size(const dfx_basis* b) { return b ? haloCount(b) : 0; }
 
 int dfx_halo_pack(const dfx_basis* b, int32_t side, const double* coeff, double* buf, void* stream) {
+  DFX_RANGE("dfx_halo_pack");
   int rc = ensureDevice(b); if (rc) return rc;
   return haloCopy(b, side, true, const_cast<double*>(coeff), buf, haloCount(b), (cudaStream_t)stream);
 }
 int dfx_halo_unpack(const dfx_basis* b, int32_t side, const double* buf, double* coeff, void* stream) {
+  DFX_RANGE("dfx_halo_unpack");
   int rc = ensureDevice(b); if (rc) return rc;
   return haloCopy(b, side, false, coeff, const_cast<double*>(buf), haloCount(b), (cudaStream_t)stream);
 }
@@ -994,6 +1013,7 @@ uint64_t dfx_halo_link_error(dfx_halo_link* l) {
 }
 
 int dfx_halo_push(const dfx_basis* b, dfx_halo_link* l, const double* coeff, uint64_t step, void* stream) {
+  DFX_RANGE("dfx_halo_push");
   int rc = ensureDevice(b); if (rc) return rc;
   if (!l || !coeff || step == 0) return fail(DFX_ERR_INVALID, "bad argument");
   if (l->n != haloCount(b)) return fail(DFX_ERR_INVALID, "halo link belongs to another basis");
@@ -1001,6 +1021,7 @@ int dfx_halo_push(const dfx_basis* b, dfx_halo_link* l, const double* coeff, uin
 }
 
 int dfx_halo_pull(const dfx_basis* b, dfx_halo_link* l, double* coeff, uint64_t step, void* stream) {
+  DFX_RANGE("dfx_halo_pull");
   int rc = ensureDevice(b); if (rc) return rc;
   if (!l || !coeff || step == 0) return fail(DFX_ERR_INVALID, "bad argument");
   if (l->n != haloCount(b)) return fail(DFX_ERR_INVALID, "halo link belongs to another basis");

@@ -1,6 +1,7 @@
 // dfx_launch.h — host-side launcher prototypes (kernels are defined in the .cu files).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 
@@ -9,6 +10,16 @@
 namespace dfx {
 
 extern std::atomic<unsigned long long> g_launchCount;
+
+// NVTX range around an ABI entry point (header-only NVTX 3: a no-op unless a profiler is attached;
+// `ncu --nvtx --nvtx-include "dfx_evaluate/"` then selects the kernels of one call)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define DFX_RANGE(name) ::dfx::NvtxRange dfx_nvtx_range_(name)
 const char* lastErrorCStr();
 
 // offsets (in doubles) of each layout's shape / shape-jacobian table
