@@ -144,3 +144,54 @@ def test_c5_q2_512_single_gpu():
     assert float((last - z[None, :]).abs().max()) < 1e-14
     del v
     _free()
+
+
+def test_c2_q2_256_boundary_grid_function_and_matrix_free_operator():
+    """the rows next to the path at the size of configs[1]: boundary-DOF
+    count = lattice surface; interpolating the discrete function back returns its coefficients;
+    the matrix-free Laplace operator annihilates constants, gives zero at interior nodes for a
+    linear function and the energy |Omega| = 1 for u = x_0."""
+    import torch
+    basis = dfx.makeBasis(dfx.YaspGrid([256, 256, 256]), dfx.lagrange(2))
+    n = basis.dimension()
+    mask = dfx.boundaryDOFs(basis)
+    assert int(mask.sum()) == 513 ** 3 - 511 ** 3
+    x = basis.newVector(0.0)
+    dfx.interpolate(basis, x, dfx.gaussian(1.0))
+    y = basis.newVector(float("nan"))
+    dfx.interpolate(basis, y, dfx.makeDiscreteGlobalBasisFunction(basis, x))
+    assert float((y - x).abs().max()) < 1e-13
+    del y
+    _free()
+    op = dfx.LaplaceOperator(basis)
+    ones = basis.newVector(1.0)
+    assert float(op.mv(ones).abs().max()) < 1e-12
+    dfx.interpolate(basis, x, dfx.coord(0))
+    ax = op.mv(x)
+    assert abs(float((ax * x).sum()) - 1.0) < 1e-9
+    assert float(ax[~mask.bool()].abs().max()) < 1e-12
+    # with the Dirichlet rows: identity on the boundary, untouched interior rows
+    opd = dfx.LaplaceOperator(basis, mask)
+    z = torch.rand(n, dtype=torch.float64, device="cuda")
+    az = opd.mv(z)
+    assert bool((az[mask.bool()] == z[mask.bool()]).all())
+    del op, opd, ax, az, z, ones
+    _free()
+
+
+def test_c2_world_coordinate_evaluation_of_many_points():
+    """10^7 random world points on the Q2 256^3 function: the interpolant of a quadratic is exact"""
+    import torch
+    basis = dfx.makeBasis(dfx.YaspGrid([256, 256, 256]), dfx.lagrange(2))
+    x = basis.newVector(0.0)
+    dfx.interpolate(basis, x, dfx.quadratic(0.5, [1.0, -2.0, 3.0], [1.0, 0.5, -1.0, 2.0, 0.25, -0.5]))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    p = torch.rand((10_000_000, 3), dtype=torch.float64, device="cuda", generator=g)
+    f = dfx.makeDiscreteGlobalBasisFunction(basis, x)
+    v, el = f.evaluateGlobal(p, return_elements=True)
+    assert int(el.min()) >= 0 and int(el.max()) < basis.numElements()
+    exact = (0.5 + p[:, 0] - 2 * p[:, 1] + 3 * p[:, 2] + p[:, 0] ** 2 + 0.5 * p[:, 0] * p[:, 1] - p[:, 0] * p[:, 2]
+             + 2 * p[:, 1] ** 2 + 0.25 * p[:, 1] * p[:, 2] - 0.5 * p[:, 2] ** 2)
+    assert float((v[:, 0] - exact).abs().max()) < 1e-12
+    del v, el, p
+    _free()
