@@ -12,5 +12,5 @@ from .basis import (  # noqa: F401
     gaussian, identity, constant, coord, quadratic, sinprod, gaussian_vec, make_function,
     tensor_gauss, gauss_points_1d, tree_array,
 )
-from .operators import CSRMatrix, LaplaceOperator, getOccupationPattern, assembleLaplaceMatrix, applyDirichlet  # noqa: F401
+from .operators import CSRMatrix, LaplaceOperator, getOccupationPattern, assembleLaplaceMatrix, assembleStokesMatrix, applyDirichlet  # noqa: F401
 from ._capi import DfxError, RangeError, NotImplementedDfx, CudaError  # noqa: F401

@@ -818,6 +818,14 @@ int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint3
   return dirichletRows(b->dimension, (const u64*)row_ptr, col_idx, values, dirichlet, x, rhs, (cudaStream_t)stream, meanRowLength(b));
 }
 
+int dfx_assemble_stokes(const dfx_basis* cb, const uint64_t* row_ptr, const uint32_t* col_idx, double* values, void* stream) {
+  DFX_RANGE("dfx_assemble_stokes");
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr || !col_idx || !values) return fail(DFX_ERR_INVALID, "null argument");
+  return assembleStokes(b, (const u64*)row_ptr, col_idx, values, (cudaStream_t)stream);
+}
+
 int dfx_apply_laplace(const dfx_basis* cb, const double* x, double* y, const uint8_t* dirichlet, double* scratch,
                       void* stream) {
   DFX_RANGE("dfx_apply_laplace");

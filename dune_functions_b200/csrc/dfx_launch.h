@@ -68,6 +68,7 @@ int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, 
 int matrixPattern(dfx_basis* b, u64* rowPtr, uint32_t* col, u64* nnzHost, cudaStream_t st);
 int assembleLaplace(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double* values, const dfx_function* f,
                     double* rhs, cudaStream_t st);
+int assembleStokes(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double* values, cudaStream_t st);
 int applyLaplace(dfx_basis* b, const double* x, double* y, const uint8_t* dirichlet, double* local, cudaStream_t st);
 int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, const double* x, double* y, bool subtract,
           cudaStream_t st, int meanRow);

@@ -315,6 +315,80 @@ k_laplace_rows(const DevBasis* __restrict__ Bp, const __grid_constant__ LaplaceA
   for (int v = lane; v < rowLen; v += 32) values[p0 + v] = a[v];
 }
 
+// Stokes rows for a Taylor-Hood tree composite(power<dim>(Q2), Q1) (examples/stokes-taylorhood.cc
+// :49-160, :252-297).  Reference-cube integrals at the example's quadrature order:
+//   K[d][i][j] = sum_q w_q d_d phi_i d_d phi_j   (Q2 x Q2),   G[d][i][j] = sum_q w_q d_d phi_i psi_j   (Q2 x Q1)
+// so that for an axis-aligned element   A_{v_k v_k} = sum_d |det J| (J^-1_dd)^2 K[d],
+// A_{v_k p} = A_{p v_k}^T = -|det J| J^-1_kk G[k],   everything else 0.  One warp per matrix row,
+// elements in ascending order, columns located in the sorted row by binary search.
+struct StokesArgs { int dim, nv, np; };
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_stokes_rows(const DevBasis* __restrict__ Bp, const __grid_constant__ StokesArgs A, int rowLeaf,
+              const double* __restrict__ K, const double* __restrict__ G, const u64* __restrict__ rowPtr,
+              const uint32_t* __restrict__ col, double* __restrict__ values) {
+  __shared__ double acc[kRowWarps][kMaxLaplaceRow];
+  const DevBasis& B = *Bp;
+  const DevGrid& g = B.grid;
+  const DevLeaf& rleaf = B.leaves[rowLeaf];
+  const DevLayout& L = B.layouts[rleaf.layout];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u64 t = (u64)blockIdx.x * kRowWarps + warp;
+  if (t >= L.dimension) return;
+  const RowNode nd = locateNode(L, g, t);
+  int lo[3], hi[3];
+  elementBox(g, nd, lo, hi);
+  const u64 row = rleaf.posA * t + rleaf.posB;
+  const u64 p0 = rowPtr[row], p1 = rowPtr[row + 1];
+  const int rowLen = (int)(p1 - p0);
+  double* a = acc[warp];
+  for (int v = lane; v < rowLen; v += 32) a[v] = 0.0;
+  __syncwarp();
+  const int dim = A.dim, nv = A.nv, np = A.np, k = L.k;
+  const bool rowIsPressure = rowLeaf == dim;
+  const DevLayout& LV = B.layouts[B.leaves[0].layout];
+  const DevLayout& LP = B.layouts[B.leaves[dim].layout];
+  for (int e2 = lo[2]; e2 <= hi[2]; ++e2)
+    for (int e1 = lo[1]; e1 <= hi[1]; ++e1)
+      for (int e0 = lo[0]; e0 <= hi[0]; ++e0) {
+        const int e[3] = {e0, e1, e2};
+        int al[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) al[j] = ((nd.s >> j) & 1) ? nd.r[j] : (j < g.dim && e[j] < nd.c[j] ? k : 0);
+        const int iLoc = al[0] + (k + 1) * (al[1] + (k + 1) * al[2]);
+        double detJ = 1.0, ji[3] = {1, 1, 1};
+        for (int j = 0; j < dim; ++j) {
+          const double l0 = gridCoordinate(g, j, g.off[j] + e[j]), u0 = gridCoordinate(g, j, g.off[j] + e[j] + 1);
+          detJ *= u0 - l0; ji[j] = 1.0 / (u0 - l0);
+        }
+        // local columns: [v_0 (nv) | ... | v_{dim-1} (nv) | p (np)]
+        const int nloc = dim * nv + np;
+        for (int jl = lane; jl < nloc; jl += 32) {
+          const int cl = jl < dim * nv ? jl / nv : dim;              // column leaf
+          const int jc = jl - (cl < dim ? cl * nv : dim * nv);      // local index inside that leaf
+          double s = 0.0;
+          bool coupled = true;
+          if (!rowIsPressure && cl < dim) {
+            if (cl != rowLeaf) coupled = false;
+            else for (int d = 0; d < dim; ++d) s += detJ * ji[d] * ji[d] * K[((size_t)d * nv + iLoc) * nv + jc];
+          } else if (!rowIsPressure) {
+            s = -detJ * ji[rowLeaf] * G[((size_t)rowLeaf * nv + iLoc) * np + jc];
+          } else if (cl < dim) {
+            s = -detJ * ji[cl] * G[((size_t)cl * nv + jc) * np + iLoc];
+          } else coupled = false;
+          if (!coupled) continue;                                    // structural zero: stays 0
+          const DevLeaf& cleaf = B.leaves[cl];
+          const DevLayout& LC = cl < dim ? LV : LP;
+          int aj[3];
+          localAlpha(LC.k, jc, aj);
+          const uint32_t c = (uint32_t)(cleaf.posA * layoutIndex(LC, g, e, aj, jc) + cleaf.posB);
+          a[findColumn(col, p0, p1, c) - p0] += s;
+        }
+        __syncwarp();
+      }
+  for (int v = lane; v < rowLen; v += 32) values[p0 + v] = a[v];
+}
+
 // f at the quadrature points: pts[e][q] = f(x_q(e)) * w_q * |det J(e)|
 template <class F>
 __global__ void __launch_bounds__(256)
@@ -840,6 +914,56 @@ int applyLaplace(dfx_basis* b, const double* x, double* y, const uint8_t* dirich
     if (rc) return rc;
   }
   return DFX_OK;
+}
+
+int assembleStokes(dfx_basis* b, const u64* rowPtr, const uint32_t* col, double* values, cudaStream_t st) {
+  const DevBasis& D = b->dev;
+  const int dim = D.grid.dim;
+  bool th = D.nLeaves == dim + 1 && dim >= 2;
+  for (int l = 0; th && l < dim; ++l) {
+    const DevLayout& L = D.layouts[D.leaves[l].layout];
+    th = L.kind == DFX_NODE_LAGRANGE && L.k == 2 && D.leaves[l].layout == D.leaves[0].layout;
+  }
+  if (th) { const DevLayout& L = D.layouts[D.leaves[dim].layout]; th = L.kind == DFX_NODE_LAGRANGE && L.k == 1; }
+  if (!th) return fail(DFX_ERR_NOT_IMPLEMENTED, "the Stokes assembler needs a Taylor-Hood tree composite(power<dim>(lagrange<2>), lagrange<1>)");
+  const DevLayout& LV = D.layouts[D.leaves[0].layout];
+  const DevLayout& LP = D.layouts[D.leaves[dim].layout];
+  const int nv = LV.nloc, np = LP.nloc;
+  {
+    u64 longest = 0, v = 1, p = 1;
+    for (int j = 0; j < dim; ++j) { v *= 5; p *= 3; }
+    longest = (u64)dim * v + p;
+    if (longest > (u64)kMaxLaplaceRow) return fail(DFX_ERR_NOT_IMPLEMENTED, "matrix rows longer than the staging buffer");
+  }
+  std::vector<double> pos, wt, valV, gradV, valP, gradP;
+  tensorRule(dim, 2 * (dim * 2 - 1), pos, wt);
+  std::vector<double> K((size_t)dim * nv * nv, 0.0), G((size_t)dim * nv * np, 0.0);
+  for (size_t q = 0; q < wt.size(); ++q) {
+    shapeAt(dim, 2, &pos[q * dim], valV, gradV);
+    shapeAt(dim, 1, &pos[q * dim], valP, gradP);
+    for (int d = 0; d < dim; ++d)
+      for (int i = 0; i < nv; ++i) {
+        const double gi = gradV[(size_t)i * dim + d] * wt[q];
+        for (int j = 0; j < nv; ++j) K[((size_t)d * nv + i) * nv + j] += gi * gradV[(size_t)j * dim + d];
+        for (int j = 0; j < np; ++j) G[((size_t)d * nv + i) * np + j] += gi * valP[j];
+      }
+  }
+  double* dTab = nullptr;
+  DFX_CUDA(cudaMallocAsync(&dTab, (K.size() + G.size()) * sizeof(double), st));
+  DFX_CUDA(cudaMemcpyAsync(dTab, K.data(), K.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  DFX_CUDA(cudaMemcpyAsync(dTab + K.size(), G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  StokesArgs A; A.dim = dim; A.nv = nv; A.np = np;
+  int rc = DFX_OK;
+  for (int l = 0; l <= dim && !rc; ++l) {
+    const u64 rows = D.layouts[D.leaves[l].layout].dimension;
+    const u64 blocks = (rows + kRowWarps - 1) / kRowWarps;
+    if (blocks > 0x7fffffffull) { rc = fail(DFX_ERR_RANGE, "basis too large for one launch"); break; }
+    k_stokes_rows<<<(unsigned)blocks, kRowWarps * 32, 0, st>>>((const DevBasis*)b->dDev, A, l, dTab, dTab + K.size(), rowPtr, col, values);
+    rc = postLaunch("k_stokes_rows");
+  }
+  cudaFreeAsync(dTab, st);
+  return rc;
 }
 
 int csrMv(u64 n, const u64* rowPtr, const uint32_t* col, const double* values, const double* x, double* y, bool subtract,

@@ -78,6 +78,16 @@ def assembleLaplaceMatrix(basis, volumeTerm=None, pattern=None):
     return CSRMatrix(basis, row_ptr, col_idx, values), rhs
 
 
+def assembleStokesMatrix(basis, pattern=None):
+    """assembleStokesMatrix(basis, matrix), examples/stokes-taylorhood.cc:252-297, for a Taylor-Hood
+    basis; the nested matrix of the example flattened to container positions.  Returns a CSRMatrix."""
+    import torch
+    row_ptr, col_idx = pattern if pattern is not None else getOccupationPattern(basis)
+    values = torch.empty(col_idx.numel(), dtype=torch.float64, device=row_ptr.device)
+    capi.check(basis._lib.dfx_assemble_stokes(basis._h, _ptr(row_ptr), _ptr(col_idx), _ptr(values), _stream()))
+    return CSRMatrix(basis, row_ptr, col_idx, values)
+
+
 def applyDirichlet(matrix, dirichletNodes, x, rhs):
     """poisson-pq2.cc:356-386: rhs -= A x, Dirichlet rows/columns -> identity, rhs = x on them"""
     import torch

@@ -320,6 +320,12 @@ int dfx_csr_mv(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_
 int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,
                         const uint8_t* dirichlet, const double* x, double* rhs, void* stream);
 
+/* assembleStokesMatrix (examples/stokes-taylorhood.cc:252-297, getLocalMatrix :49-160) for a
+ * Taylor-Hood tree composite(power<dim>(lagrange<2>), lagrange<1>) (or taylorHood()) with any index
+ * merging strategies: values[nnz] in the order of the pattern of dfx_matrix_pattern — the example's
+ * nested matrix flattened to container positions; velocity-velocity blocks of different
+ * components and the pressure-pressure block are structural zeros.                           */
+int dfx_assemble_stokes(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values, void* stream);
 /* y = A x with the same Laplace stiffness matrix, never assembled (matrix-free): per element
  * gather, sum-factorised gradients at (order+1)^dim Gauss points, scale, transposed contraction;
  * every DOF then sums its element contributions in ascending element order (deterministic).

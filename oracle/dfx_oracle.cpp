@@ -1150,6 +1150,74 @@ int32_t orc_assemble_laplace(void* h, const uint64_t* row_ptr, const uint32_t* c
   return 0;
 }
 
+// assembleStokesMatrix (examples/stokes-taylorhood.cc:252-297) with getLocalMatrix (:49-160) for a
+// Taylor-Hood tree composite(power<dim>(Q2), Q1) with any index-merging strategies: values in the
+// order of the given CSR pattern over flat container positions (the example's nested
+// matrix[row[0]][col[0]][row[1]][col[1]] flattened).  Returns non-zero for other trees.
+int32_t orc_assemble_stokes(void* h, const uint64_t* row_ptr, const uint32_t* col_idx, double* values) {
+  auto* b = (orc::Basis*)h;
+  const orc::Grid& g = b->grid;
+  const int dim = g.dim;
+  if ((int)b->leaves.size() != dim + 1) return 1;
+  for (int k = 0; k < dim; ++k) if (b->leaves[k].fe->k != 2) return 1;
+  if (b->leaves[dim].fe->k != 1) return 1;
+  if (b->maxDigits > 1) b->buildPositions();
+  const size_t n = b->pre->dimension();
+  std::fill(values, values + row_ptr[n], 0.0);                                        // matrix = 0
+  const orc::LagrangeCubeFE& velocityLocalFiniteElement = *b->leaves[0].fe;           // child(_0, 0)
+  const orc::LagrangeCubeFE& pressureLocalFiniteElement = *b->leaves[dim].fe;         // child(_1)
+  const int nv = velocityLocalFiniteElement.size(), np = pressureLocalFiniteElement.size();
+  const size_t nl = b->localSize();
+  const int order = 2 * (dim * velocityLocalFiniteElement.k - 1);
+  const orc::QuadratureRule quad = orc::quadratureRule(dim, order);
+  std::vector<orc::MultiIndex> idx;
+  std::vector<double> elementMatrix(nl * nl), referenceJacobians((size_t)nv * dim), jacobians((size_t)nv * dim), pressureValues(np);
+  for (size_t e = 0; e < g.numElements(); ++e) {
+    b->bind(e, idx);
+    std::fill(elementMatrix.begin(), elementMatrix.end(), 0.0);
+    int ec[3]; g.elementCoords(e, ec);
+    double lower[3], upper[3], jacInv[3], integrationElement;
+    orc::elementGeometry(g, ec, lower, upper, jacInv, integrationElement);
+    for (int pt = 0; pt < quad.n; ++pt) {
+      const double* quadPos = &quad.pos[(size_t)pt * dim];
+      velocityLocalFiniteElement.evaluateJacobian(quadPos, referenceJacobians.data());
+      for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < dim; ++j) jacobians[(size_t)i * dim + j] = referenceJacobians[(size_t)i * dim + j] * jacInv[j];
+      // velocity-velocity coupling (:111-121)
+      for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < nv; ++j) {
+          double dot = 0;
+          for (int d = 0; d < dim; ++d) dot += jacobians[(size_t)i * dim + d] * jacobians[(size_t)j * dim + d];
+          for (int k = 0; k < dim; ++k) {
+            const size_t row = b->leaves[k].offset + i, col = b->leaves[k].offset + j;
+            elementMatrix[row * nl + col] += dot * quad.weight[pt] * integrationElement;
+          }
+        }
+      // velocity-pressure coupling (:127-152)
+      pressureLocalFiniteElement.evaluateFunction(quadPos, pressureValues.data());
+      for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < np; ++j)
+          for (int k = 0; k < dim; ++k) {
+            const size_t vIndex = b->leaves[k].offset + i, pIndex = b->leaves[dim].offset + j;
+            const double v = jacobians[(size_t)i * dim + k] * pressureValues[j] * quad.weight[pt] * integrationElement;
+            elementMatrix[vIndex * nl + pIndex] -= v;
+            elementMatrix[pIndex * nl + vIndex] -= v;
+          }
+    }
+    for (size_t i = 0; i < nl; ++i) {
+      const size_t row = b->flat(idx[i]);
+      for (size_t j = 0; j < nl; ++j) {
+        const uint32_t col = (uint32_t)b->flat(idx[j]);
+        const uint32_t* lo = col_idx + row_ptr[row];
+        const uint32_t* hi = col_idx + row_ptr[row + 1];
+        const uint32_t* it = std::lower_bound(lo, hi, col);
+        values[it - col_idx] += elementMatrix[i * nl + j];          // matrixEntry(matrix, row, col) += elementMatrix[i][j]
+      }
+    }
+  }
+  return 0;
+}
+
 // Symmetric incorporation of Dirichlet values (poisson-pq2.cc:356-386): rhs -= A x (x holds the
 // Dirichlet values, zero elsewhere), Dirichlet rows/columns -> identity, rhs[i] = x[i] there.
 void orc_dirichlet(uint64_t n, const uint64_t* row_ptr, const uint32_t* col_idx, double* values,

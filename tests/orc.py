@@ -49,6 +49,8 @@ def lib():
         L.orc_occupation_pattern.argtypes = [vp, vp, vp]
         L.orc_assemble_laplace.restype = i32
         L.orc_assemble_laplace.argtypes = [vp, vp, vp, vp, C.POINTER(capi.Function), vp]
+        L.orc_assemble_stokes.restype = i32
+        L.orc_assemble_stokes.argtypes = [vp, vp, vp, vp]
         L.orc_dirichlet.argtypes = [u64, vp, vp, vp, vp, vp, vp]
         L.orc_csr_mv.argtypes = [u64, vp, vp, vp, vp, vp]
         _lib = L
@@ -194,6 +196,15 @@ class OracleBasis:
         if rc:
             raise ValueError("oracle: the Laplace assembler needs a single-leaf basis")
         return (row_ptr, col, values), rhs
+
+
+def oracle_stokes(basis, pattern=None):
+    """assembleStokesMatrix of examples/stokes-taylorhood.cc on flat positions: (row_ptr, col, values)"""
+    row_ptr, col = pattern if pattern is not None else basis.occupationPattern()
+    values = np.zeros(len(col))
+    if lib().orc_assemble_stokes(basis._h, row_ptr.ctypes.data, col.ctypes.data, values.ctypes.data):
+        raise ValueError("oracle: the Stokes assembler needs a Taylor-Hood tree")
+    return row_ptr, col, values
 
 
 def oracle_dirichlet(csr, dirichlet, x, rhs):

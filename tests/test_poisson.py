@@ -90,6 +90,34 @@ def test_oracle_dirichlet_treatment():
     assert np.allclose(rhs[~b], (rhs0 - A0 @ x)[~b], atol=1e-13)
 
 
+@pytest.mark.parametrize("n", [[3, 2], [2, 2, 2]])
+def test_oracle_stokes_matrix_properties(n):
+    """assembleStokesMatrix restated (examples/stokes-taylorhood.cc): symmetric saddle-point matrix,
+    velocity blocks = the Q2 Laplace matrix per component, no coupling between different velocity
+    components or inside the pressure block, and B^T applied to a constant pressure vanishes on
+    velocity rows away from the boundary (int div(phi) = 0 for interior shape functions)."""
+    grid = YaspGrid(n)
+    d = len(n)
+    ob = orc.OracleBasis(grid, dfx.taylorHood())
+    A = scipy_of(orc.oracle_stokes(ob)).toarray()
+    assert np.abs(A - A.T).max() == 0.0
+    o2 = orc.OracleBasis(grid, lagrange(2))
+    csr2, _ = o2.assembleLaplace()
+    K = scipy_of(csr2).toarray()
+    n2 = o2.dimension()
+    for c in range(d):                                        # TaylorHoodBasis = BL(FI): (0, i*d + c)
+        assert np.abs(A[c:d * n2:d, c:d * n2:d] - K).max() <= 1e-13
+        for c2 in range(d):
+            if c2 != c:
+                assert not A[c:d * n2:d, c2:d * n2:d].any()
+    assert not A[d * n2:, d * n2:].any()
+    bnd, _ = o2.boundaryDOFs()
+    ones = np.ones(A.shape[0] - d * n2)
+    bt1 = A[:d * n2, d * n2:] @ ones
+    for c in range(d):
+        assert np.abs(bt1[c::d][~bnd.astype(bool)]).max() <= 1e-13
+
+
 # ---- GPU parity ----------------------------------------------------------------------------------
 def all_cases():
     for gname, grid in GRIDS.items():
@@ -218,6 +246,26 @@ def test_matrix_free_laplace_slab_and_unsupported():
         bb = dfx.makeBasis(YaspGrid([2, 2, 2]), tree)
         with pytest.raises(capi.NotImplementedDfx):
             dfx.LaplaceOperator(bb).mv(bb.newVector(1.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gname", ["2d_3x2", "2d_10x10", "3d_3x4x5", "3d_2x1x3"])
+@pytest.mark.parametrize("tname", ["taylorHood", "TH_FL(FL)", "TH_BL(BI)", "TH_FL(FI)", "TH_BL(BL)"])
+def test_stokes_matrix(gname, tname):
+    from dune_functions_b200 import _capi as capi
+    grid = GRIDS[gname]
+    tree = trees(grid.dim)[tname]
+    b = dfx.makeBasis(grid, tree)
+    ob = orc.OracleBasis(grid, tree)
+    A = dfx.assembleStokesMatrix(b)
+    erp, ecol, eval_ = orc.oracle_stokes(ob)
+    assert np.array_equal(A.row_ptr.cpu().numpy().astype(np.uint64), erp)
+    assert np.array_equal(A.col_idx.cpu().numpy().view(np.uint32), ecol)
+    assert rel(A.values.cpu().numpy(), eval_) <= TOL
+    if gname == "2d_3x2" and tname == "taylorHood":
+        for bad in (lagrange(2), trees(2)["power2_q2_BL"], trees(2)["nested_FL_FI_BL"]):
+            with pytest.raises(capi.NotImplementedDfx):
+                dfx.assembleStokesMatrix(dfx.makeBasis(grid, bad))
 
 
 def conjugate_gradient(A, rhs, x, tol=1e-12, maxit=2000):
