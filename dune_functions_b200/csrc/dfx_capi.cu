@@ -1,6 +1,8 @@
 // dfx_capi.cu — the extern "C" boundary declared in include/dfx.h.
 #include <algorithm>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "dfx_eval_fast.h"
 #include "dfx_launch.h"
@@ -442,6 +444,28 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
   FastPlan plan;
   const int path = g_forcedPath == 3 ? 0 : planFastEval(b, fl, nl, xhat_host, n_q, out_jac != nullptr, g_forcedPath, plan);
   if (path > 0) return runFastEval(b, plan, fl, nl, coeff, e0, e1, out_values, out_jac, st);
+  // a subtree of mixed orders (Taylor-Hood: Q2 velocity + Q1 pressure): every run of same-order leaves
+  // gets its own plan and writes its range entries into the interleaved output
+  if (g_forcedPath < 0 && nl > 1) {
+    std::vector<FastPlan> plans;
+    std::vector<std::pair<int, int>> runs;
+    const DevBasis& D = b->dev;
+    bool allFast = true;
+    for (int l = 0; l < nl && allFast;) {
+      int r = l + 1;
+      while (r < nl && D.layouts[D.leaves[fl + r].layout].k == D.layouts[D.leaves[fl + l].layout].k) ++r;
+      plans.emplace_back();
+      allFast = planFastEval(b, fl + l, r - l, xhat_host, n_q, out_jac != nullptr, -1, plans.back()) > 0;
+      runs.push_back({l, r - l});
+      l = r;
+    }
+    if (allFast && runs.size() > 1) {
+      for (size_t q = 0; q < runs.size(); ++q)
+        if ((rc = runFastEval(b, plans[q], fl + runs[q].first, runs[q].second, coeff, e0, e1, out_values, out_jac, st,
+                              runs[q].first, nl))) return rc;
+      return DFX_OK;
+    }
+  }
   // no tensor-product structure: dense contraction on the FP64 tensor cores when the element is big enough
   if ((g_forcedPath == 3 || g_forcedPath < 0) && dmmaPathHas(b, fl, nl) && dfx_basis_num_elements(b) <= 0xffffffffull)
     return runDmmaEval(b, node, fl, nl, xhat_host, n_q, coeff, e0, e1, out_values, out_jac, st);

@@ -246,20 +246,23 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   }
   __syncthreads();
   // partial tile, unaligned output or a sub-range of the range entries: cooperative stores
+  // (tile sizes are far below 2^32: 32-bit index arithmetic)
   const int nT = R.ncompTotal, cOff = R.compOffset;
   if (values) {
-    const u64 cnt = nAct * (u64)rowLen;
-    for (u64 i = tid; i < cnt; i += EPB) {
-      const u64 row = i / (u64)nG, gI = i - row * (u64)nG;       // row = el_local*NQ + q
-      values[(blk0 * (u64)NQ + row) * (u64)nT + cOff + gI] = vTile[i];
+    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen;
+    double* dst = values + blk0 * (u64)NQ * (u64)nT + cOff;
+    for (unsigned i = tid; i < cnt; i += EPB) {
+      const unsigned row = i / (unsigned)nG, gI = i - row * (unsigned)nG;       // row = el_local*NQ + q
+      dst[(size_t)row * nT + gI] = vTile[i];
     }
   }
   if (JAC) {
-    const u64 cnt = nAct * (u64)rowLen * DIM;
-    for (u64 i = tid; i < cnt; i += EPB) {
-      const u64 rg = i / DIM, d = i - rg * DIM;
-      const u64 row = rg / (u64)nG, gI = rg - row * (u64)nG;
-      jac[((blk0 * (u64)NQ + row) * (u64)nT + cOff + gI) * DIM + d] = jTile[i];
+    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen * DIM;
+    double* dst = jac + (blk0 * (u64)NQ * (u64)nT + cOff) * DIM;
+    for (unsigned i = tid; i < cnt; i += EPB) {
+      const unsigned rg = i / DIM, d = i - rg * DIM;
+      const unsigned row = rg / (unsigned)nG, gI = rg - row * (unsigned)nG;
+      dst[((size_t)row * nT + gI) * DIM + d] = jTile[i];
     }
   }
 }
@@ -298,9 +301,10 @@ static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const
 }
 
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
-                double* values, double* jac, cudaStream_t st) {
+                double* values, double* jac, cudaStream_t st, int compBase, int compTotal) {
   if (e1 == e0) return DFX_OK;
-  if (plan.path == 2) return runSmemEval(b, plan, firstLeaf, nLeaves, coeff, e0, e1, values, jac, st);
+  if (compTotal < 0) compTotal = nLeaves;
+  if (plan.path == 2) return runSmemEval(b, plan, firstLeaf, nLeaves, coeff, e0, e1, values, jac, st, compBase, compTotal);
   const DevBasis& D = b->dev;
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
     return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
@@ -317,14 +321,14 @@ int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
       if (r - l > maxG) r = l + maxG;
     }
     RegArgs R;
-    R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = l; R.ncompTotal = nLeaves;
+    R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = compBase + l; R.ncompTotal = compTotal;
     for (int q = 0; q < R.nGroup; ++q) { R.posA[q] = D.leaves[firstLeaf + l + q].posA; R.posB[q] = D.leaves[firstLeaf + l + q].posB; }
     const int m = plan.m, dim = plan.dim;
     if (plan.firstFastest) { R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m; }
     else { int s = 1; R.qs[0] = R.qs[1] = R.qs[2] = 0; for (int j = dim - 1; j >= 0; --j) { R.qs[j] = s; s *= m; } }
     R.e0 = e0; R.ne = e1 - e0;
     R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
-    const bool whole = R.nGroup == nLeaves;
+    const bool whole = R.nGroup == compTotal;
     const bool aligned = (!values || ((uintptr_t)values & 15) == 0) && (!jac || ((uintptr_t)jac & 15) == 0);
     R.bulk = whole && aligned ? 1 : 0;
     int rc = DFX_OK;

@@ -36,9 +36,11 @@ extern int g_smemGrad;
 bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);
 int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, const double* coeff,
                 u64 e0, u64 e1, double* values, double* jac, cudaStream_t st);
+// compBase / compTotal: position of the group's first range entry in the output and the total
+// number of range entries per point (a mixed-order subtree is evaluated run by run)
 int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
-                double* values, double* jac, cudaStream_t st);
+                double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
-                double* values, double* jac, cudaStream_t st);
+                double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 
 }  // namespace dfx

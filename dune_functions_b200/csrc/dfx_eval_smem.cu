@@ -408,8 +408,9 @@ static int launchSmem(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, con
 }
 
 int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
-                double* values, double* jac, cudaStream_t st) {
+                double* values, double* jac, cudaStream_t st, int compBase, int compTotal) {
   if (e1 == e0) return DFX_OK;
+  if (compTotal < 0) compTotal = nLeaves;
   const DevBasis& D = b->dev;
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
     return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
@@ -426,7 +427,7 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
       if (r - l > maxG) r = l + maxG;
     }
     SmemArgs R;
-    R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = l; R.ncompTotal = nLeaves;
+    R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = compBase + l; R.ncompTotal = compTotal;
     // the kernel's first contracted direction is the fastest output index: for points ordered
     // last-coordinate-fastest the axes are permuted (z, y, x) instead of the output strides,
     // so that the staging tile is always written with unit stride across the lanes
@@ -435,7 +436,7 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     R.e0 = e0; R.ne = e1 - e0;
     R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
     R.divItems = FastDiv(2u * (unsigned)R.nGroup);
-    const bool whole = R.nGroup == nLeaves;
+    const bool whole = R.nGroup == compTotal;
     const bool aligned = (!values || ((uintptr_t)values & 15) == 0) && (!jac || ((uintptr_t)jac & 15) == 0);
     R.bulk = whole && aligned ? 1 : 0;
     int rc = DFX_ERR_NOT_IMPLEMENTED;
