@@ -5,7 +5,7 @@ load the CUDA library; the first call that needs it does, and fails loudly if
 `lib/libdfx.so` has not been built.
 """
 from .basis import (  # noqa: F401
-    YaspGrid, makeBasis, GlobalBasis, lagrange, lagrangeDG, power, composite, taylorHood,
+    YaspGrid, makeBasis, GlobalBasis, LocalView, lagrange, lagrangeDG, power, composite, taylorHood,
     flatLexicographic, flatInterleaved, blockedLexicographic, blockedInterleaved,
     subspaceBasis, SubspaceBasis, interpolate, interpolationPoints, interpolateFromValues,
     makeDiscreteGlobalBasisFunction, DiscreteGlobalBasisFunction, subEntityDOFs, boundaryDOFs,

@@ -293,12 +293,91 @@ class GlobalBasis:
         capi.check(fn(self._h, elem_begin, elem_end, _ptr(out), _stream()))
         return out
 
+    # the reference's Python front door (dune/python/functions/globalbasis.hh:141-252)
+    def __len__(self):
+        return self.dimension()
+
+    def localView(self):
+        return LocalView(self)
+
+    def interpolate(self, coeff, f, mask=None):
+        """basis.interpolate(dofVector, f): globalbasis.hh:199-210 / dune/python/functions/interpolate.hh:17-28"""
+        return interpolate(self, coeff, f, mask)
+
+    def asFunction(self, coeff):
+        """basis.asFunction(dofVector) -> DiscreteFunction, globalbasis.hh:245-248"""
+        return DiscreteGlobalBasisFunction(self, coeff)
+
     def newVector(self, fill=None):
         import torch
         v = torch.empty(self.dimension(), dtype=torch.float64, device=f"cuda:{self.device}")
         if fill is not None:
             v.fill_(fill)
         return v
+
+
+class LocalView:
+    """LocalViewWrapper of the reference's Python binding (globalbasis.hh:82-121, :179-192):
+    bind(element) / unbind() / index(i) / len() / size() / maxSize() / tree().  An element is its
+    position in elements(gridView) (x fastest) or its coordinate tuple.  index(i) is served from a
+    window of the batched device index table (one device call per 16384 elements)."""
+
+    WINDOW = 1 << 14
+
+    def __init__(self, basis):
+        self.basis = basis
+        self._nloc = basis.maxNodeSize()
+        self._lens = basis.localIndexSizes()
+        self._e = None
+        self._w0 = self._w1 = 0
+        self._cache = None
+
+    def bind(self, element):
+        g = self.basis.grid
+        n = list(g.local_n) if g.local_n is not None else list(g.n)
+        if not isinstance(element, (int, np.integer)):
+            e, stride = 0, 1
+            for j, c in enumerate(element):
+                e += int(c) * stride
+                stride *= n[j]
+            element = e
+        ne = self.basis.numElements()
+        if not 0 <= element < ne:
+            raise capi.RangeError("element outside the grid view")
+        self._e = int(element)
+        if not (self._w0 <= self._e < self._w1):
+            self._w0 = self._e - self._e % self.WINDOW
+            self._w1 = min(ne, self._w0 + self.WINDOW)
+            import torch
+            self._cache = self.basis.indices(self._w0, self._w1, dtype=torch.int64).cpu().numpy()
+
+    def unbind(self):
+        self._e = None
+
+    def bound(self):
+        return self._e is not None
+
+    def element(self):
+        return self._e
+
+    def index(self, i):
+        """global multi-index of local DOF i as a list of ints (LocalViewWrapper::index)"""
+        if self._e is None:
+            raise capi.DfxError("local view is not bound")
+        return [int(v) for v in self._cache[self._e - self._w0, i, :self._lens[i]]]
+
+    def __len__(self):
+        return self._nloc
+
+    def size(self):
+        return self._nloc
+
+    def maxSize(self):
+        return self._nloc
+
+    def tree(self):
+        """root node info of the local ansatz tree: dict(local_offset, size, first_leaf, n_leaves)"""
+        return self.basis.nodeInfo(0)
 
 
 def makeBasis(grid, factory, device=0):

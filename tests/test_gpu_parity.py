@@ -436,6 +436,36 @@ def test_evaluate_at_world_coordinates_on_a_slab():
     assert rel(v.cpu().numpy()[ok], vr[ok]) <= TOL
 
 
+def test_python_front_door_local_view():
+    """the reference's Python interface (dune/python/functions/globalbasis.hh:141-252): len(basis),
+    localView().bind/index/len, basis.interpolate, basis.asFunction"""
+    import torch
+    grid, tree = GRIDS["3d_3x4x5"], trees(3)["TH_BL(BI)"]
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    assert len(b) == o.dimension()
+    dig, lens = o.indices()
+    lv = b.localView()
+    assert len(lv) == lv.size() == lv.maxSize() == o.maxNodeSize() and not lv.bound()
+    for e in (0, 7, 59):
+        lv.bind(e)
+        for i in (0, 26, 80, 88):
+            assert lv.index(i) == [int(x) for x in dig[e, i, :lens[e, i]]]
+    lv.bind((2, 3, 4))
+    assert lv.element() == 2 + 3 * (3 + 4 * 4)
+    lv.unbind()
+    with pytest.raises(capi.DfxError):
+        lv.index(0)
+    with pytest.raises(capi.RangeError):
+        lv.bind(60)
+    q2 = dfx.makeBasis(grid, lagrange(2))
+    x = q2.newVector(0.0)
+    q2.interpolate(x, dfx.gaussian(1.0))
+    u = q2.asFunction(x)
+    v = u.evaluate(np.array([[0.5, 0.5, 0.5]]))
+    assert v.shape == (60, 1, 1) and bool(torch.isfinite(v).all())
+
+
 def test_peer_memory_halo_link_between_two_slabs():
     """dfx_halo_link_* / dfx_halo_push / dfx_halo_pull with both slabs on one GPU (raw-pointer
     attachment instead of CUDA IPC): the upper slab's bottom plane lands in the lower slab's top
