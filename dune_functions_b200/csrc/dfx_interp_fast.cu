@@ -383,7 +383,7 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       // rows per block: the table-driven kernel streams best with few rows per block (the blocks in
       // flight then cover a compact band of every index-set component: 0.19 -> 0.175 ms at 256^3, 1.67 ->
       // 1.27 ms at 512^3), the kernel that evaluates f at every node amortises its per-thread x-data over many
-      A.rowsPerBlock = sep ? 4 : kRowsPerBlock;
+      A.rowsPerBlock = sep ? (L.dimension >= 50000000ull ? 4 : 16) : kRowsPerBlock;    // L2-resident vectors like more rows
       const unsigned grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
       const unsigned nEnt = (unsigned)g.N[0], chunks = (nEnt + 255) / 256;
