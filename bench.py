@@ -404,13 +404,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step(False)
-    barrier()
-    # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches
+    # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches.
+    # Sampling starts with the warm-up steps (the same load as the timed ones): the timed region of the
+    # default run lasts 18 ms, too short for more than a few samples on its own.
     sampler = ClockSampler(physical_gpu_index(local_rank))
     if rank == 0:
         sampler.start()
+    for _ in range(warmup):
+        step(False)
+    barrier()
     launches0 = L.dfx_kernel_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
