@@ -404,15 +404,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches.
-    # Sampling starts with the warm-up steps (the same load as the timed ones): the timed region of the
-    # default run lasts 18 ms, too short for more than a few samples on its own.
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    if rank == 0:
-        sampler.start()
     for _ in range(warmup):
         step(False)
     barrier()
+    # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if rank == 0:
+        sampler.start()
     launches0 = L.dfx_kernel_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -420,10 +418,17 @@ def main():
         step(True)
     stop.record()
     barrier()
+    launches = int(L.dfx_kernel_launch_count() - launches0)
+    # the timed region of a short run (20 steps = 18 ms) gives NVML time for very few samples: the same
+    # steps keep running, untimed, until the sampler has seen the load for a while
+    samples_timed = len(sampler.samples)
+    t_extra = time.perf_counter()
+    while len(sampler.samples) < 25 and time.perf_counter() - t_extra < 0.5 and sampler.ok and world == 1:
+        step(False)
+        torch.cuda.synchronize()
     sampler.stop_flag.set()
     if rank == 0:
         sampler.join()
-    launches = int(L.dfx_kernel_launch_count() - launches0)
     t_ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     parts = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) if v else 0.0 for k, v in ev.items()}
     pt = torch.tensor([parts["interp"], parts["halo"], parts["eval"], parts["index"]], dtype=torch.float64, device=dev)
@@ -494,7 +499,7 @@ def main():
                                          "frac": interp_bytes / t_interp / 1e9 / peak if t_interp > 0 else None,
                                          "algorithmic_bytes": interp_bytes,
                                          "traffic": traffic_from_profiles("interpolate", args.workload)}},
-            "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e,
+            "clocks": dict(sampler.result(), samples_in_timed_region=samples_timed), "gpu_launches": launches, "e2e": e2e,
         }
         if not args.no_cpu and world == 1:
             import orc
