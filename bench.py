@@ -101,6 +101,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def clocks_report(sampler, n_timed):
+    """sm_mhz = median over the samples taken DURING the timed region when there are at least 3 of them,
+    otherwise over all samples; sm_mhz_sustained = median over everything (timed region + the untimed
+    continuation of the same steps)"""
+    r = sampler.result()
+    if sampler.ok and sampler.samples:
+        r["sm_mhz_sustained"] = float(np.median(sampler.samples))
+        if n_timed >= 3:
+            r["sm_mhz"] = float(np.median(sampler.samples[:n_timed]))
+        r["samples_in_timed_region"] = n_timed
+    return r
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -499,7 +512,7 @@ def main():
                                          "frac": interp_bytes / t_interp / 1e9 / peak if t_interp > 0 else None,
                                          "algorithmic_bytes": interp_bytes,
                                          "traffic": traffic_from_profiles("interpolate", args.workload)}},
-            "clocks": dict(sampler.result(), samples_in_timed_region=samples_timed), "gpu_launches": launches, "e2e": e2e,
+            "clocks": clocks_report(sampler, samples_timed), "gpu_launches": launches, "e2e": e2e,
         }
         if not args.no_cpu and world == 1:
             import orc
