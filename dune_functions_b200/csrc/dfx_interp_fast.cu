@@ -33,6 +33,8 @@ struct RowArgs {
   FastDiv divK;            // lattice coordinate -> (entity, node inside)
   FastDiv divLY;           // row index -> (Z, Y)
   int rowsPerBlock;        // lattice rows per block (<= kRowsPerBlock)
+  int tabN;                // table length of one range entry (separable mode)
+  int vectorTables;        // separable mode: one table set per range entry (vector-valued f)
   int nActive;             // leaves of the subtree that live on this lattice
   int leafId[DFX_MAX_LEAVES];     // their ids, range entries and in-entity position stride
   int leafComp[DFX_MAX_LEAVES];
@@ -63,13 +65,18 @@ __device__ __forceinline__ double nodeCoord(const DevGrid& g, int k, int j, int 
   return elementGlobal(g, j, ie, xhat);
 }
 
-// factor of a separable registry function in direction j
-__device__ __forceinline__ double sepFactor(const dfx_function& f, int j, double x) {
+// factor of range entry c of a separable registry function in direction j:
+// y_c(x) = prod_j sepFactor(f, c, j, x_j)
+__device__ __forceinline__ double sepFactor(const dfx_function& f, int c, int j, double x) {
   switch (f.id) {
     case DFX_FN_GAUSSIAN: return exp(__dmul_rn(-f.p[0], __dmul_rn(x, x)));
     case DFX_FN_SINPROD: return sin(__dmul_rn(f.p[0], x));
     case DFX_FN_COORD: return j == (int)f.p[0] ? x : 1.0;
-    case DFX_FN_CONSTANT: return j == 0 ? f.p[0] : 1.0;
+    case DFX_FN_CONSTANT: return j == 0 ? f.p[c] : 1.0;
+    case DFX_FN_IDENTITY: return j == c ? x : 1.0;                     // y_c = x_c (0 for c >= dim, see the table kernel)
+    case DFX_FN_GAUSSIAN_VEC: {                                         // y_c = x_c exp(-a |x|^2)
+      const double e = exp(__dmul_rn(-f.p[0], __dmul_rn(x, x)));
+      return j == c ? __dmul_rn(x, e) : e; }
   }
   return 0.0;
 }
@@ -77,21 +84,24 @@ __device__ __forceinline__ double sepFactor(const dfx_function& f, int j, double
 __global__ void __launch_bounds__(256)
 k_sep_tables(const __grid_constant__ DevGrid g, const __grid_constant__ dfx_function f, const __grid_constant__ RowArgs A,
              int k, int cellMode, double* __restrict__ tab) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = A.tabOff[2] + A.LX[2];
-  if (t >= n) return;
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = A.tabOff[2] + A.LX[2];                 // table length of one range entry
+  if (tt >= n * f.n_comp) return;
+  const int c = tt / n, t = tt - c * n;
   const int j = t >= A.tabOff[2] ? 2 : (t >= A.tabOff[1] ? 1 : 0);
-  if (j >= g.dim) { tab[t] = 1.0; return; }
+  if (j >= g.dim) { tab[tt] = 1.0; return; }
+  // IDENTITY has no coordinate for range entries beyond the dimension: they are 0
+  if (f.id == DFX_FN_IDENTITY && c >= g.dim) { tab[tt] = 0.0; return; }
   const int X = t - A.tabOff[j];
   int ie, a;
   if (cellMode) { ie = g.off[j] + X / (k + 1); a = X % (k + 1); }
   else { const Dir d = latticeDir(g, A.divK, k, j, X); ie = d.ie; a = d.a; }
-  tab[t] = sepFactor(f, j, nodeCoord(g, k, j, ie, a));
+  tab[tt] = sepFactor(f, c, j, nodeCoord(g, k, j, ie, a));
 }
 
 // per lattice row (Y, Z fixed) and active leaf: flat position of x-entity 0's vertex-type
 // node / first edge-type node and the position stride between consecutive x-entities
-struct RowLeaf { u64 baseV, baseE; unsigned strideV, strideE, posA, comp; };
+struct RowLeaf { u64 baseV, baseE; unsigned strideV, strideE, posA, comp; double yz; };   // yz: MODE 1, t_y t_z of the leaf's range entry
 struct RowCommon { double u1, u2; };   // MODE 0: node coordinates x_1, x_2;  MODE 1: factors t_y, t_z
 constexpr int kRowsPerBlock = 32;      // most lattice rows one block sweeps (A.rowsPerBlock <= this)
 constexpr int kMaxHoist = 4;           // orders 1..4 keep the x-direction data in registers
@@ -112,6 +122,8 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
   const unsigned row0 = blockIdx.x * (unsigned)A.rowsPerBlock;
   const unsigned nr = min((unsigned)A.rowsPerBlock, nRows - row0);
   const int nAct = ONE ? 1 : A.nActive;
+  // MODE 1 with a single active leaf: the tables of that leaf's range entry
+  const double* tab1 = (MODE == 1 && ONE && A.vectorTables) ? tab + (size_t)A.leafComp[0] * A.tabN : tab;
   // ---- per-row setup by the first nr*nAct threads ----
   for (unsigned w = threadIdx.x; w < nr * (unsigned)nAct; w += blockDim.x) {
     const unsigned rI = w / (unsigned)nAct, lI = w - rI * (unsigned)nAct;
@@ -133,6 +145,11 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
     rl.strideV = (unsigned)(leaf.posA * (u64)L.blk[sV]);
     rl.strideE = (unsigned)(leaf.posA * (u64)L.blk[sE]);
     rl.posA = (unsigned)leaf.posA; rl.comp = (unsigned)A.leafComp[lI];
+    rl.yz = 0.0;
+    if (MODE == 1) {
+      const double* tc = tab + (size_t)(A.vectorTables ? A.leafComp[lI] : 0) * A.tabN;
+      rl.yz = __dmul_rn(tc[A.tabOff[1] + (int)Y], tc[A.tabOff[2] + (int)Z]);
+    }
     rowl[lI][rI] = rl;
     if (lI == 0) {
       RowCommon rc;
@@ -140,7 +157,7 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
         rc.u1 = g.dim > 1 ? nodeCoord(g, k, 1, dy.ie, dy.a) : 0.0;
         rc.u2 = g.dim > 2 ? nodeCoord(g, k, 2, dz.ie, dz.a) : 0.0;
       } else {
-        rc.u1 = __dmul_rn(tab[A.tabOff[1] + (int)Y], tab[A.tabOff[2] + (int)Z]);   // t_y * t_z
+        rc.u1 = __dmul_rn(tab1[A.tabOff[1] + (int)Y], tab1[A.tabOff[2] + (int)Z]);   // t_y * t_z
         rc.u2 = 0.0;
       }
       rowc[rI] = rc;
@@ -150,7 +167,7 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
   const bool scalar = MODE == 1 || f.ncomp() == 1;
   // x-direction datum of node a of x-entity c0: coordinate (MODE 0) or table factor (MODE 1)
   auto xdata = [&](unsigned c0, int a) -> double {
-    if (MODE == 1) return tab[A.tabOff[0] + k * (int)c0 + a];
+    if (MODE == 1) return tab1[A.tabOff[0] + k * (int)c0 + a];
     int ie = g.off[0] + (int)c0, aa = a;
     if (a == 0 && ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }    // last lattice plane: owner on the left
     return nodeCoord(g, k, 0, ie, aa);
@@ -162,8 +179,12 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
       const RowLeaf rl = rowl[lI][rI];
       const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
                            : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)rl.posA * (u64)(a - 1);
-      if (mask == nullptr || mask[p])
-        coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : (int)rl.comp, cm, xa, rc.u1, rc.u2);
+      if (mask == nullptr || mask[p]) {
+        if (MODE == 1 && !ONE && A.vectorTables)        // range entry of this leaf: its own x-table and row factor
+          coeff[p] = __dmul_rn(tab[(size_t)rl.comp * A.tabN + A.tabOff[0] + k * (int)c0 + a], rl.yz);
+        else
+          coeff[p] = MODE == 1 ? cm : f.comp(scalar ? 0 : (int)rl.comp, cm, xa, rc.u1, rc.u2);
+      }
     }
   };
   // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... < N_x and sweeps the rows ----
@@ -330,8 +351,9 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
 }
 
 static bool separable(const dfx_function& f) {
-  return f.n_comp == 1 && (f.id == DFX_FN_GAUSSIAN || f.id == DFX_FN_SINPROD || f.id == DFX_FN_COORD ||
-                           f.id == DFX_FN_CONSTANT);
+  if (f.n_comp == 1) return f.id == DFX_FN_GAUSSIAN || f.id == DFX_FN_SINPROD || f.id == DFX_FN_COORD || f.id == DFX_FN_CONSTANT;
+  // vector-valued: every range entry is a product of per-direction factors (one table set each)
+  return f.id == DFX_FN_IDENTITY || f.id == DFX_FN_GAUSSIAN_VEC || f.id == DFX_FN_CONSTANT;
 }
 
 int g_interpMode = -1;   // -1 automatic, 0 per-node evaluation of f
@@ -355,9 +377,14 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
     A.tabOff[0] = 0; A.tabOff[1] = A.LX[0]; A.tabOff[2] = A.LX[0] + A.LX[1];
     A.divK = FastDiv((unsigned)(k > 0 ? k : 1));
     const int tabN = A.LX[0] + A.LX[1] + A.LX[2];
+    A.tabN = tabN; A.vectorTables = fn.n_comp > 1 ? 1 : 0;
     double* tab = nullptr;
+    // vector-valued tables are wired into the lattice-row kernel only; element-local layouts (DG)
+    // evaluate such an f at every node
+    const bool sepAll = sep;
+    const bool sep = sepAll && (fn.n_comp == 1 || !cell);
     if (sep) {
-      const size_t need = (size_t)tabN * sizeof(double);
+      const size_t need = (size_t)tabN * fn.n_comp * sizeof(double);
       if (b->dSepBytes < need) {
         if (b->dSep) cudaFree(b->dSep);
         b->dSep = nullptr; b->dSepBytes = 0;
@@ -365,7 +392,7 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
         b->dSepBytes = need;
       }
       tab = (double*)b->dSep;
-      k_sep_tables<<<(tabN + 255) / 256, 256, 0, st>>>(g, fn, A, k, cell ? 1 : 0, tab);
+      k_sep_tables<<<(tabN * fn.n_comp + 255) / 256, 256, 0, st>>>(g, fn, A, k, cell ? 1 : 0, tab);
       int rc = postLaunch("k_sep_tables");
       if (rc) return rc;
     }

@@ -133,6 +133,31 @@ def test_interpolate_vector_valued_and_subspaces():
         assert rel(x.cpu().numpy(), ref) <= TOL
 
 
+@pytest.mark.parametrize("gname", ["2d_3x2", "3d_2x1x3", "3d_3x4x5"])
+@pytest.mark.parametrize("path", [-1, 1, 0])
+def test_interpolate_vector_valued_separable_tables(kernel_path, gname, path):
+    """vector-valued registry functions whose range entries are products of per-direction factors
+    (x -> x, x -> x exp(-a|x|^2), constants) go through one table set per range entry; every kernel
+    family gives the oracle's answer (bit-exact for x -> x and constants)"""
+    grid = GRIDS[gname]
+    d = grid.dim
+    kernel_path(capi.OP_INTERPOLATE, path)
+    for tname in ("power3_q2_BI", "power2_q1_FI", "power2_q2_BL", "power3_dg1_FL", "nested_FL_FI_BL"):
+        tree = trees(d)[tname]
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        nl = b.numLeaves()
+        for f, exact in ((dfx.identity(nl), True), (dfx.constant(*[1.5 * c - 2 for c in range(nl)]), True),
+                         (dfx.gaussian_vec(nl, 0.7), False)):
+            x = b.newVector(-9.0)
+            dfx.interpolate(b, x, f)
+            ref = o.interpolate(f, coeff=np.full(o.dimension(), -9.0))
+            if exact:
+                assert np.array_equal(x.cpu().numpy(), ref), (tname, f.id)
+            else:
+                assert rel(x.cpu().numpy(), ref) <= TOL, (tname, f.id)
+
+
 def test_interpolate_masked():
     import torch
     grid = GRIDS["2d_10x10"]
