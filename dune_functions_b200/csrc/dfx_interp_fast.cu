@@ -35,6 +35,7 @@ struct RowArgs {
   int rowsPerBlock;        // lattice rows per block (<= kRowsPerBlock)
   int tabN;                // table length of one range entry (separable mode)
   int vectorTables;        // separable mode: one table set per range entry (vector-valued f)
+  int interleaved;         // the active leaves are the components of an interleaved power node (position = C j + c)
   int nActive;             // leaves of the subtree that live on this lattice
   int leafId[DFX_MAX_LEAVES];     // their ids, range entries and in-entity position stride
   int leafComp[DFX_MAX_LEAVES];
@@ -187,6 +188,27 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
       }
     }
   };
+  // ---- table mode on an interleaved group (power node with FlatInterleaved / BlockedInterleaved
+  // merging: position = C j + c): the leaves are spread over the threads, thread u owns (x-entity
+  // u / C, leaf u % C), so the lanes of a warp write consecutive positions instead of C strided runs ----
+  if (MODE == 1 && !ONE && A.interleaved) {
+    const unsigned C = (unsigned)nAct;
+    for (unsigned u = threadIdx.x; u < ((unsigned)g.N[0] + 1u) * C; u += blockDim.x) {
+      const unsigned c0 = u / C, lI = u - c0 * C;
+      const bool closing = c0 == (unsigned)g.N[0];                 // the last lattice plane: vertex-type node only
+      const unsigned comp = (unsigned)(A.vectorTables ? A.leafComp[lI] : 0);
+      const double* tx = tab + (size_t)comp * A.tabN + A.tabOff[0] + k * (int)c0;
+      for (unsigned rI = 0; rI < nr; ++rI) {
+        const RowLeaf rl = rowl[lI][rI];
+        for (int a = 0; a < (closing ? 1 : k); ++a) {
+          const u64 p = a == 0 ? rl.baseV + (u64)rl.strideV * (u64)c0
+                               : rl.baseE + (u64)rl.strideE * (u64)c0 + (u64)rl.posA * (u64)(a - 1);
+          if (mask == nullptr || mask[p]) coeff[p] = __dmul_rn(tx[a], rl.yz);
+        }
+      }
+    }
+    return;
+  }
   // ---- each thread owns x-entities c0 = tid, tid + blockDim, ... < N_x and sweeps the rows ----
   for (unsigned c0 = threadIdx.x; c0 < (unsigned)g.N[0]; c0 += blockDim.x) {
     // nodes X = k c0 + a, a = 0 (vertex-type) .. k-1 (edge-type); their x-data stay in registers
@@ -411,9 +433,19 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       // flight then cover a compact band of every index-set component: 0.19 -> 0.175 ms at 256^3, 1.67 ->
       // 1.27 ms at 512^3), the kernel that evaluates f at every node amortises its per-thread x-data over many
       A.rowsPerBlock = sep ? (L.dimension >= 50000000ull ? 4 : 16) : kRowsPerBlock;    // L2-resident vectors like more rows
+      // interleaved group: C leaves with position stride C and consecutive offsets
+      A.interleaved = 0;
+      if (sep && A.nActive > 1) {
+        bool il = true;
+        for (int q2 = 0; q2 < A.nActive; ++q2) {
+          const DevLeaf& lf = D.leaves[A.leafId[q2]];
+          il = il && lf.posA == (u64)A.nActive && lf.posB == D.leaves[A.leafId[0]].posB + (u64)q2;
+        }
+        A.interleaved = il ? 1 : 0;
+      }
       const unsigned grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
-      const unsigned nEnt = (unsigned)g.N[0], chunks = (nEnt + 255) / 256;
+      const unsigned nEnt = (unsigned)g.N[0] * (A.interleaved ? (unsigned)A.nActive : 1u), chunks = (nEnt + 255) / 256;
       const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
 #define DFX_ROWS2(KT_, ONE_)                                                                                 \
   { if (sep) k_interp_rows<RegistryFn, 1, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask);      \
