@@ -246,23 +246,20 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   }
   __syncthreads();
   // partial tile, unaligned output or a sub-range of the range entries: cooperative stores
-  // (tile sizes are far below 2^32: 32-bit index arithmetic)
   const int nT = R.ncompTotal, cOff = R.compOffset;
   if (values) {
-    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen;
-    double* dst = values + blk0 * (u64)NQ * (u64)nT + cOff;
-    for (unsigned i = tid; i < cnt; i += EPB) {
-      const unsigned row = i / (unsigned)nG, gI = i - row * (unsigned)nG;       // row = el_local*NQ + q
-      dst[(size_t)row * nT + gI] = vTile[i];
+    const u64 cnt = nAct * (u64)rowLen;
+    for (u64 i = tid; i < cnt; i += EPB) {
+      const u64 row = i / (u64)nG, gI = i - row * (u64)nG;       // row = el_local*NQ + q
+      values[(blk0 * (u64)NQ + row) * (u64)nT + cOff + gI] = vTile[i];
     }
   }
   if (JAC) {
-    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen * DIM;
-    double* dst = jac + (blk0 * (u64)NQ * (u64)nT + cOff) * DIM;
-    for (unsigned i = tid; i < cnt; i += EPB) {
-      const unsigned rg = i / DIM, d = i - rg * DIM;
-      const unsigned row = rg / (unsigned)nG, gI = rg - row * (unsigned)nG;
-      dst[((size_t)row * nT + gI) * DIM + d] = jTile[i];
+    const u64 cnt = nAct * (u64)rowLen * DIM;
+    for (u64 i = tid; i < cnt; i += EPB) {
+      const u64 rg = i / DIM, d = i - rg * DIM;
+      const u64 row = rg / (u64)nG, gI = rg - row * (u64)nG;
+      jac[((blk0 * (u64)NQ + row) * (u64)nT + cOff + gI) * DIM + d] = jTile[i];
     }
   }
 }
