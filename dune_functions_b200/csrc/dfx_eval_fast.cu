@@ -247,7 +247,16 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   __syncthreads();
   // partial tile, unaligned output or a sub-range of the range entries: cooperative stores
   const int nT = R.ncompTotal, cOff = R.compOffset;
-  if (values) {
+  if (values && !JAC) {
+    // values-only instantiations: tile sizes are far below 2^32, 32-bit index arithmetic (the Jacobian
+    // instantiations keep the 64-bit loop below: they sit at the register limit and spill otherwise)
+    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen;
+    double* dst = values + blk0 * (u64)NQ * (u64)nT + cOff;
+    for (unsigned i = tid; i < cnt; i += EPB) {
+      const unsigned row = i / (unsigned)nG, gI = i - row * (unsigned)nG;       // row = el_local*NQ + q
+      dst[(size_t)row * nT + gI] = vTile[i];
+    }
+  } else if (values) {
     const u64 cnt = nAct * (u64)rowLen;
     for (u64 i = tid; i < cnt; i += EPB) {
       const u64 row = i / (u64)nG, gI = i - row * (u64)nG;       // row = el_local*NQ + q
