@@ -33,3 +33,37 @@ extern "C" int harness_indices(const dfx_grid_desc* g, const dfx_tree_node* t, i
   delete static_cast<dfx_basis*>(impl);
   return 0;
 }
+
+// The band bookkeeping of the pipelined dfx_evaluate_host (csrc/dfx_hostbands.h): for the element
+// bands [bounds[i], bounds[i+1]) of the whole tree, which flat coefficient positions does band i
+// newly bring to the device?  out_band[p] = index of the band whose upload contains position p
+// (-1 = never uploaded).  The test checks with the oracle's index table that every band finds what
+// its elements gather.
+#include "../../dune_functions_b200/csrc/dfx_hostbands.h"
+
+extern "C" int harness_band_uploads(const dfx_grid_desc* g, const dfx_tree_node* t, int n, const unsigned long long* bounds,
+                                    int nBands, int* out_band) {
+  dfx_basis_impl* impl = nullptr;
+  int rc = buildBasis(g, t, n, 0, &impl);
+  if (rc) return rc;
+  const DevBasis& B = impl->dev;
+  u64 layer = 1;
+  for (int j = 0; j + 1 < B.grid.dim; ++j) layer *= (u64)B.grid.N[j];
+  for (u64 p = 0; p < impl->dimension; ++p) out_band[p] = -1;
+  Intervals have;
+  for (int i = 0; i < nBands; ++i) {
+    const u64 c0 = bounds[i], c1 = bounds[i + 1];
+    if (c1 <= c0) continue;
+    Intervals need = subtract(layerBandRanges(impl, 0, B.nLeaves, c0 / layer, (c1 - 1) / layer + 1), have);
+    for (auto& r : need) {
+      for (u64 p = r.first; p < r.second; ++p) {
+        if (p >= impl->dimension || out_band[p] != -1) { delete static_cast<dfx_basis*>(impl); return 100; }   // out of range / uploaded twice
+        out_band[p] = i;
+      }
+      have.push_back(r);
+    }
+    normalise(have);
+  }
+  delete static_cast<dfx_basis*>(impl);
+  return 0;
+}

@@ -24,7 +24,8 @@ BASIS_SRC = os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_basis.cu")
 
 @pytest.fixture(scope="module")
 def harness():
-    srcs = [HARNESS_SRC, BASIS_SRC, os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_internal.h")]
+    srcs = [HARNESS_SRC, BASIS_SRC, os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_internal.h"),
+            os.path.join(ROOT, "dune_functions_b200", "csrc", "dfx_hostbands.h")]
     if not os.path.exists(HARNESS_SO) or any(os.path.getmtime(s) > os.path.getmtime(HARNESS_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", HARNESS_SO,
                                HARNESS_SRC, BASIS_SRC])
@@ -92,6 +93,35 @@ def declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "dfx.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(dfx_[a-z0-9_]+)\s*\(", hdr)))
+
+
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_3x4x5", "3d_2x1x3"])
+def test_pipeline_bands_upload_what_their_elements_gather(harness, gname):
+    """dfx_evaluate_host cuts the element range into bands and uploads, per band, only the
+    coefficient ranges not yet on the device (csrc/dfx_hostbands.h).  With the oracle's index table:
+    every coefficient an element of band i gathers is uploaded by band i or an earlier one, nothing
+    is uploaded twice, and everything that is gathered at all gets uploaded."""
+    grid = GRIDS[gname]
+    desc = grid.desc()
+    rng = np.random.default_rng(3)
+    harness.harness_band_uploads.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p,
+                                             C.c_int, C.c_void_p]
+    for name, tree in trees(grid.dim).items():
+        o = orc.OracleBasis(grid, tree)
+        ne = o.numElements()
+        flat = o.flatIndices().astype(np.int64)
+        arr, n = tree_array(tree)
+        for trial in range(3):
+            # element-range boundaries: whole layers, ragged cuts inside layers, single elements
+            cuts = sorted(set([0, ne] + rng.integers(0, ne + 1, size=rng.integers(0, 5)).tolist()))
+            bounds = np.array(cuts, dtype=np.uint64)
+            band = np.zeros(o.dimension(), dtype=np.int32)
+            rc = harness.harness_band_uploads(C.byref(desc), arr, n, bounds.ctypes.data, len(cuts) - 1, band.ctypes.data)
+            assert rc == 0, (name, rc)
+            for i in range(len(cuts) - 1):
+                used = np.unique(flat[cuts[i]:cuts[i + 1]])
+                assert (band[used] >= 0).all() and (band[used] <= i).all(), (name, cuts, i)
+            assert (band[np.unique(flat)] >= 0).all()
 
 
 def test_library_exports_every_declared_symbol():
