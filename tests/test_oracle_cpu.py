@@ -304,3 +304,57 @@ def test_last_writer_wins_matches_serial_order():
     h = 0.3 / 3
     expect = [0.0 + 0.0 * (h - 0.0), h + 0.0 * (2 * h - h), 2 * h + 0.0 * (3 * h - 2 * h), 2 * h + 1.0 * (3 * h - 2 * h)]
     assert c.tolist() == expect
+
+
+# ---- grid-function interpolation and world-coordinate evaluation of the oracle ---------------------
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_2x1x3"])
+def test_oracle_interpolation_consistency_of_discrete_functions(gname):
+    """checkInterpolationConsistency (gridfunctions/test/discreteglobalbasisfunctiontest.cc:49-77):
+    interpolate(basis, y, makeDiscreteGlobalBasisFunction(basis, x)) == x within 1e-10, for every tree"""
+    grid = GRIDS[gname]
+    rng = np.random.default_rng(2)
+    for name, tree in trees(grid.dim).items():
+        o = orc.OracleBasis(grid, tree)
+        x = rng.uniform(-1, 1, o.dimension())
+        y = o.interpolateGridFunction(o, x, coeff=np.full(o.dimension(), np.nan))
+        assert np.abs(y - x).max() <= 1e-10, name
+
+
+def test_oracle_grid_function_interpolation_between_bases():
+    """a Q2 interpolant of a quadratic interpolated into Q1 / Q3 / DG2 bases equals the direct
+    interpolation of the quadratic (all of them reproduce it at their nodes)"""
+    grid = GRIDS["3d_2x1x3"]
+    f = quadratic(0.5, [1.0, -2.0, 3.0], [1.0, 0.5, -1.0, 2.0, 0.25, -0.5])
+    q2 = orc.OracleBasis(grid, lagrange(2))
+    c2 = q2.interpolate(f)
+    for tree in (lagrange(1), lagrange(3), lagrangeDG(2), lagrange(0)):
+        o = orc.OracleBasis(grid, tree)
+        assert np.abs(o.interpolateGridFunction(q2, c2) - o.interpolate(f)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_2x1x3"])
+def test_oracle_world_coordinate_evaluation_agrees_with_local_evaluation(gname):
+    """DiscreteGlobalBasisFunction::operator()(x) (discreteglobalbasisfunction.hh:402-410) = local
+    evaluation in the element that contains x at geometry.local(x): take interior local points,
+    map them to world coordinates and compare"""
+    grid = GRIDS[gname]
+    d = grid.dim
+    lo = np.array(grid.lower if grid.lower is not None else [0.0] * d)
+    up = np.array(grid.upper if grid.upper is not None else [1.0] * d)
+    h = (up - lo) / np.array(grid.n)
+    rng = np.random.default_rng(4)
+    xhat = rng.uniform(0.1, 0.9, (3, d))
+    for name in ("lagrange2", "lagrangeDG1", "taylorHood", "nested_FL_FI_BL"):
+        o = orc.OracleBasis(grid, trees(d)[name])
+        c = rng.uniform(-1, 1, o.dimension())
+        v, j = o.evaluate(c, xhat, jacobians=True)
+        ne = o.numElements()
+        ec = np.stack(np.unravel_index(np.arange(ne), grid.n[::-1])[::-1], -1)          # x fastest
+        world = (lo + (ec[:, None, :] + xhat[None]) * h).reshape(-1, d)
+        vg, jg, el = o.evaluateGlobal(c, world, jacobians=True)
+        assert np.array_equal(el, np.repeat(np.arange(ne), 3))
+        assert np.abs(vg.reshape(v.shape) - v).max() <= 1e-12
+        assert np.abs(jg.reshape(j.shape) - j).max() <= 1e-10
+    # outside the grid: no element
+    _, _, el = o.evaluateGlobal(c, np.array([up + 1.0]))
+    assert el[0] == -1
