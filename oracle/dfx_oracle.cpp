@@ -78,6 +78,11 @@ struct Grid {
   int G[MAXDIM];      // global grid
   int off[MAXDIM];    // local_begin
   double lower[MAXDIM], upper[MAXDIM], h[MAXDIM];
+  // grid().globalIdSet() restricted to vertices: id of the vertex with lexicographic position p
+  // of the LOCAL box.  Empty = the structured grid's own ids, monotone in the lexicographic
+  // position of the GLOBAL grid [EXT YaspGlobalIdSet / persistent index].  A non-empty table
+  // stands for a grid manager whose ids are not (UGGrid / ALUGrid cube meshes, refined grids).
+  std::vector<size_type> vertexId;
 
   explicit Grid(const dfx_grid_desc& g) {
     dim = g.dim;
@@ -100,6 +105,17 @@ struct Grid {
   }
   // EquidistantOffsetCoordinates::coordinate(d, i) = origin + i*h   [EXT]
   double coordinate(int j, int iGlobal) const { return lower[j] + iGlobal * h[j]; }
+  // globalIdSet().subId(element, v, dim) for the vertex at lattice coordinates c of the local box
+  size_type vertexIdAt(const int c[MAXDIM]) const {
+    if (vertexId.empty()) {
+      size_type lex = 0, stride = 1;
+      for (int j = 0; j < dim; ++j) { lex += stride * (size_type)(off[j] + c[j]); stride *= (size_type)(G[j] + 1); }
+      return lex;
+    }
+    size_type lex = 0, stride = 1;
+    for (int j = 0; j < dim; ++j) { lex += stride * (size_type)c[j]; stride *= (size_type)(N[j] + 1); }
+    return vertexId[lex];
+  }
 
   // ---- index set [EXT YaspIndexSet]: entities of a codim are split into
   // components by shift bitset (bit j set = entity extends in direction j),
@@ -322,6 +338,121 @@ struct LagrangeCubeFE {
 };
 
 // ---------------------------------------------------------------------------
+// Experimental::FaceOrientations<dim> restricted to cubes (lagrangebasis.hh:207-423).
+// bits 0..11: edge e is flipped against the reference element (:232-235); bits 12+4f..15+4f:
+// orientation index 8..15 of quadrilateral facet f (:279-331).
+struct FaceOrientations {
+  static constexpr int maxEdges = 12, bitsPerFacet = 4;
+  uint64_t data = 0;
+  static int facetBitOffset(int subEntity) { return maxEdges + bitsPerFacet * subEntity; }   // :218-221
+  bool edgeBit(int e) const { return (data >> e) & 1u; }
+
+  // [EXT dune-geometry] re.subEntities(i, codim, dim): local vertex numbers of a sub-entity, ascending
+  static int subEntityVertices(int dim, int codim, int i, int v[4]) {
+    int st[MAXDIM]; refCubeSubEntity(dim, codim, i, st);
+    int n = 0;
+    for (int w = 0; w < (1 << dim); ++w) {
+      bool in = true;
+      for (int j = 0; j < dim; ++j) in = in && (st[j] == 2 || st[j] == ((w >> j) & 1));
+      if (in) v[n++] = w;
+    }
+    return n;
+  }
+  // [EXT dune-geometry] re.subEntity(facet, 1, i, 2) of the 3-d cube: the facet's i-th edge in the
+  // facet's own (quadrilateral) numbering 0:x'=0 1:x'=1 2:y'=0 3:y'=1, x' < y' being the facet's
+  // free directions in ascending order
+  static int facetEdge(int facet, int i) {
+    int st[MAXDIM]; refCubeSubEntity(3, 1, facet, st);
+    int fr[2], n = 0;
+    for (int j = 0; j < 3; ++j) if (st[j] == 2) fr[n++] = j;
+    st[fr[i / 2]] = i % 2;
+    return refCubeSubEntityNumber(3, 2, st);
+  }
+
+  FaceOrientations() = default;
+  // :360-398.  edges: codims <= dim-1 requested; facets: dim == 3 and codim 1 requested
+  FaceOrientations(int dim, const size_type* vertexIds, bool edges, bool facets) {
+    if (dim == 1 || !edges) return;
+    const int edgeCodim = dim - 1;
+    for (int e = 0; e < refCubeSize(dim, edgeCodim); ++e) {                 // computeEdgeOrientation :232-235
+      int v[4]; subEntityVertices(dim, edgeCodim, e, v);
+      if (vertexIds[v[0]] > vertexIds[v[1]]) data |= (uint64_t)1 << e;
+    }
+    if (dim == 3 && facets)
+      for (int f = 0; f < 6; ++f) {                                         // computeQuadrilateralOrientation :279-331
+        int v[4]; subEntityVertices(3, 1, f, v);
+        const size_type id[4] = {vertexIds[v[0]], vertexIds[v[1]], vertexIds[v[2]], vertexIds[v[3]]};
+        const uint32_t edgeOrientationsToMinVertex = 0b11110101110000001000000110001000u;
+        unsigned eo = 0;
+        for (int i = 0; i < 4; ++i) eo |= (unsigned)edgeBit(facetEdge(f, i)) << i;
+        unsigned i_min;
+        if (eo == 5) i_min = id[1] < id[2] ? 1 : 2;
+        else if (eo == 10) i_min = id[0] < id[3] ? 0 : 3;
+        else i_min = (edgeOrientationsToMinVertex >> (2 * eo)) & 3u;
+        uint64_t fo = 0;
+        if (i_min == 0) fo = 0b1000 | ((uint64_t)(id[2] < id[1]) << 2);
+        else if (i_min == 1) fo = 0b1011 | ((uint64_t)(id[0] < id[3]) << 2);
+        else if (i_min == 2) fo = 0b1001 | ((uint64_t)(id[3] < id[0]) << 2);
+        else fo = 0b1010 | ((uint64_t)(id[1] < id[2]) << 2);
+        data |= fo << facetBitOffset(f);
+      }
+  }
+  // :403-410
+  unsigned faceOrientationIndex(int dim, int subEntity, int codim) const {
+    if (codim == dim - 1) return edgeBit(subEntity);
+    if (codim == 1) return (unsigned)((data >> facetBitOffset(subEntity)) & 15u);
+    return 0;
+  }
+};
+
+// Experimental::LagrangeFaceDOFPermutation restricted to cubes (lagrangebasis.hh:429-697)
+struct LagrangeFaceDOFPermutation {
+  int dim, order;
+  std::vector<std::vector<unsigned>> quadTable;    // rows 8..15 of facetFlipTable_ (:596-603)
+  // globallyOrientedQuadrilateralDOFTable :518-559
+  LagrangeFaceDOFPermutation(int dim_, int order_) : dim(dim_), order(order_), quadTable(8) {
+    if (dim != 3 || order < 2) return;
+    const unsigned m = order - 1, n = m * m;
+    for (unsigned j = 0; j < 8; ++j) {
+      quadTable[j].resize(n);
+      for (unsigned i = 0; i < n; ++i) {
+        unsigned c[2] = {i % m, i / m};
+        if ((j & 3u) == 1) { std::swap(c[0], c[1]); c[0] = m - 1 - c[0]; }
+        if ((j & 3u) == 2) { c[0] = m - 1 - c[0]; c[1] = m - 1 - c[1]; }
+        if ((j & 3u) == 3) { c[0] = m - 1 - c[0]; std::swap(c[0], c[1]); }
+        if (j & 4u) std::swap(c[0], c[1]);
+        quadTable[j][i] = c[0] + m * c[1];
+      }
+    }
+  }
+  // computeFaceOrientations :616-634 (cubes: never the "k == 3 and tetrahedron" branch)
+  FaceOrientations computeFaceOrientations(const Grid& g, const int ec[MAXDIM]) const {
+    size_type ids[8];
+    for (int v = 0; v < (1 << g.dim); ++v) {
+      int c[MAXDIM] = {0, 0, 0};
+      for (int j = 0; j < g.dim; ++j) c[j] = ec[j] + ((v >> j) & 1);
+      ids[v] = g.vertexIdAt(c);
+    }
+    if (dim == 1 || order < 3) return FaceOrientations(dim, ids, false, false);
+    return FaceOrientations(dim, ids, true, true);
+  }
+  // permuteFaceDOF :652-675
+  unsigned permuteFaceDOF(int subEntity, int codim, unsigned index, const FaceOrientations& o) const {
+    const int k = order;
+    if (dim == 1) return index;
+    if (dim == 2) {
+      if (k > 2 && codim == 1 && o.faceOrientationIndex(dim, subEntity, codim)) return k - 2 - index;
+      return index;
+    }
+    if (k > 2) {
+      if (codim == 2 && o.faceOrientationIndex(dim, subEntity, codim)) return k - 2 - index;
+      if (codim == 1) return quadTable[o.faceOrientationIndex(dim, subEntity, codim) - 8][index];
+    }
+    return index;
+  }
+};
+
+// ---------------------------------------------------------------------------
 // functions f (CPU restatement of the registry in include/dfx.h)
 static void evalFunction(const dfx_function& f, int dim, const double* x, double* y) {
   switch (f.id) {
@@ -374,9 +505,9 @@ struct PreBasis {
 
 // lagrangebasis.hh:740-889
 struct LagrangePreBasis : PreBasis {
-  const Grid& g; int k; LagrangeCubeFE fe; MCMGMapper mapper;
+  const Grid& g; int k; LagrangeCubeFE fe; LagrangeFaceDOFPermutation faceDOFPermutation; MCMGMapper mapper;
   LagrangePreBasis(const Grid& grid, int order)
-      : g(grid), k(order), fe(grid.dim, order),
+      : g(grid), k(order), fe(grid.dim, order), faceDOFPermutation(grid.dim, order),
         // dofLayout, lagrangebasis.hh:747-762: order 0 -> 1 per element, cube -> (order-1)^dim
         mapper(grid, [order, &grid](int entityDim) -> size_type {
           if (order == 0) return entityDim == grid.dim;
@@ -399,12 +530,13 @@ struct LagrangePreBasis : PreBasis {
       }
       return it;
     }
-    // computeFaceOrientations: identity on an unrefined structured grid (vertex ids
-    // monotone in lexicographic position), lagrangebasis.hh:615-674; for k<=2 a no-op.
+    // Precompute orientations of all faces (:863); with the structured grid's own vertex ids
+    // (monotone in lexicographic position) every orientation is the identity
+    FaceOrientations faceOrientations = faceDOFPermutation.computeFaceOrientations(g, e.c);
     for (int li = 0; li < fe.size(); ++li) {
       const LocalKey& key = fe.keys[li];
       size_type gi = mapper.subIndex(e.c, key.subEntity, key.codim);
-      gi += key.index;    // LocalKey index addressing within the sub-entity block  [EXT MCMG usage]
+      gi += faceDOFPermutation.permuteFaceDOF(key.subEntity, key.codim, (unsigned)key.index, faceOrientations);   // :868
       it->n = 1; it->d[0] = gi; ++it;
     }
     return it;
@@ -732,6 +864,33 @@ void* orc_basis_create(const dfx_grid_desc* g, const dfx_tree_node* t, int32_t n
   return b.release();
 }
 void orc_basis_destroy(void* h) { delete (orc::Basis*)h; }
+// Vertex ids of the grid's globalIdSet (lagrangebasis.hh:787), one per vertex of the local box in
+// lexicographic order; n = 0 restores the structured grid's own (monotone) ids.
+int32_t orc_set_vertex_ids(void* h, const uint64_t* ids, uint64_t n) {
+  auto* b = (orc::Basis*)h;
+  uint64_t nv = 1;
+  for (int j = 0; j < b->grid.dim; ++j) nv *= (uint64_t)(b->grid.N[j] + 1);
+  if (n != 0 && n != nv) return 1;
+  b->grid.vertexId.assign(ids, ids + n);
+  b->position.clear(); b->positionBuilt = false;
+  return 0;
+}
+// FaceOrientations of ONE cube with the given vertex ids (2^dim of them), all codimensions
+// requested: edge bits (4 in 2-d, 12 in 3-d) and facet orientation indices (6 in 3-d).  Test hook
+// for the truth tables of lagrangebasis.hh:132-174.
+void orc_face_orientations(int32_t dim, const uint64_t* ids, int32_t* edge_bits, int32_t* facet_index) {
+  orc::size_type v[8];
+  for (int i = 0; i < (1 << dim); ++i) v[i] = ids[i];
+  orc::FaceOrientations o(dim, v, true, true);
+  const int ne = dim == 1 ? 0 : orc::refCubeSize(dim, dim - 1);
+  for (int e = 0; e < ne; ++e) edge_bits[e] = o.faceOrientationIndex(dim, e, dim - 1);
+  if (dim == 3) for (int f = 0; f < 6; ++f) facet_index[f] = o.faceOrientationIndex(dim, f, 1);
+}
+// T[j][i] of globallyOrientedQuadrilateralDOFTable (lagrangebasis.hh:518-559), j = 0..7
+void orc_quad_dof_table(int32_t order, int32_t j, uint32_t* out) {
+  orc::LagrangeFaceDOFPermutation p(3, order);
+  for (size_t i = 0; i < p.quadTable[j].size(); ++i) out[i] = p.quadTable[j][i];
+}
 uint64_t orc_dimension(void* h) { return ((orc::Basis*)h)->pre->dimension(); }
 uint64_t orc_size_prefix(void* h, const uint64_t* prefix, int32_t len) {
   orc::MultiIndex p; for (int i = 0; i < len; ++i) p.push_back(prefix[i]);

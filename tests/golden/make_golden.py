@@ -12,6 +12,11 @@ Fixtures written
   merging_strategies.json     the four doc-comment tables of
                               dune/functions/functionspacebases/basistags.hh (what each index
                               merging strategy does to two children {f}, {g}), parsed literally.
+  face_orientations.json      the truth tables of Experimental::FaceOrientations in the doc comment of
+                              dune/functions/functionspacebases/lagrangebasis.hh (:132-174): for every
+                              ordering of the global vertex ids of a quadrilateral (and triangle) the
+                              edge orientations and the orientation index, parsed literally ("^" rows
+                              inherit the index of the row above, as in the comment).
   numbering_examples.json     the hand-derived numbering vectors of SURVEY.md Appendix A (A1-A3);
                               these are NOT from the reference (they document the dune-grid
                               conventions the oracle assumes) and are marked as such.
@@ -75,6 +80,38 @@ def parse_merging_tables():
     return {"source": "dune/functions/functionspacebases/basistags.hh:52-184", "tables": out}
 
 
+def parse_face_orientation_tables():
+    path = os.path.join(REF, "dune/functions/functionspacebases/lagrangebasis.hh")
+    lines = open(path, encoding="utf-8").read().split("\n")
+    out = {"source": "dune/functions/functionspacebases/lagrangebasis.hh doc comment of Experimental::FaceOrientations",
+           "triangle": [], "quadrilateral": []}
+    section = None
+    last = None
+    for ln in lines:
+        if "**Triangle orientations**" in ln:
+            section = "triangle"
+        elif "**Quadrilateral orientations**" in ln:
+            section = "quadrilateral"
+        elif "**Complexity bounds**" in ln:
+            break
+        if section is None or "|" not in ln:
+            continue
+        cells = [c.strip() for c in ln.strip().lstrip("*").strip().strip("|").split("|")]
+        if len(cells) != 9 or not re.fullmatch(r"[\d,]+", cells[0]):
+            continue
+        ids = [int(x) for x in cells[0].split(",")]
+        edges = [int(x) for x in cells[1].split(",")]
+        if cells[8] == "^":
+            row = dict(last, vertex_ids=ids, edge_orientations=edges)
+        else:
+            row = {"vertex_ids": ids, "edge_orientations": edges, "primary_edge": cells[2],
+                   "rotations": int(cells[3]), "reflection": cells[4] == "yes", "bits": cells[7], "index": int(cells[8])}
+        last = {k: v for k, v in row.items() if k not in ("vertex_ids", "edge_orientations")}
+        out[section].append(row)
+    assert len(out["triangle"]) == 6 and len(out["quadrilateral"]) == 24, (len(out["triangle"]), len(out["quadrilateral"]))
+    return out
+
+
 def numbering_examples():
     return {
         "source": "SURVEY.md Appendix A (hand-derived from lagrangebasis.hh:843-873 plus the recalled dune-grid "
@@ -97,6 +134,7 @@ def main():
         REF = sys.argv[1]
     for name, data in (("th_indexing_variants.json", parse_th_table()),
                        ("merging_strategies.json", parse_merging_tables()),
+                       ("face_orientations.json", parse_face_orientation_tables()),
                        ("numbering_examples.json", numbering_examples())):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(data, f, indent=1, sort_keys=True)

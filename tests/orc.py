@@ -53,6 +53,10 @@ def lib():
         L.orc_assemble_stokes.argtypes = [vp, vp, vp, vp]
         L.orc_dirichlet.argtypes = [u64, vp, vp, vp, vp, vp, vp]
         L.orc_csr_mv.argtypes = [u64, vp, vp, vp, vp, vp]
+        L.orc_set_vertex_ids.restype = i32
+        L.orc_set_vertex_ids.argtypes = [vp, vp, u64]
+        L.orc_face_orientations.argtypes = [i32, vp, vp, vp]
+        L.orc_quad_dof_table.argtypes = [i32, i32, vp]
         _lib = L
     return _lib
 
@@ -73,6 +77,17 @@ class OracleBasis:
 
     def dimension(self):
         return int(lib().orc_dimension(self._h))
+
+    def setVertexIds(self, ids):
+        """ids of the grid's globalIdSet for the vertices of the local box (lexicographic order);
+        None restores the structured grid's own monotone ids"""
+        if ids is None:
+            rc = lib().orc_set_vertex_ids(self._h, None, 0)
+        else:
+            a = np.ascontiguousarray(ids, dtype=np.uint64)
+            rc = lib().orc_set_vertex_ids(self._h, a.ctypes.data, a.size)
+        if rc:
+            raise ValueError("oracle: wrong number of vertex ids")
 
     def size(self, prefix=()):
         p = (C.c_uint64 * max(1, len(prefix)))(*prefix)
@@ -219,3 +234,20 @@ def oracle_mv(csr, x):
     y = np.zeros(len(row_ptr) - 1)
     lib().orc_csr_mv(len(row_ptr) - 1, row_ptr.ctypes.data, col.ctypes.data, values.ctypes.data, x.ctypes.data, y.ctypes.data)
     return y
+
+
+def faceOrientations(dim, ids):
+    """(edge bits, facet orientation indices) of one cube with the given vertex ids"""
+    a = np.ascontiguousarray(ids, dtype=np.uint64)
+    assert a.size == 1 << dim
+    edges = np.zeros(12, dtype=np.int32)
+    facets = np.zeros(6, dtype=np.int32)
+    lib().orc_face_orientations(dim, a.ctypes.data, edges.ctypes.data, facets.ctypes.data)
+    ne = {1: 0, 2: 4, 3: 12}[dim]
+    return edges[:ne].tolist(), (facets.tolist() if dim == 3 else [])
+
+
+def quadDofTable(order, j):
+    out = np.zeros((order - 1) ** 2, dtype=np.uint32)
+    lib().orc_quad_dof_table(order, j, out.ctypes.data)
+    return out

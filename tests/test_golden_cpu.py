@@ -191,3 +191,4 @@ def test_fixtures_are_in_sync_with_the_reference_when_it_is_present():
     spec.loader.exec_module(mg)
     assert mg.parse_th_table() == load("th_indexing_variants.json")
     assert json.loads(json.dumps(mg.parse_merging_tables())) == load("merging_strategies.json")
+    assert json.loads(json.dumps(mg.parse_face_orientation_tables())) == load("face_orientations.json")
