@@ -55,6 +55,9 @@ SIGNATURES = {
     "dfx_kernel_launch_count": (_u64, []),
     "dfx_basis_create": (C.c_int, [C.POINTER(GridDesc), C.POINTER(TreeNode), _i32, _i32, C.POINTER(_vp)]),
     "dfx_basis_destroy": (None, [_vp]),
+    "dfx_basis_set_vertex_ids": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "dfx_basis_set_vertex_ids_host": (C.c_int, [_vp, _vp, _u64]),
+    "dfx_basis_has_permuted_face_dofs": (_i32, [_vp]),
     "dfx_basis_dimension": (_u64, [_vp]),
     "dfx_basis_size": (_u64, [_vp, _pu64, _i32]),
     "dfx_basis_max_node_size": (_i32, [_vp]),

@@ -102,6 +102,9 @@ class YaspGrid:
     lower: Optional[Sequence[float]] = None
     local_begin: Optional[Sequence[int]] = None
     local_n: Optional[Sequence[int]] = None
+    # ids of the grid's globalIdSet for the vertices of the local box (lexicographic, x fastest);
+    # None = the grid's own monotone ids.  See dfx_basis_set_vertex_ids in include/dfx.h.
+    vertex_ids: Optional[Sequence[int]] = None
 
     @property
     def dim(self):
@@ -133,7 +136,14 @@ class YaspGrid:
         ln = list(self.n)
         lb[d - 1] = b
         ln[d - 1] = e - b
-        return YaspGrid(self.n, self.upper, self.lower, lb, ln)
+        ids = None
+        if self.vertex_ids is not None:
+            # z is the slowest direction of the vertex lattice: a slab's vertices are one contiguous run
+            plane = 1
+            for j in range(d - 1):
+                plane *= self.n[j] + 1
+            ids = self.vertex_ids[b * plane:(e + 1) * plane]
+        return YaspGrid(self.n, self.upper, self.lower, lb, ln, ids)
 
 
 def tree_array(factory):
@@ -214,12 +224,38 @@ class GlobalBasis:
         h = C.c_void_p()
         capi.check(self._lib.dfx_basis_create(C.byref(self._desc), arr, n, device, C.byref(h)))
         self._h = h
+        if getattr(grid, "vertex_ids", None) is not None:
+            self.setVertexIds(grid.vertex_ids)
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             self._lib.dfx_basis_destroy(h)
             self._h = None
+
+    def setVertexIds(self, ids):
+        """ids of grid().globalIdSet() for the vertices of the local box, the input of
+        LagrangeFaceDOFPermutation (lagrangebasis.hh:787); None restores the grid's own ids.
+        Accepts a host sequence / numpy array or a CUDA uint64/int64 torch tensor."""
+        if ids is None:
+            capi.check(self._lib.dfx_basis_set_vertex_ids_host(self._h, None, 0))
+            return
+        try:
+            import torch
+            is_dev = isinstance(ids, torch.Tensor) and ids.is_cuda
+        except ImportError:
+            is_dev = False
+        if is_dev:
+            t = ids.contiguous()
+            assert t.dtype in (torch.int64, torch.uint64), "vertex ids: 64-bit integers expected"
+            capi.check(self._lib.dfx_basis_set_vertex_ids(self._h, t.data_ptr(), t.numel(), _stream()))
+            return
+        import numpy as np
+        a = np.ascontiguousarray(np.asarray(ids), dtype=np.uint64)
+        capi.check(self._lib.dfx_basis_set_vertex_ids_host(self._h, a.ctypes.data, a.size))
+
+    def hasPermutedFaceDOFs(self):
+        return bool(self._lib.dfx_basis_has_permuted_face_dofs(self._h))
 
     # GlobalBasis concept
     def dimension(self):

@@ -176,6 +176,7 @@ void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
   if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
   if (b->dJinv) { cudaSetDevice(b->device); cudaFree(b->dJinv); }
+  if (b->dVid) { cudaSetDevice(b->device); cudaFree(b->dVid); }
   if (b->dNodal) { cudaSetDevice(b->device); cudaFree(b->dNodal); }
   if (b->evStream[0]) { cudaSetDevice(b->device); cudaStreamDestroy((cudaStream_t)b->evStream[0]); }
   if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
@@ -190,6 +191,41 @@ void dfx_basis_destroy(dfx_basis* b) {
   }
   delete b;
 }
+
+// ---- vertex ids for the face-DOF permutation (lagrangebasis.hh:787, :616-634) ---------------------
+static u64 numVertices(const dfx_basis* b) {
+  u64 n = 1;
+  for (int j = 0; j < b->dev.grid.dim; ++j) n *= (u64)(b->dev.grid.N[j] + 1);
+  return n;
+}
+static int setVertexIds(dfx_basis* b, const uint64_t* ids, uint64_t n, bool fromHost, cudaStream_t st) {
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (ids && n != numVertices(b)) return fail(DFX_ERR_RANGE, "one id per vertex of the local box expected");
+  if (!ids) {
+    b->dev.vid = nullptr;             // the table itself stays allocated until destroy: kernels in flight may read it
+    b->oriented = false;
+  } else {
+    if (!b->dVid) DFX_CUDA(cudaMalloc(&b->dVid, n * sizeof(u64)));
+    DFX_CUDA(cudaMemcpyAsync(b->dVid, ids, n * sizeof(u64), fromHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    if (fromHost) DFX_CUDA(cudaStreamSynchronize(st));
+    b->dev.vid = (const u64*)b->dVid;
+    b->oriented = false;
+    if (b->dev.grid.dim > 1)
+      for (int l = 0; l < b->dev.nLeaves; ++l) {
+        const DevLayout& L = b->dev.layouts[b->dev.leaves[l].layout];
+        if (L.kind == DFX_NODE_LAGRANGE && L.k >= 3) b->oriented = true;
+      }
+  }
+  if (b->dDev) DFX_CUDA(cudaMemcpyAsync(b->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice, st));
+  return DFX_OK;
+}
+int dfx_basis_set_vertex_ids(dfx_basis* b, const uint64_t* ids, uint64_t n, void* stream) {
+  return setVertexIds(b, ids, n, false, (cudaStream_t)stream);
+}
+int dfx_basis_set_vertex_ids_host(dfx_basis* b, const uint64_t* ids_host, uint64_t n) {
+  return setVertexIds(b, ids_host, n, true, nullptr);
+}
+int32_t dfx_basis_has_permuted_face_dofs(const dfx_basis* b) { return b && b->oriented ? 1 : 0; }
 
 uint64_t dfx_basis_dimension(const dfx_basis* b) { return b ? b->dimension : 0; }
 uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t len) {
@@ -243,7 +279,7 @@ int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* ou
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_multi_u64");
-  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, true>(b, e0, e1, out, stride, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<uint32_t, true>(b, e0, e1, out, stride, (cudaStream_t)stream);
   return indicesMulti32(b, e0, e1, out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, int32_t stride, void* stream) {
@@ -251,7 +287,7 @@ int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
-  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, true>(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<u64, true>(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
   return indicesMulti64(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, void* stream) {
@@ -259,14 +295,14 @@ int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_flat_u64");
-  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, false>(b, e0, e1, out, 1, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<uint32_t, false>(b, e0, e1, out, 1, (cudaStream_t)stream);
   return indicesFlat32(b, e0, e1, out, (cudaStream_t)stream);
 }
 int dfx_indices_flat_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, void* stream) {
   DFX_RANGE("dfx_indices_flat_u64");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
-  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
   return indicesFlat64(b, e0, e1, (u64*)out, (cudaStream_t)stream);
 }
 
@@ -289,7 +325,7 @@ int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, dou
   if ((rc = subtree(b, node, fl, nl))) return rc;
   if ((rc = checkFunction(f, nl))) return rc;
   if (!coeff) return fail(DFX_ERR_INVALID, "null coefficient vector");
-  if (g_interpPath != 0 && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
+  if (g_interpPath != 0 && !b->oriented && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
     g_interpMode = g_interpPath == 1 ? 0 : -1;
     return interpolateFast(const_cast<dfx_basis*>(b), fl, nl, *f, coeff, mask, (cudaStream_t)stream);
   }
@@ -425,6 +461,7 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host,
   int fl, nl;
   if (subtree(b, node, fl, nl)) return -1;
   FastPlan plan;
+  if (b->oriented) return 0;
   if (g_forcedPath == 3) return dmmaPathHas(b, fl, nl) ? 3 : 0;
   const int path = planFastEval(b, fl, nl, xhat_host, n_q, want_jac != 0, g_forcedPath, plan);
   if (path == 0 && g_forcedPath < 0 && dmmaPathHas(b, fl, nl)) return 3;
@@ -442,6 +479,13 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
   if (!coeff || !xhat_host || n_q < 1) return fail(DFX_ERR_INVALID, "null argument");
   if (!out_values && !out_jac) return DFX_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (b->oriented) {
+    // permuted face DOFs (dfx_basis_set_vertex_ids): the closed-form gathers of the fast paths do not
+    // apply, every coefficient is located through layoutIndexOriented
+    ShapeOffsets so; const double *dS, *dDS;
+    if ((rc = prepareShape(b, node, fl, nl, xhat_host, n_q, so, dS, dDS, st))) return rc;
+    return evalGeneric(b, fl, nl, coeff, dS, dDS, so, n_q, e0, e1, out_values, out_jac, st);
+  }
   FastPlan plan;
   const int path = g_forcedPath == 3 ? 0 : planFastEval(b, fl, nl, xhat_host, n_q, out_jac != nullptr, g_forcedPath, plan);
   if (path > 0) return runFastEval(b, plan, fl, nl, coeff, e0, e1, out_values, out_jac, st);
@@ -773,6 +817,7 @@ int dfx_assemble_laplace(const dfx_basis* cb, const uint64_t* row_ptr, const uin
   int rc = ensureDevice(b); if (rc) return rc;
   if (!row_ptr || !col_idx) return fail(DFX_ERR_INVALID, "null pattern");
   if (rhs && (rc = checkFunction(f, 1))) return rc;
+  if (b->oriented) return fail(DFX_ERR_NOT_IMPLEMENTED, "Laplace assembly with permuted face DOFs (dfx_basis_set_vertex_ids)");
   return assembleLaplace(b, (const u64*)row_ptr, col_idx, values, f, rhs, (cudaStream_t)stream);
 }
 
@@ -806,6 +851,7 @@ int dfx_apply_laplace(const dfx_basis* cb, const double* x, double* y, const uin
   dfx_basis* b = const_cast<dfx_basis*>(cb);
   int rc = ensureDevice(b); if (rc) return rc;
   if (!x || !y || !scratch) return fail(DFX_ERR_INVALID, "null argument");
+  if (b->oriented) return fail(DFX_ERR_NOT_IMPLEMENTED, "matrix-free Laplace with permuted face DOFs (dfx_basis_set_vertex_ids)");
   return applyLaplace(b, x, y, dirichlet, scratch, (cudaStream_t)stream);
 }
 

@@ -67,6 +67,11 @@ struct DevBasis {
   int nLeaves, nLayouts, nlocTotal, maxDigits;
   DevLayout layouts[kMaxLayouts];
   DevLeaf leaves[DFX_MAX_LEAVES];
+  // ids of the grid's globalIdSet for the vertices of the local box, lexicographic (device memory,
+  // owned by the handle); nullptr = the structured grid's own ids, monotone in lexicographic
+  // position, for which every face orientation is the identity (lagrangebasis.hh:787, :615-634).
+  // Last member on purpose: the offsets of everything the tuned kernels read stay what they were.
+  const u64* vid;
 };
 
 // scalar index of local node alpha of element e in a continuous/DG layout
@@ -93,6 +98,116 @@ DFX_HD u64 layoutIndex(const DevLayout& L, const DevGrid& g, const int e[3], con
   return L.compOffset[s] + ent * (u64)L.blk[s] + fr;
 }
 
+// ---- face-DOF permutation of continuous Lagrange k >= 3 ----------------------
+// Experimental::LagrangeFaceDOFPermutation::permuteFaceDOF (lagrangebasis.hh:652-675) for cube
+// grids whose vertex ids are not monotone.  `fr` is the index of a node inside its entity as the
+// ELEMENT numbers it (LocalKey::index: lexicographic over the entity's free directions, base k-1);
+// the result is the index with respect to the entity's globally unique orientation — and the other
+// way round with INVERSE.  Edges (:232-235): flipped iff id(first vertex) > id(second).  Quadrilateral
+// facets (:279-331, table :518-559): r counter-clockwise rotations bring the vertex with the smallest
+// id to corner 0, then a reflection across the diagonal if that vertex's second neighbour has a
+// smaller id than its first; the vertex with the smallest id is found directly (the reference derives
+// it from the edge bits to save comparisons, ":291-297 ... is equivalent to").  The orientation depends
+// on the entity only, so every element that contains it computes the same one.
+template <bool INVERSE>
+DFX_HD unsigned orientFaceDOF(const DevGrid& g, const u64* vid, int k, unsigned s, const int c[3], unsigned fr) {
+  const u64 v0s = (u64)(g.N[0] + 1), v1s = v0s * (u64)(g.N[1] + 1);
+  const u64 base = (u64)c[0] + v0s * (u64)c[1] + v1s * (u64)c[2];
+  const u64 st[3] = {1, v0s, v1s};
+  const int nfree = ((s >> 0) & 1) + ((s >> 1) & 1) + ((s >> 2) & 1);
+  if (nfree == 1 && g.dim > 1) {
+    const int f = (s & 1u) ? 0 : ((s & 2u) ? 1 : 2);
+    return vid[base] > vid[base + st[f]] ? (unsigned)(k - 2) - fr : fr;
+  }
+  if (nfree == 2 && g.dim == 3) {
+    const int f0 = (s & 1u) ? 0 : 1, f1 = (s & 4u) ? 2 : 1;
+    const u64 id0 = vid[base], id1 = vid[base + st[f0]], id2 = vid[base + st[f1]], id3 = vid[base + st[f0] + st[f1]];
+    unsigned r, refl;
+    if (id0 < id1 && id0 < id2 && id0 < id3) { r = 0; refl = id2 < id1; }
+    else if (id1 < id2 && id1 < id3) { r = 3; refl = id0 < id3; }
+    else if (id2 < id3) { r = 1; refl = id3 < id0; }
+    else { r = 2; refl = id1 < id2; }
+    const unsigned m = (unsigned)(k - 1);
+    unsigned c0 = fr % m, c1 = fr / m, t;
+    if (INVERSE) {
+      if (refl) { t = c0; c0 = c1; c1 = t; }
+      r = (4u - r) & 3u;
+    }
+    if (r == 1) { t = c0; c0 = m - 1 - c1; c1 = t; }            // swap, then mirror c0
+    else if (r == 2) { c0 = m - 1 - c0; c1 = m - 1 - c1; }
+    else if (r == 3) { t = c0; c0 = c1; c1 = m - 1 - t; }       // mirror c0, then swap
+    if (!INVERSE && refl) { t = c0; c0 = c1; c1 = t; }
+    return c0 + m * c1;
+  }
+  return fr;
+}
+
+// layoutIndex with the face-DOF permutation applied (PreBasis::indices, lagrangebasis.hh:863-869)
+DFX_HD u64 layoutIndexOriented(const DevLayout& L, const DevGrid& g, const u64* vid, const int e[3], const int a[3], int li) {
+  if (vid == nullptr || L.kind != DFX_NODE_LAGRANGE || L.k < 3 || g.dim < 2) return layoutIndex(L, g, e, a, li);
+  const int k = L.k;
+  unsigned s = 0, fr = 0, frs = 1;
+  int c[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (a[j] > 0 && a[j] < k) { s |= 1u << j; c[j] = e[j]; fr += (unsigned)(a[j] - 1) * frs; frs *= (unsigned)(k - 1); }
+    else c[j] = e[j] + (a[j] == k ? 1 : 0);
+  }
+  fr = orientFaceDOF<false>(g, vid, k, s, c, fr);
+  const u64 ent = (u64)c[0] + (u64)L.csize[s][0] * ((u64)c[1] + (u64)L.csize[s][1] * (u64)c[2]);
+  return L.compOffset[s] + ent * (u64)L.blk[s] + (u64)fr;
+}
+
+// The element that owns scalar DOF t of layout L in interpolate(), and the DOF's lattice multi-index in
+// it: the LAST element (in grid-view iteration order of the GLOBAL grid) that contains the node — its
+// write is the one that survives in the reference loop (interpolate.hh:254-259 visits the elements in
+// order and :166-171 overwrites).  ie = GLOBAL element coordinates, a = alpha in {0..k}^dim.
+DFX_HD void dofOwnerNode(const DevBasis& B, const DevLayout& L, u64 t, int ie[3], int a[3]) {
+  const DevGrid& g = B.grid;
+  const int k = L.k;
+  ie[0] = ie[1] = ie[2] = 0;
+  a[0] = a[1] = a[2] = 0;
+  if (L.kind == DFX_NODE_LAGRANGE_DG) {
+    const u64 e = t / (u64)L.nloc;
+    int i = (int)(t - e * (u64)L.nloc);
+    const int n1 = k + 1;
+    a[0] = i % n1; i /= n1;
+    a[1] = i % n1; i /= n1;
+    a[2] = i;
+    ie[0] = (int)(e % (u64)g.N[0]) + g.off[0];
+    const u64 r = e / (u64)g.N[0];
+    ie[1] = (int)(r % (u64)g.N[1]) + g.off[1];
+    ie[2] = (int)(r / (u64)g.N[1]) + g.off[2];
+    return;
+  }
+  // component of t
+  int s = L.order[0];
+  for (int q = 1; q < L.ncomp; ++q)
+    if (t >= L.compOffset[L.order[q]]) s = L.order[q];
+  const u64 r = t - L.compOffset[s];
+  const u64 ent = r / (u64)L.blk[s];
+  unsigned fr = (unsigned)(r - ent * (u64)L.blk[s]);
+  int c[3];
+  c[0] = (int)(ent % (u64)L.csize[s][0]);
+  const u64 r2 = ent / (u64)L.csize[s][0];
+  c[1] = (int)(r2 % (u64)L.csize[s][1]);
+  c[2] = (int)(r2 / (u64)L.csize[s][1]);
+  // t counts the entity's nodes in its globally unique orientation; the element that writes the node
+  // numbers them in its own (lagrangebasis.hh:868, inverted)
+  if (B.vid != nullptr && k > 2 && g.dim > 1) fr = orientFaceDOF<true>(g, B.vid, k, (unsigned)s, c, fr);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= g.dim) continue;
+    if ((s >> j) & 1) {            // node strictly inside the entity along j
+      ie[j] = g.off[j] + c[j];
+      if (k > 1) { a[j] = (int)(fr % (unsigned)(k - 1)) + 1; fr /= (unsigned)(k - 1); }
+    } else {                       // node on a lattice plane: owner = upper neighbour if any
+      const int gc = g.off[j] + c[j];
+      if (gc < g.G[j]) { ie[j] = gc; a[j] = 0; } else { ie[j] = g.G[j] - 1; a[j] = k; }
+    }
+  }
+}
+
 // ---- host-side basis --------------------------------------------------------
 struct HostNode {           // expanded local ansatz tree, preorder
   int kind, order, ims;
@@ -115,6 +230,8 @@ struct dfx_basis_impl {
   std::vector<unsigned> localTab;                       // per local index: leaf | alpha (see k_indices_fast)
   void* dLocalTab = nullptr;                            // uploaded on first use
   void* dDev = nullptr;                                 // device copy of `dev`
+  void* dVid = nullptr;                                 // vertex ids (dev.grid.vid points here)
+  bool oriented = false;                                // ids given AND some continuous leaf of order >= 3 in 2-d/3-d
   void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f
   void* dShape = nullptr; size_t dShapeBytes = 0;       // shape tables of the last evaluate
   void* dNodal = nullptr; size_t dNodalBytes = 0;       // nodal values of a grid function (dfx_interpolate_dgbf)

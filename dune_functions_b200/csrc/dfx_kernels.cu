@@ -45,7 +45,7 @@ k_indices(const __grid_constant__ DevBasis B, u64 e0, u64 total, T* __restrict__
   const int i = li - leaf.localOffset;
   int a[3];
   localAlpha(L.k, i, a);
-  const u64 j = layoutIndex(L, B.grid, ec, a, i);
+  const u64 j = layoutIndexOriented(L, B.grid, B.vid, ec, a, i);
   if (MULTI) {
     for (int p = 0; p < stride; ++p)
       out[t * (u64)stride + p] = p < leaf.ndig ? (T)(leaf.digA[p] * j + leaf.digB[p]) : (T)0;
@@ -85,41 +85,9 @@ int indicesFlat64(const dfx_basis* b, u64 e0, u64 e1, u64* out, cudaStream_t st)
 // overwrites).  Returns false if t is out of range.
 __device__ __forceinline__ void nodePosition(const DevBasis& B, const DevLayout& L, u64 t, double x[3]) {
   const DevGrid& g = B.grid;
-  int ie[3] = {0, 0, 0}, a[3] = {0, 0, 0};
+  int ie[3], a[3];
   const int k = L.k;
-  if (L.kind == DFX_NODE_LAGRANGE_DG) {
-    const u64 e = t / (u64)L.nloc;
-    const int i = (int)(t - e * (u64)L.nloc);
-    localAlpha(k, i, a);
-    ie[0] = (int)(e % (u64)g.N[0]) + g.off[0];
-    const u64 r = e / (u64)g.N[0];
-    ie[1] = (int)(r % (u64)g.N[1]) + g.off[1];
-    ie[2] = (int)(r / (u64)g.N[1]) + g.off[2];
-  } else {
-    // component of t
-    int s = L.order[0];
-    for (int q = 1; q < L.ncomp; ++q)
-      if (t >= L.compOffset[L.order[q]]) s = L.order[q];
-    const u64 r = t - L.compOffset[s];
-    const u64 ent = r / (u64)L.blk[s];
-    unsigned fr = (unsigned)(r - ent * (u64)L.blk[s]);
-    int c[3];
-    c[0] = (int)(ent % (u64)L.csize[s][0]);
-    const u64 r2 = ent / (u64)L.csize[s][0];
-    c[1] = (int)(r2 % (u64)L.csize[s][1]);
-    c[2] = (int)(r2 / (u64)L.csize[s][1]);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (j >= g.dim) continue;
-      if ((s >> j) & 1) {            // node strictly inside the entity along j
-        ie[j] = g.off[j] + c[j];
-        if (k > 1) { a[j] = (int)(fr % (unsigned)(k - 1)) + 1; fr /= (unsigned)(k - 1); }
-      } else {                       // node on a lattice plane: owner = upper neighbour if any
-        const int gc = g.off[j] + c[j];
-        if (gc < g.G[j]) { ie[j] = gc; a[j] = 0; } else { ie[j] = g.G[j] - 1; a[j] = k; }
-      }
-    }
-  }
+  dofOwnerNode(B, L, t, ie, a);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     if (j >= g.dim) { x[j] = 0.0; continue; }
@@ -284,6 +252,10 @@ k_scatter_nodes(const __grid_constant__ DevBasis B, const __grid_constant__ Scat
       if (a0 > 0 && (int)a0 < k) { s |= 1u; fr += (a0 - 1) * frs; frs *= (unsigned)(k - 1); } else c0 += (int)a0 == k ? 1u : 0u;
       if (a1 > 0 && (int)a1 < k) { s |= 2u; fr += (a1 - 1) * frs; frs *= (unsigned)(k - 1); } else c1 += (int)a1 == k ? 1u : 0u;
       if (a2 > 0 && (int)a2 < k) { s |= 4u; fr += (a2 - 1) * frs; } else c2 += (int)a2 == k ? 1u : 0u;
+      if (B.vid != nullptr && k > 2 && g.dim > 1) {
+        const int cc[3] = {(int)c0, (int)c1, (int)c2};
+        fr = orientFaceDOF<false>(g, B.vid, k, s, cc, fr);
+      }
       const u64 ent = (u64)c0 + (u64)sCs0[s] * ((u64)c1 + (u64)sCs1[s] * (u64)c2);
       jdx = sOff[s] + ent * (u64)sBlk[s] + fr;
     } else {
@@ -356,7 +328,7 @@ k_eval_generic(const __grid_constant__ DevBasis B, int firstLeaf, int nLeaves, c
     for (int i = 0; i < L.nloc; ++i) {
       int a[3];
       localAlpha(L.k, i, a);
-      const u64 j = layoutIndex(L, g, ec, a, i);
+      const u64 j = layoutIndexOriented(L, g, B.vid, ec, a, i);
       const double c = coeff[leaf.posA * j + leaf.posB];
       if (VAL) v = __dadd_rn(v, __dmul_rn(c, sh[i]));
       if (JAC)
@@ -533,7 +505,7 @@ k_eval_global(const __grid_constant__ DevBasis B, int firstLeaf, int nLeaves, co
     for (int i = 0; i < L.nloc; ++i) {
       int a[3];
       localAlpha(k, i, a);
-      const u64 jdx = layoutIndex(L, g, ec, a, i);
+      const u64 jdx = layoutIndexOriented(L, g, B.vid, ec, a, i);
       const double c = coeff[leaf.posA * jdx + leaf.posB];
       if (VAL) {
         double phi = 1.0;

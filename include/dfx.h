@@ -140,6 +140,26 @@ int  dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_
                       int32_t n_nodes, int32_t device, dfx_basis** out);
 void dfx_basis_destroy(dfx_basis* b);
 
+/* Vertex ids for the face-DOF permutation of continuous Lagrange bases of order >= 3.
+ * Replaces: the `gridView.grid().globalIdSet()` argument of Experimental::LagrangeFaceDOFPermutation
+ * (lagrangebasis.hh:787, :585-604) as read by computeFaceOrientations (:616-634).  `ids` holds one
+ * pairwise different id per vertex of the LOCAL box in lexicographic order (x fastest),
+ * n = prod (local_n[j] + 1); the library keeps its own copy.  Without ids (the default, or
+ * ids = NULL) the grid's own ids are used: they are monotone in lexicographic position, every edge
+ * and facet orientation is the identity and permuteFaceDOF (:652-675) is a no-op.  With ids — a grid
+ * manager whose ids are not ordered like the lattice (UGGrid / ALUGrid cube meshes, refined grids;
+ * lagrangebasistest.cc:34-70) — edge DOFs are flipped (:232-235, :660-668) and the DOFs of
+ * quadrilateral facets run through the table of :518-559 selected by the facet's orientation index
+ * (:279-331) in bind/index, interpolate and evaluate.  Orders <= 2 and 1-d grids are unaffected.
+ * Set ids before computing anything that depends on the numbering; in a slab-partitioned run every
+ * rank passes the ids of its own box (same id for the same vertex on both sides of an interface).
+ * dfx_assemble_laplace and dfx_apply_laplace return DFX_ERR_NOT_IMPLEMENTED on a basis whose face
+ * DOFs are permuted.                                                                              */
+int     dfx_basis_set_vertex_ids(dfx_basis* b, const uint64_t* ids, uint64_t n, void* stream);
+int     dfx_basis_set_vertex_ids_host(dfx_basis* b, const uint64_t* ids_host, uint64_t n);
+/* 1 iff ids are set AND some continuous leaf has order >= 3 on a 2-d/3-d grid (the general kernels run) */
+int32_t dfx_basis_has_permuted_face_dofs(const dfx_basis* b);
+
 /* ---- GlobalBasis concept: functionspacebases/concepts.hh:253-273 -----------*/
 uint64_t dfx_basis_dimension(const dfx_basis* b);                 /* defaultglobalbasis.hh:144-147 */
 uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t len); /* :150-160 */

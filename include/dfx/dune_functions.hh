@@ -109,8 +109,19 @@ class YaspGrid {
     for (int j = 0; j < dim; ++j) { el.coord[j] = (int)(e % N_[j]); e /= N_[j]; }
     return el;
   }
+  // grid.globalIdSet() restricted to vertices: what Experimental::LagrangeFaceDOFPermutation orients edges
+  // and facets with (lagrangebasis.hh:787).  YaspGrid's own ids are monotone in lexicographic position
+  // (empty table).  setGlobalVertexIds stands for a grid manager that numbers differently (UGGrid /
+  // ALUGrid cube meshes): one id per vertex, lexicographic, x fastest.  Bases read it at construction.
+  void setGlobalVertexIds(std::vector<std::uint64_t> ids) {
+    std::size_t nv = 1; for (int j = 0; j < dim; ++j) nv *= (std::size_t)N_[j] + 1;
+    if (!ids.empty() && ids.size() != nv) throw RangeError("one id per vertex expected");
+    vertexIds_ = std::move(ids);
+  }
+  const std::vector<std::uint64_t>& globalVertexIds() const { return vertexIds_; }
   FieldVector<double, dim> L_, lower_;
   std::array<int, dim> N_;
+  std::vector<std::uint64_t> vertexIds_;
 };
 
 // elements(gridView): the reference's range-based element loop
@@ -338,6 +349,8 @@ class DefaultGlobalBasis {
       g.upper[j] = j < dim ? gv.grid().L_[j] : 1.0;
     }
     Impl::check(dfx_basis_create(&g, f.nodes.data(), (int32_t)f.nodes.size(), device, &h_->h));
+    const auto& ids = gv.grid().globalVertexIds();
+    if (!ids.empty()) Impl::check(dfx_basis_set_vertex_ids_host(h_->h, ids.data(), ids.size()));
   }
   const GV& gridView() const { return gv_; }
   size_type dimension() const { return dfx_basis_dimension(h_->h); }

@@ -6,6 +6,8 @@
 // lagrangebasistest.cc, lagrangedgbasistest.cc:31-66, taylorhoodbasistest.cc:35-146,
 // compositebasistest.cc:66-122, gridviewfunctionspacebasistest.cc:115-183.
 // Runs on the GPU through libdfx.so; exit code 0 = all checks passed.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <map>
 #include <set>
@@ -163,6 +165,52 @@ int main() {
       diff = 0;
       for (std::size_t i = 0; i < c1.size(); ++i) diff = std::max(diff, std::abs(c1[i] - c1ref[i]));
       CHECK(diff < 1e-14, "Q2 discrete function interpolated into Q1 = nodal values");
+    }
+    // lagrangebasistest.cc:134-310 (createNonUniformCubeGrid, orders 1..5): cube grids whose vertex ids are
+    // not ordered like the lattice, so that edge and facet DOFs of order >= 3 have to be permuted
+    // (Experimental::LagrangeFaceDOFPermutation, lagrangebasis.hh:429-697) for the basis to conform.
+    // Conformity is checked through what it implies: a cubic is reproduced exactly at points on both
+    // sides of every element interface.
+    {
+      Grid2 tw2(FieldVector<double, 2>(1.0), {{3, 2}});
+      Grid3 tw3(FieldVector<double, 3>(1.0), {{2, 2, 2}});
+      std::vector<std::uint64_t> ids2(12), ids3(27);
+      for (std::size_t v = 0; v < ids2.size(); ++v) ids2[v] = (v * 7 + 3) % 12;     // 7 is coprime to 12 and 27:
+      for (std::size_t v = 0; v < ids3.size(); ++v) ids3[v] = (v * 7 + 3) % 27;     // permutations of the ids
+      tw2.setGlobalVertexIds(ids2);
+      tw3.setGlobalVertexIds(ids3);
+      auto cubic2 = [](const FieldVector<double, 2>& p) { return p[0] * p[0] * p[0] + 2 * p[0] * p[1] * p[1] - p[1]; };
+      auto cubic3 = [](const FieldVector<double, 3>& p) { return p[0] * p[0] * p[0] + 2 * p[0] * p[1] * p[1] - p[1] + p[2] * p[2] * p[0]; };
+      for (int order = 1; order <= 5; ++order) {
+        auto b2 = makeBasis(tw2.leafGridView(), lagrange(order));
+        auto b3 = makeBasis(tw3.leafGridView(), lagrange(order));
+        checkBasis(b2, "lagrange(order) 2d, permuted vertex ids");
+        checkBasis(b3, "lagrange(order) 3d, permuted vertex ids");
+        if (order < 3) continue;
+        std::vector<double> x2, x3;
+        interpolate(b2, x2, cubic2);
+        interpolate(b3, x3, cubic3);
+        auto f2 = makeDiscreteGlobalBasisFunction<double>(b2, x2);
+        auto f3 = makeDiscreteGlobalBasisFunction<double>(b3, x3);
+        double err = 0;
+        for (int i = 0; i < 40; ++i) {
+          FieldVector<double, 2> p{std::fmod(0.137 * i + 0.05, 1.0), std::fmod(0.291 * i + 0.11, 1.0)};
+          FieldVector<double, 3> q{p[0], p[1], std::fmod(0.173 * i + 0.07, 1.0)};
+          err = std::max(err, std::abs(f2(p)[0] - cubic2(p)));
+          err = std::max(err, std::abs(f3(q)[0] - cubic3(q)));
+        }
+        CHECK(err < 1e-12, "cubic reproduced by lagrange(order >= 3) with permuted face DOFs");
+      }
+      // without ids the same grid gives another numbering of the same space: coefficients are a permutation
+      Grid3 plain(FieldVector<double, 3>(1.0), {{2, 2, 2}});
+      auto bp = makeBasis(plain.leafGridView(), lagrange(4));
+      auto bt = makeBasis(tw3.leafGridView(), lagrange(4));
+      std::vector<double> xp, xt;
+      interpolate(bp, xp, cubic3);
+      interpolate(bt, xt, cubic3);
+      CHECK(xp != xt, "permuted vertex ids change the numbering of order-4 DOFs");
+      std::sort(xp.begin(), xp.end()); std::sort(xt.begin(), xt.end());
+      CHECK(xp == xt, "same coefficients in another order");
     }
     // error behaviour: RangeError for an unsupported order (lagrangebasis.hh:795-796)
     bool threw = false;

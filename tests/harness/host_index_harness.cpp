@@ -67,3 +67,64 @@ extern "C" int harness_band_uploads(const dfx_grid_desc* g, const dfx_tree_node*
   delete static_cast<dfx_basis*>(impl);
   return 0;
 }
+
+// Face-DOF permutation (dfx_basis_set_vertex_ids): layoutIndexOriented / orientFaceDOF / dofOwnerNode of
+// dfx_internal.h are host-device functions, so the exact code the generic kernels run is walked here on
+// the CPU with the vertex ids in host memory.  flat[e][li] = what k_indices writes; the return value
+// counts (a) DOFs t whose owner node does not map back to t through the oriented index (the node
+// k_interpolate / k_points pick for t would belong to another DOF), (b) in-entity indices that the
+// inverse permutation does not bring back.
+extern "C" long long harness_oriented(const dfx_grid_desc* g, const dfx_tree_node* t, int n, const unsigned long long* vid,
+                                      unsigned long long* flat) {
+  dfx_basis_impl* impl = nullptr;
+  int rc = buildBasis(g, t, n, 0, &impl);
+  if (rc) return -rc;
+  DevBasis B = impl->dev;
+  B.vid = vid;
+  const u64 ne = (u64)B.grid.N[0] * B.grid.N[1] * B.grid.N[2];
+  for (u64 e = 0; e < ne; ++e) {
+    int ec[3] = {(int)(e % B.grid.N[0]), (int)((e / B.grid.N[0]) % B.grid.N[1]), (int)(e / ((u64)B.grid.N[0] * B.grid.N[1]))};
+    for (int li = 0; li < B.nlocTotal; ++li) {
+      int l = 0;
+      while (l + 1 < B.nLeaves && li >= B.leaves[l + 1].localOffset) ++l;
+      const DevLeaf& leaf = B.leaves[l];
+      const DevLayout& L = B.layouts[leaf.layout];
+      int i = li - leaf.localOffset, a[3], ii = i;
+      a[0] = ii % (L.k + 1); ii /= (L.k + 1); a[1] = ii % (L.k + 1); ii /= (L.k + 1); a[2] = ii;
+      flat[e * B.nlocTotal + li] = leaf.posA * layoutIndexOriented(L, B.grid, B.vid, ec, a, i) + leaf.posB;
+    }
+  }
+  long long bad = 0;
+  for (int q = 0; q < B.nLayouts; ++q) {
+    const DevLayout& L = B.layouts[q];
+    for (u64 d = 0; d < L.dimension; ++d) {
+      int ie[3], a[3];
+      dofOwnerNode(B, L, d, ie, a);
+      int ec[3], li = 0, stride = 1;
+      bool inside = true;
+      for (int j = 0; j < 3; ++j) {
+        ec[j] = ie[j] - B.grid.off[j];
+        if (j < B.grid.dim && (ec[j] < 0 || ec[j] >= B.grid.N[j])) inside = false;
+        if (j < B.grid.dim) { li += a[j] * stride; stride *= L.k + 1; }
+      }
+      // an owner in the neighbouring slab sees the node at alpha = 0 of its first layer: the same entity
+      // is alpha = k of our last layer
+      for (int j = 0; j < B.grid.dim && !inside; ++j)
+        if (ec[j] == B.grid.N[j] && a[j] == 0) { ec[j] -= 1; li += L.k * (j == 0 ? 1 : j == 1 ? (L.k + 1) : (L.k + 1) * (L.k + 1)); a[j] = L.k; }
+      if (layoutIndexOriented(L, B.grid, B.vid, ec, a, li) != d) ++bad;
+    }
+    if (L.kind == DFX_NODE_LAGRANGE && L.k > 2 && B.grid.dim > 1)
+      for (unsigned s = 1; s < (1u << B.grid.dim); ++s) {
+        int c[3] = {0, 0, 0};
+        for (c[2] = 0; c[2] < L.csize[s][2]; ++c[2])
+          for (c[1] = 0; c[1] < L.csize[s][1]; ++c[1])
+            for (c[0] = 0; c[0] < L.csize[s][0]; ++c[0])
+              for (unsigned fr = 0; fr < (unsigned)L.blk[s]; ++fr) {
+                const unsigned f = orientFaceDOF<false>(B.grid, B.vid, L.k, s, c, fr);
+                if (f >= (unsigned)L.blk[s] || orientFaceDOF<true>(B.grid, B.vid, L.k, s, c, f) != fr) ++bad;
+              }
+      }
+  }
+  delete static_cast<dfx_basis*>(impl);
+  return bad;
+}

@@ -69,6 +69,8 @@ class OracleBasis:
         self._h = lib().orc_basis_create(C.byref(self._desc), arr, n)
         if not self._h:
             raise ValueError("oracle: bad tree")
+        if getattr(grid, "vertex_ids", None) is not None:
+            self.setVertexIds(grid.vertex_ids)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -213,3 +213,35 @@ def test_compute_without_gpu_fails_loudly():
     n = C.c_int32()
     lst = (C.c_int32 * b.maxNodeSize())()
     assert L.dfx_subentity_dofs(b._h, 0, 1, 1, None, lst, C.byref(n)) == capi.DFX_OK and n.value == 3
+
+
+@pytest.mark.parametrize("n", [(3, 2), (1, 1), (5, 4), (2, 2, 2), (3, 2, 4), (1, 1, 1), (2, 1, 3)], ids=str)
+def test_face_dof_permutation_of_the_kernels_matches_oracle(harness, n):
+    """layoutIndexOriented / orientFaceDOF / dofOwnerNode (csrc/dfx_internal.h, what k_indices, k_interpolate,
+    k_points, k_eval_generic run when vertex ids are set) walked on the CPU: indices equal the oracle's
+    FaceOrientations / LagrangeFaceDOFPermutation restatement bit for bit, every DOF's owner node maps
+    back to the DOF, and the inverse permutation inverts."""
+    harness.harness_oriented.restype = C.c_longlong
+    harness.harness_oriented.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p, C.c_void_p]
+    dim = len(n)
+    nv = int(np.prod([m + 1 for m in n]))
+    some_trees = {"Q1": lagrange(1), "Q2": lagrange(2), "Q3": lagrange(3), "Q4": lagrange(4), "Q5": lagrange(5), "Q7": lagrange(7),
+                  "powFI_Q3": power(lagrange(3), dim, FI()), "comp_Q4_Q2_DG2": composite(lagrange(4), lagrange(2), lagrangeDG(2))}
+    for seed in range(3):
+        ids = np.random.default_rng(seed).permutation(nv).astype(np.uint64) * 3 + 2
+        for slab in (None, (0, 2), (1, 2)):
+            whole = YaspGrid(list(n), vertex_ids=ids)
+            if slab is not None:
+                if n[-1] < 2:
+                    continue
+                whole = whole.slab(*slab)
+            for name, tree in some_trees.items():
+                ob = orc.OracleBasis(whole, tree)
+                ref = ob.flatIndices()
+                out = np.zeros(ref.shape, dtype=np.uint64)
+                desc = whole.desc()
+                arr, cnt = tree_array(tree)
+                vid = np.ascontiguousarray(whole.vertex_ids, dtype=np.uint64)
+                bad = harness.harness_oriented(C.byref(desc), arr, cnt, vid.ctypes.data, out.ctypes.data)
+                assert bad == 0, (name, seed, slab, bad)
+                assert (out == ref).all(), (name, seed, slab)
