@@ -23,6 +23,8 @@ DFX_OK, DFX_ERR_INVALID, DFX_ERR_RANGE, DFX_ERR_NOT_IMPLEMENTED, DFX_ERR_CUDA, D
 NODE_LAGRANGE, NODE_LAGRANGE_DG, NODE_POWER, NODE_COMPOSITE, NODE_TAYLOR_HOOD = range(5)
 # dfx_ims
 IMS_NONE, IMS_FLAT_LEXICOGRAPHIC, IMS_FLAT_INTERLEAVED, IMS_BLOCKED_LEXICOGRAPHIC, IMS_BLOCKED_INTERLEAVED = range(5)
+# dfx_cd_kind
+CD_UNKNOWN, CD_VALUE, CD_TUPLE, CD_ARRAY, CD_VECTOR, CD_UNIFORM_ARRAY, CD_UNIFORM_VECTOR = range(7)
 # dfx_fn_id
 FN_CONSTANT, FN_GAUSSIAN, FN_IDENTITY, FN_COORD, FN_QUADRATIC, FN_SINPROD, FN_GAUSSIAN_VEC = range(7)
 
@@ -39,6 +41,10 @@ class GridDesc(C.Structure):
 class TreeNode(C.Structure):
     _fields_ = [("kind", C.c_int32), ("order", C.c_int32),
                 ("n_children", C.c_int32), ("ims", C.c_int32)]
+
+
+class ContainerNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_stored", C.c_int32), ("size", C.c_uint64)]
 
 
 class Function(C.Structure):
@@ -60,6 +66,7 @@ SIGNATURES = {
     "dfx_basis_has_permuted_face_dofs": (_i32, [_vp]),
     "dfx_basis_dimension": (_u64, [_vp]),
     "dfx_basis_size": (_u64, [_vp, _pu64, _i32]),
+    "dfx_basis_container_descriptor": (C.c_int, [_vp, C.POINTER(ContainerNode), _i32, _pi32, C.c_char_p, _i32]),
     "dfx_basis_max_node_size": (_i32, [_vp]),
     "dfx_basis_max_multi_index_size": (_i32, [_vp]),
     "dfx_basis_min_multi_index_size": (_i32, [_vp]),

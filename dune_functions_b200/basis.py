@@ -254,6 +254,9 @@ class GlobalBasis:
         a = np.ascontiguousarray(np.asarray(ids), dtype=np.uint64)
         capi.check(self._lib.dfx_basis_set_vertex_ids_host(self._h, a.ctypes.data, a.size))
 
+    def containerDescriptor(self):
+        return _container_descriptor(self)
+
     def hasPermutedFaceDOFs(self):
         return bool(self._lib.dfx_basis_has_permuted_face_dofs(self._h))
 
@@ -416,6 +419,67 @@ class LocalView:
         return self.basis.nodeInfo(0)
 
 
+class ContainerDescriptor:
+    """Run-time form of the descriptor types of containerdescriptors.hh:91-209 (Unknown, Value, Tuple,
+    Array, Vector, UniformArray, UniformVector; FlatVector = UniformVector of Value): `size()` children,
+    `cd[i]` the i-th child descriptor (the shared prototype for the uniform kinds), `type()` the
+    reference type spelled out."""
+    KINDS = {capi.CD_UNKNOWN: "Unknown", capi.CD_VALUE: "Value", capi.CD_TUPLE: "Tuple", capi.CD_ARRAY: "Array",
+             capi.CD_VECTOR: "Vector", capi.CD_UNIFORM_ARRAY: "UniformArray", capi.CD_UNIFORM_VECTOR: "UniformVector"}
+
+    def __init__(self, kind, size, children):
+        self.kind, self._size, self.children = kind, size, children
+
+    def size(self):
+        return self._size
+
+    def __len__(self):
+        return self._size
+
+    def __getitem__(self, i):
+        if self.kind == capi.CD_VALUE:
+            return self                                    # Value::operator[] returns a Value (:104-105)
+        if self.kind == capi.CD_UNKNOWN:
+            raise IndexError("Unknown container descriptor has no children")
+        if not 0 <= i < self._size:
+            raise IndexError("child index out of range")
+        return self.children[0] if self.kind in (capi.CD_UNIFORM_ARRAY, capi.CD_UNIFORM_VECTOR) else self.children[i]
+
+    def isFlatVector(self):
+        return self.kind == capi.CD_UNIFORM_VECTOR and self.children[0].kind == capi.CD_VALUE
+
+    def type(self):
+        k = self.KINDS[self.kind]
+        if self.kind in (capi.CD_UNKNOWN, capi.CD_VALUE):
+            return k
+        if self.kind == capi.CD_TUPLE:
+            return "Tuple<" + ",".join(c.type() for c in self.children) + ">"
+        inner = self.children[0].type()
+        return f"{k}<{inner}>" if self.kind in (capi.CD_UNIFORM_VECTOR, capi.CD_VECTOR) else f"{k}<{inner},{self._size}>"
+
+    def __repr__(self):
+        return self.type()
+
+
+def _container_descriptor(basis):
+    """basis.containerDescriptor(), defaultglobalbasis.hh:180-186 (a SubspaceBasis forwards to its root,
+    subspacebasis.hh:115-118)"""
+    root, _ = _root_and_node(basis)
+    n = C.c_int32()
+    capi.check(root._lib.dfx_basis_container_descriptor(root._h, None, 0, C.byref(n), None, 0))
+    arr = (capi.ContainerNode * n.value)()
+    capi.check(root._lib.dfx_basis_container_descriptor(root._h, arr, n.value, C.byref(n), None, 0))
+    pos = 0
+
+    def build():
+        nonlocal pos
+        nd = arr[pos]
+        pos += 1
+        kids = [build() for _ in range(nd.n_stored)]
+        return ContainerDescriptor(nd.kind, int(nd.size), kids)
+    return build()
+
+
 def makeBasis(grid, factory, device=0):
     """BasisFactory::makeBasis, defaultglobalbasis.hh:205-209"""
     return GlobalBasis(grid, factory, device)
@@ -432,6 +496,9 @@ class SubspaceBasis:
 
     def dimension(self):
         return self.root.dimension()
+
+    def containerDescriptor(self):
+        return _container_descriptor(self)
 
 
 def subspaceBasis(root, *path):

@@ -195,6 +195,106 @@ u64 preSize(const dfx_basis_impl* b, const u64* prefix, int len) {
   return sizeOf(*b->pre, std::vector<u64>(prefix, prefix + len));
 }
 
+// ---- containerDescriptor() -------------------------------------------------------------------
+// The reference describes the nested container that fits a basis' index tree with compile-time types
+// (containerdescriptors.hh:91-209); here the same tree at run time.  `ch` holds the stored children:
+// all of them for Tuple / Array / Vector, the single prototype for UniformArray / UniformVector.
+// Whether makeDescriptor yields a Tuple or an Array depends on the children's TYPES being equal
+// (:115-141), so every node carries the spelled-out type.
+struct CD { int kind = DFX_CD_UNKNOWN; u64 size = 0; std::vector<CD> ch; };
+
+static std::string cdType(const CD& d) {
+  switch (d.kind) {
+    case DFX_CD_VALUE: return "Value";
+    case DFX_CD_UNIFORM_VECTOR: return "UniformVector<" + cdType(d.ch[0]) + ">";
+    case DFX_CD_UNIFORM_ARRAY: return "UniformArray<" + cdType(d.ch[0]) + "," + std::to_string(d.size) + ">";
+    case DFX_CD_ARRAY: return "Array<" + cdType(d.ch[0]) + "," + std::to_string(d.size) + ">";
+    case DFX_CD_VECTOR: return "Vector<" + (d.ch.empty() ? std::string("?") : cdType(d.ch[0])) + ">";
+    case DFX_CD_TUPLE: {
+      std::string r = "Tuple<";
+      for (size_t i = 0; i < d.ch.size(); ++i) r += (i ? "," : "") + cdType(d.ch[i]);
+      return r + ">"; }
+  }
+  return "Unknown";
+}
+static CD cdUnknown() { return CD{}; }
+static CD cdValue() { CD d; d.kind = DFX_CD_VALUE; return d; }
+static CD cdUniformVector(u64 n, CD child) { CD d; d.kind = DFX_CD_UNIFORM_VECTOR; d.size = n; d.ch.push_back(std::move(child)); return d; }
+static CD cdUniformArray(u64 n, CD child) { CD d; d.kind = DFX_CD_UNIFORM_ARRAY; d.size = n; d.ch.push_back(std::move(child)); return d; }
+// makeDescriptor(child0, children...): Array if all types agree, Tuple otherwise (:115-141)
+static CD cdMake(std::vector<CD> children) {
+  bool same = true;
+  for (size_t i = 1; i < children.size(); ++i) same = same && cdType(children[i]) == cdType(children[0]);
+  CD d; d.kind = same ? DFX_CD_ARRAY : DFX_CD_TUPLE; d.size = children.size(); d.ch = std::move(children);
+  return d;
+}
+// Impl::appendToTree(s, tree) with a static s (:282-289, TreeTransform :209-279)
+static CD cdAppend(u64 s, const CD& t) {
+  switch (t.kind) {
+    case DFX_CD_VALUE: return cdUniformArray(s, t);
+    case DFX_CD_TUPLE:
+    case DFX_CD_ARRAY: { std::vector<CD> c; for (auto& x : t.ch) c.push_back(cdAppend(s, x)); return cdMake(std::move(c)); }
+    case DFX_CD_VECTOR: { CD d = t; for (auto& x : d.ch) x = cdAppend(s, x); return d; }
+    case DFX_CD_UNIFORM_ARRAY: return cdUniformArray(t.size, cdAppend(s, t.ch[0]));
+    case DFX_CD_UNIFORM_VECTOR: return cdUniformVector(t.size, cdAppend(s, t.ch[0]));
+  }
+  return cdUnknown();
+}
+// Impl::flatLexicographicN / flatInterleavedN with a static n (:305-420): the children of the child are
+// repeated n times, block-wise (lexicographic) or one after the other (interleaved)
+static CD cdFlatN(u64 n, const CD& t, bool interleaved) {
+  switch (t.kind) {
+    case DFX_CD_UNIFORM_VECTOR: return cdUniformVector(t.size * n, t.ch[0]);
+    case DFX_CD_UNIFORM_ARRAY: return cdUniformArray(t.size * n, t.ch[0]);
+    case DFX_CD_VECTOR:
+    case DFX_CD_ARRAY:
+    case DFX_CD_TUPLE: {
+      const size_t m = t.ch.size();
+      std::vector<CD> c;
+      for (size_t i = 0; i < n * m; ++i) c.push_back(t.ch[interleaved ? i / n : i % m]);
+      if (t.kind == DFX_CD_TUPLE) return cdMake(std::move(c));
+      CD d; d.kind = t.kind; d.size = n * m; d.ch = std::move(c);
+      return d; }
+  }
+  return cdUnknown();
+}
+static CD cdOf(const PreNode& p) {
+  if (p.kind == DFX_NODE_LAGRANGE || p.kind == DFX_NODE_LAGRANGE_DG)
+    return cdUniformVector(p.size0, cdValue());                                // leafprebasismixin.hh:66-69
+  if (p.kind == DFX_NODE_POWER) {                                              // dynamicpowerbasis.hh:373-387 via powerbasis.hh:119-122
+    CD sub = cdOf(*p.ch[0]);
+    switch (p.ims) {
+      case DFX_IMS_FLAT_INTERLEAVED: return cdFlatN((u64)p.C, sub, true);
+      case DFX_IMS_FLAT_LEXICOGRAPHIC: return cdFlatN((u64)p.C, sub, false);
+      case DFX_IMS_BLOCKED_LEXICOGRAPHIC: return cdUniformArray((u64)p.C, std::move(sub));
+      case DFX_IMS_BLOCKED_INTERLEAVED: return cdAppend((u64)p.C, sub);
+    }
+    return cdUnknown();
+  }
+  std::vector<CD> c;                                                           // compositebasis.hh:274-289
+  for (auto& q : p.ch) c.push_back(cdOf(*q));
+  if (p.ims == DFX_IMS_BLOCKED_LEXICOGRAPHIC) return cdMake(std::move(c));
+  // Impl::flatLexicographic (:291-298): only flat children merge
+  u64 total = 0;
+  for (auto& x : c) {
+    if (x.kind != DFX_CD_UNIFORM_VECTOR || x.ch[0].kind != DFX_CD_VALUE) return cdUnknown();
+    total += x.size;
+  }
+  return cdUniformVector(total, cdValue());
+}
+static void cdFlatten(const CD& d, std::vector<dfx_container_node>& out) {
+  dfx_container_node n;
+  n.kind = d.kind; n.n_stored = (int32_t)d.ch.size(); n.size = d.size;
+  out.push_back(n);
+  for (auto& c : d.ch) cdFlatten(c, out);
+}
+void containerDescriptor(const dfx_basis_impl* b, std::vector<dfx_container_node>& nodes, std::string& type) {
+  const CD d = cdOf(*b->pre);
+  nodes.clear();
+  cdFlatten(d, nodes);
+  type = cdType(d);
+}
+
 // leaves below p with their multi-index digits as affine maps of the leaf index j
 static std::vector<LeafIdx> leavesOf(const PreNode& p) {
   std::vector<LeafIdx> out;

@@ -232,6 +232,21 @@ uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t
   if (!b || len < 0 || (len > 0 && !prefix_host)) return 0;
   return preSize(b, (const u64*)prefix_host, len);
 }
+int dfx_basis_container_descriptor(const dfx_basis* b, dfx_container_node* out_host, int32_t capacity, int32_t* n_nodes,
+                                   char* type_out, int32_t type_capacity) {
+  if (!b || !n_nodes || capacity < 0 || (capacity > 0 && !out_host)) return fail(DFX_ERR_INVALID, "null argument");
+  std::vector<dfx_container_node> nodes;
+  std::string type;
+  containerDescriptor(b, nodes, type);
+  *n_nodes = (int32_t)nodes.size();
+  for (int32_t i = 0; i < capacity && i < (int32_t)nodes.size(); ++i) out_host[i] = nodes[i];
+  if (type_out && type_capacity > 0) {
+    const size_t n = std::min((size_t)type_capacity - 1, type.size());
+    std::memcpy(type_out, type.data(), n);
+    type_out[n] = 0;
+  }
+  return DFX_OK;
+}
 int32_t dfx_basis_max_node_size(const dfx_basis* b) { return b ? b->dev.nlocTotal : 0; }
 int32_t dfx_basis_max_multi_index_size(const dfx_basis* b) { return b ? b->maxDigits : 0; }
 int32_t dfx_basis_min_multi_index_size(const dfx_basis* b) { return b ? b->minDigits : 0; }

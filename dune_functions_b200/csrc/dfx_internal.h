@@ -253,6 +253,7 @@ const char* lastErrorCStr();
 // host basis construction (dfx_basis.cu)
 int buildBasis(const dfx_grid_desc* g, const dfx_tree_node* t, int n, int device, dfx_basis_impl** out);
 u64 preSize(const dfx_basis_impl* b, const u64* prefix, int len);
+void containerDescriptor(const dfx_basis_impl* b, std::vector<dfx_container_node>& nodes, std::string& type);
 
 // 1-d Lagrange shape functions on nodes m/k, as LagrangeCubeLocalBasis evaluates them
 double lagrangeP(int k, int i, double x);

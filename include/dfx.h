@@ -163,6 +163,26 @@ int32_t dfx_basis_has_permuted_face_dofs(const dfx_basis* b);
 /* ---- GlobalBasis concept: functionspacebases/concepts.hh:253-273 -----------*/
 uint64_t dfx_basis_dimension(const dfx_basis* b);                 /* defaultglobalbasis.hh:144-147 */
 uint64_t dfx_basis_size(const dfx_basis* b, const uint64_t* prefix_host, int32_t len); /* :150-160 */
+/* basis.containerDescriptor(): defaultglobalbasis.hh:180-186 -> PreBasis::containerDescriptor
+ * (leafprebasismixin.hh:66-69, dynamicpowerbasis.hh:373-387, compositebasis.hh:274-289,
+ * taylorhoodbasis.hh:204-216) with the descriptor types of containerdescriptors.hh:91-209 as a
+ * run-time tree: preorder array of nodes; a node is followed by its n_stored children — all `size`
+ * of them for TUPLE / ARRAY / VECTOR, the single prototype for UNIFORM_ARRAY / UNIFORM_VECTOR, none
+ * for VALUE / UNKNOWN.  FlatVector = UNIFORM_VECTOR of VALUE, FlatArray<n> = UNIFORM_ARRAY of VALUE.
+ * Host-only bookkeeping (no device needed).  *n_nodes receives the number of nodes the descriptor has;
+ * nothing is written beyond `capacity`.  type_out (optional, type_capacity bytes) receives the
+ * spelled-out reference type, e.g. "Tuple<UniformVector<UniformArray<Value,3>>,UniformVector<Value>>". */
+typedef enum {
+  DFX_CD_UNKNOWN = 0, DFX_CD_VALUE = 1, DFX_CD_TUPLE = 2, DFX_CD_ARRAY = 3, DFX_CD_VECTOR = 4,
+  DFX_CD_UNIFORM_ARRAY = 5, DFX_CD_UNIFORM_VECTOR = 6
+} dfx_cd_kind;
+typedef struct {
+  int32_t  kind;       /* dfx_cd_kind                                           */
+  int32_t  n_stored;   /* children stored behind this node in the array         */
+  uint64_t size;       /* number of children the container has at this level    */
+} dfx_container_node;
+int dfx_basis_container_descriptor(const dfx_basis* b, dfx_container_node* out_host, int32_t capacity,
+                                   int32_t* n_nodes, char* type_out, int32_t type_capacity);
 int32_t  dfx_basis_max_node_size(const dfx_basis* b);             /* LocalView::maxSize, defaultlocalview.hh:147-150 */
 int32_t  dfx_basis_max_multi_index_size(const dfx_basis* b);      /* PreBasis::maxMultiIndexSize */
 int32_t  dfx_basis_min_multi_index_size(const dfx_basis* b);

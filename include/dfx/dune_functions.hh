@@ -329,6 +329,50 @@ class DefaultLocalView {
   std::size_t w0_ = 0, w1_ = 0;
 };
 
+// ---- ContainerDescriptors (containerdescriptors.hh:91-209) as one run-time type -----------------
+// The reference builds the descriptor from compile-time types (Unknown, Value, Tuple, Array, Vector,
+// UniformArray, UniformVector; FlatVector = UniformVector<Value>, FlatArray<n> = UniformArray<Value,n>);
+// the tree description of this façade is a run-time value, so the descriptor is one too: kind(), size(),
+// operator[](i), and type() — the reference's type spelled out.
+namespace ContainerDescriptors {
+class Descriptor {
+ public:
+  Descriptor() = default;
+  Descriptor(int kind, std::size_t size, std::vector<Descriptor> children) : kind_(kind), size_(size), ch_(std::move(children)) {}
+  int kind() const { return kind_; }
+  std::size_t size() const { return size_; }
+  bool isUnknown() const { return kind_ == DFX_CD_UNKNOWN; }
+  bool isValue() const { return kind_ == DFX_CD_VALUE; }
+  const Descriptor& operator[](std::size_t i) const {
+    if (kind_ == DFX_CD_VALUE) return *this;                            // Value::operator[] gives a Value (:104-105)
+    if (kind_ == DFX_CD_UNKNOWN || i >= size_) throw RangeError("container descriptor: child index out of range");
+    return (kind_ == DFX_CD_UNIFORM_ARRAY || kind_ == DFX_CD_UNIFORM_VECTOR) ? ch_[0] : ch_[i];
+  }
+  std::string type() const {
+    static const char* names[] = {"Unknown", "Value", "Tuple", "Array", "Vector", "UniformArray", "UniformVector"};
+    if (kind_ == DFX_CD_UNKNOWN || kind_ == DFX_CD_VALUE) return names[kind_];
+    std::string r = std::string(names[kind_]) + "<";
+    if (kind_ == DFX_CD_TUPLE) { for (std::size_t i = 0; i < ch_.size(); ++i) r += (i ? "," : "") + ch_[i].type(); return r + ">"; }
+    r += ch_[0].type();
+    if (kind_ == DFX_CD_ARRAY || kind_ == DFX_CD_UNIFORM_ARRAY) r += "," + std::to_string(size_);
+    return r + ">";
+  }
+ private:
+  int kind_ = DFX_CD_UNKNOWN;
+  std::size_t size_ = 0;
+  std::vector<Descriptor> ch_;
+};
+}  // namespace ContainerDescriptors
+
+namespace Impl {
+inline ContainerDescriptors::Descriptor buildDescriptor(const std::vector<dfx_container_node>& nodes, std::size_t& pos) {
+  const dfx_container_node nd = nodes[pos++];
+  std::vector<ContainerDescriptors::Descriptor> ch;
+  for (int i = 0; i < nd.n_stored; ++i) ch.push_back(buildDescriptor(nodes, pos));
+  return ContainerDescriptors::Descriptor(nd.kind, (std::size_t)nd.size, std::move(ch));
+}
+}  // namespace Impl
+
 // ---- DefaultGlobalBasis (defaultglobalbasis.hh:51-191) -----------------------------------
 template <class GV>
 class DefaultGlobalBasis {
@@ -361,6 +405,15 @@ class DefaultGlobalBasis {
     return dfx_basis_size(h_->h, p.data(), (int32_t)p.size());
   }
   LocalView localView() const { return LocalView(*this); }
+  // containerDescriptor(), defaultglobalbasis.hh:180-186
+  ContainerDescriptors::Descriptor containerDescriptor() const {
+    int32_t n = 0;
+    Impl::check(dfx_basis_container_descriptor(h_->h, nullptr, 0, &n, nullptr, 0));
+    std::vector<dfx_container_node> nodes((std::size_t)n);
+    Impl::check(dfx_basis_container_descriptor(h_->h, nodes.data(), n, &n, nullptr, 0));
+    std::size_t pos = 0;
+    return Impl::buildDescriptor(nodes, pos);
+  }
   const dfx_basis* handle() const { return h_->h; }
   const DefaultGlobalBasis& rootBasis() const { return *this; }
   int rootNode() const { return 0; }
@@ -423,6 +476,7 @@ class SubspaceBasis {
   const DefaultGlobalBasis<GV>& rootBasis() const { return *root_; }
   int rootNode() const { return node_; }
   std::size_t dimension() const { return root_->dimension(); }     // the root's, :79-94
+  auto containerDescriptor() const { return root_->containerDescriptor(); }   // subspacebasis.hh:115-118
   const GV& gridView() const { return root_->gridView(); }
   const dfx_basis* handle() const { return root_->handle(); }
  private:

@@ -53,6 +53,42 @@ void checkBasis(const Basis& basis, const char* name) {
   std::printf("checkBasis %-34s dimension %8zu  %s\n", name, (std::size_t)basis.dimension(), failures ? "FAILED" : "ok");
 }
 
+// containerdescriptortest.cc:87-131: checkSize (the descriptor's size below every prefix equals
+// basis.size(prefix)) and checkMultiIndices (every multi-index walks through the descriptor)
+template <class CD, class Basis>
+void checkDescriptorSize(const CD& cd, const Basis& basis, std::vector<std::size_t> prefix, std::size_t maxLen) {
+  CHECK(basis.size(prefix) == cd.size(), "size(prefix) == containerDescriptor size at prefix");
+  if (prefix.size() < maxLen)
+    for (std::size_t i = 0; i < cd.size(); ++i) {
+      auto p = prefix; p.push_back(i);
+      checkDescriptorSize(cd[i], basis, p, maxLen);
+    }
+}
+template <class Basis>
+void checkContainerDescriptor(const Basis& basis, const char* name, const char* expectedType = nullptr) {
+  auto cd = basis.containerDescriptor();
+  CHECK(!cd.isUnknown(), "container descriptor known");
+  std::size_t maxLen = 0;
+  auto localView = basis.localView();
+  for (const auto& e : elements(basis.gridView())) {
+    localView.bind(e);
+    for (std::size_t i = 0; i < localView.size(); ++i) {
+      auto mi = localView.index(i);
+      maxLen = std::max<std::size_t>(maxLen, mi.size());
+      const auto* d = &cd;
+      for (std::size_t j = 0; j < mi.size(); ++j) {
+        CHECK(mi[j] < d->size(), "mi[j] < cd.size()");
+        if (mi[j] >= d->size()) break;
+        d = &(*d)[mi[j]];
+      }
+      CHECK(d->isValue(), "a full multi-index addresses a Value");
+    }
+  }
+  checkDescriptorSize(cd, basis, {}, maxLen);
+  if (expectedType) CHECK(cd.type() == expectedType, "descriptor type as in the reference");
+  std::printf("containerDescriptor %-26s %s  %s\n", name, cd.type().c_str(), failures ? "FAILED" : "ok");
+}
+
 // tensor Gauss rule with 3 points per direction on [0,1]^dim
 template <int dim>
 void gauss3(std::vector<FieldVector<double, dim>>& x, std::vector<double>& w) {
@@ -110,6 +146,23 @@ int main() {
     checkBasis(makeBasis(gv3, composite(power<3>(lagrange<2>(), blockedInterleaved()), lagrange<1>())), "BL(BI) Taylor-Hood 3d");
     checkBasis(makeBasis(gv2, power<2>(composite(lagrange<1>(), lagrangeDG<1>(), blockedLexicographic()), blockedInterleaved())), "BI(BL(Q1,DG1))");
     checkBasis(makeBasis(gv2, composite(power<2>(power<2>(lagrange<1>(), flatLexicographic()), blockedInterleaved()), lagrange<2>())), "BL(BI(FL(Q1)),Q2)");
+
+    // containerdescriptortest.cc:236-262 on its 2x2 grid
+    {
+      Grid2 small(FieldVector<double, 2>(1.0), {{2, 2}});
+      auto gvs = small.leafGridView();
+      checkContainerDescriptor(makeBasis(gvs, lagrange<1>()), "lagrange<1>", "UniformVector<Value>");
+      checkContainerDescriptor(makeBasis(gvs, power<2>(lagrange<1>(), blockedInterleaved())), "power<2>(Q1,BI)",
+                               "UniformVector<UniformArray<Value,2>>");
+      checkContainerDescriptor(makeBasis(gvs, composite(lagrange<1>(), lagrange<2>(), blockedLexicographic())), "composite(Q1,Q2,BL)",
+                               "Array<UniformVector<Value>,2>");
+      checkContainerDescriptor(makeBasis(gvs, power<2>(power<3>(lagrange<2>(), blockedLexicographic()), flatLexicographic())), "FL(BL(Q2))");
+      checkContainerDescriptor(makeBasis(gvs, power<2>(power<3>(lagrange<2>(), blockedInterleaved()), blockedLexicographic())), "BL(BI(Q2))");
+      checkContainerDescriptor(makeBasis(gvs, power<2>(power<3>(lagrange<2>(), flatInterleaved()), blockedInterleaved())), "BI(FI(Q2))");
+      checkContainerDescriptor(TaylorHoodBasis<Grid2::LeafGridView>(gvs), "TaylorHoodBasis", "Array<UniformVector<Value>,2>");
+      checkContainerDescriptor(makeBasis(gv3, composite(power<3>(lagrange<2>(), blockedInterleaved()), lagrange<1>())), "BL(BI) Taylor-Hood 3d",
+                               "Tuple<UniformVector<UniformArray<Value,3>>,UniformVector<Value>>");
+    }
 
     checkIntegralOfX0(makeBasis(gv2, lagrange<0>()), "lagrange<0> 2d");
     checkIntegralOfX0(LagrangeBasis<Grid2::LeafGridView, 3>(gv2), "LagrangeBasis<3> 2d");
