@@ -61,6 +61,7 @@ SIGNATURES = {
     "dfx_kernel_launch_count": (_u64, []),
     "dfx_basis_create": (C.c_int, [C.POINTER(GridDesc), C.POINTER(TreeNode), _i32, _i32, C.POINTER(_vp)]),
     "dfx_basis_destroy": (None, [_vp]),
+    "dfx_basis_update": (C.c_int, [_vp, C.POINTER(GridDesc)]),
     "dfx_basis_set_vertex_ids": (C.c_int, [_vp, _vp, _u64, _vp]),
     "dfx_basis_set_vertex_ids_host": (C.c_int, [_vp, _vp, _u64]),
     "dfx_basis_has_permuted_face_dofs": (_i32, [_vp]),

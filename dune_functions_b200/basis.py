@@ -233,6 +233,14 @@ class GlobalBasis:
             self._lib.dfx_basis_destroy(h)
             self._h = None
 
+    def update(self, grid):
+        """basis.update(gridView), defaultglobalbasis.hh:137-141: the same tree on another grid"""
+        desc = grid.desc()
+        capi.check(self._lib.dfx_basis_update(self._h, C.byref(desc)))
+        self.grid, self._desc = grid, desc
+        if getattr(grid, "vertex_ids", None) is not None:
+            self.setVertexIds(grid.vertex_ids)
+
     def setVertexIds(self, ids):
         """ids of grid().globalIdSet() for the vertices of the local box, the input of
         LagrangeFaceDOFPermutation (lagrangebasis.hh:787); None restores the grid's own ids.

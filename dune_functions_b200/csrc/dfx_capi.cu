@@ -172,24 +172,40 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
   return DFX_OK;
 }
 
+// everything the handle owns on the device / in pinned memory; the handle can be rebuilt afterwards
+static void releaseResources(dfx_basis_impl* b) {
+  const bool any = b->dDense || b->dJinv || b->dNodal || b->dVid || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
+                   b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream;
+  if (!any) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize((cudaStream_t)b->stream);
+  for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dShape, &b->dLocalTab, &b->dDev, &b->dSep,
+                   &b->dScratch[0], &b->dScratch[1], &b->dScratch[2]})
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  if (b->pinned) { cudaFreeHost(b->pinned); b->pinned = nullptr; }
+  for (void** p : {&b->evStream[0], &b->evStream[1], &b->stream})
+    if (*p) { cudaStreamDestroy((cudaStream_t)*p); *p = nullptr; }
+}
+
 void dfx_basis_destroy(dfx_basis* b) {
   if (!b) return;
-  if (b->dDense) { cudaSetDevice(b->device); cudaFree(b->dDense); }
-  if (b->dJinv) { cudaSetDevice(b->device); cudaFree(b->dJinv); }
-  if (b->dVid) { cudaSetDevice(b->device); cudaFree(b->dVid); }
-  if (b->dNodal) { cudaSetDevice(b->device); cudaFree(b->dNodal); }
-  if (b->evStream[0]) { cudaSetDevice(b->device); cudaStreamDestroy((cudaStream_t)b->evStream[0]); }
-  if (b->dLocalTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream) {
-    cudaSetDevice(b->device);
-    if (b->dShape) cudaFree(b->dShape);
-    if (b->dLocalTab) cudaFree(b->dLocalTab);
-    if (b->dDev) cudaFree(b->dDev);
-    if (b->dSep) cudaFree(b->dSep);
-    if (b->pinned) cudaFreeHost(b->pinned);
-    for (int i = 0; i < 3; ++i) if (b->dScratch[i]) cudaFree(b->dScratch[i]);
-    if (b->stream) cudaStreamDestroy((cudaStream_t)b->stream);
-  }
+  releaseResources(b);
   delete b;
+}
+
+// DefaultGlobalBasis::update(gridView), defaultglobalbasis.hh:137-141: preBasis_.update(gv) +
+// initializeIndices() — the same tree on another grid (box).  The handle stays valid; index tables,
+// coefficient vectors and vertex ids that belonged to the old grid do not.
+int dfx_basis_update(dfx_basis* b, const dfx_grid_desc* grid_host) {
+  if (!b || !grid_host) return fail(DFX_ERR_INVALID, "null argument");
+  dfx_basis_impl* fresh = nullptr;
+  const std::vector<dfx_tree_node> tree = b->treeDesc;
+  int rc = buildBasis(grid_host, tree.data(), (int)tree.size(), b->device, &fresh);
+  if (rc) return rc;                                     // the old state is untouched on failure
+  releaseResources(b);
+  *static_cast<dfx_basis_impl*>(b) = std::move(*fresh);
+  delete static_cast<dfx_basis*>(fresh);
+  return DFX_OK;
 }
 
 // ---- vertex ids for the face-DOF permutation (lagrangebasis.hh:787, :616-634) ---------------------

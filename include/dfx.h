@@ -139,6 +139,12 @@ uint64_t    dfx_kernel_launch_count(void);
 int  dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_host,
                       int32_t n_nodes, int32_t device, dfx_basis** out);
 void dfx_basis_destroy(dfx_basis* b);
+/* basis.update(gridView): defaultglobalbasis.hh:137-141 (preBasis_.update(gv); initializeIndices()).
+ * The same tree on another grid box; the handle stays valid, everything that belonged to the old
+ * grid (index tables, coefficient vectors, vertex ids set with dfx_basis_set_vertex_ids) does not.
+ * On failure the handle keeps its old state.  Not stream-ordered: work in flight on the handle must
+ * have finished (the reference has the same rule, :134-136).                                       */
+int  dfx_basis_update(dfx_basis* b, const dfx_grid_desc* grid_host);
 
 /* Vertex ids for the face-DOF permutation of continuous Lagrange bases of order >= 3.
  * Replaces: the `gridView.grid().globalIdSet()` argument of Experimental::LagrangeFaceDOFPermutation

@@ -383,20 +383,21 @@ class DefaultGlobalBasis {
   using SizePrefix = std::vector<std::size_t>;
 
   DefaultGlobalBasis(const GV& gv, const BasisFactory::PreBasisFactory& f, int device = 0) : gv_(gv), h_(std::make_shared<Impl::Handle>()) {
-    constexpr int dim = GV::dimension;
-    dfx_grid_desc g{};
-    g.dim = dim;
-    for (int j = 0; j < 3; ++j) {
-      g.n_global[j] = g.local_n[j] = j < dim ? gv.grid().N_[j] : 1;
-      g.local_begin[j] = 0;
-      g.lower[j] = j < dim ? gv.grid().lower_[j] : 0.0;
-      g.upper[j] = j < dim ? gv.grid().L_[j] : 1.0;
-    }
+    dfx_grid_desc g = gridDesc(gv);
     Impl::check(dfx_basis_create(&g, f.nodes.data(), (int32_t)f.nodes.size(), device, &h_->h));
     const auto& ids = gv.grid().globalVertexIds();
     if (!ids.empty()) Impl::check(dfx_basis_set_vertex_ids_host(h_->h, ids.data(), ids.size()));
   }
   const GV& gridView() const { return gv_; }
+  // update(gridView), defaultglobalbasis.hh:137-141: must be called if the grid has changed; local
+  // views have to be bound again afterwards
+  void update(const GV& gv) {
+    dfx_grid_desc g = gridDesc(gv);
+    Impl::check(dfx_basis_update(h_->h, &g));
+    gv_ = gv;
+    const auto& ids = gv.grid().globalVertexIds();
+    if (!ids.empty()) Impl::check(dfx_basis_set_vertex_ids_host(h_->h, ids.data(), ids.size()));
+  }
   size_type dimension() const { return dfx_basis_dimension(h_->h); }
   size_type size() const { return dfx_basis_size(h_->h, nullptr, 0); }
   template <class Prefix> size_type size(const Prefix& prefix) const {
@@ -415,6 +416,18 @@ class DefaultGlobalBasis {
     return Impl::buildDescriptor(nodes, pos);
   }
   const dfx_basis* handle() const { return h_->h; }
+  static dfx_grid_desc gridDesc(const GV& gv) {
+    constexpr int dim = GV::dimension;
+    dfx_grid_desc g{};
+    g.dim = dim;
+    for (int j = 0; j < 3; ++j) {
+      g.n_global[j] = g.local_n[j] = j < dim ? gv.grid().N_[j] : 1;
+      g.local_begin[j] = 0;
+      g.lower[j] = j < dim ? gv.grid().lower_[j] : 0.0;
+      g.upper[j] = j < dim ? gv.grid().L_[j] : 1.0;
+    }
+    return g;
+  }
   const DefaultGlobalBasis& rootBasis() const { return *this; }
   int rootNode() const { return 0; }
  private:

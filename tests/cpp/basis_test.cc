@@ -265,6 +265,16 @@ int main() {
       std::sort(xp.begin(), xp.end()); std::sort(xt.begin(), xt.end());
       CHECK(xp == xt, "same coefficients in another order");
     }
+    // basis.update(gridView) (defaultglobalbasis.hh:137-141; lagrangebasistest.cc:163-175 updates and checks again)
+    {
+      auto basis = makeBasis(gv3, composite(power<3>(lagrange<2>(), blockedInterleaved()), lagrange<1>()));
+      const std::size_t before = basis.dimension();
+      Grid3 other(FieldVector<double, 3>(1.0), {{2, 5, 3}});
+      basis.update(other.leafGridView());
+      CHECK(basis.dimension() != before && basis.dimension() == 3 * 5 * 11 * 7 + 3 * 6 * 4, "dimension after update");
+      checkBasis(basis, "BL(BI) Taylor-Hood 3d, updated");
+      checkContainerDescriptor(basis, "updated Taylor-Hood");
+    }
     // error behaviour: RangeError for an unsupported order (lagrangebasis.hh:795-796)
     bool threw = false;
     try { makeBasis(gv3, lagrange(18)); } catch (const RangeError&) { threw = true; }

@@ -232,3 +232,29 @@ def test_slabs_with_their_share_of_the_ids_reproduce_the_whole_grid():
         x = dfx.interpolate(b, b.newVector(0.0), FUNCS["quadratic"]).cpu().numpy()
         lflat = b.flatIndices().cpu().numpy().reshape(2, 6, -1)
         assert (x[lflat] == ref[gflat[2 * r:2 * r + 2]]).all()
+
+
+def test_update_to_another_grid_matches_a_fresh_basis():
+    """basis.update(gridView), defaultglobalbasis.hh:137-141 (lagrangebasistest.cc:163-175 updates its bases
+    after adapting the grid and checks them again): same results as a basis made on the new grid; device
+    tables of the old grid are dropped, vertex ids are taken from the new grid"""
+    import torch
+    pts = tensor_gauss(3, 3)[0]
+    for tree in (lagrange(2), lagrange(4), composite(power(lagrange(2), 3, BI()), lagrange(1), BL()), lagrangeDG(3)):
+        b = dfx.makeBasis(YaspGrid([5, 3, 2]), tree)
+        x = dfx.interpolate(b, b.newVector(0.0), dfx.gaussian(1.0))              # fills the handle's device tables
+        dfx.makeDiscreteGlobalBasisFunction(b, x).evaluate(pts, jacobians=True)
+        for new in (YaspGrid([3, 4, 6], upper=[1.0, 0.7, 1.3]), grid_with_ids((2, 3, 3), 21)):
+            b.update(new)
+            f = dfx.makeBasis(new, tree)
+            assert b.dimension() == f.dimension()
+            assert (b.flatIndices().cpu().numpy() == f.flatIndices().cpu().numpy()).all()
+            xb = dfx.interpolate(b, b.newVector(0.0), dfx.gaussian(1.0))
+            xf = dfx.interpolate(f, f.newVector(0.0), dfx.gaussian(1.0))
+            assert (xb.cpu().numpy() == xf.cpu().numpy()).all()
+            vb, jb = dfx.makeDiscreteGlobalBasisFunction(b, xb).evaluate(pts, jacobians=True)
+            vf, jf = dfx.makeDiscreteGlobalBasisFunction(f, xf).evaluate(pts, jacobians=True)
+            assert (vb.cpu().numpy() == vf.cpu().numpy()).all() and (jb.cpu().numpy() == jf.cpu().numpy()).all()
+            o = orc.OracleBasis(new, tree)
+            assert (b.flatIndices().cpu().numpy().astype(np.uint64) == o.flatIndices()).all()
+        torch.cuda.synchronize()

@@ -245,3 +245,26 @@ def test_face_dof_permutation_of_the_kernels_matches_oracle(harness, n):
                 bad = harness.harness_oriented(C.byref(desc), arr, cnt, vid.ctypes.data, out.ctypes.data)
                 assert bad == 0, (name, seed, slab, bad)
                 assert (out == ref).all(), (name, seed, slab)
+
+
+def test_update_moves_the_handle_to_another_grid():
+    """basis.update(gridView) (defaultglobalbasis.hh:137-141): same tree, new grid; host bookkeeping only here"""
+    from dune_functions_b200 import taylorHood
+    for tree in (lagrange(3), taylorHood(), composite(power(lagrange(2), 3, BI()), lagrangeDG(1))):
+        a, bgrid = YaspGrid([2, 3, 2]), YaspGrid([4, 2, 5], upper=[1.0, 2.0, 0.5])
+        b = GlobalBasis(a, tree)
+        fresh = GlobalBasis(bgrid, tree)
+        assert b.dimension() != fresh.dimension()
+        b.update(bgrid)
+        assert b.dimension() == fresh.dimension() and b.numElements() == fresh.numElements() == 40
+        assert b.containerDescriptor().type() == fresh.containerDescriptor().type()
+        ob = orc.OracleBasis(bgrid, tree)
+        assert b.dimension() == ob.dimension()
+        for prefix in ((), (0,), (1,), (0, 0)):
+            assert b.size(prefix) == ob.size(prefix)
+        # a descriptor the library rejects leaves the handle as it was
+        bad = bgrid.desc()
+        bad.n_global[1] = 0
+        bad.local_n[1] = 0
+        assert capi.lib().dfx_basis_update(b._h, C.byref(bad)) != 0
+        assert b.dimension() == fresh.dimension()
