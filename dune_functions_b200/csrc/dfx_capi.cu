@@ -27,6 +27,15 @@ int ensureDevice(const dfx_basis* b) {
   }
   if (b->device < 0 || b->device >= n) return fail(DFX_ERR_CUDA, "device ordinal out of range");
   DFX_CUDA(cudaSetDevice(b->device));
+  if (b->vidPending) {
+    // ids set from host memory (dfx_basis_set_vertex_ids_host works without a device, like basis creation)
+    dfx_basis* mb = const_cast<dfx_basis*>(b);
+    if (!mb->dVid) DFX_CUDA(cudaMalloc(&mb->dVid, b->vidHost.size() * sizeof(u64)));
+    DFX_CUDA(cudaMemcpy(mb->dVid, b->vidHost.data(), b->vidHost.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    mb->dev.vid = (const u64*)mb->dVid;
+    mb->vidPending = false;
+    if (mb->dDev) DFX_CUDA(cudaMemcpy(mb->dDev, &mb->dev, sizeof(DevBasis), cudaMemcpyHostToDevice));
+  }
   if (!b->dLocalTab && !b->localTab.empty()) {
     dfx_basis* mb = const_cast<dfx_basis*>(b);
     DFX_CUDA(cudaMalloc(&mb->dLocalTab, b->localTab.size() * sizeof(unsigned)));
@@ -214,24 +223,42 @@ static u64 numVertices(const dfx_basis* b) {
   for (int j = 0; j < b->dev.grid.dim; ++j) n *= (u64)(b->dev.grid.N[j] + 1);
   return n;
 }
+static bool wantsOrientation(const dfx_basis* b) {
+  if (b->dev.grid.dim < 2) return false;
+  for (int l = 0; l < b->dev.nLeaves; ++l) {
+    const DevLayout& L = b->dev.layouts[b->dev.leaves[l].layout];
+    if (L.kind == DFX_NODE_LAGRANGE && L.k >= 3) return true;
+  }
+  return false;
+}
 static int setVertexIds(dfx_basis* b, const uint64_t* ids, uint64_t n, bool fromHost, cudaStream_t st) {
-  int rc = ensureDevice(b); if (rc) return rc;
+  if (!b) return fail(DFX_ERR_INVALID, "null basis handle");
   if (ids && n != numVertices(b)) return fail(DFX_ERR_RANGE, "one id per vertex of the local box expected");
   if (!ids) {
-    b->dev.vid = nullptr;             // the table itself stays allocated until destroy: kernels in flight may read it
+    b->dev.vid = nullptr;                  // the table itself stays allocated until destroy: kernels in flight may read it
     b->oriented = false;
-  } else {
-    if (!b->dVid) DFX_CUDA(cudaMalloc(&b->dVid, n * sizeof(u64)));
-    DFX_CUDA(cudaMemcpyAsync(b->dVid, ids, n * sizeof(u64), fromHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
-    if (fromHost) DFX_CUDA(cudaStreamSynchronize(st));
-    b->dev.vid = (const u64*)b->dVid;
-    b->oriented = false;
-    if (b->dev.grid.dim > 1)
-      for (int l = 0; l < b->dev.nLeaves; ++l) {
-        const DevLayout& L = b->dev.layouts[b->dev.leaves[l].layout];
-        if (L.kind == DFX_NODE_LAGRANGE && L.k >= 3) b->oriented = true;
-      }
+    b->vidPending = false;
+    b->vidHost.clear();
+    if (b->dDev) {
+      int rc = ensureDevice(b); if (rc) return rc;
+      DFX_CUDA(cudaMemcpyAsync(b->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice, st));
+    }
+    return DFX_OK;
   }
+  if (fromHost) {
+    // host bookkeeping only; the upload happens in ensureDevice() at the next device call
+    b->vidHost.assign(ids, ids + n);
+    b->vidPending = true;
+    b->oriented = wantsOrientation(b);
+    return DFX_OK;
+  }
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!b->dVid) DFX_CUDA(cudaMalloc(&b->dVid, n * sizeof(u64)));
+  DFX_CUDA(cudaMemcpyAsync(b->dVid, ids, n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+  b->vidPending = false;
+  b->vidHost.clear();
+  b->dev.vid = (const u64*)b->dVid;
+  b->oriented = wantsOrientation(b);
   if (b->dDev) DFX_CUDA(cudaMemcpyAsync(b->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice, st));
   return DFX_OK;
 }

@@ -230,7 +230,8 @@ struct dfx_basis_impl {
   std::vector<unsigned> localTab;                       // per local index: leaf | alpha (see k_indices_fast)
   void* dLocalTab = nullptr;                            // uploaded on first use
   void* dDev = nullptr;                                 // device copy of `dev`
-  void* dVid = nullptr;                                 // vertex ids (dev.grid.vid points here)
+  void* dVid = nullptr;                                 // vertex ids (dev.vid points here)
+  std::vector<u64> vidHost; bool vidPending = false;    // ids given from host memory, uploaded at the next device call
   bool oriented = false;                                // ids given AND some continuous leaf of order >= 3 in 2-d/3-d
   void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f
   void* dShape = nullptr; size_t dShapeBytes = 0;       // shape tables of the last evaluate

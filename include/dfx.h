@@ -160,7 +160,9 @@ int  dfx_basis_update(dfx_basis* b, const dfx_grid_desc* grid_host);
  * Set ids before computing anything that depends on the numbering; in a slab-partitioned run every
  * rank passes the ids of its own box (same id for the same vertex on both sides of an interface).
  * dfx_assemble_laplace and dfx_apply_laplace return DFX_ERR_NOT_IMPLEMENTED on a basis whose face
- * DOFs are permuted.                                                                              */
+ * DOFs are permuted.  The _host form is host bookkeeping (it works without a device, like
+ * dfx_basis_create; the table is uploaded by the next device call), the device form copies
+ * stream-ordered.                                                                                  */
 int     dfx_basis_set_vertex_ids(dfx_basis* b, const uint64_t* ids, uint64_t n, void* stream);
 int     dfx_basis_set_vertex_ids_host(dfx_basis* b, const uint64_t* ids_host, uint64_t n);
 /* 1 iff ids are set AND some continuous leaf has order >= 3 on a 2-d/3-d grid (the general kernels run) */

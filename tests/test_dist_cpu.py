@@ -24,15 +24,21 @@ def _worker(rank, world, port, tree_name, results):
         import dune_functions_b200 as dfx
         from dune_functions_b200 import slab
         from cases import trees
-        tree = trees(3)[tree_name]
-        whole = dfx.YaspGrid([3, 2, 6], upper=[1.0, 0.5, 2.0])
+        ids = None
+        if tree_name.endswith("_ids"):
+            # permuted face DOFs (dfx_basis_set_vertex_ids): every rank takes its share of the global id table
+            tree = dfx.lagrange(int(tree_name[len("lagrange"):-len("_ids")]))
+            ids = np.random.default_rng(5).permutation(4 * 3 * 7).astype(np.uint64)
+        else:
+            tree = trees(3)[tree_name]
+        whole = dfx.YaspGrid([3, 2, 6], upper=[1.0, 0.5, 2.0], vertex_ids=ids)
         og = orc.OracleBasis(whole, tree)
         gx = np.random.default_rng(7).uniform(-1, 1, og.dimension())
         nz = 6 // world
         gflat = og.flatIndices().reshape(6, 6, -1).astype(np.int64)
         mine = whole.slab(rank, world)
         b = dfx.makeBasis(mine, tree)                 # host-side handle only: no compute call
-        ol = orc.OracleBasis(dfx.YaspGrid(list(mine.local_n)), tree)
+        ol = orc.OracleBasis(dfx.YaspGrid(list(mine.local_n), vertex_ids=mine.vertex_ids), tree)
         lflat = ol.flatIndices().reshape(nz, 6, -1).astype(np.int64)
         # local vector: owned entries from the global vector, top plane unknown (NaN)
         x = np.full(b.dimension(), np.nan)
@@ -54,7 +60,7 @@ def _worker(rank, world, port, tree_name, results):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("tree_name", ["lagrange2", "lagrange3", "TH_FL(FL)", "lagrangeDG1"])
+@pytest.mark.parametrize("tree_name", ["lagrange2", "lagrange3", "TH_FL(FL)", "lagrangeDG1", "lagrange4_ids"])
 def test_slab_halo_and_gather_gloo(world, tree_name):
     port = 29500 + (os.getpid() + hash(tree_name) + world) % 2000
     with mp.Manager() as m:

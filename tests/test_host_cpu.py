@@ -268,3 +268,20 @@ def test_update_moves_the_handle_to_another_grid():
         bad.local_n[1] = 0
         assert capi.lib().dfx_basis_update(b._h, C.byref(bad)) != 0
         assert b.dimension() == fresh.dimension()
+
+
+def test_vertex_ids_are_host_bookkeeping_until_a_device_call():
+    """dfx_basis_set_vertex_ids_host needs no device (slab set-up on a CPU-only rank, tests/test_dist_cpu.py);
+    wrong counts are a RangeError either way"""
+    grid = YaspGrid([3, 2, 2], vertex_ids=np.random.default_rng(0).permutation(36))
+    b = GlobalBasis(grid, lagrange(4))
+    assert b.hasPermutedFaceDOFs()
+    assert not GlobalBasis(grid, lagrange(2)).hasPermutedFaceDOFs()
+    assert not GlobalBasis(YaspGrid([5], vertex_ids=range(6)), lagrange(4)).hasPermutedFaceDOFs()
+    with pytest.raises(capi.RangeError):
+        b.setVertexIds(np.arange(35))
+    b.setVertexIds(None)
+    assert not b.hasPermutedFaceDOFs()
+    # slabs take contiguous runs of the id table
+    s1 = grid.slab(1, 2)
+    assert list(s1.vertex_ids) == list(grid.vertex_ids[12:36]) and list(grid.slab(0, 2).vertex_ids) == list(grid.vertex_ids[:24])
