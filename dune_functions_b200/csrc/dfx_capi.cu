@@ -183,11 +183,14 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 
 // everything the handle owns on the device / in pinned memory; the handle can be rebuilt afterwards
 static void releaseResources(dfx_basis_impl* b) {
-  const bool any = b->dDense || b->dJinv || b->dNodal || b->dVid || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
+  if (b->companion) { dfx_basis_destroy(static_cast<dfx_basis*>(b->companion)); b->companion = nullptr; }
+  b->companionTried = false;
+  const bool any = b->dLocalCoeff || b->dDense || b->dJinv || b->dNodal || b->dVid || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
                    b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream;
   if (!any) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize((cudaStream_t)b->stream);
+  if (b->dLocalCoeff) { cudaFree(b->dLocalCoeff); b->dLocalCoeff = nullptr; b->dLocalCoeffBytes = 0; }
   for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dShape, &b->dLocalTab, &b->dDev, &b->dSep,
                    &b->dScratch[0], &b->dScratch[1], &b->dScratch[2]})
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -514,6 +517,46 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_SMEM_GRADIENT) g_smemGrad = path;
 }
 
+// Companion of a basis with permuted face DOFs: the same tree with every Lagrange leaf replaced by the
+// LagrangeDG leaf of the same order (TaylorHood written out as composite(power<dim>(Q2, FI), Q1, BL),
+// taylorhoodbasis.hh:229-251), plus a coefficient buffer in its layout.  false = not available.
+static bool orientedCompanion(dfx_basis* b) {
+  if (b->companion && b->dLocalCoeff) return true;
+  if (b->companionTried) return false;
+  b->companionTried = true;
+  std::vector<dfx_tree_node> tree;
+  for (const dfx_tree_node& n : b->treeDesc) {
+    if (n.kind == DFX_NODE_TAYLOR_HOOD) {
+      tree.push_back({DFX_NODE_COMPOSITE, 0, 2, DFX_IMS_BLOCKED_LEXICOGRAPHIC});
+      tree.push_back({DFX_NODE_POWER, 0, b->dev.grid.dim, DFX_IMS_FLAT_INTERLEAVED});
+      tree.push_back({DFX_NODE_LAGRANGE_DG, 2, 0, DFX_IMS_NONE});
+      tree.push_back({DFX_NODE_LAGRANGE_DG, 1, 0, DFX_IMS_NONE});
+      continue;
+    }
+    dfx_tree_node m = n;
+    if (m.kind == DFX_NODE_LAGRANGE) {
+      if (m.order > kMaxDGOrder) return false;
+      m.kind = DFX_NODE_LAGRANGE_DG;
+    }
+    tree.push_back(m);
+  }
+  dfx_basis_impl* c = nullptr;
+  if (buildBasis(&b->gridDesc, tree.data(), (int)tree.size(), b->device, &c) != DFX_OK) return false;
+  // same local ansatz tree, leaf by leaf
+  bool same = c->dev.nLeaves == b->dev.nLeaves && c->dev.nlocTotal == b->dev.nlocTotal && c->nodes.size() == b->nodes.size();
+  for (int l = 0; same && l < b->dev.nLeaves; ++l)
+    same = c->dev.leaves[l].nloc == b->dev.leaves[l].nloc && c->dev.leaves[l].localOffset == b->dev.leaves[l].localOffset;
+  void* buf = nullptr;
+  if (!same || cudaMalloc(&buf, c->dimension * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    delete static_cast<dfx_basis*>(c);
+    return false;
+  }
+  b->companion = c;
+  b->dLocalCoeff = buf; b->dLocalCoeffBytes = c->dimension * sizeof(double);
+  return true;
+}
+
 int dfx_evaluate_path(const dfx_basis* b, int32_t node, const double* xhat_host, int32_t n_q, int32_t want_jac) {
   if (!b || !xhat_host || n_q < 1) return -1;
   int fl, nl;
@@ -539,7 +582,16 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
   cudaStream_t st = (cudaStream_t)stream;
   if (b->oriented) {
     // permuted face DOFs (dfx_basis_set_vertex_ids): the closed-form gathers of the fast paths do not
-    // apply, every coefficient is located through layoutIndexOriented
+    // apply.  LocalFunction::bind as its own pass — the element-local coefficients are gathered through
+    // layoutIndexOriented into the layout of the companion basis (same tree, discontinuous leaves) —
+    // then the companion evaluates on the element-local fast kernels.
+    if (g_forcedPath != 0 && orientedCompanion(b)) {
+      dfx_basis* c = static_cast<dfx_basis*>(b->companion);
+      if ((rc = gatherLocal(b, c, fl, nl, coeff, (double*)b->dLocalCoeff, e0, e1, st))) return rc;
+      return dfx_evaluate(c, node, (const double*)b->dLocalCoeff, xhat_host, n_q, e0, e1, out_values, out_jac, stream);
+    }
+    // no companion (order beyond the discontinuous kernels, no memory, or path 0 forced): every
+    // coefficient is located through layoutIndexOriented at every point
     ShapeOffsets so; const double *dS, *dDS;
     if ((rc = prepareShape(b, node, fl, nl, xhat_host, n_q, so, dS, dDS, st))) return rc;
     return evalGeneric(b, fl, nl, coeff, dS, dDS, so, n_q, e0, e1, out_values, out_jac, st);

@@ -231,6 +231,10 @@ struct dfx_basis_impl {
   void* dLocalTab = nullptr;                            // uploaded on first use
   void* dDev = nullptr;                                 // device copy of `dev`
   void* dVid = nullptr;                                 // vertex ids (dev.vid points here)
+  // evaluation with permuted face DOFs: the same tree with every leaf discontinuous, and the
+  // element-local coefficients gathered for it (csrc/dfx_kernels.cu, k_gather_local)
+  dfx_basis_impl* companion = nullptr; bool companionTried = false;
+  void* dLocalCoeff = nullptr; size_t dLocalCoeffBytes = 0;
   std::vector<u64> vidHost; bool vidPending = false;    // ids given from host memory, uploaded at the next device call
   bool oriented = false;                                // ids given AND some continuous leaf of order >= 3 in 2-d/3-d
   void* dSep = nullptr; size_t dSepBytes = 0;           // per-direction tables of a separable f

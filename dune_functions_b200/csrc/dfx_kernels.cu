@@ -357,6 +357,57 @@ int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* co
 }
 
 // ---------------------------------------------------------------------------
+// LocalFunction::bind for a basis with permuted face DOFs (discreteglobalbasisfunction.hh:124-148 with the
+// indices of lagrangebasis.hh:863-869): localDoFs[e][i] = dofs[localView.index(i)] for a range of elements,
+// written in the coefficient layout of the COMPANION basis (same tree, every leaf discontinuous), whose
+// evaluation then runs on the fast element-local kernels.  One thread per (element, local index of the
+// subtree); consecutive threads write consecutive entries of an element.
+struct GatherArgs {
+  int firstLeaf, nLeaves, firstLocal, nLocal;      // subtree: leaves and local index range
+  u64 e0, total;
+  u64 posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES];  // companion: flat position = posA * (e * nloc_leaf + i) + posB
+};
+
+__global__ void __launch_bounds__(256)
+k_gather_local(const __grid_constant__ DevBasis B, const __grid_constant__ GatherArgs A, const double* __restrict__ src,
+               double* __restrict__ dst) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.total) return;
+  const u64 el = t / (unsigned)A.nLocal;
+  const int li = A.firstLocal + (int)(t - el * (unsigned)A.nLocal);
+  const u64 e = A.e0 + el;
+  int ec[3];
+  ec[0] = (int)(e % (u64)B.grid.N[0]);
+  const u64 r = e / (u64)B.grid.N[0];
+  ec[1] = (int)(r % (u64)B.grid.N[1]);
+  ec[2] = (int)(r / (u64)B.grid.N[1]);
+  const int l = findLeaf(B, li);
+  const DevLeaf& leaf = B.leaves[l];
+  const DevLayout& L = B.layouts[leaf.layout];
+  const int i = li - leaf.localOffset;
+  int a[3];
+  localAlpha(L.k, i, a);
+  const u64 j = layoutIndexOriented(L, B.grid, B.vid, ec, a, i);
+  dst[A.posA[l] * (e * (u64)leaf.nloc + (u64)i) + A.posB[l]] = src[leaf.posA * j + leaf.posB];
+}
+
+int gatherLocal(const dfx_basis* b, const dfx_basis* companion, int firstLeaf, int nLeaves, const double* src, double* dst,
+                u64 e0, u64 e1, cudaStream_t st) {
+  GatherArgs A;
+  A.firstLeaf = firstLeaf; A.nLeaves = nLeaves;
+  A.firstLocal = b->dev.leaves[firstLeaf].localOffset;
+  A.nLocal = 0;
+  for (int l = firstLeaf; l < firstLeaf + nLeaves; ++l) A.nLocal += b->dev.leaves[l].nloc;
+  for (int l = 0; l < DFX_MAX_LEAVES; ++l) { A.posA[l] = companion->dev.leaves[l].posA; A.posB[l] = companion->dev.leaves[l].posB; }
+  A.e0 = e0; A.total = (e1 - e0) * (u64)A.nLocal;
+  if (A.total == 0) return DFX_OK;
+  const u64 blocks = (A.total + 255) / 256;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  k_gather_local<<<(unsigned)blocks, 256, 0, st>>>(b->dev, A, src, dst);
+  return postLaunch("k_gather_local");
+}
+
+// ---------------------------------------------------------------------------
 // Boundary DOFs: forEachBoundaryDOF (boundarydofs.hh:110-128) + SubEntityDOFs::bind
 // (subentitydofs.hh:71-95) in closed form.  A DOF is visited by the reference iff it is
 // attached to a sub-entity of a boundary facet, i.e. iff in some direction its entity is

@@ -258,3 +258,51 @@ def test_update_to_another_grid_matches_a_fresh_basis():
             o = orc.OracleBasis(new, tree)
             assert (b.flatIndices().cpu().numpy().astype(np.uint64) == o.flatIndices()).all()
         torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n", [(3, 2), (3, 2, 4)], ids=str)
+def test_evaluation_through_the_companion_basis_equals_the_general_kernel(n):
+    """with permuted face DOFs dfx_evaluate gathers the element-local coefficients (k_gather_local) and
+    evaluates them on the companion basis' fast kernels; kernel path 0 keeps the general kernel.  Both
+    against the oracle, for sub-ranges of elements, subtrees and Jacobians."""
+    import torch
+    dim = len(n)
+    grid = grid_with_ids(n, 23, upper=[1.0, 0.7, 1.3][:dim])
+    rng = np.random.default_rng(8)
+    trees_ = [lagrange(3), lagrange(5), power(lagrange(4), dim, FI()), composite(power(lagrange(3), dim, BI()), lagrange(2), BL()),
+              composite(lagrange(4), lagrangeDG(2), FL())]
+    try:
+        for tree in trees_:
+            b = dfx.makeBasis(grid, tree)
+            o = orc.OracleBasis(grid, tree)
+            c = rng.uniform(-1, 1, b.dimension())
+            ct = torch.from_numpy(c).cuda()
+            ne = b.numElements()
+            for pts in (tensor_gauss(dim, 4)[0], tensor_gauss(dim, 3, last_fastest=False)[0], rng.random((6, dim))):
+                vr, jr = o.evaluate(c, pts, jacobians=True)
+                for path in (-1, 0):
+                    capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, path)
+                    f = dfx.makeDiscreteGlobalBasisFunction(b, ct)
+                    v, j = f.evaluate(pts, jacobians=True)
+                    assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL
+                    v2 = f.evaluate(pts, elem_begin=1, elem_end=ne - 1)
+                    assert rel(v2.cpu().numpy(), vr[1:ne - 1]) <= TOL
+            if b.numLeaves() > 1:
+                sub = dfx.subspaceBasis(b, 0)
+                pts = tensor_gauss(dim, 3)[0]
+                node = b.child(0, 0)
+                vr = o.evaluate(c, pts, node=node)
+                for path in (-1, 0):
+                    capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, path)
+                    v = dfx.makeDiscreteGlobalBasisFunction(sub, ct).evaluate(pts)
+                    assert rel(v.cpu().numpy(), vr) <= TOL
+            # the host entry point (bands of z-layers) goes the same way
+            capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
+            pts = np.ascontiguousarray(tensor_gauss(dim, 3)[0])
+            nc = b.numLeaves()
+            out = np.zeros((ne, len(pts), nc))
+            capi.check(capi.lib().dfx_evaluate_host(b._h, 0, c.ctypes.data, pts.ctypes.data_as(C.POINTER(C.c_double)), len(pts), 0, ne,
+                                                    out.ctypes.data, None))
+            assert rel(out, o.evaluate(c, pts)) <= TOL
+    finally:
+        capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
