@@ -427,13 +427,14 @@ struct LagrangeFaceDOFPermutation {
   }
   // computeFaceOrientations :616-634 (cubes: never the "k == 3 and tetrahedron" branch)
   FaceOrientations computeFaceOrientations(const Grid& g, const int ec[MAXDIM]) const {
+    // no codimension requested: the constructor returns before it touches the (lazy) id range, :364-365
+    if (dim == 1 || order < 3) return FaceOrientations();
     size_type ids[8];
     for (int v = 0; v < (1 << g.dim); ++v) {
       int c[MAXDIM] = {0, 0, 0};
       for (int j = 0; j < g.dim; ++j) c[j] = ec[j] + ((v >> j) & 1);
       ids[v] = g.vertexIdAt(c);
     }
-    if (dim == 1 || order < 3) return FaceOrientations(dim, ids, false, false);
     return FaceOrientations(dim, ids, true, true);
   }
   // permuteFaceDOF :652-675
@@ -475,7 +476,8 @@ static void evalFunction(const dfx_function& f, int dim, const double* x, double
     case DFX_FN_GAUSSIAN_VEC: {
       double s = 0; for (int j = 0; j < dim; ++j) s += x[j] * x[j];
       double e = std::exp(-f.p[0] * s);
-      for (int c = 0; c < f.n_comp; ++c) y[c] = (c < dim ? x[c] : 1.0) * e; break; }
+      for (int c = 0; c < f.n_comp; ++c) y[c] = (c < dim ? x[c] : 1.0) * e;
+      break; }
     default: for (int c = 0; c < f.n_comp; ++c) y[c] = 0;
   }
 }

@@ -133,7 +133,7 @@ def main():
         f = dfx.makeDiscreteGlobalBasisFunction(basis, x)
         v = torch.empty((ne, len(pts), 1), dtype=torch.float64, device="cuda")
         ms, best = timeit(lambda: f.evaluate(pts, out_values=v), args.reps)
-        report("evaluate values 4^3 [permuted face DOFs, general kernel]", "q3_128_oriented", ms, best, nd * 8 + v.numel() * 8)
+        report("evaluate values 4^3 [permuted face DOFs: gather + companion basis]", "q3_128_oriented", ms, best, nd * 8 + v.numel() * 8)
         idx = torch.empty((ne, 64), dtype=torch.int32, device="cuda")
         ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
         report("indices flat u32 [permuted face DOFs, general kernel]", "q3_128_oriented", ms, best, idx.numel() * 4)
