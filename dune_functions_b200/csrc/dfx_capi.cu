@@ -340,7 +340,7 @@ int dfx_indices_multi(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* ou
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_multi_u64");
-  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<uint32_t, true>(b, e0, e1, out, stride, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, true>(b, e0, e1, out, stride, (cudaStream_t)stream);
   return indicesMulti32(b, e0, e1, out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, int32_t stride, void* stream) {
@@ -348,7 +348,7 @@ int dfx_indices_multi_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (stride < b->maxDigits) return fail(DFX_ERR_INVALID, "stride smaller than the longest multi-index");
-  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<u64, true>(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, true>(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
   return indicesMulti64(b, e0, e1, (u64*)out, stride, (cudaStream_t)stream);
 }
 int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out, void* stream) {
@@ -356,14 +356,14 @@ int dfx_indices_flat(const dfx_basis* b, uint64_t e0, uint64_t e1, uint32_t* out
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
   if (b->dimension > 0xffffffffull) return fail(DFX_ERR_RANGE, "indices exceed 32 bits, use dfx_indices_flat_u64");
-  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<uint32_t, false>(b, e0, e1, out, 1, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<uint32_t, false>(b, e0, e1, out, 1, (cudaStream_t)stream);
   return indicesFlat32(b, e0, e1, out, (cudaStream_t)stream);
 }
 int dfx_indices_flat_u64(const dfx_basis* b, uint64_t e0, uint64_t e1, uint64_t* out, void* stream) {
   DFX_RANGE("dfx_indices_flat_u64");
   int rc = ensureDevice(b); if (rc) return rc;
   if ((rc = checkRange(b, e0, e1))) return rc;
-  if (g_indicesPath != 0 && !b->oriented && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
+  if (g_indicesPath != 0 && fits32(b, e0, e1)) return indicesFast<u64, false>(b, e0, e1, (u64*)out, 1, (cudaStream_t)stream);
   return indicesFlat64(b, e0, e1, (u64*)out, (cudaStream_t)stream);
 }
 
@@ -587,7 +587,10 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
     // then the companion evaluates on the element-local fast kernels.
     if (g_forcedPath != 0 && orientedCompanion(b)) {
       dfx_basis* c = static_cast<dfx_basis*>(b->companion);
-      if ((rc = gatherLocal(b, c, fl, nl, coeff, (double*)b->dLocalCoeff, e0, e1, st))) return rc;
+      // the gather walks like the fast index table (path 1 of DFX_OP_INDICES) or like k_indices (path 0)
+      if (g_indicesPath != 0 && fits32(b, e0, e1)) rc = gatherLocalFast(b, c, fl, nl, coeff, (double*)b->dLocalCoeff, e0, e1, st);
+      else rc = gatherLocal(b, c, fl, nl, coeff, (double*)b->dLocalCoeff, e0, e1, st);
+      if (rc) return rc;
       return dfx_evaluate(c, node, (const double*)b->dLocalCoeff, xhat_host, n_q, e0, e1, out_values, out_jac, stream);
     }
     // no companion (order beyond the discontinuous kernels, no memory, or path 0 forced): every

@@ -512,17 +512,28 @@ struct IdxArgs {
   FastDiv divN0, divN1;
   int stride;       // digits per multi-index (MULTI)
   int lpb, m, iters;   // local indices per pass, elements in flight, iterations per block
+  int liBegin, liEnd;  // local index range (GATHER: the subtree's; otherwise the whole tree)
 };
+// GATHER: where local index li of element e goes in the companion basis' coefficient layout,
+// position = posA[leaf] * (e * nloc_leaf + i) + posB[leaf]  (csrc/dfx_capi.cu, orientedCompanion)
+struct GatherTab { u64 posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES]; };
 
-template <class T, bool MULTI>
+// ORIENT (dfx_basis_set_vertex_ids): the thread's node sits in an edge / quadrilateral facet whose DOFs
+// the reference renumbers by the entity's orientation (lagrangebasis.hh:863-869).  Entity, component
+// and the unpermuted in-entity index fr stay fixed for the thread; per element the permuted index
+// fr' = orientFaceDOF(ids of the entity's vertices) replaces it: out = P0 + S ent + posA (fr' - fr).
+// GATHER (needs !MULTI): instead of writing the table, dst[companion position] = src[position]
+// (LocalFunction::bind, discreteglobalbasisfunction.hh:124-148).
+template <class T, bool MULTI, bool ORIENT, bool GATHER>
 __global__ void __launch_bounds__(256)
 k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs A,
-               const unsigned* __restrict__ localTab, T* __restrict__ out) {
+               const unsigned* __restrict__ localTab, T* __restrict__ out,
+               const double* __restrict__ src, double* __restrict__ dst, const __grid_constant__ GatherTab G) {
   const DevGrid& g = Bp->grid;
   const int nloc = Bp->nlocTotal;
   const int sub = threadIdx.x / A.lpb, lane = threadIdx.x - sub * A.lpb;
   const u64 blkEl0 = (u64)blockIdx.x * (u64)(A.m * A.iters);
-  for (int li = lane; li < nloc; li += A.lpb) {
+  for (int li = (GATHER ? A.liBegin : 0) + lane; li < (GATHER ? A.liEnd : nloc); li += A.lpb) {
     const unsigned packed = __ldg(localTab + li);
     const DevLeaf& leaf = Bp->leaves[packed & 31u];
     const DevLayout& L = Bp->layouts[leaf.layout];
@@ -540,12 +551,29 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
     // (checked by the caller), so wrapping 32-bit multiply-adds give the same bits as 64-bit ones
     const T P0 = (T)(leaf.posA * jbase + leaf.posB);
     const T S = (T)(leaf.posA * blk);
-    T dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
+    T dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS], dF[DFX_MAX_DIGITS];
     if (MULTI) {
 #pragma unroll
       for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
         dA[p] = p < leaf.ndig ? (T)(leaf.digA[p] * blk) : (T)0;
         dB[p] = p < leaf.ndig ? (T)(leaf.digA[p] * jbase + leaf.digB[p]) : (T)0;
+        if (ORIENT) dF[p] = p < leaf.ndig ? (T)leaf.digA[p] : (T)0;
+      }
+    }
+    // ORIENT: is this node's in-entity index subject to the permutation, and what is it unpermuted
+    bool perm = false;
+    unsigned fr = 0;
+    int sh[3] = {0, 0, 0};
+    const T PA = (T)leaf.posA;
+    const u64* __restrict__ vid = ORIENT ? Bp->vid : nullptr;
+    const int kOrd = L.k;
+    if (ORIENT && vid != nullptr && L.kind == DFX_NODE_LAGRANGE && kOrd > 2 && g.dim > 1) {
+      const int nfree = (int)((s & 1u) + ((s >> 1) & 1u) + ((s >> 2) & 1u));
+      perm = nfree == 1 || (nfree == 2 && g.dim == 3);
+      unsigned frs = 1;
+      for (int j = 0; j < 3; ++j) {
+        if ((s >> j) & 1u) { fr += (unsigned)(a[j] - 1) * frs; frs *= (unsigned)(kOrd - 1); }
+        else sh[j] = a[j] == kOrd ? 1 : 0;
       }
     }
     // walk this thread's elements el = blkEl0 + sub, + m, + 2m, ...: coordinates advance with carry,
@@ -567,9 +595,14 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
       T* po = out + (el * (u64)nloc + (u64)li) * (u64)A.stride;
       const size_t step = (size_t)m * nloc * A.stride;
       for (int it = 0; it < nIt; ++it) {
+        T df = (T)0;
+        if (ORIENT && perm) {
+          const int c[3] = {(int)ec0 + sh[0], (int)ec1 + sh[1], (int)ec2 + sh[2]};
+          df = (T)orientFaceDOF<false>(g, vid, kOrd, s, c, fr) - (T)fr;
+        }
 #pragma unroll
         for (int p = 0; p < DFX_MAX_DIGITS; ++p)
-          if (p < A.stride) po[p] = (T)(dB[p] + dA[p] * (T)ent);
+          if (p < A.stride) po[p] = ORIENT ? (T)(dB[p] + dA[p] * (T)ent + dF[p] * df) : (T)(dB[p] + dA[p] * (T)ent);
         po += step; ec0 += m; ent += m;
         if (ec0 >= N0) {
           do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
@@ -577,13 +610,26 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
         }
       }
     } else {
-      T* po = out + (el * (u64)nloc + (u64)li);
-      const size_t step = (size_t)m * nloc;
+      T* po = GATHER ? nullptr : out + (el * (u64)nloc + (u64)li);
+      size_t step = (size_t)m * nloc;
+      double* pd = nullptr;
+      if (GATHER) {
+        const unsigned lf = packed & 31u;
+        const u64 stepEl = G.posA[lf] * (u64)leaf.nloc;              // companion positions of one element further on
+        pd = dst + (G.posB[lf] + G.posA[lf] * ((A.e0 + el) * (u64)leaf.nloc + (u64)(li - leaf.localOffset)));
+        step = (size_t)(stepEl * (u64)m);
+      }
       T v = (T)(P0 + S * (T)ent);
       const T dv = (T)(S * (T)m);
       for (int it = 0; it < nIt; ++it) {
-        *po = v;
-        po += step; ec0 += m; v += dv;
+        T w = v;
+        if (ORIENT && perm) {
+          const int c[3] = {(int)ec0 + sh[0], (int)ec1 + sh[1], (int)ec2 + sh[2]};
+          w = (T)(v + PA * ((T)orientFaceDOF<false>(g, vid, kOrd, s, c, fr) - (T)fr));
+        }
+        if (GATHER) { *pd = src[w]; pd += step; }
+        else { *po = w; po += step; }
+        ec0 += m; v += dv;
         if (ec0 >= N0) {
           do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
           v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
@@ -593,12 +639,14 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
   }
 }
 
-template <class T, bool MULTI>
-int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
+template <class T, bool MULTI, bool ORIENT, bool GATHER>
+static int launchIndicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, int liBegin, int liEnd, const double* src,
+                             double* dst, const GatherTab& G, cudaStream_t st) {
   IdxArgs A;
   A.e0 = e0; A.ne = e1 - e0; A.stride = stride;
-  if (A.ne == 0) return DFX_OK;
-  const int nloc = b->dev.nlocTotal;
+  A.liBegin = liBegin; A.liEnd = liEnd;
+  if (A.ne == 0 || liEnd <= liBegin) return DFX_OK;
+  const int nloc = liEnd - liBegin;
   A.lpb = std::min(nloc, 256);
   A.m = std::max(1, 256 / A.lpb);
   A.iters = 64;
@@ -606,13 +654,33 @@ int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStre
   const u64 perBlock = (u64)A.m * A.iters;
   const u64 blocks = (A.ne + perBlock - 1) / perBlock;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
-  k_indices_fast<T, MULTI><<<(unsigned)blocks, A.lpb * A.m, 0, st>>>((const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out);
+  k_indices_fast<T, MULTI, ORIENT, GATHER><<<(unsigned)blocks, A.lpb * A.m, 0, st>>>(
+      (const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out, src, dst, G);
   return postLaunch("k_indices_fast");
+}
+
+template <class T, bool MULTI>
+int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
+  GatherTab G{};
+  if (b->oriented) return launchIndicesFast<T, MULTI, true, false>(b, e0, e1, out, stride, 0, b->dev.nlocTotal, nullptr, nullptr, G, st);
+  return launchIndicesFast<T, MULTI, false, false>(b, e0, e1, out, stride, 0, b->dev.nlocTotal, nullptr, nullptr, G, st);
 }
 
 template int indicesFast<uint32_t, true>(const dfx_basis*, u64, u64, uint32_t*, int, cudaStream_t);
 template int indicesFast<u64, true>(const dfx_basis*, u64, u64, u64*, int, cudaStream_t);
 template int indicesFast<uint32_t, false>(const dfx_basis*, u64, u64, uint32_t*, int, cudaStream_t);
 template int indicesFast<u64, false>(const dfx_basis*, u64, u64, u64*, int, cudaStream_t);
+
+// LocalFunction::bind for elements [e0, e1) of a basis with permuted face DOFs, written in the
+// coefficient layout of its companion basis (same walk as the index table, 64-bit positions)
+int gatherLocalFast(const dfx_basis* b, const dfx_basis* companion, int firstLeaf, int nLeaves, const double* src, double* dst,
+                    u64 e0, u64 e1, cudaStream_t st) {
+  GatherTab G;
+  for (int l = 0; l < DFX_MAX_LEAVES; ++l) { G.posA[l] = companion->dev.leaves[l].posA; G.posB[l] = companion->dev.leaves[l].posB; }
+  const int liBegin = b->dev.leaves[firstLeaf].localOffset;
+  int liEnd = liBegin;
+  for (int l = firstLeaf; l < firstLeaf + nLeaves; ++l) liEnd += b->dev.leaves[l].nloc;
+  return launchIndicesFast<u64, false, true, true>(b, e0, e1, (u64*)nullptr, 1, liBegin, liEnd, src, dst, G, st);
+}
 
 }  // namespace dfx

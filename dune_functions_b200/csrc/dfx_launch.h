@@ -56,6 +56,8 @@ int evalGlobal(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coe
                double* values, double* jac, int* elementOut, cudaStream_t st);
 int scatterNodes(const dfx_basis* b, int layoutId, int firstLeaf, int nLeaves, int ncompVals, u64 e0, u64 e1,
                  const double* vals, double* coeff, const uint8_t* mask, cudaStream_t st);
+int gatherLocalFast(const dfx_basis* b, const dfx_basis* companion, int firstLeaf, int nLeaves, const double* src, double* dst,
+                    u64 e0, u64 e1, cudaStream_t st);
 int gatherLocal(const dfx_basis* b, const dfx_basis* companion, int firstLeaf, int nLeaves, const double* src, double* dst,
                 u64 e0, u64 e1, cudaStream_t st);
 int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* coeff, const double* shape,

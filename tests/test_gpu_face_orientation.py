@@ -280,8 +280,10 @@ def test_evaluation_through_the_companion_basis_equals_the_general_kernel(n):
             ne = b.numElements()
             for pts in (tensor_gauss(dim, 4)[0], tensor_gauss(dim, 3, last_fastest=False)[0], rng.random((6, dim))):
                 vr, jr = o.evaluate(c, pts, jacobians=True)
-                for path in (-1, 0):
+                # (evaluate path, index path): companion basis with the fast / the general gather walk, general kernel
+                for path, ipath in ((-1, -1), (-1, 0), (0, -1)):
                     capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, path)
+                    capi.lib().dfx_set_kernel_path(capi.OP_INDICES, ipath)
                     f = dfx.makeDiscreteGlobalBasisFunction(b, ct)
                     v, j = f.evaluate(pts, jacobians=True)
                     assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL
@@ -292,12 +294,14 @@ def test_evaluation_through_the_companion_basis_equals_the_general_kernel(n):
                 pts = tensor_gauss(dim, 3)[0]
                 node = b.child(0, 0)
                 vr = o.evaluate(c, pts, node=node)
-                for path in (-1, 0):
+                for path, ipath in ((-1, -1), (-1, 0), (0, -1)):
                     capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, path)
+                    capi.lib().dfx_set_kernel_path(capi.OP_INDICES, ipath)
                     v = dfx.makeDiscreteGlobalBasisFunction(sub, ct).evaluate(pts)
                     assert rel(v.cpu().numpy(), vr) <= TOL
             # the host entry point (bands of z-layers) goes the same way
             capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
+            capi.lib().dfx_set_kernel_path(capi.OP_INDICES, -1)
             pts = np.ascontiguousarray(tensor_gauss(dim, 3)[0])
             nc = b.numLeaves()
             out = np.zeros((ne, len(pts), nc))
@@ -306,3 +310,28 @@ def test_evaluation_through_the_companion_basis_equals_the_general_kernel(n):
             assert rel(out, o.evaluate(c, pts)) <= TOL
     finally:
         capi.lib().dfx_set_kernel_path(capi.OP_EVALUATE, -1)
+        capi.lib().dfx_set_kernel_path(capi.OP_INDICES, -1)
+
+
+@pytest.mark.parametrize("n", [(5, 4), (3, 2, 4), (7, 3, 2)], ids=str)
+def test_index_kernel_families_with_permuted_face_dofs(n):
+    """the walking index kernel (one local index per thread, orientation per element) and the general one
+    (one thread per entry) give the oracle's table, also for element sub-ranges and both index widths"""
+    import torch
+    dim = len(n)
+    grid = grid_with_ids(n, 29)
+    try:
+        for tree in (lagrange(3), lagrange(6), power(lagrange(4), dim, BL()), composite(power(lagrange(3), dim, FI()), lagrange(1), BL())):
+            b = dfx.makeBasis(grid, tree)
+            o = orc.OracleBasis(grid, tree)
+            dig, _ = o.indices()
+            flat = o.flatIndices()
+            ne = b.numElements()
+            for path in (-1, 0):
+                capi.lib().dfx_set_kernel_path(capi.OP_INDICES, path)
+                for dt in (None, torch.int64):
+                    assert (b.indices(dtype=dt).cpu().numpy().astype(np.uint64) == dig).all()
+                    assert (b.flatIndices(dtype=dt).cpu().numpy().astype(np.uint64) == flat).all()
+                    assert (b.flatIndices(2, ne - 1, dtype=dt).cpu().numpy().astype(np.uint64) == flat[2:ne - 1]).all()
+    finally:
+        capi.lib().dfx_set_kernel_path(capi.OP_INDICES, -1)
