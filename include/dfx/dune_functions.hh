@@ -37,6 +37,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -533,6 +534,48 @@ template <class C> double* coeffData(C& c, std::size_t n) {
   if (c.size() * per != n) c.resize((n + per - 1) / per);      // vector.resize(basis), interpolate.hh:235
   return reinterpret_cast<double*>(c.data());
 }
+
+// ---- nested coefficient containers (ISTLVectorBackend, backends/istlvectorbackend.hh:104-312) --------
+// vector[multiIndex] resolves digit j at nesting level j (:267-277), so the entries of a nested container
+// in lexicographic order ARE the flat container order of include/dfx.h.  A container whose storage is
+// one contiguous run of doubles (std::vector<double>, std::vector<FieldVector<double,n>>, ...) is used
+// in place; anything else — std::tuple<...> for a Tuple descriptor (TupleVector / MultiTypeBlockVector in
+// the reference's Stokes example), std::array / std::vector of vectors — is copied entry by entry.
+template <class T> struct IsTuple : std::false_type {};
+template <class... T> struct IsTuple<std::tuple<T...>> : std::true_type {};
+template <class T, class = void> struct IsFlatBits : std::false_type {};
+template <class T> struct IsFlatBits<T, std::void_t<typename T::value_type>> : std::bool_constant<std::is_arithmetic_v<typename T::value_type>> {};
+template <class T, class = void> struct HasResize : std::false_type {};
+template <class T> struct HasResize<T, std::void_t<decltype(std::declval<T&>().resize(std::size_t(0)))>> : std::true_type {};
+template <class T, class = void> struct IsContiguousRun : std::false_type {};
+template <class T>
+struct IsContiguousRun<T, std::void_t<typename T::value_type, decltype(std::declval<T&>().data()), decltype(std::declval<T&>().resize(std::size_t(0)))>>
+    : std::bool_constant<std::is_trivially_copyable_v<typename T::value_type> && sizeof(typename T::value_type) % sizeof(double) == 0> {};
+
+// ISTLVectorBackend::resize(sizeProvider), :153-233: every level gets the size the descriptor prescribes;
+// a fixed-size level of another size is the reference's RangeError (:170, :208, :232)
+template <class C, class D> void resizeNested(C& c, const D& d) {
+  if constexpr (std::is_arithmetic_v<C>) { (void)c; (void)d; }
+  else if constexpr (IsTuple<C>::value) {
+    if (std::tuple_size_v<C> != d.size()) throw RangeError("Can't resize statically sized vector entry: tuple size does not match the basis");
+    std::size_t i = 0;
+    std::apply([&](auto&... e) { (resizeNested(e, d[i++]), ...); }, c);
+  } else {
+    if constexpr (HasResize<C>::value) { if (c.size() != d.size()) c.resize(d.size()); }
+    else if (c.size() != d.size()) throw RangeError("Can't resize statically sized vector entry to the size the basis requires");
+    for (std::size_t i = 0; i < c.size(); ++i) resizeNested(c[i], d[i]);
+  }
+}
+template <class C> void flattenNested(const C& c, std::vector<double>& out) {
+  if constexpr (std::is_arithmetic_v<C>) out.push_back((double)c);
+  else if constexpr (IsTuple<C>::value) std::apply([&](const auto&... e) { (flattenNested(e, out), ...); }, c);
+  else for (std::size_t i = 0; i < c.size(); ++i) flattenNested(c[i], out);
+}
+template <class C> void unflattenNested(C& c, const double*& p) {
+  if constexpr (std::is_arithmetic_v<C>) c = (C)*p++;
+  else if constexpr (IsTuple<C>::value) std::apply([&](auto&... e) { (unflattenNested(e, p), ...); }, c);
+  else for (std::size_t i = 0; i < c.size(); ++i) unflattenNested(c[i], p);
+}
 struct AllTrue {};
 }  // namespace Impl
 
@@ -541,15 +584,38 @@ template <class B, class C, class F, class BV>
 void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
   const dfx_basis* h = basis.handle();
   const std::size_t n = dfx_basis_dimension(h);
-  double* x = Impl::coeffData(coeff, n);
+  using CV = std::remove_cv_t<std::remove_reference_t<C>>;
   const uint8_t* mask = nullptr;
   std::vector<uint8_t> m;
   if constexpr (!std::is_same_v<BV, Impl::AllTrue>) {
-    if (bv.size() != n) throw RangeError("bit vector size does not match basis");
-    m.resize(n);
-    for (std::size_t i = 0; i < n; ++i) m[i] = bv[i] ? 1 : 0;
+    if constexpr (Impl::IsFlatBits<BV>::value) {
+      if (bv.size() != n) throw RangeError("bit vector size does not match basis");
+      m.resize(n);
+      for (std::size_t i = 0; i < n; ++i) m[i] = bv[i] ? 1 : 0;
+    } else {
+      // a nested bit vector of the same shape as the coefficient container (interpolate.hh:226-233)
+      std::vector<double> flat;
+      Impl::flattenNested(bv, flat);
+      if (flat.size() != n) throw RangeError("bit vector size does not match basis");
+      m.resize(n);
+      for (std::size_t i = 0; i < n; ++i) m[i] = flat[i] != 0.0 ? 1 : 0;
+    }
     mask = m.data();
   }
+  if constexpr (!Impl::IsContiguousRun<CV>::value) {
+    // nested container: size it like ISTLVectorBackend::resize, run on its flat image, copy back
+    Impl::resizeNested(coeff, basis.containerDescriptor());
+    std::vector<double> flat;
+    flat.reserve(n);
+    Impl::flattenNested(coeff, flat);
+    if (flat.size() != n) throw RangeError("nested coefficient container does not match the basis");
+    if constexpr (std::is_same_v<BV, Impl::AllTrue>) interpolate(basis, flat, f, Impl::AllTrue{});
+    else interpolate(basis, flat, f, m);
+    const double* p = flat.data();
+    Impl::unflattenNested(coeff, p);
+    return;
+  } else {
+  double* x = Impl::coeffData(coeff, n);
   if constexpr (std::is_same_v<F, Registry::Function>) {
     Impl::check(dfx_interpolate_host(h, basis.rootNode(), &f.f, x, mask));
   } else if constexpr (Impl::IsDiscreteGlobalBasisFunction<F>::value) {
@@ -573,6 +639,7 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
       for (int j = 0; j < dim; ++j) pos[j] = xyz[p * dim + j];
       x[p] = Impl::rangeEntry(f(pos), l, nLeaves);
     }
+  }
   }
 }
 template <class B, class C, class F>
@@ -670,8 +737,10 @@ class DiscreteGlobalBasisFunction {
   // the basis is stored by value (rvalues are moved in, discreteglobalbasisfunction.hh:389-395);
   // the coefficient vector is referenced like an lvalue passed to the reference
   DiscreteGlobalBasisFunction(const B& basis, const C& coeff) : basis_(basis), coeff_(&coeff) {
-    if (coeff.size() * sizeof(typename C::value_type) != basis.dimension() * sizeof(double))
-      throw RangeError("coefficient vector size does not match basis");
+    if constexpr (Impl::IsContiguousRun<C>::value) {
+      if (coeff.size() * sizeof(typename C::value_type) != basis.dimension() * sizeof(double))
+        throw RangeError("coefficient vector size does not match basis");
+    } else if (flatImage() == nullptr) throw RangeError("coefficient vector size does not match basis");
     int off, size, firstLeaf;
     Impl::check(dfx_basis_node_info(basis.handle(), basis.rootNode(), &off, &size, &firstLeaf, &ncomp_));
   }
@@ -691,7 +760,7 @@ class DiscreteGlobalBasisFunction {
     values.resize(n * ncomp_);
     if (jac) jac->resize(n * ncomp_ * dim);
     std::vector<int32_t> el(n);
-    Impl::check(dfx_evaluate_global_host(basis_.handle(), basis_.rootNode(), reinterpret_cast<const double*>(coeff_->data()),
+    Impl::check(dfx_evaluate_global_host(basis_.handle(), basis_.rootNode(), coefficientData(),
                                          pts.data(), n, values.data(), jac ? jac->data() : nullptr, el.data()));
     for (std::size_t p = 0; p < n; ++p) if (el[p] < 0) throw Exception("GridError: coordinates are outside of the grid");
   }
@@ -704,7 +773,7 @@ class DiscreteGlobalBasisFunction {
     for (std::size_t q = 0; q < nq; ++q) for (int j = 0; j < dim; ++j) pts[q * dim + j] = xhat[q][j];
     values.resize(ne * nq * ncomp_);
     if (jac) jac->resize(ne * nq * ncomp_ * dim);
-    Impl::check(dfx_evaluate_host(basis_.handle(), basis_.rootNode(), reinterpret_cast<const double*>(coeff_->data()),
+    Impl::check(dfx_evaluate_host(basis_.handle(), basis_.rootNode(), coefficientData(),
                                   pts.data(), (int32_t)nq, 0, ne, values.data(), jac ? jac->data() : nullptr));
   }
 
@@ -720,7 +789,7 @@ class DiscreteGlobalBasisFunction {
       if (!bound_) throw Exception("local function is not bound");
       std::vector<double> v(f_->ncomp_), j(f_->ncomp_ * dim);
       Impl::check(dfx_evaluate_host(f_->basis_.handle(), f_->basis_.rootNode(),
-                                    reinterpret_cast<const double*>(f_->coeff_->data()), x.data(), 1, e_.index, e_.index + 1,
+                                    f_->coefficientData(), x.data(), 1, e_.index, e_.index + 1,
                                     derivative_ ? nullptr : v.data(), derivative_ ? j.data() : nullptr));
       return derivative_ ? j : v;       // flat range entries (values) or [comp][dim] (Jacobian)
     }
@@ -736,10 +805,25 @@ class DiscreteGlobalBasisFunction {
   friend LocalFunction localFunction(const DiscreteGlobalBasisFunction& f) { return LocalFunction(f); }
   int numComponents() const { return ncomp_; }
   const B& basis() const { return basis_; }
-  const double* coefficientData() const { return reinterpret_cast<const double*>(coeff_->data()); }
+  // flat container order of the coefficients: the container itself if it is one contiguous run, else its
+  // flat image, rebuilt at every use because the vector is referenced, not copied (:389-395)
+  const double* coefficientData() const {
+    if constexpr (Impl::IsContiguousRun<C>::value) return reinterpret_cast<const double*>(coeff_->data());
+    else {
+      const double* p = flatImage();
+      if (!p) throw RangeError("coefficient vector size does not match basis");
+      return p;
+    }
+  }
  private:
+  const double* flatImage() const {
+    flat_.clear();
+    Impl::flattenNested(*coeff_, flat_);
+    return flat_.size() == basis_.dimension() ? flat_.data() : nullptr;
+  }
   B basis_;
   const C* coeff_;
+  mutable std::vector<double> flat_;
   int ncomp_ = 1;
 };
 

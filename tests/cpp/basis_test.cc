@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <map>
 #include <set>
+#include <tuple>
 
 #include <dfx/dune_functions.hh>
 
@@ -264,6 +265,59 @@ int main() {
       CHECK(xp != xt, "permuted vertex ids change the numbering of order-4 DOFs");
       std::sort(xp.begin(), xp.end()); std::sort(xt.begin(), xt.end());
       CHECK(xp == xt, "same coefficients in another order");
+    }
+    // nested coefficient containers as in examples/stokes-taylorhood.cc:323-346 (MultiTypeBlockVector of a
+    // BlockVector<FieldVector<double,dim>> and a BlockVector<double>; here std::tuple / std::vector) and the
+    // Array<FlatVector,2> of TaylorHoodBasis: sized like ISTLVectorBackend::resize (istlvectorbackend.hh:153-233),
+    // entries in lexicographic order = the flat container order
+    {
+      using VelocityVector = std::vector<FieldVector<double, 3>>;
+      using PressureVector = std::vector<double>;
+      using VectorType = std::tuple<VelocityVector, PressureVector>;
+      auto th = makeBasis(gv3, composite(power<3>(lagrange<2>(), blockedInterleaved()), lagrange<1>()));
+      auto velocity = [](const FieldVector<double, 3>& p) { return FieldVector<double, 3>{p[1], -p[0], p[2] * p[0]}; };
+      auto pressure = [](const FieldVector<double, 3>& p) { return p[0] + 2 * p[1]; };
+      VectorType x;
+      std::vector<double> flat;
+      interpolate(subspaceBasis(th, Indices::_0), x, velocity);
+      interpolate(subspaceBasis(th, Indices::_1), x, pressure);
+      interpolate(subspaceBasis(th, Indices::_0), flat, velocity);
+      interpolate(subspaceBasis(th, Indices::_1), flat, pressure);
+      const std::size_t n2 = 7 * 9 * 5, n1 = 4 * 5 * 3;
+      CHECK(std::get<0>(x).size() == n2 && std::get<1>(x).size() == n1, "nested container sized from the container descriptor");
+      bool same = flat.size() == 3 * n2 + n1;
+      for (std::size_t i = 0; same && i < n2; ++i) for (int c = 0; c < 3; ++c) same = std::get<0>(x)[i][c] == flat[3 * i + c];
+      for (std::size_t j = 0; same && j < n1; ++j) same = std::get<1>(x)[j] == flat[3 * n2 + j];
+      CHECK(same, "nested entries in lexicographic order are the flat container order");
+      // a discrete function over the nested container evaluates like the one over the flat vector
+      std::vector<FieldVector<double, 3>> pts; std::vector<double> w, vn, vf;
+      gauss3<3>(pts, w);
+      makeDiscreteGlobalBasisFunction<FieldVector<double, 3>>(subspaceBasis(th, Indices::_0), x).evaluateAll(pts, vn);
+      makeDiscreteGlobalBasisFunction<FieldVector<double, 3>>(subspaceBasis(th, Indices::_0), flat).evaluateAll(pts, vf);
+      CHECK(vn == vf && !vn.empty(), "DiscreteGlobalBasisFunction over a nested coefficient container");
+      // masked interpolation with a nested bit vector of the same shape
+      std::tuple<std::vector<std::array<char, 3>>, std::vector<char>> bits;
+      std::get<0>(bits).assign(n2, std::array<char, 3>{1, 0, 1});
+      std::get<1>(bits).assign(n1, 0);
+      VectorType y = x;
+      interpolate(subspaceBasis(th, Indices::_0), y, [](const FieldVector<double, 3>&) { return FieldVector<double, 3>{7.0, 7.0, 7.0}; }, bits);
+      same = true;
+      for (std::size_t i = 0; same && i < n2; ++i)
+        same = std::get<0>(y)[i][0] == 7.0 && std::get<0>(y)[i][1] == std::get<0>(x)[i][1] && std::get<0>(y)[i][2] == 7.0;
+      CHECK(same && std::get<1>(y) == std::get<1>(x), "nested bit vector masks the nested coefficients");
+      // TaylorHoodBasis: Array<FlatVector,2>
+      TaylorHoodBasis<Grid3::LeafGridView> thb(gv3);
+      std::array<std::vector<double>, 2> z;
+      interpolate(subspaceBasis(thb, Indices::_1), z, pressure);
+      CHECK(z[0].size() == 3 * n2 && z[1].size() == n1, "Array<FlatVector,2> of TaylorHoodBasis");
+      same = true;
+      for (std::size_t j = 0; same && j < n1; ++j) same = z[1][j] == flat[3 * n2 + j];
+      CHECK(same, "pressure coefficients in the second block");
+      // a statically sized level of the wrong size: RangeError (istlvectorbackend.hh:170, :208, :232)
+      bool threwNested = false;
+      std::tuple<std::vector<double>> wrong;
+      try { interpolate(th, wrong, Registry::constant(1.0)); } catch (const RangeError&) { threwNested = true; }
+      CHECK(threwNested, "tuple of the wrong size throws RangeError");
     }
     // basis.update(gridView) (defaultglobalbasis.hh:137-141; lagrangebasistest.cc:163-175 updates and checks again)
     {

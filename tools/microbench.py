@@ -136,7 +136,7 @@ def main():
         report("evaluate values 4^3 [permuted face DOFs: gather + companion basis]", "q3_128_oriented", ms, best, nd * 8 + v.numel() * 8)
         idx = torch.empty((ne, 64), dtype=torch.int32, device="cuda")
         ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
-        report("indices flat u32 [permuted face DOFs, general kernel]", "q3_128_oriented", ms, best, idx.numel() * 4)
+        report("indices flat u32 [permuted face DOFs, walking kernel]", "q3_128_oriented", ms, best, idx.numel() * 4)
         del basis, x, v, f, idx, ids
         torch.cuda.empty_cache()
 
