@@ -104,6 +104,7 @@ SIGNATURES = {
     "dfx_matrix_pattern_host": (C.c_int, [_vp, _vp, _vp, _pu64]),
     "dfx_assemble_laplace_host": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Function), _vp]),
     "dfx_assemble_stokes": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "dfx_assemble_stokes_host": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dfx_apply_laplace": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "dfx_csr_mv": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dfx_apply_dirichlet": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1014,6 +1014,28 @@ int dfx_assemble_laplace_host(const dfx_basis* cb, const uint64_t* row_ptr_host,
   return DFX_OK;
 }
 
+int dfx_assemble_stokes_host(const dfx_basis* cb, const uint64_t* row_ptr_host, const uint32_t* col_idx_host,
+                             double* values_host) {
+  dfx_basis* b = const_cast<dfx_basis*>(cb);
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (!row_ptr_host || !col_idx_host || !values_host) return fail(DFX_ERR_INVALID, "null argument");
+  cudaStream_t st; if ((rc = privateStream(b, st))) return rc;
+  const size_t n = b->dimension;
+  const u64 nnz = row_ptr_host[n];
+  if ((rc = growScratch(b, 1, (n + 1) * sizeof(u64)))) return rc;
+  if ((rc = growScratch(b, 2, std::max<size_t>(1, nnz) * sizeof(uint32_t)))) return rc;
+  if ((rc = growScratch(b, 0, std::max<size_t>(1, nnz) * sizeof(double)))) return rc;
+  u64* dRow = (u64*)b->dScratch[1];
+  uint32_t* dCol = (uint32_t*)b->dScratch[2];
+  double* dVal = (double*)b->dScratch[0];
+  DFX_CUDA(cudaMemcpyAsync(dRow, row_ptr_host, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+  DFX_CUDA(cudaMemcpyAsync(dCol, col_idx_host, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if ((rc = assembleStokes(b, dRow, dCol, dVal, st))) return rc;
+  DFX_CUDA(cudaMemcpyAsync(values_host, dVal, nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DFX_CUDA(cudaStreamSynchronize(st));
+  return DFX_OK;
+}
+
 // ---- slab partition helpers ------------------------------------------------------------
 int dfx_halo_ranges(const dfx_basis* b, int32_t side, uint64_t* out_begin, uint64_t* out_count, int32_t max_ranges,
                     int32_t* n) {

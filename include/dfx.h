@@ -374,6 +374,8 @@ int dfx_apply_dirichlet(const dfx_basis* b, const uint64_t* row_ptr, const uint3
  * nested matrix flattened to container positions; velocity-velocity blocks of different
  * components and the pressure-pressure block are structural zeros.                           */
 int dfx_assemble_stokes(const dfx_basis* b, const uint64_t* row_ptr, const uint32_t* col_idx, double* values, void* stream);
+int dfx_assemble_stokes_host(const dfx_basis* b, const uint64_t* row_ptr_host, const uint32_t* col_idx_host,
+                             double* values_host);
 /* y = A x with the same Laplace stiffness matrix, never assembled (matrix-free): per element
  * gather, sum-factorised gradients at (order+1)^dim Gauss points, scale, transposed contraction;
  * every DOF then sums its element contributions in ascending element order (deterministic).

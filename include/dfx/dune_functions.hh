@@ -316,10 +316,23 @@ class DefaultLocalView {
     for (std::size_t d = 0; d < m.n_; ++d) m.d_[d] = (std::size_t)p[d];
     return m;
   }
+  // Not in the reference: the flat container position of index(i), i.e. what a contiguously stored nested
+  // container resolves the multi-index to (istlvectorbackend.hh:267-277) — the row / column numbering of
+  // the CSR stand-in for the reference's (nested) matrix types
+  size_type flatIndex(size_type i) const {
+    if (flatW0_ != w0_ || flatW1_ != w1_) {
+      flat_.resize((w1_ - w0_) * nloc_);
+      Impl::check(dfx_indices_flat_host(basis_->handle(), w0_, w1_, flat_.data()));
+      flatW0_ = w0_; flatW1_ = w1_;
+    }
+    return flat_[(element_.index - w0_) * nloc_ + i];
+  }
   const GlobalBasis& globalBasis() const { return *basis_; }
   const dfx_basis* handle() const { return basis_->handle(); }
   int subtreeNode() const { return 0; }
  private:
+  mutable std::vector<uint32_t> flat_;
+  mutable std::size_t flatW0_ = 1, flatW1_ = 0;
   const GlobalBasis* basis_;
   Tree tree_;
   Element element_{};
@@ -576,8 +589,44 @@ template <class C> void unflattenNested(C& c, const double*& p) {
   else if constexpr (IsTuple<C>::value) std::apply([&](auto&... e) { (unflattenNested(e, p), ...); }, c);
   else for (std::size_t i = 0; i < c.size(); ++i) unflattenNested(c[i], p);
 }
+// scalar type at the leaves of a nested container (the first leaf's)
+template <class C, class = void> struct LeafScalar { using type = C; };
+template <class C> struct LeafScalar<C, std::enable_if_t<IsTuple<C>::value>> { using type = typename LeafScalar<std::tuple_element_t<0, C>>::type; };
+template <class C> struct LeafScalar<C, std::void_t<typename C::value_type>> { using type = typename LeafScalar<typename C::value_type>::type; };
+// vector[multiIndex]: digit j indexes nesting level j (resolveDynamicMultiIndex, common/indexaccess.hh:376-403)
+template <class S, class C, class MI> S& resolveNested(C& c, const MI& mi, std::size_t level) {
+  if constexpr (std::is_arithmetic_v<C>) { (void)mi; (void)level; return c; }
+  else if constexpr (IsTuple<C>::value) {
+    S* r = nullptr;
+    std::size_t i = 0;
+    std::apply([&](auto&... e) { ((i++ == mi[level] ? (void)(r = &resolveNested<S>(e, mi, level + 1)) : (void)0), ...); }, c);
+    if (!r) throw RangeError("multi-index digit exceeds the tuple size");
+    return *r;
+  } else return resolveNested<S>(c[mi[level]], mi, level + 1);
+}
 struct AllTrue {};
 }  // namespace Impl
+
+// istlVectorBackend(v) (backends/istlvectorbackend.hh:297-312): a non-owning view with resize(basis) and
+// operator[](multiIndex) on nested standard containers
+template <class V>
+class ISTLVectorBackend {
+ public:
+  using Scalar = typename Impl::LeafScalar<V>::type;
+  explicit ISTLVectorBackend(V& v) : v_(&v) {}
+  template <class Basis> void resize(const Basis& basis) { Impl::resizeNested(*v_, basis.containerDescriptor()); }   // :259-265
+  template <class MI> Scalar& operator[](const MI& mi) const { return Impl::resolveNested<Scalar>(*v_, mi, 0); }   // :267-277
+  template <class T> ISTLVectorBackend& operator=(const T& value) { fill(*v_, value); return *this; }
+  V& vector() const { return *v_; }
+ private:
+  template <class C, class T> static void fill(C& c, const T& value) {
+    if constexpr (std::is_arithmetic_v<C>) c = (C)value;
+    else if constexpr (Impl::IsTuple<C>::value) std::apply([&](auto&... e) { (fill(e, value), ...); }, c);
+    else for (std::size_t i = 0; i < c.size(); ++i) fill(c[i], value);
+  }
+  V* v_;
+};
+template <class V> ISTLVectorBackend<V> istlVectorBackend(V& v) { return ISTLVectorBackend<V>(v); }
 
 // interpolate(basis, coeff, f, bitVector) — interpolate.hh:204-282
 template <class B, class C, class F, class BV>

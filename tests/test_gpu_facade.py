@@ -10,7 +10,7 @@ import __graft_entry__ as entry
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["basis_test", "interpolation_example", "user_functor", "poisson_pq2"])
+@pytest.mark.parametrize("name", ["basis_test", "interpolation_example", "user_functor", "poisson_pq2", "stokes_taylorhood"])
 def test_facade_program(name):
     exes = {os.path.basename(e): e for e in entry.build_facade_tests()}
     out = subprocess.run([exes[name]], capture_output=True, text=True, timeout=600)
