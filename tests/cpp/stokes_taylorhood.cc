@@ -139,12 +139,12 @@ int main() {
       }
     }
 
-    // stokes_solve: start from the rhs vector, GMRES(restart 50) to a reduction of 1e-10
+    // stokes_solve: start from the rhs vector, GMRES to a reduction of 1e-10
     std::vector<double> b, x;
     Functions::Impl::flattenNested(rhs, b);
     x = b;
     int it = 0;
-    const double red = gmres(stiffnessMatrix, x, b, 1e-10, 50, 500, it);
+    const double red = gmres(stiffnessMatrix, x, b, 1e-10, 500, 500, it);     // reduction, restart, maxit as in the example (:482-484)
     std::printf("GMRES: %d iterations, reduction %.2e\n", it, red);
     CHECK(red <= 1e-10, "GMRES converged");
     VectorType sol = rhs;
