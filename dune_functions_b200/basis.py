@@ -497,10 +497,20 @@ class SubspaceBasis:
     """subspaceBasis(rootBasis, path...), subspacebasis.hh:27-157: same root indices,
     tree = child at the prefix path; dimension()/size() are the root's."""
 
-    def __init__(self, root: GlobalBasis, *path):
+    def __init__(self, root, *path):
+        # a SubspaceBasis as root: no nesting, the tree paths are joined (subspacebasis.hh:130-133)
+        if isinstance(root, SubspaceBasis):
+            path = tuple(root.path) + tuple(path)
+            root = root.root
         self.root = root
-        self.path = path
-        self.node = root.child(0, *path)
+        self.path = tuple(path)
+        self.node = root.child(0, *self.path)
+
+    def rootBasis(self):
+        return self.root
+
+    def prefixPath(self):
+        return self.path
 
     def dimension(self):
         return self.root.dimension()

@@ -499,8 +499,11 @@ class SubspaceBasis {
   using GridView = GV;
   using LocalView = SubspaceLocalView<GV>;
   LocalView localView() const { return LocalView(*root_, node_); }
-  SubspaceBasis(const DefaultGlobalBasis<GV>& root, int node) : root_(&root), node_(node) {}
+  SubspaceBasis(const DefaultGlobalBasis<GV>& root, int node, std::vector<std::size_t> prefixPath = {})
+      : root_(&root), node_(node), prefixPath_(std::move(prefixPath)) {}
   const DefaultGlobalBasis<GV>& rootBasis() const { return *root_; }
+  // tree path of the sub-tree in the root's local ansatz tree (subspacebasis.hh:96-99)
+  const std::vector<std::size_t>& prefixPath() const { return prefixPath_; }
   int rootNode() const { return node_; }
   std::size_t dimension() const { return root_->dimension(); }     // the root's, :79-94
   auto containerDescriptor() const { return root_->containerDescriptor(); }   // subspacebasis.hh:115-118
@@ -509,15 +512,31 @@ class SubspaceBasis {
  private:
   const DefaultGlobalBasis<GV>* root_;
   int node_;
+  std::vector<std::size_t> prefixPath_;
 };
 template <class GV, class... I>
 SubspaceBasis<GV> subspaceBasis(const DefaultGlobalBasis<GV>& root, I... path) {
   int node = 0;
-  for (std::size_t c : {(std::size_t)path...}) {
+  std::vector<std::size_t> tp;
+  for (std::size_t c : std::initializer_list<std::size_t>{(std::size_t)path...}) {
     node = dfx_basis_node_child(root.handle(), node, (int)c);
     if (node < 0) throw RangeError("subspaceBasis: no such child");
+    tp.push_back(c);
   }
-  return SubspaceBasis<GV>(root, node);
+  return SubspaceBasis<GV>(root, node, std::move(tp));
+}
+// subspaceBasis of a SubspaceBasis: no nesting, the tree paths are joined and the result refers to the
+// root's root (subspacebasis.hh:130-133, :139-157; subspacebasistest.cc)
+template <class GV, class... I>
+SubspaceBasis<GV> subspaceBasis(const SubspaceBasis<GV>& sub, I... path) {
+  int node = sub.rootNode();
+  std::vector<std::size_t> tp = sub.prefixPath();
+  for (std::size_t c : std::initializer_list<std::size_t>{(std::size_t)path...}) {
+    node = dfx_basis_node_child(sub.handle(), node, (int)c);
+    if (node < 0) throw RangeError("subspaceBasis: no such child");
+    tp.push_back(c);
+  }
+  return SubspaceBasis<GV>(sub.rootBasis(), node, std::move(tp));
 }
 
 // ---- functions: registry entries run on the device, any other callable at the nodes ------

@@ -1,0 +1,125 @@
+// host_only_test.cc — the parts of the façade that are host bookkeeping (no device call), so this program
+// runs in the CPU suite (tests/test_facade_host_cpu.py):
+//   subspacebasistest.cc            subspaceBasis from tree-path indices, subspaceBasis of a SubspaceBasis
+//                                   joins the paths and refers to the root's root
+//   containerdescriptortest.cc      checkSize (:87-103) for the basis list of its main() (:236-300)
+//   istlvectorbackend.hh:153-233    resize of nested containers, RangeError for static levels of the wrong size
+//   basis.update / dimension / size(prefix), RangeError for an unsupported order (lagrangebasis.hh:795-796)
+#include <cstdio>
+#include <tuple>
+
+#include <dfx/dune_functions.hh>
+
+using namespace Dune;
+using namespace Dune::Functions;
+using namespace Dune::Functions::BasisFactory;
+using namespace Dune::Indices;
+
+static int failures = 0;
+#define CHECK(cond, what)                                                        \
+  do { if (!(cond)) { std::printf("FAILED %s (%s:%d)\n", what, __FILE__, __LINE__); ++failures; } } while (0)
+
+template <class CD, class Basis>
+void checkSize(const CD& cd, const Basis& basis, std::vector<std::size_t> prefix, std::size_t maxLen) {
+  CHECK(basis.size(prefix) == cd.size(), "size(prefix) == containerDescriptor size at prefix");
+  if (prefix.size() < maxLen && !cd.isValue())
+    for (std::size_t i = 0; i < cd.size(); ++i) {
+      auto p = prefix; p.push_back(i);
+      checkSize(cd[i], basis, p, maxLen);
+    }
+}
+template <class Factory>
+void checkBasis(const YaspGrid<2>::LeafGridView& gv, const Factory& f, const char* name, const char* type = nullptr) {
+  auto basis = makeBasis(gv, f);
+  auto cd = basis.containerDescriptor();
+  CHECK(!cd.isUnknown(), "descriptor known");
+  checkSize(cd, basis, {}, 4);
+  if (type) CHECK(cd.type() == type, "descriptor type");
+  std::printf("containerDescriptor %-30s %s\n", name, cd.type().c_str());
+}
+
+int main() {
+  using Grid = YaspGrid<2>;
+  Grid grid(FieldVector<double, 2>(1.0), {{2, 2}});
+  auto gv = grid.leafGridView();
+  try {
+    // ---- subspacebasistest.cc
+    auto sameSubspace = [](const auto& a, const auto& b) { return &a.rootBasis() == &b.rootBasis() && a.prefixPath() == b.prefixPath() && a.rootNode() == b.rootNode(); };
+    {
+      auto basis = makeBasis(gv, composite(power<3>(lagrange<3>(), blockedInterleaved()), lagrange<1>(), blockedLexicographic()));
+      auto sb0 = subspaceBasis(basis, _0);
+      auto sb01_a = subspaceBasis(sb0, 1);
+      auto sb01_b = subspaceBasis(basis, _0, 1);
+      CHECK(sameSubspace(sb01_a, sb01_b), "subspaceBasis(subspaceBasis(b,tp1),tp2) equals subspaceBasis(b,(tp1,tp2))");
+      CHECK((sb01_a.prefixPath() == std::vector<std::size_t>{0, 1}), "joined tree path");
+      CHECK(!sameSubspace(sb0, sb01_a) && !sameSubspace(sb01_a, subspaceBasis(basis, _0, 2)), "different sub-trees differ");
+      CHECK(sb01_a.dimension() == basis.dimension(), "dimension() is the root's (subspacebasis.hh:79-94)");
+      bool threw = false;
+      try { subspaceBasis(basis, _0, 3); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "no such child");
+    }
+    // ---- containerdescriptortest.cc main()
+    checkBasis(gv, lagrange<1>(), "lagrange<1>", "UniformVector<Value>");
+    checkBasis(gv, power<2>(lagrange<1>(), blockedInterleaved()), "power<2>(Q1,BI)", "UniformVector<UniformArray<Value,2>>");
+    checkBasis(gv, composite(lagrange<1>(), lagrange<2>(), blockedLexicographic()), "composite(Q1,Q2,BL)", "Array<UniformVector<Value>,2>");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), flatLexicographic()), flatLexicographic()), "FL(FL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), flatInterleaved()), flatLexicographic()), "FL(FI)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedLexicographic()), flatLexicographic()), "FL(BL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedInterleaved()), flatLexicographic()), "FL(BI)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), flatLexicographic()), flatInterleaved()), "FI(FL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedLexicographic()), flatInterleaved()), "FI(BL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedInterleaved()), flatInterleaved()), "FI(BI)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), flatInterleaved()), blockedLexicographic()), "BL(FI)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedLexicographic()), blockedLexicographic()), "BL(BL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedInterleaved()), blockedLexicographic()), "BL(BI)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), flatLexicographic()), blockedInterleaved()), "BI(FL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedLexicographic()), blockedInterleaved()), "BI(BL)");
+    checkBasis(gv, power<2>(power<3>(lagrange<2>(), blockedInterleaved()), blockedInterleaved()), "BI(BI)");
+    checkBasis(gv, power<2>(composite(power<1>(power<1>(lagrange<1>(), blockedInterleaved()), blockedLexicographic()),
+                                      power<2>(lagrange<1>(), blockedInterleaved()), power<3>(lagrange<1>(), blockedLexicographic()),
+                                      blockedLexicographic()), blockedLexicographic()), "nested blocked tree");
+    checkBasis(gv, composite(composite(power<2>(lagrange<1>(), flatInterleaved()), power<1>(power<2>(lagrange<1>(), flatLexicographic()), flatLexicographic()), flatLexicographic()),
+                             composite(power<1>(power<1>(lagrange<1>(), flatLexicographic()), flatInterleaved()), power<2>(lagrange<1>(), flatInterleaved()),
+                                       power<3>(lagrange<1>(), flatLexicographic()), flatLexicographic()),
+                             flatLexicographic()), "nested flat tree", "UniformVector<Value>");
+    // ---- istlVectorBackend(v).resize(basis) on nested containers
+    {
+      auto th = makeBasis(gv, composite(power<2>(lagrange<2>(), blockedInterleaved()), lagrange<1>(), blockedLexicographic()));
+      std::tuple<std::vector<FieldVector<double, 2>>, std::vector<double>> v;
+      auto backend = istlVectorBackend(v);
+      backend.resize(th);
+      backend = 3.0;
+      CHECK(std::get<0>(v).size() == 25 && std::get<1>(v).size() == 9, "tuple of block vectors sized like the basis");
+      MultiIndex mi; mi.n_ = 3; mi.d_[0] = 0; mi.d_[1] = 7; mi.d_[2] = 1;
+      backend[mi] = 5.0;
+      CHECK(std::get<0>(v)[7][1] == 5.0 && std::get<0>(v)[7][0] == 3.0, "vector[multiIndex] resolves digit by digit");
+      MultiIndex mp; mp.n_ = 2; mp.d_[0] = 1; mp.d_[1] = 4;
+      backend[mp] = -1.0;
+      CHECK(std::get<1>(v)[4] == -1.0, "pressure entry");
+      bool threw = false;
+      std::tuple<std::vector<FieldVector<double, 3>>, std::vector<double>> wrongBlock;
+      try { istlVectorBackend(wrongBlock).resize(th); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "FieldVector<double,3> blocks for a 2-d velocity: RangeError");
+      std::array<std::vector<double>, 2> arr;
+      TaylorHoodBasis<Grid::LeafGridView> thb(gv);
+      istlVectorBackend(arr).resize(thb);
+      CHECK(arr[0].size() == 50 && arr[1].size() == 9, "Array<FlatVector,2> of TaylorHoodBasis");
+    }
+    // ---- update, dimension, errors
+    {
+      auto basis = makeBasis(gv, lagrange(3));
+      CHECK(basis.dimension() == 49, "Q3 on 2x2");
+      Grid other(FieldVector<double, 2>(1.0), {{5, 3}});
+      basis.update(other.leafGridView());
+      CHECK(basis.dimension() == 16 * 10 && basis.size() == 160, "after update");
+      bool threw = false;
+      try { makeBasis(gv, lagrange(18)); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "order > 17 throws RangeError");
+    }
+  } catch (const std::exception& e) {
+    std::printf("EXCEPTION %s\n", e.what());
+    return 2;
+  }
+  std::printf("%s\n", failures ? "host_only_test FAILED" : "host_only_test passed");
+  return failures ? 1 : 0;
+}
