@@ -90,6 +90,41 @@ def test_oracle_dirichlet_treatment():
     assert np.allclose(rhs[~b], (rhs0 - A0 @ x)[~b], atol=1e-13)
 
 
+def test_oracle_driven_cavity_of_the_stokes_example():
+    """examples/stokes-taylorhood.cc main() (:299-480) step by step on the oracle — BL(BI) Taylor-Hood basis on
+    YaspGrid 4x4, velocity boundary DOFs, Dirichlet data (0, [x0 < 1e-8]), identity rows, GMRES(500) to 1e-10
+    from x0 = rhs.  These are the numbers tests/cpp/stokes_taylorhood.cc (the same main() on the façade,
+    GPU suite) checks: 64 boundary DOFs, u(0.5, 0.5) = (0, -0.1567), discrete divergence ~ 0."""
+    import scipy.sparse.linalg as spl
+    from dune_functions_b200 import power, composite, blockedInterleaved as BI, blockedLexicographic as BL
+    grid = YaspGrid([4, 4])
+    ob = orc.OracleBasis(grid, composite(power(lagrange(2), 2, BI()), lagrange(1), BL()))
+    n = ob.dimension()
+    assert n == 2 * 81 + 25
+    A = scipy_of(orc.oracle_stokes(ob)).toarray()
+    assert np.abs(A - A.T).max() == 0.0 and not A[162:, 162:].any()
+    bnd = ob.boundaryDOFs(node=1)[0].astype(bool)                 # forEachBoundaryDOF(subspaceBasis(basis, _0), ...)
+    assert bnd.sum() == 64 and not bnd[162:].any()
+    o2 = orc.OracleBasis(grid, lagrange(2))
+    X, Y = o2.interpolate(coord(0)), o2.interpolate(coord(1))
+    rhs = np.zeros(n)
+    for i in range(81):                                           # (0, i, c) -> 2 i + c
+        if bnd[2 * i + 1]:
+            rhs[2 * i + 1] = float(X[i] < 1e-8)
+    M = A.copy()
+    M[bnd, :] = 0.0
+    M[bnd, bnd] = 1.0
+    its = [0]
+    x, info = spl.gmres(sp.csr_matrix(M), rhs, x0=rhs.copy(), rtol=1e-10, restart=500, maxiter=2,
+                        callback=lambda r: its.__setitem__(0, its[0] + 1), callback_type="pr_norm")
+    assert info == 0 and its[0] < 187
+    assert np.abs((A @ x)[162:]).max() < 1e-9                     # B u = 0
+    mid = int(np.argmin((X - 0.5) ** 2 + (Y - 0.5) ** 2))
+    left = int(np.argmin(X ** 2 + (Y - 0.5) ** 2))
+    assert abs(x[2 * mid]) < 1e-9 and abs(x[2 * mid + 1] + 0.156722) < 1e-5
+    assert x[2 * left] == 0.0 and x[2 * left + 1] == 1.0
+
+
 @pytest.mark.parametrize("n", [[3, 2], [2, 2, 2]])
 def test_oracle_stokes_matrix_properties(n):
     """assembleStokesMatrix restated (examples/stokes-taylorhood.cc): symmetric saddle-point matrix,
