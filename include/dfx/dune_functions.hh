@@ -506,6 +506,8 @@ class SubspaceBasis {
   const std::vector<std::size_t>& prefixPath() const { return prefixPath_; }
   int rootNode() const { return node_; }
   std::size_t dimension() const { return root_->dimension(); }     // the root's, :79-94
+  std::size_t size() const { return root_->size(); }
+  template <class Prefix> std::size_t size(const Prefix& prefix) const { return root_->size(prefix); }
   auto containerDescriptor() const { return root_->containerDescriptor(); }   // subspacebasis.hh:115-118
   const GV& gridView() const { return root_->gridView(); }
   const dfx_basis* handle() const { return root_->handle(); }
@@ -584,19 +586,54 @@ template <class T>
 struct IsContiguousRun<T, std::void_t<typename T::value_type, decltype(std::declval<T&>().data()), decltype(std::declval<T&>().resize(std::size_t(0)))>>
     : std::bool_constant<std::is_trivially_copyable_v<typename T::value_type> && sizeof(typename T::value_type) % sizeof(double) == 0> {};
 
-// ISTLVectorBackend::resize(sizeProvider), :153-233: every level gets the size the descriptor prescribes;
-// a fixed-size level of another size is the reference's RangeError (:170, :208, :232)
-template <class C, class D> void resizeNested(C& c, const D& d) {
-  if constexpr (std::is_arithmetic_v<C>) { (void)c; (void)d; }
-  else if constexpr (IsTuple<C>::value) {
-    if (std::tuple_size_v<C> != d.size()) throw RangeError("Can't resize statically sized vector entry: tuple size does not match the basis");
+// ISTLVectorBackend::resize(sizeProvider), :153-233.  `sizes` is anything with size() and operator[](i) that
+// says how many entries follow a prefix: a container descriptor, or PrefixSizes around a size provider.
+//  - resizable level (:153-184): resized to size(prefix); size 0 means "this is a coefficient" — a non-empty
+//    container is then accepted as it is (operator[] pads multi-indices with zeros), an empty one is an error;
+//  - statically sized level (:186-221; std::tuple, std::array, FieldVector): must already have that size;
+//  - scalar (:223-231): size(prefix) must be 0.
+template <class SizeProvider>
+struct PrefixSizes {
+  const SizeProvider* provider;
+  std::vector<std::size_t> prefix;
+  std::size_t size() const { return provider->size(prefix); }
+  PrefixSizes operator[](std::size_t i) const { PrefixSizes r{provider, prefix}; r.prefix.push_back(i); return r; }
+};
+template <class C, class D> void resizeNested(C& c, const D& sizes) {
+  const std::size_t size = sizes.size();
+  if constexpr (std::is_arithmetic_v<C>) {
+    (void)c;
+    if (size != 0) throw RangeError("Can't resize scalar vector entry to size " + std::to_string(size));
+  } else if constexpr (IsTuple<C>::value) {
+    if (size == 0) return;
+    if (std::tuple_size_v<C> != size)
+      throw RangeError("Can't resize non-resizable entry of size " + std::to_string(std::tuple_size_v<C>) + " to size " + std::to_string(size));
     std::size_t i = 0;
-    std::apply([&](auto&... e) { (resizeNested(e, d[i++]), ...); }, c);
+    std::apply([&](auto&... e) { (resizeNested(e, sizes[i++]), ...); }, c);
+  } else if constexpr (HasResize<C>::value) {
+    if (size == 0) {
+      if (c.size() == 0) throw RangeError("The vector entry should refer to a scalar coefficient, but is a dynamically sized vector of size==0");
+      return;
+    }
+    c.resize(size);
+    for (std::size_t i = 0; i < size; ++i) resizeNested(c[i], sizes[i]);
   } else {
-    if constexpr (HasResize<C>::value) { if (c.size() != d.size()) c.resize(d.size()); }
-    else if (c.size() != d.size()) throw RangeError("Can't resize statically sized vector entry to the size the basis requires");
-    for (std::size_t i = 0; i < c.size(); ++i) resizeNested(c[i], d[i]);
+    if (size == 0) return;
+    if (c.size() != size)
+      throw RangeError("Can't resize non-resizable entry of size " + std::to_string(c.size()) + " to size " + std::to_string(size));
+    for (std::size_t i = 0; i < size; ++i) resizeNested(c[i], sizes[i]);
   }
+}
+// the sizes of a basis: its container descriptor when it has one (uniform levels share one child, no ABI
+// call per entry), size(prefix) otherwise
+template <class T, class = void> struct HasContainerDescriptor : std::false_type {};
+template <class T> struct HasContainerDescriptor<T, std::void_t<decltype(std::declval<const T&>().containerDescriptor())>> : std::true_type {};
+template <class C, class SizeProvider> void resizeFor(C& c, const SizeProvider& sizeProvider) {
+  if constexpr (HasContainerDescriptor<SizeProvider>::value) {
+    const auto cd = sizeProvider.containerDescriptor();
+    if (!cd.isUnknown()) { resizeNested(c, cd); return; }
+  }
+  resizeNested(c, PrefixSizes<SizeProvider>{&sizeProvider, {}});
 }
 template <class C> void flattenNested(const C& c, std::vector<double>& out) {
   if constexpr (std::is_arithmetic_v<C>) out.push_back((double)c);
@@ -613,15 +650,19 @@ template <class C, class = void> struct LeafScalar { using type = C; };
 template <class C> struct LeafScalar<C, std::enable_if_t<IsTuple<C>::value>> { using type = typename LeafScalar<std::tuple_element_t<0, C>>::type; };
 template <class C> struct LeafScalar<C, std::void_t<typename C::value_type>> { using type = typename LeafScalar<typename C::value_type>::type; };
 // vector[multiIndex]: digit j indexes nesting level j (resolveDynamicMultiIndex, common/indexaccess.hh:376-403)
+// a multi-index that ends before a scalar is reached is padded with zeros (:127-133, :369-370)
 template <class S, class C, class MI> S& resolveNested(C& c, const MI& mi, std::size_t level) {
   if constexpr (std::is_arithmetic_v<C>) { (void)mi; (void)level; return c; }
-  else if constexpr (IsTuple<C>::value) {
-    S* r = nullptr;
-    std::size_t i = 0;
-    std::apply([&](auto&... e) { ((i++ == mi[level] ? (void)(r = &resolveNested<S>(e, mi, level + 1)) : (void)0), ...); }, c);
-    if (!r) throw RangeError("multi-index digit exceeds the tuple size");
-    return *r;
-  } else return resolveNested<S>(c[mi[level]], mi, level + 1);
+  else {
+    const std::size_t digit = level < mi.size() ? (std::size_t)mi[level] : 0;
+    if constexpr (IsTuple<C>::value) {
+      S* r = nullptr;
+      std::size_t i = 0;
+      std::apply([&](auto&... e) { ((i++ == digit ? (void)(r = &resolveNested<S>(e, mi, level + 1)) : (void)0), ...); }, c);
+      if (!r) throw RangeError("multi-index digit exceeds the tuple size");
+      return *r;
+    } else return resolveNested<S>(c[digit], mi, level + 1);
+  }
 }
 struct AllTrue {};
 }  // namespace Impl
@@ -633,7 +674,7 @@ class ISTLVectorBackend {
  public:
   using Scalar = typename Impl::LeafScalar<V>::type;
   explicit ISTLVectorBackend(V& v) : v_(&v) {}
-  template <class Basis> void resize(const Basis& basis) { Impl::resizeNested(*v_, basis.containerDescriptor()); }   // :259-265
+  template <class SizeProvider> void resize(const SizeProvider& sizeProvider) { Impl::resizeFor(*v_, sizeProvider); }   // :259-265
   template <class MI> Scalar& operator[](const MI& mi) const { return Impl::resolveNested<Scalar>(*v_, mi, 0); }   // :267-277
   template <class T> ISTLVectorBackend& operator=(const T& value) { fill(*v_, value); return *this; }
   V& vector() const { return *v_; }
@@ -672,7 +713,7 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
   }
   if constexpr (!Impl::IsContiguousRun<CV>::value) {
     // nested container: size it like ISTLVectorBackend::resize, run on its flat image, copy back
-    Impl::resizeNested(coeff, basis.containerDescriptor());
+    Impl::resizeFor(coeff, basis);
     std::vector<double> flat;
     flat.reserve(n);
     Impl::flattenNested(coeff, flat);

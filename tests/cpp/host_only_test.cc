@@ -38,6 +38,46 @@ void checkBasis(const YaspGrid<2>::LeafGridView& gv, const Factory& f, const cha
   std::printf("containerDescriptor %-30s %s\n", name, cd.type().c_str());
 }
 
+// ---- backends/test/istlvectorbackendtest.cc: a mock size provider with non-uniform multi-index lengths
+// (:33-80) and checkISTLVectorBackend (:83-138) on the standard-library stand-ins of its vector types
+template <std::size_t dim>
+struct GlobalBasisMoc {
+  std::size_t size(const std::vector<std::size_t>& prefix) const {
+    if (prefix.size() == 0) return 2;
+    if (prefix.size() == 1) return prefix[0] == 0 ? 23 : (prefix[0] == 1 ? 42 : 0);
+    if (prefix.size() == 2) return prefix[0] == 0 ? dim : 0;
+    return 0;
+  }
+};
+template <class Vector, std::size_t dim>
+void checkISTLVectorBackend(const char* name) {
+  GlobalBasisMoc<dim> basis;
+  Vector x_raw;
+  auto x = istlVectorBackend(x_raw);
+  x.resize(basis);
+  CHECK(std::tuple_size_v<Vector> == basis.size({}), "resize check: root");
+  CHECK(std::get<0>(x_raw).size() == basis.size({0}), "resize check: x_raw[_0]");
+  auto sizeOf = [](const auto& c) {
+    if constexpr (Dune::Functions::Impl::IsTuple<std::decay_t<decltype(c)>>::value) return std::tuple_size_v<std::decay_t<decltype(c)>>;
+    else return c.size();
+  };
+  for (std::size_t i = 0; i < basis.size({0}); ++i) CHECK(sizeOf(std::get<0>(x_raw)[i]) == basis.size({0, i}), "resize check: x_raw[_0][i]");
+  CHECK(std::get<1>(x_raw).size() == basis.size({1}), "resize check: x_raw[_1]");
+  auto mi3 = [](std::size_t a, std::size_t b, std::size_t c) { MultiIndex m; m.n_ = 3; m.d_[0] = a; m.d_[1] = b; m.d_[2] = c; return m; };
+  auto mi2 = [](std::size_t a, std::size_t b) { MultiIndex m; m.n_ = 2; m.d_[0] = a; m.d_[1] = b; return m; };
+  for (std::size_t i = 0; i < 23; ++i) for (std::size_t j = 0; j < dim; ++j) x[mi3(0, i, j)] = 0 + i + j;
+  for (std::size_t i = 0; i < 42; ++i) x[mi2(1, i)] = 1 + i;
+  const auto& x_const = x;
+  bool ok = true;
+  for (std::size_t i = 0; i < 23; ++i) for (std::size_t j = 0; j < dim; ++j) ok = ok && x_const[mi3(0, i, j)] == double(0 + i + j);
+  for (std::size_t i = 0; i < 42; ++i) ok = ok && x_const[mi2(1, i)] == double(1 + i);
+  CHECK(ok, "entries written through multi-indices are read back");
+  std::vector<double> flat;
+  Dune::Functions::Impl::flattenNested(x_raw, flat);
+  CHECK(flat.size() == 23 * dim + 42 && flat[dim + 1] == 2.0 && flat[23 * dim + 5] == 6.0, "lexicographic flat image");
+  std::printf("istlVectorBackend %-46s ok\n", name);
+}
+
 int main() {
   using Grid = YaspGrid<2>;
   Grid grid(FieldVector<double, 2>(1.0), {{2, 2}});
@@ -104,6 +144,24 @@ int main() {
       TaylorHoodBasis<Grid::LeafGridView> thb(gv);
       istlVectorBackend(arr).resize(thb);
       CHECK(arr[0].size() == 50 && arr[1].size() == 9, "Array<FlatVector,2> of TaylorHoodBasis");
+    }
+    // ---- istlvectorbackendtest.cc main(): TupleVector / MultiTypeBlockVector -> std::tuple, BlockVector -> std::vector
+    {
+      using FV1 = FieldVector<double, 1>;
+      checkISTLVectorBackend<std::tuple<std::vector<std::vector<double>>, std::vector<double>>, 2>("TV<V<V<double>>, V<double>>");
+      checkISTLVectorBackend<std::tuple<std::vector<std::vector<FV1>>, std::vector<FV1>>, 2>("TV<V<BV<FV<double,1>>>, V<FV<double,1>>>");
+      checkISTLVectorBackend<std::tuple<std::vector<std::array<FV1, 5>>, std::vector<double>>, 5>("TV<V<A<FV<double,1>,5>>, V<double>>");
+      checkISTLVectorBackend<std::tuple<std::vector<FieldVector<double, 5>>, std::vector<FV1>>, 5>("MTBV<BV<FV<double,5>>, BV<FV<double,1>>>");
+      checkISTLVectorBackend<std::tuple<std::vector<std::tuple<FV1, double, FV1>>, std::vector<FV1>>, 3>("MTBV<V<MTBV<FV1, double, FV1>>, BV<FV1>>");
+      // an empty resizable entry where a coefficient is expected (:158-167)
+      bool threw = false;
+      std::tuple<std::vector<std::vector<std::vector<double>>>, std::vector<double>> tooDeep;
+      try { istlVectorBackend(tooDeep).resize(GlobalBasisMoc<2>{}); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "dynamically sized vector of size 0 in place of a scalar coefficient");
+      threw = false;
+      std::tuple<std::vector<double>, std::vector<double>> tooFlat;
+      try { istlVectorBackend(tooFlat).resize(GlobalBasisMoc<2>{}); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "scalar entry where size(prefix) = dim (:223-231)");
     }
     // ---- update, dimension, errors
     {
