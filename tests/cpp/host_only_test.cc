@@ -140,6 +140,19 @@ int main() {
       std::tuple<std::vector<FieldVector<double, 3>>, std::vector<double>> wrongBlock;
       try { istlVectorBackend(wrongBlock).resize(th); } catch (const RangeError&) { threw = true; }
       CHECK(threw, "FieldVector<double,3> blocks for a 2-d velocity: RangeError");
+      // the copy pair of the nested interpolate / DiscreteGlobalBasisFunction paths: flat image and back
+      std::vector<double> flat;
+      Dune::Functions::Impl::flattenNested(v, flat);
+      CHECK(flat.size() == th.dimension() && flat[2 * 7 + 1] == 5.0 && flat[50 + 4] == -1.0, "flat image in container order");
+      for (std::size_t i = 0; i < flat.size(); ++i) flat[i] = (double)i;
+      const double* pf = flat.data();
+      Dune::Functions::Impl::unflattenNested(v, pf);
+      CHECK(pf == flat.data() + flat.size() && std::get<0>(v)[3][1] == 7.0 && std::get<1>(v)[2] == 52.0, "unflatten restores every entry");
+      // resize through the sub-space basis (what interpolate(subspaceBasis(b, _0), x, f) does) and a second time
+      std::tuple<std::vector<FieldVector<double, 2>>, std::vector<double>> w;
+      Dune::Functions::Impl::resizeFor(w, subspaceBasis(th, _0));
+      Dune::Functions::Impl::resizeFor(w, subspaceBasis(th, _1));
+      CHECK(std::get<0>(w).size() == 25 && std::get<1>(w).size() == 9, "resize through a SubspaceBasis uses the root's sizes");
       std::array<std::vector<double>, 2> arr;
       TaylorHoodBasis<Grid::LeafGridView> thb(gv);
       istlVectorBackend(arr).resize(thb);
