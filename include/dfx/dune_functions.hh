@@ -25,6 +25,11 @@
 //   SubspaceLocalView                  subspacelocalview.hh:32-153
 //   subEntityDOFs / SubEntityDOFs      subentitydofs.hh:45-236
 //   forEachBoundaryDOF                 boundarydofs.hh:39-127
+//   containerDescriptor                defaultglobalbasis.hh:180-186, containerdescriptors.hh:91-209
+//   istlVectorBackend                  backends/istlvectorbackend.hh:104-312 (on nested standard containers)
+//   AnalyticGridViewFunction, makeGridViewFunction
+//                                      gridfunctions/analyticgridviewfunction.hh:33-245, gridviewfunction.hh:68-101
+//   basis.update(gridView)             defaultglobalbasis.hh:137-141
 // Errors: non-zero dfx_status becomes Dune::RangeError / Dune::NotImplemented /
 // Dune::Exception, like the DUNE_THROW sites of the reference.  No CPU fallback: every
 // compute call goes through libdfx.so and fails if no device is present.
@@ -78,9 +83,37 @@ class YaspGrid {
  public:
   static constexpr int dimension = dim;
   using ctype = double;
+  // AxisAlignedCubeGeometry of an element: lower = origin + i h, upper = origin + (i+1) h,
+  // global(x) = lower + x (upper - lower)   [dune-grid YaspGeometry / dune-geometry AxisAlignedCubeGeometry]
+  struct Geometry {
+    FieldVector<double, dim> lower, upper;
+    FieldVector<double, dim> global(const FieldVector<double, dim>& local) const {
+      FieldVector<double, dim> x;
+      for (int j = 0; j < dim; ++j) x[j] = lower[j] + local[j] * (upper[j] - lower[j]);
+      return x;
+    }
+    FieldVector<double, dim> local(const FieldVector<double, dim>& global) const {
+      FieldVector<double, dim> x;
+      for (int j = 0; j < dim; ++j) x[j] = (global[j] - lower[j]) / (upper[j] - lower[j]);
+      return x;
+    }
+    double integrationElement(const FieldVector<double, dim>&) const { return volume(); }
+    double volume() const { double v = 1; for (int j = 0; j < dim; ++j) v *= upper[j] - lower[j]; return v; }
+    FieldVector<double, dim> center() const { return global(FieldVector<double, dim>(0.5)); }
+  };
   struct Element {
     std::size_t index;                     // position in elements(gridView), x fastest
     std::array<int, dim> coord;
+    const YaspGrid* grid = nullptr;
+    Geometry geometry() const {
+      Geometry g;
+      for (int j = 0; j < dim; ++j) {
+        const double h = (grid->L_[j] - grid->lower_[j]) / grid->N_[j];
+        g.lower[j] = grid->lower_[j] + coord[j] * h;
+        g.upper[j] = grid->lower_[j] + (coord[j] + 1) * h;
+      }
+      return g;
+    }
   };
   class LeafGridView {
    public:
@@ -106,7 +139,7 @@ class YaspGrid {
   LeafGridView leafGridView() const { return LeafGridView(this); }
   std::size_t numElements() const { std::size_t n = 1; for (int j = 0; j < dim; ++j) n *= N_[j]; return n; }
   Element element(std::size_t e) const {
-    Element el; el.index = e;
+    Element el; el.index = e; el.grid = this;
     for (int j = 0; j < dim; ++j) { el.coord[j] = (int)(e % N_[j]); e /= N_[j]; }
     return el;
   }
@@ -753,6 +786,53 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
 }
 template <class B, class C, class F>
 void interpolate(const B& basis, C&& coeff, const F& f) { interpolate(basis, coeff, f, Impl::AllTrue{}); }
+
+// ---- AnalyticGridViewFunction (gridfunctions/analyticgridviewfunction.hh:33-245) -----------------
+// A callable f(GlobalCoordinate) as a grid function: operator()(x) = f(x); its local function is bound to
+// an element and evaluates f(geometry.global(xLocal)) (:77-81, :105-109).  Host code: this is how an
+// arbitrary f reaches interpolate() (gridviewfunction.hh:68-101), which evaluates it at the node positions
+// the device produces.
+template <class F, class GV>
+class AnalyticGridViewFunction {
+ public:
+  using GridView = GV;
+  static constexpr int dim = GV::dimension;
+  using Domain = FieldVector<double, dim>;
+  using Element = typename GV::Grid::Element;
+  AnalyticGridViewFunction(const F& f, const GV& gridView) : f_(f), gv_(gridView) {}
+  auto operator()(const Domain& x) const { return f_(x); }
+  const GV& gridView() const { return gv_; }
+  class LocalFunction {
+   public:
+    explicit LocalFunction(const F& f) : f_(f) {}
+    void bind(const Element& element) { element_ = element; geometry_ = element.geometry(); bound_ = true; }
+    void unbind() { bound_ = false; }
+    bool bound() const { return bound_; }
+    auto operator()(const Domain& xLocal) const {
+      if (!bound_) throw Exception("local function is not bound");
+      return f_(geometry_.global(xLocal));
+    }
+    const Element& localContext() const { return element_; }
+   private:
+    F f_;
+    Element element_{};
+    typename GV::Grid::Geometry geometry_{};
+    bool bound_ = false;
+  };
+  friend LocalFunction localFunction(const AnalyticGridViewFunction& t) { return LocalFunction(t.f_); }
+ private:
+  F f_;
+  GV gv_;
+};
+template <class F, class GV>
+AnalyticGridViewFunction<F, GV> makeAnalyticGridViewFunction(const F& f, const GV& gridView) { return AnalyticGridViewFunction<F, GV>(f, gridView); }
+// makeGridViewFunction (gridviewfunction.hh:68-101): a grid function is handed through unchanged, anything
+// else callable is wrapped
+template <class F, class GV>
+auto makeGridViewFunction(const F& f, const GV& gridView) {
+  if constexpr (Impl::IsDiscreteGlobalBasisFunction<F>::value) { (void)gridView; return f; }
+  else return AnalyticGridViewFunction<F, GV>(f, gridView);
+}
 
 // ---- SubEntityDOFs (subentitydofs.hh:45-236) ------------------------------------------------
 // Range of the local indices of the DOFs attached to a sub-entity (or its sub-sub-entities)

@@ -78,6 +78,24 @@ void checkISTLVectorBackend(const char* name) {
   std::printf("istlVectorBackend %-46s ok\n", name);
 }
 
+// ---- gridfunctions/test/gridfunctiontest.hh:23-44 integrateGridViewFunction with the midpoint rule
+// (quadOrder = 1), used by analyticgridviewfunctiontest.cc:52-95 with exactIntegral = 0.5 for f(x) = x_0
+template <class GridView, class F>
+double integrateGridViewFunction(const GridView& gridView, const F& f) {
+  double integral = 0;
+  auto fLocal = localFunction(f);
+  for (const auto& e : elements(gridView)) {
+    auto geometry = e.geometry();
+    fLocal.bind(e);
+    if (!fLocal.bound()) throw Exception("Function is not bound after bind()");
+    FieldVector<double, GridView::dimension> quadPos(0.5);
+    integral += fLocal(quadPos) * 1.0 * geometry.integrationElement(quadPos);
+    fLocal.unbind();
+  }
+  return integral;
+}
+static double x_component_A(const FieldVector<double, 2>& x) { return x[0]; }
+
 int main() {
   using Grid = YaspGrid<2>;
   Grid grid(FieldVector<double, 2>(1.0), {{2, 2}});
@@ -175,6 +193,31 @@ int main() {
       std::tuple<std::vector<double>, std::vector<double>> tooFlat;
       try { istlVectorBackend(tooFlat).resize(GlobalBasisMoc<2>{}); } catch (const RangeError&) { threw = true; }
       CHECK(threw, "scalar entry where size(prefix) = dim (:223-231)");
+    }
+    // ---- analyticgridviewfunctiontest.cc on YaspGrid<2> 10x10
+    {
+      Grid grid10(FieldVector<double, 2>(1.0), {{10, 10}});
+      auto gridView = grid10.leafGridView();
+      using Domain = FieldVector<double, 2>;
+      auto f = [](const Domain& x) { return x[0]; };
+      CHECK(std::abs(integrateGridViewFunction(gridView, AnalyticGridViewFunction<decltype(f), Grid::LeafGridView>(f, gridView)) - 0.5) < 1e-10, "manual construction");
+      CHECK(std::abs(integrateGridViewFunction(gridView, makeAnalyticGridViewFunction(f, gridView)) - 0.5) < 1e-10, "makeAnalyticGridViewFunction");
+      CHECK(std::abs(integrateGridViewFunction(gridView, makeGridViewFunction(f, gridView)) - 0.5) < 1e-10, "makeGridViewFunction");
+      CHECK(std::abs(integrateGridViewFunction(gridView, makeAnalyticGridViewFunction(&x_component_A, gridView)) - 0.5) < 1e-10, "free function");
+      auto gf = makeAnalyticGridViewFunction([](Domain) { return 1.0; }, gridView);
+      auto gf2 = gf;                                   // copyable
+      auto lf = localFunction(gf2);
+      auto lf2 = lf;
+      CHECK(!lf2.bound(), "not bound before bind()");
+      lf2.bind(grid10.element(37));
+      CHECK(lf2.bound() && lf2(Domain{0.0, 0.0}) == 1.0 && gf(Domain{0.0, 0.0}) == 1.0 && lf2.localContext().index == 37, "evaluation of function and local function");
+      auto g = grid10.element(37).geometry();
+      CHECK(std::abs(g.global(Domain{0.5, 0.5})[0] - 0.75) < 1e-15 && std::abs(g.global(Domain{0.5, 0.5})[1] - 0.35) < 1e-15, "element geometry");
+      CHECK(std::abs(g.local(g.global(Domain{0.25, 0.75}))[1] - 0.75) < 1e-14 && std::abs(g.volume() - 0.01) < 1e-15, "local / volume");
+      bool threw = false;
+      lf2.unbind();
+      try { lf2(Domain{0.0, 0.0}); } catch (const Exception&) { threw = true; }
+      CHECK(threw, "unbound local function");
     }
     // ---- update, dimension, errors
     {
