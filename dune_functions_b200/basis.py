@@ -238,6 +238,7 @@ class GlobalBasis:
         desc = grid.desc()
         capi.check(self._lib.dfx_basis_update(self._h, C.byref(desc)))
         self.grid, self._desc = grid, desc
+        self._numbering = getattr(self, "_numbering", 0) + 1
         if getattr(grid, "vertex_ids", None) is not None:
             self.setVertexIds(grid.vertex_ids)
 
@@ -245,6 +246,7 @@ class GlobalBasis:
         """ids of grid().globalIdSet() for the vertices of the local box, the input of
         LagrangeFaceDOFPermutation (lagrangebasis.hh:787); None restores the grid's own ids.
         Accepts a host sequence / numpy array or a CUDA uint64/int64 torch tensor."""
+        self._numbering = getattr(self, "_numbering", 0) + 1           # local views refetch their index window
         if ids is None:
             capi.check(self._lib.dfx_basis_set_vertex_ids_host(self._h, None, 0))
             return
@@ -378,8 +380,16 @@ class LocalView:
         self._e = None
         self._w0 = self._w1 = 0
         self._cache = None
+        self._numbering = getattr(basis, "_numbering", 0)
 
     def bind(self, element):
+        if self._numbering != getattr(self.basis, "_numbering", 0):
+            # basis.update(gridView) / new vertex ids since the window was fetched: the numbering changed
+            self._numbering = self.basis._numbering
+            self._w0 = self._w1 = 0
+            self._cache = None
+            self._nloc = self.basis.maxNodeSize()
+            self._lens = self.basis.localIndexSizes()
         g = self.basis.grid
         n = list(g.local_n) if g.local_n is not None else list(g.n)
         if not isinstance(element, (int, np.integer)):

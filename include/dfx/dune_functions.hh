@@ -212,6 +212,7 @@ inline void check(int status) {
 }
 struct Handle {
   dfx_basis* h = nullptr;
+  std::size_t numbering = 0;
   ~Handle() { if (h) dfx_basis_destroy(h); }
 };
 }  // namespace Impl
@@ -327,9 +328,14 @@ class DefaultLocalView {
     nloc_ = dfx_basis_max_node_size(b.handle());
     lens_.resize(nloc_);
     Impl::check(dfx_basis_local_index_sizes(b.handle(), lens_.data()));
+    numbering_ = b.numbering();
   }
   void bind(const Element& e) {
     element_ = e; bound_ = true;
+    if (numbering_ != basis_->numbering()) {     // basis.update(gridView) since the window was fetched
+      numbering_ = basis_->numbering();
+      w0_ = w1_ = 0; flatW0_ = 1; flatW1_ = 0;
+    }
     if (e.index < w0_ || e.index >= w1_) {
       w0_ = e.index - e.index % window;
       w1_ = std::min<std::size_t>(w0_ + window, dfx_basis_num_elements(basis_->handle()));
@@ -366,6 +372,7 @@ class DefaultLocalView {
  private:
   mutable std::vector<uint32_t> flat_;
   mutable std::size_t flatW0_ = 1, flatW1_ = 0;
+  std::size_t numbering_ = 0;
   const GlobalBasis* basis_;
   Tree tree_;
   Element element_{};
@@ -442,6 +449,7 @@ class DefaultGlobalBasis {
     dfx_grid_desc g = gridDesc(gv);
     Impl::check(dfx_basis_update(h_->h, &g));
     gv_ = gv;
+    ++h_->numbering;
     const auto& ids = gv.grid().globalVertexIds();
     if (!ids.empty()) Impl::check(dfx_basis_set_vertex_ids_host(h_->h, ids.data(), ids.size()));
   }
@@ -463,6 +471,7 @@ class DefaultGlobalBasis {
     return Impl::buildDescriptor(nodes, pos);
   }
   const dfx_basis* handle() const { return h_->h; }
+  std::size_t numbering() const { return h_->numbering; }   // changes whenever update() renumbers the basis
   static dfx_grid_desc gridDesc(const GV& gv) {
     constexpr int dim = GV::dimension;
     dfx_grid_desc g{};
