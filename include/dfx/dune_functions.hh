@@ -795,6 +795,13 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
 }
 template <class B, class C, class F>
 void interpolate(const B& basis, C&& coeff, const F& f) { interpolate(basis, coeff, f, Impl::AllTrue{}); }
+// coefficient (and bit) vectors wrapped in istlVectorBackend(...), as the reference's examples pass them
+template <class B, class V, class F>
+void interpolate(const B& basis, ISTLVectorBackend<V> coeff, const F& f) { interpolate(basis, coeff.vector(), f, Impl::AllTrue{}); }
+template <class B, class V, class F, class BV>
+void interpolate(const B& basis, ISTLVectorBackend<V> coeff, const F& f, const BV& bv) { interpolate(basis, coeff.vector(), f, bv); }
+template <class B, class C, class F, class W>
+void interpolate(const B& basis, C&& coeff, const F& f, ISTLVectorBackend<W> bv) { interpolate(basis, coeff, f, bv.vector()); }
 
 // ---- AnalyticGridViewFunction (gridfunctions/analyticgridviewfunction.hh:33-245) -----------------
 // A callable f(GlobalCoordinate) as a grid function: operator()(x) = f(x); its local function is bound to
@@ -1028,6 +1035,12 @@ class DiscreteGlobalBasisFunction {
 template <class R, class B, class C>
 DiscreteGlobalBasisFunction<R, B, C> makeDiscreteGlobalBasisFunction(const B& basis, const C& coeff) {
   return DiscreteGlobalBasisFunction<R, B, C>(basis, coeff);
+}
+// the coefficient vector given as a backend (localfunctioncopytest.cc:58-62 passes istlVectorBackend(x)):
+// the wrapped vector is referenced
+template <class R, class B, class V>
+DiscreteGlobalBasisFunction<R, B, V> makeDiscreteGlobalBasisFunction(const B& basis, const ISTLVectorBackend<V>& backend) {
+  return DiscreteGlobalBasisFunction<R, B, V>(basis, backend.vector());
 }
 
 }  // namespace Functions

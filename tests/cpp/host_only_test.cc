@@ -219,6 +219,42 @@ int main() {
       try { lf2(Domain{0.0, 0.0}); } catch (const Exception&) { threw = true; }
       CHECK(threw, "unbound local function");
     }
+    // ---- localfunctioncopytest.cc (the host part: a copy of a bound local function is bound) and the
+    // construction checks of DiscreteGlobalBasisFunction
+    {
+      Grid grid2(FieldVector<double, 2>(1.0), {{2, 2}});
+      LagrangeBasis<Grid::LeafGridView, 1> basis(grid2.leafGridView());
+      std::vector<double> x;
+      auto xbe = istlVectorBackend(x);
+      xbe.resize(basis);
+      xbe = 1.0;
+      CHECK(x.size() == basis.dimension() && x[3] == 1.0, "BlockVector<double> sized and filled through the backend");
+      auto f = makeDiscreteGlobalBasisFunction<double>(basis, xbe);
+      auto localF = localFunction(f);
+      for (const auto& element : elements(grid2.leafGridView())) {
+        localF.bind(element);
+        CHECK(localF.bound(), "Check if LocalFunction was bound.");
+        auto localF_copy = localF;
+        CHECK(localF_copy.bound(), "Check if copied LocalFunction was bound.");
+      }
+      bool threw = false;
+      try { derivative(derivative(localF)); } catch (const NotImplemented&) { threw = true; }
+      CHECK(threw, "second derivative throws NotImplemented (discreteglobalbasisfunction.hh:630-633)");
+      threw = false;
+      std::vector<double> tooShort(basis.dimension() - 1);
+      try { makeDiscreteGlobalBasisFunction<double>(basis, tooShort); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "coefficient vector of the wrong size");
+      threw = false;
+      auto th = makeBasis(grid2.leafGridView(), composite(power<2>(lagrange<2>(), blockedInterleaved()), lagrange<1>()));
+      std::tuple<std::vector<FieldVector<double, 2>>, std::vector<double>> nested;
+      try { makeDiscreteGlobalBasisFunction<double>(subspaceBasis(th, _1), nested); } catch (const RangeError&) { threw = true; }
+      CHECK(threw, "empty nested coefficient container");
+      istlVectorBackend(nested).resize(th);
+      auto p = makeDiscreteGlobalBasisFunction<double>(subspaceBasis(th, _1), nested);
+      using V2 = FieldVector<double, 2>;
+      auto u = makeDiscreteGlobalBasisFunction<V2>(subspaceBasis(th, _0), nested);
+      CHECK(p.numComponents() == 1 && u.numComponents() == 2, "range entries of the sub-trees");
+    }
     // ---- update, dimension, errors
     {
       auto basis = makeBasis(gv, lagrange(3));
