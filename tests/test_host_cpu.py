@@ -285,3 +285,33 @@ def test_vertex_ids_are_host_bookkeeping_until_a_device_call():
     # slabs take contiguous runs of the id table
     s1 = grid.slab(1, 2)
     assert list(s1.vertex_ids) == list(grid.vertex_ids[12:36]) and list(grid.slab(0, 2).vertex_ids) == list(grid.vertex_ids[:24])
+
+
+def test_kernel_orientation_code_on_all_24_orderings_of_every_facet(harness):
+    """the truth table's 24 orderings (tests/golden/face_orientations.json) put on each of the three facet
+    directions of a single cube in turn, orders 3-6: the kernels' orientFaceDOF (direct search of the smallest
+    id) gives the oracle's table-driven numbering for every one of them"""
+    import itertools
+    harness.harness_oriented.restype = C.c_longlong
+    harness.harness_oriented.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p, C.c_void_p]
+    facets = {"z": ((0, 1, 2, 3), (4, 5, 6, 7)), "y": ((0, 1, 4, 5), (2, 3, 6, 7)), "x": ((0, 2, 4, 6), (1, 3, 5, 7))}
+    seen = set()
+    for name, (lo, hi) in facets.items():
+        for perm in itertools.permutations(range(4)):
+            ids = np.zeros(8, dtype=np.uint64)
+            for i in range(4):
+                ids[lo[i]] = 10 + perm[i]
+                ids[hi[i]] = 3 - perm[i]          # the opposite facet runs through the mirrored orderings
+            grid = YaspGrid([1, 1, 1], vertex_ids=ids)
+            for k in (3, 4, 5, 6):
+                tree = lagrange(k)
+                ob = orc.OracleBasis(grid, tree)
+                ref = ob.flatIndices()
+                out = np.zeros(ref.shape, dtype=np.uint64)
+                desc = grid.desc()
+                arr, cnt = tree_array(tree)
+                bad = harness.harness_oriented(C.byref(desc), arr, cnt, ids.ctypes.data, out.ctypes.data)
+                assert bad == 0 and (out == ref).all(), (name, perm, k)
+            seen.add((name, orc.faceOrientations(3, ids)[1][{"z": 4, "y": 2, "x": 0}[name]]))
+    # all eight quadrilateral orientations occurred on every facet direction
+    assert seen == {(n, o) for n in facets for o in range(8, 16)}
