@@ -108,3 +108,34 @@ def test_random_trees_cover_the_interesting_shapes():
     assert any(GlobalBasis(YaspGrid([2, 2]), t).containerDescriptor().kind == capi.CD_UNKNOWN for t in TREES)
     assert any(GlobalBasis(YaspGrid([2, 2]), t).containerDescriptor().kind == capi.CD_TUPLE for t in TREES)
     assert max(GlobalBasis(YaspGrid([2, 2]), t).maxMultiIndexSize() for t in TREES) >= 4
+
+
+def test_random_trees_with_permuted_face_dofs(harness):
+    """the same for trees with continuous leaves of order 3 and 4 on grids with random vertex ids: the kernels'
+    layoutIndexOriented / dofOwnerNode (walked on the CPU) against the oracle's FaceOrientations restatement"""
+    global LEAVES
+    harness.harness_oriented.restype = C.c_longlong
+    harness.harness_oriented.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    saved = LEAVES
+    LEAVES = [lagrange(3), lagrange(4), lagrange(2), lagrangeDG(1)]
+    try:
+        done = 0
+        while done < 40:
+            tree, nleaves, digits = random_tree(rng, 2, 8)
+            if nleaves > 8 or digits > 6:
+                continue
+            n = (2, 2) if done % 2 == 0 else (2, 1, 2)
+            nv = int(np.prod([m + 1 for m in n]))
+            ids = rng.permutation(nv).astype(np.uint64) + 100
+            grid = YaspGrid(list(n), vertex_ids=ids)
+            ob = orc.OracleBasis(grid, tree)
+            ref = ob.flatIndices()
+            out = np.zeros(ref.shape, dtype=np.uint64)
+            desc = grid.desc()
+            arr, cnt = tree_array(tree)
+            bad = harness.harness_oriented(C.byref(desc), arr, cnt, ids.ctypes.data, out.ctypes.data)
+            assert bad == 0 and (out == ref).all(), describe(tree)
+            done += 1
+    finally:
+        LEAVES = saved
