@@ -113,7 +113,7 @@ extern "C" long long harness_oriented(const dfx_grid_desc* g, const dfx_tree_nod
         if (ec[j] == B.grid.N[j] && a[j] == 0) { ec[j] -= 1; li += L.k * (j == 0 ? 1 : j == 1 ? (L.k + 1) : (L.k + 1) * (L.k + 1)); a[j] = L.k; }
       if (layoutIndexOriented(L, B.grid, B.vid, ec, a, li) != d) ++bad;
     }
-    if (L.kind == DFX_NODE_LAGRANGE && L.k > 2 && B.grid.dim > 1)
+    if (B.vid != nullptr && L.kind == DFX_NODE_LAGRANGE && L.k > 2 && B.grid.dim > 1)
       for (unsigned s = 1; s < (1u << B.grid.dim); ++s) {
         int c[3] = {0, 0, 0};
         for (c[2] = 0; c[2] < L.csize[s][2]; ++c[2])

@@ -315,3 +315,28 @@ def test_kernel_orientation_code_on_all_24_orderings_of_every_facet(harness):
             seen.add((name, orc.faceOrientations(3, ids)[1][{"z": 4, "y": 2, "x": 0}[name]]))
     # all eight quadrilateral orientations occurred on every facet direction
     assert seen == {(n, o) for n in facets for o in range(8, 16)}
+
+
+@pytest.mark.parametrize("gname", list(GRIDS))
+def test_every_dof_owner_node_maps_back_to_the_dof(harness, gname):
+    """dofOwnerNode (what k_interpolate / k_points use to find the node behind a DOF) and layoutIndex are
+    inverse to each other on every grid / tree of the parity suite and on z-slabs of them — identity
+    orientations here, the permuted case is test_face_dof_permutation_of_the_kernels_matches_oracle"""
+    harness.harness_oriented.restype = C.c_longlong
+    harness.harness_oriented.argtypes = [C.POINTER(capi.GridDesc), C.POINTER(capi.TreeNode), C.c_int, C.c_void_p, C.c_void_p]
+    whole = GRIDS[gname]
+    grids = [whole]
+    if whole.n[-1] >= 2:
+        grids += [whole.slab(0, 2), whole.slab(1, 2)]
+    for grid in grids:
+        for name, tree in trees(grid.dim).items():
+            if "TH_" in name and grid.dim != 3:
+                continue
+            ob = orc.OracleBasis(YaspGrid(list(grid.local_n)) if grid.local_n is not None else grid, tree)
+            ref = ob.flatIndices()
+            out = np.zeros(ref.shape, dtype=np.uint64)
+            desc = grid.desc()
+            arr, cnt = tree_array(tree)
+            bad = harness.harness_oriented(C.byref(desc), arr, cnt, None, out.ctypes.data)
+            assert bad == 0, (gname, name, bad)
+            assert (out == ref).all(), (gname, name)
