@@ -500,6 +500,12 @@ struct PreBasis {
   virtual MultiIndex* indices(const Element& e, MultiIndex* it) const = 0;
   virtual int maxMultiIndexSize() const = 0;
   virtual int minMultiIndexSize() const = 0;
+  // Vector-backend bookkeeping of the oracle (not a reference method): the number of complete
+  // multi-indices of this pre-basis that are lexicographically smaller than every index starting with
+  // `prefix` — for a complete index its position in a contiguously stored nested container, which is
+  // how vector[multiIndex] resolves (istlvectorbackend.hh:267-277).  The last digit may be one past
+  // the end (lower((size())) == dimension()).  Derived from the same merging rules as indices().
+  virtual size_type lower(MultiIndex prefix) const = 0;
   // tree bookkeeping: append this subtree's nodes (preorder) and leaves
   virtual void collect(int& nodeCounter, int& offset, std::vector<LeafNode>& leaves,
                        std::vector<std::array<int, 4>>& nodes) const = 0;
@@ -520,6 +526,7 @@ struct LagrangePreBasis : PreBasis {
     return prefix.size() == 0 ? dimension() : 0;
   }
   size_type dimension() const override { return mapper.size(); }            // :830-833
+  size_type lower(MultiIndex prefix) const override { return prefix.size() == 0 ? 0 : prefix[0]; }
   size_type maxNodeSize() const override { return ipow(k + 1, g.dim); }     // :836-841
   int maxMultiIndexSize() const override { return 1; }
   int minMultiIndexSize() const override { return 1; }
@@ -564,6 +571,7 @@ struct LagrangeDGPreBasis : PreBasis {
   using PreBasis::size;
   size_type size(MultiIndex prefix) const override { return prefix.size() == 0 ? dimension() : 0; }
   size_type dimension() const override { return mapper.size(); }
+  size_type lower(MultiIndex prefix) const override { return prefix.size() == 0 ? 0 : prefix[0]; }
   size_type maxNodeSize() const override { return ipow(k + 1, g.dim); }
   int maxMultiIndexSize() const override { return 1; }
   int minMultiIndexSize() const override { return 1; }
@@ -613,6 +621,32 @@ struct PowerPreBasis : PreBasis {
     return 0;
   }
   size_type dimension() const override { return children * sub->dimension(); }        // :224-227
+  size_type lower(MultiIndex prefix) const override {
+    if (prefix.size() == 0) return 0;
+    const size_type D = sub->dimension();
+    switch (ims) {
+      case DFX_IMS_FLAT_INTERLEAVED: {            // first digit j*C + c (:264-288)
+        const size_type j = prefix[0] / children, c = prefix[0] % children;
+        MultiIndex pj; pj.push_back(j);
+        MultiIndex pj1; pj1.push_back(j + 1);
+        prefix[0] = j;
+        const size_type lj = sub->lower(pj);
+        return children * lj + c * (sub->lower(pj1) - lj) + (sub->lower(prefix) - lj); }
+      case DFX_IMS_FLAT_LEXICOGRAPHIC: {          // first digit c*S + j (:291-312)
+        const size_type S = sub->size(), c = prefix[0] / S;
+        prefix[0] = prefix[0] % S;
+        return c * D + sub->lower(prefix); }
+      case DFX_IMS_BLOCKED_LEXICOGRAPHIC: {       // (c, sub index) (:324-347)
+        const size_type c = prefix[0];
+        multiIndexPopFront(prefix);
+        return c * D + sub->lower(prefix); }
+      case DFX_IMS_BLOCKED_INTERLEAVED: {         // (sub index, c) (:350-371)
+        MultiIndex head = prefix; head.pop_back();
+        if (head.size() > 0 && sub->size(head) == 0) return children * sub->lower(head) + prefix.back();
+        return children * sub->lower(prefix); }
+    }
+    return 0;
+  }
   size_type maxNodeSize() const override { return children * sub->maxNodeSize(); }    // :230-233
   int maxMultiIndexSize() const override {
     return sub->maxMultiIndexSize() + ((ims == DFX_IMS_BLOCKED_LEXICOGRAPHIC || ims == DFX_IMS_BLOCKED_INTERLEAVED) ? 1 : 0);
@@ -697,6 +731,23 @@ struct CompositePreBasis : PreBasis {
     return result;
   }
   size_type dimension() const override { size_type r = 0; for (auto& s : subs) r += s->dimension(); return r; }
+  size_type lower(MultiIndex prefix) const override {
+    if (prefix.size() == 0) return 0;
+    size_type before = 0;
+    if (ims == DFX_IMS_BLOCKED_LEXICOGRAPHIC) {   // (child, sub index) (:323-338)
+      const size_type child = prefix[0];
+      multiIndexPopFront(prefix);
+      for (size_type i = 0; i < subs.size() && i < child; ++i) before += subs[i]->dimension();
+      return child < subs.size() ? before + subs[child]->lower(prefix) : before;
+    }
+    for (auto& s : subs) {                         // first digit shifted by the earlier children's sizes (:293-312)
+      const size_type firstDigitSize = s->size();
+      if (prefix[0] < firstDigitSize) return before + s->lower(prefix);
+      prefix[0] -= firstDigitSize;
+      before += s->dimension();
+    }
+    return before;
+  }
   size_type maxNodeSize() const override { size_type r = 0; for (auto& s : subs) r += s->maxNodeSize(); return r; }
   int maxMultiIndexSize() const override {
     int r = 0; for (auto& s : subs) r = std::max(r, s->maxMultiIndexSize());
@@ -750,6 +801,11 @@ struct TaylorHoodPreBasis : PreBasis {
     return 0;
   }
   size_type dimension() const override { return g.dim * pq2.size() + pq1.size(); }           // :182-185
+  size_type lower(MultiIndex prefix) const override {     // (0, i*dim + c) | (1, j)
+    if (prefix.size() == 0 || prefix[0] == 0) return prefix.size() > 1 ? prefix[1] : 0;
+    if (prefix[0] == 1) return g.dim * pq2.size() + (prefix.size() > 1 ? prefix[1] : 0);
+    return dimension();
+  }
   size_type maxNodeSize() const override { return g.dim * pq2.maxNodeSize() + pq1.maxNodeSize(); }
   int maxMultiIndexSize() const override { return 2; }
   int minMultiIndexSize() const override { return 2; }
@@ -818,7 +874,11 @@ struct Basis {
   std::vector<LeafNode> leaves;
   std::vector<std::array<int, 4>> nodes;   // local offset, size, first leaf, #leaves
   int maxDigits, minDigits;
-  // vector backend for blocked bases: multi-index -> flat lexicographic position
+  // vector backend for blocked bases: multi-index -> flat lexicographic position.  Two routes:
+  //  (a) `position`: every multi-index of every element collected and sorted (small grids only; kept
+  //      as the cross-check of (b), orc_indices_flat_by_enumeration);
+  //  (b) flat(): PreBasis::lower — the rank of the multi-index among all multi-indices, built from the
+  //      merging rules node by node.
   mutable std::map<MultiIndex, size_type> position;
   mutable bool positionBuilt = false;
 
@@ -842,10 +902,8 @@ struct Basis {
     positionBuilt = true;
   }
   // vector[multiIndex] of a contiguously stored nested container
-  size_type flat(const MultiIndex& mi) const {
-    if (maxDigits == 1) return mi[0];
-    return position.find(mi)->second;
-  }
+  size_type flat(const MultiIndex& mi) const { return maxDigits == 1 ? mi[0] : pre->lower(mi); }
+  void warmFlat() const {}     // flat() is stateless (kept: call sites mark where positions are needed)
 };
 
 }  // namespace orc
@@ -926,7 +984,7 @@ void orc_indices(void* h, uint64_t e0, uint64_t e1, uint64_t* digits, uint8_t* l
 // flat container positions [ne][nloc]
 void orc_indices_flat(void* h, uint64_t e0, uint64_t e1, uint64_t* out) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   std::vector<orc::MultiIndex> idx;
   size_t nloc = b->localSize();
   for (uint64_t e = e0; e < e1; ++e) {
@@ -934,21 +992,36 @@ void orc_indices_flat(void* h, uint64_t e0, uint64_t e1, uint64_t* out) {
     for (size_t i = 0; i < nloc; ++i) out[(e - e0) * nloc + i] = b->flat(idx[i]);
   }
 }
+// the same by brute force: every multi-index of the whole grid collected, sorted lexicographically
+// and numbered (small grids only; cross-check of Basis::flat in tests/test_oracle_cpu.py)
+void orc_indices_flat_by_enumeration(void* h, uint64_t e0, uint64_t e1, uint64_t* out) {
+  auto* b = (orc::Basis*)h;
+  b->buildPositions();
+  std::vector<orc::MultiIndex> idx;
+  size_t nloc = b->localSize();
+  for (uint64_t e = e0; e < e1; ++e) {
+    b->bind(e, idx);
+    for (size_t i = 0; i < nloc; ++i) out[(e - e0) * nloc + i] = b->position.find(idx[i])->second;
+  }
+}
 
 // interpolate(basis, coeff, f, bitVector) — interpolate.hh:204-260 with
 // Imp::interpolateLocal :151-173.  coeff/mask in flat container order.
 // nthreads > 1: OpenMP over z-chunks of elements (CPU baseline only; the last
 // writer of a shared DOF then depends on thread timing, values agree to 1 ulp of x).
-void orc_interpolate(void* h, int32_t subtreeNode, const dfx_function* f, double* coeff,
-                     const uint8_t* mask, int32_t nthreads) {
+// orc_interpolate_range: the same loop restricted to the elements [e0, e1) of the grid view (parity
+// checks on a slice of a grid too large to run whole: the DOFs of those elements get the value the
+// loop writes; a DOF shared with an element outside the range may differ from the full loop's last
+// writer by the rounding of geometry.global, i.e. 1 ulp of x).
+void orc_interpolate_range(void* h, int32_t subtreeNode, const dfx_function* f, double* coeff,
+                           const uint8_t* mask, uint64_t e0, uint64_t e1, int32_t nthreads) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const orc::Grid& g = b->grid;
   const int dim = g.dim;
   const auto& nd = b->nodes[subtreeNode];
   const int firstLeaf = nd[2], nLeaves = nd[3];
-  const int64_t ne = (int64_t)g.numElements();
-  orc::parallelFor(0, ne, nthreads, [&](int64_t eBegin, int64_t eEnd) {
+  orc::parallelFor((int64_t)e0, (int64_t)e1, nthreads, [&](int64_t eBegin, int64_t eEnd) {
     std::vector<orc::MultiIndex> idx;
     for (int64_t e = eBegin; e < eEnd; ++e) {               // for (const auto& e : elements(gridView))
       b->bind((size_t)e, idx);                               // localView.bind(e)
@@ -982,6 +1055,10 @@ void orc_interpolate(void* h, int32_t subtreeNode, const dfx_function* f, double
     }
   });
 }
+void orc_interpolate(void* h, int32_t subtreeNode, const dfx_function* f, double* coeff,
+                     const uint8_t* mask, int32_t nthreads) {
+  orc_interpolate_range(h, subtreeNode, f, coeff, mask, 0, ((orc::Basis*)h)->grid.numElements(), nthreads);
+}
 
 // interpolate(targetBasis, coeff, f) where f is a DiscreteGlobalBasisFunction over another basis
 // on the same grid: makeGridViewFunction hands a grid function through unchanged
@@ -992,8 +1069,8 @@ int32_t orc_interpolate_dgbf(void* hTarget, int32_t targetNode, void* hSource, i
                              const double* sourceCoeff, double* coeff, const uint8_t* mask) {
   auto* bt = (orc::Basis*)hTarget;
   auto* bs = (orc::Basis*)hSource;
-  if (bt->maxDigits > 1) bt->buildPositions();
-  if (bs->maxDigits > 1) bs->buildPositions();
+  bt->warmFlat();
+  bs->warmFlat();
   const orc::Grid& g = bt->grid;
   const int dim = g.dim;
   const auto& nt = bt->nodes[targetNode];
@@ -1037,7 +1114,7 @@ int32_t orc_interpolate_dgbf(void* hTarget, int32_t targetNode, void* hSource, i
 void orc_evaluate(void* h, int32_t subtreeNode, const double* coeff, const double* xhat, int32_t nq,
                   uint64_t e0, uint64_t e1, double* values, double* jacobians, int32_t nthreads) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const orc::Grid& g = b->grid;
   const int dim = g.dim;
   const auto& nd = b->nodes[subtreeNode];
@@ -1118,7 +1195,7 @@ int32_t orc_subentity_dofs(void* h, int32_t subtreeNode, int32_t subEntityIndex,
 // invocations (a DOF may be visited several times, as the reference documents).
 uint64_t orc_boundary_dofs(void* h, int32_t subtreeNode, uint8_t* mask) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const orc::Grid& g = b->grid;
   const int dim = g.dim;
   std::vector<orc::MultiIndex> idx;
@@ -1255,7 +1332,7 @@ extern "C" {
 // dimension+1 entries; col_idx may be NULL (sizes only).  Returns the number of non-zeros.
 uint64_t orc_occupation_pattern(void* h, uint64_t* row_ptr, uint32_t* col_idx) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const size_t n = b->pre->dimension();
   std::vector<std::vector<uint32_t>> nb(n);
   std::vector<orc::MultiIndex> idx;
@@ -1322,7 +1399,7 @@ int32_t orc_assemble_stokes(void* h, const uint64_t* row_ptr, const uint32_t* co
   if ((int)b->leaves.size() != dim + 1) return 1;
   for (int k = 0; k < dim; ++k) if (b->leaves[k].fe->k != 2) return 1;
   if (b->leaves[dim].fe->k != 1) return 1;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const size_t n = b->pre->dimension();
   std::fill(values, values + row_ptr[n], 0.0);                                        // matrix = 0
   const orc::LagrangeCubeFE& velocityLocalFiniteElement = *b->leaves[0].fe;           // child(_0, 0)
@@ -1419,7 +1496,7 @@ void orc_csr_mv(uint64_t n, const uint64_t* row_ptr, const uint32_t* col_idx, co
 void orc_evaluate_global(void* h, int32_t subtreeNode, const double* coeff, const double* x, uint64_t nPoints,
                          double* values, double* jacobians, int64_t* elementOut) {
   auto* b = (orc::Basis*)h;
-  if (b->maxDigits > 1) b->buildPositions();
+  b->warmFlat();
   const orc::Grid& g = b->grid;
   const int dim = g.dim;
   const auto& nd = b->nodes[subtreeNode];

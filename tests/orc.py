@@ -36,6 +36,8 @@ def lib():
         L.orc_indices.argtypes = [vp, u64, u64, vp, vp, i32]
         L.orc_indices_flat.argtypes = [vp, u64, u64, vp]
         L.orc_interpolate.argtypes = [vp, i32, C.POINTER(capi.Function), vp, vp, i32]
+        L.orc_interpolate_range.argtypes = [vp, i32, C.POINTER(capi.Function), vp, vp, u64, u64, i32]
+        L.orc_indices_flat_by_enumeration.argtypes = [vp, u64, u64, vp]
         L.orc_evaluate.argtypes = [vp, i32, vp, vp, i32, u64, u64, vp, vp, i32]
         L.orc_max_threads.restype = i32
         L.orc_subentity_dofs.restype = i32
@@ -133,12 +135,26 @@ class OracleBasis:
         lib().orc_indices_flat(self._h, e0, e1, out.ctypes.data)
         return out
 
-    def interpolate(self, f, coeff=None, mask=None, node=0, nthreads=1):
+    def flatIndicesByEnumeration(self, e0=0, e1=None):
+        """flat positions by collecting and sorting every multi-index of the grid (small grids only)"""
+        e1 = self.numElements() if e1 is None else e1
+        out = np.zeros((e1 - e0, self.maxNodeSize()), dtype=np.uint64)
+        lib().orc_indices_flat_by_enumeration(self._h, e0, e1, out.ctypes.data)
+        return out
+
+    def interpolate(self, f, coeff=None, mask=None, node=0, nthreads=1, e0=None, e1=None):
+        """e0/e1: restrict the element loop to [e0, e1) (slices of grids too large to run whole)"""
         if coeff is None:
             coeff = np.zeros(self.dimension(), dtype=np.float64)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        lib().orc_interpolate(self._h, node, C.byref(f), coeff.ctypes.data,
-                              None if m is None else m.ctypes.data, nthreads)
+        if e0 is None and e1 is None:
+            lib().orc_interpolate(self._h, node, C.byref(f), coeff.ctypes.data,
+                                  None if m is None else m.ctypes.data, nthreads)
+        else:
+            e0 = 0 if e0 is None else e0
+            e1 = self.numElements() if e1 is None else e1
+            lib().orc_interpolate_range(self._h, node, C.byref(f), coeff.ctypes.data,
+                                        None if m is None else m.ctypes.data, e0, e1, nthreads)
         return coeff
 
     def evaluate(self, coeff, xhat, node=0, values=True, jacobians=False, e0=0, e1=None, nthreads=1):

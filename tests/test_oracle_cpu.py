@@ -358,3 +358,47 @@ def test_oracle_world_coordinate_evaluation_agrees_with_local_evaluation(gname):
     # outside the grid: no element
     _, _, el = o.evaluateGlobal(c, np.array([up + 1.0]))
     assert el[0] == -1
+
+
+# ---- the oracle's own bookkeeping: closed-form container position vs brute-force enumeration ----------
+@pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "2d_10x10", "3d_3x4x5", "3d_2x1x3"])
+def test_flat_position_by_tree_rank_equals_enumeration(gname):
+    """Basis::flat ranks a multi-index through size(prefix) (the way a nested container resolves
+    vector[multiIndex], istlvectorbackend.hh:267-277); the brute-force route collects and sorts every
+    multi-index of the grid.  Both must agree for every tree, and the positions must be a bijection
+    onto 0..dimension()-1."""
+    grid = GRIDS[gname]
+    for name, tree in trees(grid.dim).items():
+        if "TH_" in name and grid.dim != 3:
+            continue
+        b = orc.OracleBasis(grid, tree)
+        fast, slow = b.flatIndices(), b.flatIndicesByEnumeration()
+        assert np.array_equal(fast, slow), name
+        assert set(fast.reshape(-1).tolist()) == set(range(b.dimension())), name
+
+
+def test_interpolate_on_an_element_range_matches_the_full_loop():
+    """orc_interpolate_range writes the DOFs of the elements it visits with the full loop's values
+    (up to the rounding of the node coordinate on DOFs shared with elements outside the range)"""
+    grid = YaspGrid([5, 4, 3])
+    for tree in (lagrange(2), taylorHood(), lagrangeDG(2)):
+        b = orc.OracleBasis(grid, tree)
+        f = gaussian(1.0) if b.numLeaves() == 1 else None
+        if f is None:
+            full = np.zeros(b.dimension())
+            b.interpolate(identity(3), coeff=full, node=1)
+            b.interpolate(gaussian(1.0), coeff=full, node=5)
+        else:
+            full = b.interpolate(f)
+        part = np.full(b.dimension(), np.nan)
+        e0, e1 = 17, 41
+        if f is None:
+            b.interpolate(identity(3), coeff=part, node=1, e0=e0, e1=e1)
+            b.interpolate(gaussian(1.0), coeff=part, node=5, e0=e0, e1=e1)
+        else:
+            b.interpolate(f, coeff=part, e0=e0, e1=e1)
+        touched = np.unique(b.flatIndices(e0, e1).reshape(-1)).astype(np.int64)
+        assert not np.isnan(part[touched]).any()
+        assert np.abs(part[touched] - full[touched]).max() <= 1e-15
+        untouched = np.setdiff1d(np.arange(b.dimension()), touched)
+        assert np.isnan(part[untouched]).all()
