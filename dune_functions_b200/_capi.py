@@ -82,6 +82,7 @@ SIGNATURES = {
     "dfx_indices_flat": (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     "dfx_indices_flat_u64": (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     "dfx_interpolate": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp, _vp]),
+    "dfx_interpolate_separable": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp, _vp]),
     "dfx_interpolation_points": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dfx_interpolate_from_values": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "dfx_interpolate_dgbf": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),
@@ -118,6 +119,8 @@ SIGNATURES = {
     "dfx_halo_link_block": (_vp, [_vp]),
     "dfx_halo_link_attach": (C.c_int, [_vp, _i32, _vp, _vp]),
     "dfx_halo_link_error": (_u64, [_vp]),
+    "dfx_halo_link_reset_error": (C.c_int, [_vp]),
+    "dfx_halo_link_set_timeout": (C.c_int, [_vp, C.c_double]),
     "dfx_halo_push": (C.c_int, [_vp, _vp, _vp, _u64, _vp]),
     "dfx_halo_pull": (C.c_int, [_vp, _vp, _vp, _u64, _vp]),
     "dfx_owned_ranges": (C.c_int, [_vp, _pu64, _pu64, _pu64, _i32, _pi32]),

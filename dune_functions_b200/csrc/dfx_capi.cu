@@ -1,5 +1,6 @@
 // dfx_capi.cu — the extern "C" boundary declared in include/dfx.h.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -12,10 +13,12 @@ using namespace dfx;
 
 namespace {
 
-int g_forcedPath = -1;      // evaluate
-int g_interpPath = -1;      // interpolate
-int g_indicesPath = -1;     // indices
-int g_hostBandKiB = -1;     // result bytes per band of dfx_evaluate_host (-1: 192 MiB)
+// testing / profiling knobs of dfx_set_kernel_path (process-wide; atomics so that a test thread
+// flipping one cannot tear a read — product code never writes them)
+std::atomic<int> g_forcedPath{-1};      // evaluate
+std::atomic<int> g_interpPath{-1};      // interpolate
+std::atomic<int> g_indicesPath{-1};     // indices
+std::atomic<int> g_hostBandKiB{-1};     // result bytes per band of dfx_evaluate_host (-1: 192 MiB)
 
 int ensureDevice(const dfx_basis* b) {
   if (!b) return fail(DFX_ERR_INVALID, "null basis handle");
@@ -378,19 +381,32 @@ static int checkFunction(const dfx_function* f, int nLeaves) {
   return DFX_OK;
 }
 
-int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
-                    void* stream) {
-  DFX_RANGE("dfx_interpolate");
+// separable: the caller opted into per-direction factor tables (dfx_interpolate_separable)
+static int interpolateImpl(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
+                           bool separable, void* stream) {
   int rc = ensureDevice(b); if (rc) return rc;
   int fl, nl;
   if ((rc = subtree(b, node, fl, nl))) return rc;
   if ((rc = checkFunction(f, nl))) return rc;
   if (!coeff) return fail(DFX_ERR_INVALID, "null coefficient vector");
-  if (g_interpPath != 0 && !b->oriented && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
-    g_interpMode = g_interpPath == 1 ? 0 : -1;
-    return interpolateFast(const_cast<dfx_basis*>(b), fl, nl, *f, coeff, mask, (cudaStream_t)stream);
+  const int path = g_interpPath.load();      // -1 automatic, 0 generic, 1 structured per-node, 2 structured with tables
+  if (path != 0 && !b->oriented && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
+    const bool wantSep = path == 2 || (path == -1 && separable);
+    return interpolateFast(const_cast<dfx_basis*>(b), fl, nl, *f, coeff, mask, wantSep, (cudaStream_t)stream);
   }
   return interpolateRegistry(b, fl, nl, *f, coeff, mask, (cudaStream_t)stream);
+}
+
+int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
+                    void* stream) {
+  DFX_RANGE("dfx_interpolate");
+  return interpolateImpl(b, node, f, coeff, mask, false, stream);
+}
+
+int dfx_interpolate_separable(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
+                              void* stream) {
+  DFX_RANGE("dfx_interpolate_separable");
+  return interpolateImpl(b, node, f, coeff, mask, true, stream);
 }
 
 int dfx_interpolation_points(const dfx_basis* b, double* out_xyz, int32_t* out_leaf, void* stream) {
@@ -1129,7 +1145,33 @@ int dfx_halo_link_create(const dfx_basis* b, dfx_halo_link** out) {
   e = cudaMemset(l->local, 0, bytes);
   if (e != cudaSuccess) { cudaFree(l->local); delete l; return cudaFail(e, "cudaMemset(halo link)"); }
   *out = l;
+  return dfx_halo_link_set_timeout(l, 4.0);
+}
+
+// control words of the link block (dfx_kernels.cu): 2 = sticky error, 3 = wait limit in SM clock cycles
+static int linkWord(dfx_halo_link* l, int which, unsigned long long* get, const unsigned long long* set) {
+  if (!l) return fail(DFX_ERR_INVALID, "null halo link");
+  DFX_CUDA(cudaSetDevice(l->device));
+  char* p = reinterpret_cast<char*>(l->local) + haloLinkWordOffset(l->n, which);
+  if (set) DFX_CUDA(cudaMemcpy(p, set, sizeof(*set), cudaMemcpyHostToDevice));
+  if (get) DFX_CUDA(cudaMemcpy(get, p, sizeof(*get), cudaMemcpyDeviceToHost));
   return DFX_OK;
+}
+
+int dfx_halo_link_set_timeout(dfx_halo_link* l, double seconds) {
+  if (!l || !(seconds > 0)) return fail(DFX_ERR_INVALID, "bad halo link timeout");
+  int khz = 0;
+  DFX_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, l->device));
+  const unsigned long long cycles = (unsigned long long)(seconds * 1e3 * (double)std::max(khz, 1000000));
+  return linkWord(l, 3, nullptr, &cycles);
+}
+
+int dfx_halo_link_reset_error(dfx_halo_link* l) {
+  const unsigned long long zero = 0;
+  int rc = linkWord(l, 2, nullptr, &zero);                     // error
+  if (!rc) rc = linkWord(l, 4, nullptr, &zero);                // blocks-done counters of both directions
+  if (!rc) rc = linkWord(l, 5, nullptr, &zero);
+  return rc;
 }
 
 void dfx_halo_link_destroy(dfx_halo_link* l) {
@@ -1168,10 +1210,8 @@ int dfx_halo_link_attach(dfx_halo_link* l, int32_t which, const uint8_t* ipc_han
 }
 
 uint64_t dfx_halo_link_error(dfx_halo_link* l) {
-  if (!l) return 0;
-  cudaSetDevice(l->device);
   unsigned long long v = 0;
-  cudaMemcpy(&v, reinterpret_cast<unsigned long long*>(l->local + 2 * l->n) + 2, sizeof(v), cudaMemcpyDeviceToHost);
+  if (linkWord(l, 2, &v, nullptr) != DFX_OK) return ~0ull;
   return v;
 }
 

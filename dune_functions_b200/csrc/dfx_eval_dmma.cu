@@ -213,11 +213,8 @@ int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double
     b->dDenseNode = node; b->dDenseCols = R.ncols; b->dDenseVal = R.wantVal;
   }
   const size_t smem = ((size_t)kDmmaElems * R.lda + (size_t)R.kp * kDmmaLdb) * sizeof(double);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    DFX_CUDA(cudaFuncSetAttribute(k_eval_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(k_eval_dmma, b->device, configured); if (rc) return rc; }
   const u64 blocks = (R.ne + kDmmaElems - 1) / kDmmaElems;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
   // runs of leaves sharing a layout (the gather constants are per layout)

@@ -284,11 +284,8 @@ static int launchRegE(dfx_basis* b, const FastPlan& plan, const RegArgs& R, cons
   size_t smem = (size_t)EPB * NQ * R.nGroup * sizeof(double) * (JAC ? 1 + DIM : 1);
   auto kern = k_eval_reg<DIM, K, M, JAC, EPB>;
   if (smem > 200 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
   const u64 blocks = (R.ne + EPB - 1) / EPB;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
   kern<<<(unsigned)blocks, EPB, smem, st>>>(b->dev.grid, b->dev.layouts[b->dev.leaves[R.firstLeaf].layout], T, R, coeff,

@@ -390,11 +390,8 @@ static int launchSmem(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, con
   const size_t smem = (size_t)kSmemWarps * (Lay::work + Lay::staging(R.nGroup)) * sizeof(double);
   if (smem > 220 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
   auto kern = k_eval_smem<N1, M, GRAD>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
   // persistent warps: as many blocks as fit on the device
   int perSM = 0, sms = 0;
   DFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kSmemWarps * 32, smem));

@@ -264,7 +264,7 @@ void containerDescriptor(const dfx_basis_impl* b, std::vector<dfx_container_node
 double lagrangeP(int k, int i, double x);
 double lagrangeDP(int k, int i, double x);
 
-// peer-memory halo link (dfx_kernels.cu): block layout [buf 0 | buf 1 | arrival | consumed | error]
+// peer-memory halo link (dfx_kernels.cu): block layout [buf 0 | buf 1 | arrival | consumed | error | timeout | counters]
 struct dfx_halo_link_impl {
   int device = 0;
   u64 n = 0;                       // doubles per plane buffer
@@ -274,6 +274,7 @@ struct dfx_halo_link_impl {
   bool lowerIpc = false, upperIpc = false;
 };
 int haloLinkBytes(u64 n, size_t& bytes);
+size_t haloLinkWordOffset(u64 n, int which);     // byte offset of control word `which` (2 = error, 3 = timeout in clock cycles)
 
 }  // namespace dfx
 

@@ -378,14 +378,14 @@ static bool separable(const dfx_function& f) {
   return f.id == DFX_FN_IDENTITY || f.id == DFX_FN_GAUSSIAN_VEC || f.id == DFX_FN_CONSTANT;
 }
 
-int g_interpMode = -1;   // -1 automatic, 0 per-node evaluation of f
-
+// wantSep: the caller opted into the per-direction factor tables (dfx_interpolate_separable); otherwise
+// f is evaluated at every node, as interpolate.hh:151-173 does
 int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
-                    const uint8_t* mask, cudaStream_t st) {
+                    const uint8_t* mask, bool wantSep, cudaStream_t st) {
   const DevBasis& D = b->dev;
   const DevGrid& g = D.grid;
   RegistryFn f; f.f = fn; f.dim = g.dim;
-  const bool sep = separable(fn) && g_interpMode != 0;
+  const bool sep = wantSep && separable(fn);
   for (int q = 0; q < D.nLayouts; ++q) {
     bool used = false;
     for (int l = 0; l < nLeaves; ++l) used = used || D.leaves[firstLeaf + l].layout == q;

@@ -283,7 +283,8 @@ int scatterNodes(const dfx_basis* b, int layoutId, int firstLeaf, int nLeaves, i
   while (tl > 0 && (perEl << tl) > 40 * 1024) --tl;
   const size_t smem = perEl << tl;
   if (smem > 200 * 1024) return fail(DFX_ERR_NOT_IMPLEMENTED, "element too large for the scatter tile");
-  if (smem > 48 * 1024) DFX_CUDA(cudaFuncSetAttribute(k_scatter_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(k_scatter_nodes, b->device, configured); if (rc) return rc; }
   const u64 blocks = ((e1 - e0) + (1ull << tl) - 1) >> tl;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
   ScatterArgs A;
@@ -638,48 +639,83 @@ int haloCopy(const dfx_basis* b, int side, bool pack, double* coeff, double* buf
 // kernel) and then raises an arrival counter there; the receiver spins on its own counter,
 // unpacks, and acknowledges by writing the consumed counter in the sender's block.  No
 // rendezvous, no host involvement, two receive buffers so that a sender may run one step ahead.
-// Block layout (doubles): [buf 0 | buf 1 | arrival (u64) | consumed (u64) | error (u64)].
+// Block layout (doubles): [buf 0 | buf 1 | arrival | consumed | error | timeout cycles | push blocks done |
+// pull blocks done] (u64 each).
+// ONE kernel per direction: every block first waits (thread 0, bounded spin) for the flag it depends
+// on, moves its 256 entries, fences, and counts itself done; the last block to finish raises the
+// flag on the other side.  A wait that runs out of time records the step in the sticky error word
+// and the kernel moves nothing — and so does every later push / pull until dfx_halo_link_reset_error:
+// a stale plane is never unpacked and a buffer the neighbour has not consumed is never overwritten.
 namespace dfx {
 
 __device__ __forceinline__ unsigned long long* linkFlag(double* block, u64 n, int which) {
   return reinterpret_cast<unsigned long long*>(block + 2 * n) + which;
 }
+enum { kLinkArrival = 0, kLinkConsumed = 1, kLinkError = 2, kLinkTimeout = 3, kLinkPushDone = 4, kLinkPullDone = 5, kLinkWords = 6 };
 
-// wait until *flag >= want (written by a peer GPU); gives up after ~4 s and records an error
-__global__ void k_link_wait(double* block, u64 n, int which, unsigned long long want) {
-  volatile unsigned long long* flag = linkFlag(block, n, which);
-  const long long t0 = clock64();
-  while (*flag < want) {
-    __nanosleep(200);
-    if (clock64() - t0 > 8000000000ll) { *linkFlag(block, n, 2) = want; return; }
+// PUSH: coeff (bottom plane) -> peer buffer of parity step & 1, then peer.arrival = step.
+//       Waits for local.consumed >= step - 2 (the acknowledgement of that buffer's previous use lands in MY block).
+// PULL: local buffer -> coeff (top plane), then peer.consumed = step.  Waits for local.arrival >= step.
+template <bool PUSH>
+__global__ void __launch_bounds__(256)
+k_halo_link(const __grid_constant__ DevBasis B, u64 total, double* __restrict__ coeff, double* local, double* peer,
+            unsigned long long step) {
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* err = linkFlag(local, total, kLinkError);
+    int ok = *err == 0ull ? 1 : 0;
+    const unsigned long long want = PUSH ? (step > 2 ? step - 2 : 0ull) : step;
+    if (ok && want > 0) {
+      volatile unsigned long long* flag = linkFlag(local, total, PUSH ? kLinkConsumed : kLinkArrival);
+      const long long limit = (long long)*linkFlag(local, total, kLinkTimeout);
+      const long long t0 = clock64();
+      while (*flag < want) {
+        __nanosleep(100);
+        if (*err != 0ull) { ok = 0; break; }
+        if (clock64() - t0 > limit) { atomicCAS(linkFlag(local, total, kLinkError), 0ull, step); ok = 0; break; }
+      }
+    }
+    __threadfence_system();        // acquire: the plane was written before the flag
+    go = ok;
+  }
+  __syncthreads();
+  if (!go) return;                 // nothing moves, no flag is raised: the neighbour's wait reports it too
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 p;
+  if (t < total && haloLocate(B, PUSH ? 0 : 1, t, p)) {
+    if (PUSH) peer[(step & 1ull) * total + t] = coeff[p];
+    else coeff[p] = __ldcg(local + (step & 1ull) * total + t);       // written by the peer: not through L1
+  }
+  __threadfence_system();          // release: this thread's stores before the block counts itself done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* done = linkFlag(local, total, PUSH ? kLinkPushDone : kLinkPullDone);
+    if (atomicAdd(done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      *done = 0ull;                // the next kernel of this direction starts after this one (same stream)
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(linkFlag(peer, total, PUSH ? kLinkArrival : kLinkConsumed)) = step;
+      __threadfence_system();
+    }
   }
 }
-__global__ void k_link_set(double* block, u64 n, int which, unsigned long long value) {
-  __threadfence_system();
-  *reinterpret_cast<volatile unsigned long long*>(linkFlag(block, n, which)) = value;
-  __threadfence_system();
-}
 
-int haloLinkBytes(u64 n, size_t& bytes) { bytes = (2 * n + 4) * sizeof(double); return DFX_OK; }
+int haloLinkBytes(u64 n, size_t& bytes) { bytes = (2 * n + kLinkWords + 2) * sizeof(double); return DFX_OK; }
+size_t haloLinkWordOffset(u64 n, int which) { return 2 * n * sizeof(double) + (size_t)which * sizeof(unsigned long long); }
 
 int haloPush(const dfx_basis* b, dfx_halo_link_impl* l, const double* coeff, u64 step, cudaStream_t st) {
   if (!l->lower) return fail(DFX_ERR_INVALID, "halo link: no lower neighbour attached");
-  // the buffer of parity step % 2 is free once the neighbour has consumed step - 2 (its acknowledgement lands in MY block)
-  if (step > 2) { k_link_wait<<<1, 1, 0, st>>>(l->local, l->n, 1, step - 2); int rc = postLaunch("k_link_wait"); if (rc) return rc; }
-  int rc = haloCopy(b, 0, true, const_cast<double*>(coeff), l->lower + (step & 1) * l->n, l->n, st);
-  if (rc) return rc;
-  k_link_set<<<1, 1, 0, st>>>(l->lower, l->n, 0, step);
-  return postLaunch("k_link_set");
+  if (l->n == 0) return DFX_OK;
+  const u64 blocks = (l->n + 255) / 256;
+  k_halo_link<true><<<(unsigned)blocks, 256, 0, st>>>(b->dev, l->n, const_cast<double*>(coeff), l->local, l->lower, step);
+  return postLaunch("k_halo_link");
 }
 
 int haloPull(const dfx_basis* b, dfx_halo_link_impl* l, double* coeff, u64 step, cudaStream_t st) {
   if (!l->upper) return fail(DFX_ERR_INVALID, "halo link: no upper neighbour attached");
-  k_link_wait<<<1, 1, 0, st>>>(l->local, l->n, 0, step);
-  int rc = postLaunch("k_link_wait"); if (rc) return rc;
-  rc = haloCopy(b, 1, false, coeff, l->local + (step & 1) * l->n, l->n, st);
-  if (rc) return rc;
-  k_link_set<<<1, 1, 0, st>>>(l->upper, l->n, 1, step);
-  return postLaunch("k_link_set");
+  if (l->n == 0) return DFX_OK;
+  const u64 blocks = (l->n + 255) / 256;
+  k_halo_link<false><<<(unsigned)blocks, 256, 0, st>>>(b->dev, l->n, coeff, l->local, l->upper, step);
+  return postLaunch("k_halo_link");
 }
 
 }  // namespace dfx

@@ -43,6 +43,20 @@ inline int cudaFail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return ::dfx::cudaFail(e_, #call);  \
   } while (0)
 
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute belongs to the (function,
+// device) pair, so `configured` — a static of the calling launcher, i.e. one per kernel instantiation —
+// keeps one bit per device ordinal; the limit is set to the architecture's maximum once, which costs
+// nothing at launch (occupancy follows the size actually requested) and cannot be lowered by another
+// thread that launches a smaller tile.
+template <class Kernel>
+inline int optInSharedMemory(Kernel kern, int device, std::atomic<unsigned long long>& configured) {
+  const bool tracked = device >= 0 && device < 64;
+  if (tracked && ((configured.load(std::memory_order_acquire) >> device) & 1ull)) return DFX_OK;
+  DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (tracked) configured.fetch_or(1ull << device, std::memory_order_release);
+  return DFX_OK;
+}
+
 int indicesMulti32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, int stride, cudaStream_t st);
 int indicesMulti64(const dfx_basis* b, u64 e0, u64 e1, u64* out, int stride, cudaStream_t st);
 int indicesFlat32(const dfx_basis* b, u64 e0, u64 e1, uint32_t* out, cudaStream_t st);
@@ -64,8 +78,7 @@ int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* co
                 const double* dshape, const ShapeOffsets& so, int nq, u64 e0, u64 e1, double* values, double* jac,
                 cudaStream_t st);
 int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
-                    const uint8_t* mask, cudaStream_t st);
-extern int g_interpMode;
+                    const uint8_t* mask, bool wantSep, cudaStream_t st);
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st);
 int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, cudaStream_t st);

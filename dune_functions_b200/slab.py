@@ -153,22 +153,58 @@ class PeerHaloExchange:
             self._link = None
 
 
-def gather_global(basis, coeff, global_dimension, group=None):
-    """every rank gets the whole vector in GLOBAL flat order (result gather of DESIGN.md section 7)"""
-    world = dist.get_world_size(group)
-    ranges = owned_ranges(basis)
-    mine = torch.cat([coeff[lb:lb + c] for lb, c, _ in ranges]) if ranges else coeff[:0]
-    sizes = [None] * world
-    dist.all_gather_object(sizes, (ranges, mine.numel()), group=group)
-    pad = max(s[1] for s in sizes)
-    buf = torch.zeros(pad, dtype=coeff.dtype, device=coeff.device)
-    buf[:mine.numel()] = mine
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
-    out = torch.empty(global_dimension, dtype=coeff.dtype, device=coeff.device)
-    for (rng, _), part in zip(sizes, parts):
-        o = 0
-        for _, c, gb in rng:
-            out[gb:gb + c] = part[o:o + c]
-            o += c
-    return out
+class GlobalGather:
+    """Gather of the distributed coefficient vector: every z-slab owns one
+    contiguous flat-position range per (leaf, index-set component) and that range is contiguous in the
+    GLOBAL numbering too (dfx_owned_ranges), so the gather is a handful of range transfers per pair of
+    ranks, received straight into their place in the output — no staging buffer, no padding, no index
+    lists.  The metadata (every rank's ranges) is exchanged once at construction.
+    root=None: every rank ends up with the whole vector (all-gather); root=r: only rank r does."""
+
+    def __init__(self, basis, global_dimension, group=None, root=None):
+        self.group, self.root, self.n = group, root, int(global_dimension)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.mine = owned_ranges(basis)
+        allr = [None] * self.world
+        dist.all_gather_object(allr, self.mine, group=group)
+        self.ranges = allr
+        covered = sum(c for r in allr for _, c, _ in r)
+        if covered != self.n:
+            raise capi.RangeError(f"owned ranges cover {covered} of {self.n} global entries")
+
+    def bytes_received(self):
+        """bytes this rank receives from its peers per gather"""
+        if self.root is not None and self.rank != self.root:
+            return 0
+        return 8 * sum(c for r, rr in enumerate(self.ranges) if r != self.rank for _, c, _ in rr)
+
+    def __call__(self, coeff, out=None):
+        receiver = self.root is None or self.rank == self.root
+        if receiver and out is None:
+            out = torch.empty(self.n, dtype=coeff.dtype, device=coeff.device)
+        ops = []
+        # the same (sender, range) order on both sides of every pair
+        for dst in range(self.world):
+            if dst == self.rank or (self.root is not None and dst != self.root):
+                continue
+            for lb, c, _ in self.mine:
+                if c:
+                    ops.append(dist.P2POp(dist.isend, coeff[lb:lb + c], dst, self.group))
+        if receiver:
+            for src in range(self.world):
+                if src == self.rank:
+                    continue
+                for _, c, gb in self.ranges[src]:
+                    if c:
+                        ops.append(dist.P2POp(dist.irecv, out[gb:gb + c], src, self.group))
+            for lb, c, gb in self.mine:
+                out[gb:gb + c].copy_(coeff[lb:lb + c])
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return out
+
+
+def gather_global(basis, coeff, global_dimension, group=None, root=None):
+    """one-shot form of GlobalGather: the whole vector in GLOBAL flat order on every rank (or on `root`)"""
+    return GlobalGather(basis, global_dimension, group=group, root=root)(coeff)

@@ -15,6 +15,11 @@
  *  - `stream` is a cudaStream_t passed as void*; all device work is
  *    stream-ordered, nothing synchronises unless documented.
  *  - buffers are caller-owned; the library never reallocates them.
+ *  - a handle is thread-COMPATIBLE, not thread-safe: it owns device caches (shape tables, scratch,
+ *    the uploaded descriptor) that calls rewrite stream-ordered on the stream they are given, so use
+ *    one stream and one thread at a time per handle (LocalView / LocalFunction are per-thread
+ *    objects in the reference too, defaultlocalview.hh:95-101).  Several handles — one per thread or
+ *    per stream — on the same grid are independent.
  *  - there is NO CPU fallback: every compute entry point fails with
  *    DFX_ERR_CUDA when no sm_100 device is usable.
  *
@@ -234,6 +239,16 @@ int dfx_indices_flat_u64(const dfx_basis* b, uint64_t elem_begin, uint64_t elem_
  * entries whose mask byte is 0 are left untouched (mask may be NULL = all).   */
 int dfx_interpolate(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
                     double* coeff, const uint8_t* mask, void* stream);
+/* The same call with an algorithmic shortcut the caller opts into PER CALL: registry functions whose
+ * range entries are products of per-direction factors (exp(-a|x|^2) = prod_j exp(-a x_j^2), prod_j
+ * sin(w x_j), x_j, constants, x -> x, x -> x exp(-a|x|^2)) are tabulated per direction — O(N)
+ * transcendental evaluations instead of one per node — and every coefficient is a product of table
+ * entries.  dfx_interpolate evaluates f at every node like Imp::interpolateLocal (interpolate.hh:151-173);
+ * this variant is NOT bit-identical to it (<= 3 ulp for the Gaussians, identical for polynomials and
+ * constants) and is not what an arbitrary callable can use, so it is never picked implicitly.  A
+ * function without such a form is interpolated exactly like dfx_interpolate.                        */
+int dfx_interpolate_separable(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
+                              double* coeff, const uint8_t* mask, void* stream);
 /* form (2): positions of the interpolation nodes and range entry of every
  * coefficient, in flat container order; then a masked copy of caller values. */
 int dfx_interpolation_points(const dfx_basis* b, double* out_xyz /*[dimension][dim]*/,
@@ -289,9 +304,11 @@ int dfx_evaluate_global(const dfx_basis* b, int32_t subtree_node, const double* 
 int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xhat_host,
                       int32_t n_q, int32_t want_jacobians);
 /* force a kernel family (testing / profiling); path -1 = automatic.
+ * These knobs are process-wide and meant for tests and profiling only (product code selects
+ * behaviour per call, e.g. dfx_interpolate vs dfx_interpolate_separable).
  * op DFX_OP_EVALUATE: paths as above; DFX_OP_INTERPOLATE: 0 generic per-DOF
- * kernel, 1 structured kernel evaluating f at every node, 2 structured kernel
- * with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast;
+ * kernel, 1 structured kernel evaluating f at every node (the automatic choice), 2 structured
+ * kernel with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast;
  * DFX_OP_HOST_BAND_KIB: `path` = KiB of results per pipeline band of dfx_evaluate_host
  * (-1 = default 192 MiB); DFX_OP_SMEM_GRADIENT: how the shared-memory evaluation kernel
  * forms gradients: 1 = differentiated shape tables in every stage, -1 = automatic
@@ -414,7 +431,8 @@ int dfx_owned_ranges(const dfx_basis* b, uint64_t* local_begin_host, uint64_t* c
 /* ---- peer-memory halo link (one process per GPU, NVLink) -------------------------
  * The sender packs its bottom lattice plane straight into the lower neighbour's receive buffer
  * (P2P stores from the pack kernel) and raises an arrival counter there; the receiver waits on its
- * own counter on the stream, unpacks into its top plane and acknowledges into the sender's block.
+ * own counter on the stream, unpacks into its top plane and acknowledges into the sender's block —
+ * one kernel per direction (wait, move, fence, flag).
  * No rendezvous and no host synchronisation; two receive buffers let a sender run a step ahead.
  * Set-up: every rank creates a link (allocates its receive block), exports the 64-byte CUDA IPC
  * handle, and attaches the handles of its lower (`which` = 0) and upper (`which` = 1) neighbours;
@@ -426,8 +444,14 @@ void  dfx_halo_link_destroy(dfx_halo_link* l);
 int   dfx_halo_link_export(dfx_halo_link* l, uint8_t ipc_handle_out[64]);
 void* dfx_halo_link_block(dfx_halo_link* l);
 int   dfx_halo_link_attach(dfx_halo_link* l, int32_t which, const uint8_t* ipc_handle, void* raw_block);
-/* 0 if no wait of this link has timed out so far, else the step that did                  */
+/* 0 if no wait of this link has timed out so far, else the step that did (synchronises with the
+ * device).  The error is sticky: the exchange that timed out and every later dfx_halo_push / _pull on
+ * the link move NOTHING (no stale plane is unpacked, no unconsumed buffer is overwritten) until
+ * dfx_halo_link_reset_error — so check it before results that depend on the plane are used.  The wait
+ * limit defaults to 4 s (dfx_halo_link_set_timeout; a slow neighbour, e.g. first-call set-up, needs more). */
 uint64_t dfx_halo_link_error(dfx_halo_link* l);
+int   dfx_halo_link_reset_error(dfx_halo_link* l);
+int   dfx_halo_link_set_timeout(dfx_halo_link* l, double seconds);
 int dfx_halo_push(const dfx_basis* b, dfx_halo_link* l, const double* coeff, uint64_t step, void* stream);
 int dfx_halo_pull(const dfx_basis* b, dfx_halo_link* l, double* coeff, uint64_t step, void* stream);
 

@@ -54,6 +54,10 @@ def _worker(rank, world, port, tree_name, results):
         # every rank rebuilds the global vector from the owned ranges
         g = slab.gather_global(b, xt, og.dimension())
         ok_gather = bool(np.array_equal(g.numpy(), gx))
+        # the same onto one root only: the others send and get nothing back
+        root = world - 1
+        gr = slab.gather_global(b, xt, og.dimension(), root=root)
+        ok_gather = ok_gather and ((gr is None) if rank != root else bool(np.array_equal(gr.numpy(), gx)))
         results[rank] = (ok_halo, ok_gather, slab.halo_size(b))
     finally:
         dist.destroy_process_group()

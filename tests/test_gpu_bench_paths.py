@@ -1,0 +1,183 @@
+"""Oracle parity ON THE CODE PATHS THE BENCHMARK RUNS ("What's weak"): the small-grid
+suite (tests/cases.py: <= 100 elements) always takes the partial-tile branch of the evaluation
+kernels, never the `c0 += blockDim.x` loop of the row interpolation kernel, and nothing close to the
+index ranges of the BASELINE sizes.  Here the CPU oracle is run on
+
+  * whole grids with several full 128-element blocks and rows longer than a thread block, and
+  * element sub-ranges (first / middle / last) of the BASELINE grids themselves — 256^3 and 512^3
+    Q2, 192^3 DG4, 128^3 Taylor-Hood — with seeded random coefficients, values and Jacobians,
+
+and compared with the CUDA path through the C ABI: indices bit-exact, values within 1e-12.  The
+oracle ranks multi-indices in closed form (PreBasis::lower) and takes element ranges, so a slice of a
+512^3 grid costs seconds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import dune_functions_b200 as dfx
+from dune_functions_b200 import _capi as capi, tensor_gauss
+
+import orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def eval_path(basis, pts, jac, node=0):
+    p = np.ascontiguousarray(pts)
+    return capi.lib().dfx_evaluate_path(basis._h, node, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), 1 if jac else 0)
+
+
+def ranges_of(ne, count):
+    count = min(count, ne)
+    assert count % 128 == 0
+    return sorted({0, ((ne - count) // 2) // 128 * 128, ne - count}), count
+
+
+def check_evaluate_ranges(space, ob, pts, count, jac, onode=0, seed=3, nthreads=8):
+    """random coefficients; oracle contracts the same numbers on [e0, e0 + count).  `space`: the basis or a
+    sub-space basis of it, `onode` the oracle's tree node of the same subtree"""
+    import torch
+    basis = space.root if isinstance(space, dfx.SubspaceBasis) else space
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    x = basis.newVector(0.0).uniform_(-1.0, 1.0, generator=g)
+    f = dfx.makeDiscreteGlobalBasisFunction(space, x)
+    starts, count = ranges_of(basis.numElements(), count)
+    for e0 in starts:
+        e1 = e0 + count
+        idx = basis.flatIndices(e0, e1, dtype=torch.int64)
+        idx_o = ob.flatIndices(e0, e1).astype(np.int64)
+        assert np.array_equal(idx.cpu().numpy(), idx_o), f"index table differs on [{e0}, {e1})"
+        h = np.zeros(ob.dimension())
+        h[idx_o] = x[idx].cpu().numpy()
+        got = f.evaluate(pts, values=True, jacobians=jac, elem_begin=e0, elem_end=e1)
+        ref = ob.evaluate(h, pts, node=onode, values=True, jacobians=jac, e0=e0, e1=e1, nthreads=nthreads)
+        if jac:
+            assert rel(got[0].cpu().numpy(), ref[0]) <= TOL, (e0, "values")
+            assert rel(got[1].cpu().numpy(), ref[1]) <= TOL, (e0, "jacobians")
+        else:
+            assert rel(got.cpu().numpy(), ref) <= TOL, (e0, "values")
+        del got
+    del x
+
+
+def check_interpolate_ranges(basis, ob, fns, count, separable=False, nthreads=8):
+    """fns: [(gpu node, oracle node, function)]"""
+    import torch
+    x = basis.newVector(float("nan"))
+    L = capi.lib()
+    entry = L.dfx_interpolate_separable if separable else L.dfx_interpolate
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for node, _, fn in fns:
+        capi.check(entry(basis._h, node, C.byref(fn), C.c_void_p(x.data_ptr()), None, st))
+    assert not bool(torch.isnan(x).any())
+    starts, count = ranges_of(basis.numElements(), count)
+    for e0 in starts:
+        e1 = e0 + count
+        idx = basis.flatIndices(e0, e1, dtype=torch.int64)
+        idx_o = ob.flatIndices(e0, e1).astype(np.int64)
+        c = np.zeros(ob.dimension())
+        for _, onode, fn in fns:
+            ob.interpolate(fn, coeff=c, node=onode, e0=e0, e1=e1, nthreads=nthreads)
+        assert rel(x[idx].cpu().numpy(), c[idx_o]) <= TOL, (e0, separable)
+    del x
+
+
+# ---- whole grids: several full blocks, rows longer than a thread block -------------------------------
+@pytest.mark.parametrize("n", [[16, 8, 8], [300, 3, 2], [130, 2, 5]])
+@pytest.mark.parametrize("k", [1, 2])
+def test_full_blocks_and_long_rows_against_oracle(n, k):
+    import torch
+    grid = dfx.YaspGrid(n, upper=[1.0, 0.75, 1.25])
+    tree = dfx.lagrange(k)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    assert b.numElements() >= 4 * 128
+    assert np.array_equal(b.flatIndices(dtype=torch.int64).cpu().numpy(), o.flatIndices().astype(np.int64))
+    for f in (dfx.gaussian(1.0), dfx.quadratic(0.5, [1, -2, 3], [1, 0.5, -1, 2, 0.25, -0.5])):
+        ref = o.interpolate(f)
+        for sep in (False, True):
+            x = dfx.interpolate(b, b.newVector(-3.0), f, separable=sep)
+            assert rel(x.cpu().numpy(), ref) <= TOL, (n, k, f.id, sep)
+    rng = np.random.default_rng(11)
+    xr = rng.uniform(-1, 1, o.dimension())
+    xt = torch.from_numpy(xr).cuda()
+    for m in (2, 3):
+        pts, _ = tensor_gauss(3, m)
+        assert eval_path(b, pts, False) == 1 and eval_path(b, pts, True) == 1
+        v, j = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, jacobians=True)     # 64-element blocks, bulk
+        vo = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts)                        # 128-element blocks, bulk
+        vr, jr = o.evaluate(xr, pts, jacobians=True, nthreads=4)
+        assert rel(v.cpu().numpy(), vr) <= TOL and rel(vo.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL
+        # a sub-range that starts inside a block and ends inside another: partial tiles at both ends
+        e0, e1 = 77, b.numElements() - 51
+        vs = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, elem_begin=e0, elem_end=e1)
+        assert rel(vs.cpu().numpy(), vr[e0:e1]) <= TOL
+
+
+# ---- BASELINE grids, element sub-ranges -------------------------------------------------------------
+@pytest.mark.parametrize("n", [256, 512])
+def test_q2_baseline_grids_subranges(n):
+    """configs[1] / configs[4]: k_eval_reg<3,2,3,*,*> on full 128-element blocks (TMA bulk store branch:
+    range multiple of 128, fresh 512-byte aligned output) and k_interp_rows with N_x > blockDim"""
+    grid = dfx.YaspGrid([n, n, n])
+    tree = dfx.lagrange(2)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    assert b.dimension() == (2 * n + 1) ** 3 == o.dimension()
+    pts, _ = tensor_gauss(3, 3)
+    assert eval_path(b, pts, False) == 1 and eval_path(b, pts, True) == 1
+    check_evaluate_ranges(b, o, pts, 1 << 17, jac=False)
+    check_evaluate_ranges(b, o, pts, 1 << 15, jac=True, seed=4)
+    for sep in (False, True):
+        check_interpolate_ranges(b, o, [(0, 0, dfx.gaussian(1.0))], 1 << 16, separable=sep)
+
+
+def test_dg4_192_subranges():
+    """configs[3]: k_eval_smem<5,5,0> (values) and <5,5,2> (values + collocation gradients), element
+    pairs leaving by TMA bulk stores; k_interp_cell"""
+    grid = dfx.YaspGrid([192, 192, 192])
+    tree = dfx.lagrangeDG(4)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    pts, _ = tensor_gauss(3, 5)
+    assert eval_path(b, pts, False) == 2 and eval_path(b, pts, True) == 2
+    check_evaluate_ranges(b, o, pts, 4096, jac=False)
+    check_evaluate_ranges(b, o, pts, 2048 + 128, jac=True, seed=5)
+    quad = dfx.quadratic(0.0, [0, 0, 0], [42, 7, 0, 13, 0, 5])
+    check_interpolate_ranges(b, o, [(0, 0, quad)], 8192)
+    check_interpolate_ranges(b, o, [(0, 0, dfx.gaussian(1.0))], 8192)
+    check_interpolate_ranges(b, o, [(0, 0, dfx.gaussian(1.0))], 8192, separable=True)
+
+
+def test_taylor_hood_128_subranges():
+    """configs[2]: flat and two-digit index tables, velocity + pressure interpolation, whole-tree and
+    per-subspace evaluation on slices of the 128^3 grid"""
+    import torch
+    grid = dfx.YaspGrid([128, 128, 128])
+    tree = dfx.taylorHood()
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    assert b.dimension() == o.dimension() == 3 * 257 ** 3 + 129 ** 3
+    starts, count = ranges_of(b.numElements(), 8192)
+    for e0 in starts:
+        e1 = e0 + count
+        dig, lens = o.indices(e0, e1)
+        assert np.array_equal(b.indices(e0, e1).cpu().numpy().astype(np.uint64), dig)
+        assert np.array_equal(b.flatIndices(e0, e1, dtype=torch.int64).cpu().numpy(), o.flatIndices(e0, e1).astype(np.int64))
+        assert (lens == 2).all()
+    vel, pre = b.child(0, 0), b.child(0, 1)
+    fns = [(vel, 1, dfx.identity(3)), (pre, 5, dfx.gaussian(1.0))]
+    check_interpolate_ranges(b, o, fns, 8192)
+    check_interpolate_ranges(b, o, fns, 8192, separable=True)
+    pts, _ = tensor_gauss(3, 3)
+    check_evaluate_ranges(b, o, pts, 4096, jac=False)                            # whole tree: Q2 x 3 + Q1
+    check_evaluate_ranges(b, o, pts, 2048, jac=True, seed=6)
+    check_evaluate_ranges(dfx.subspaceBasis(b, 0), o, pts, 4096, jac=False, onode=1, seed=7)  # velocity sub-space
+    check_evaluate_ranges(dfx.subspaceBasis(b, 1), o, pts, 4096, jac=False, onode=5, seed=8)  # pressure sub-space
