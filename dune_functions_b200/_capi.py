@@ -126,7 +126,7 @@ SIGNATURES = {
     "dfx_owned_ranges": (C.c_int, [_vp, _pu64, _pu64, _pu64, _i32, _pi32]),
 }
 
-OP_EVALUATE, OP_INTERPOLATE, OP_INDICES, OP_HOST_BAND_KIB, OP_SMEM_GRADIENT = 0, 1, 2, 3, 4
+OP_EVALUATE, OP_INTERPOLATE, OP_INDICES, OP_HOST_BAND_KIB, OP_SMEM_GRADIENT, OP_TUNE_ROWS = 0, 1, 2, 3, 4, 5
 
 _lib = None
 

@@ -531,6 +531,7 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_INDICES) g_indicesPath = path;
   else if (op == DFX_OP_HOST_BAND_KIB) g_hostBandKiB = path;
   else if (op == DFX_OP_SMEM_GRADIENT) g_smemGrad = path;
+  else if (op == DFX_OP_TUNE_ROWS) g_rowsLean = path > 0 ? path : 32;
 }
 
 // Companion of a basis with permuted face DOFs: the same tree with every Lagrange leaf replaced by the

@@ -85,46 +85,61 @@ static __device__ const double kExp2Tab[64] = {
     0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
-__device__ __forceinline__ double expTab(double x) {
-  if (!(fabs(x) <= 700.0)) return exp(x);                      // NaN, infinities, sub-normal / overflow range
+// constants that do not fit a DFMA immediate come from the constant bank as direct operands (no
+// per-use UMOV pairs in the node loop)
+static __constant__ double kExpC[6] = {0x1.71547652b82fep+6 /* 64/ln2 */, -0x1.62e42fee00000p-7 /* -ln2/64, high 32 bits */,
+                                       -0x1.a39ef35793c76p-39 /* -ln2/64, rest */, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
+// CHECKED = false: the caller guarantees |x| <= 700 (the host bounds the argument over the grid box)
+template <bool CHECKED>
+__device__ __forceinline__ double expTabT(double x) {
+  if (CHECKED && !(fabs(x) <= 700.0)) return exp(x);            // NaN, infinities, sub-normal / overflow range
   constexpr double kMagic = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
-  const double t = fma(x, 0x1.71547652b82fep+6 /* 64/ln2 */, kMagic);
+  const double t = fma(x, kExpC[0], kMagic);
   const int ki = __double2loint(t);                             // 64 k + j
   const double kd = t - kMagic;
-  double r = fma(kd, -0x1.62e42fee00000p-7, x);                 // ln2/64, high 32 bits: the product is exact
-  r = fma(kd, -0x1.a39ef35793c76p-39, r);
+  double r = fma(kd, kExpC[1], x);                              // the product is exact
+  r = fma(kd, kExpC[2], r);
   const double w = r * r;
-  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
+  double q = fma(r, kExpC[3], kExpC[4]);
+  q = fma(q, r, kExpC[5]);
   q = fma(q, r, 0.5);
   const double pm1 = fma(q, w, r);                              // expm1(r)
   const double tj = __ldg(kExp2Tab + (ki & 63));
   const double y = fma(tj, pm1, tj);                            // in [1, 2): scaling by 2^k is an exponent add
   return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
 }
+__device__ __forceinline__ double expTab(double x) { return expTabT<true>(x); }
 
 // ---- registry of functions f (include/dfx.h, dfx_fn_id) ----------------------
 // Functor interface used by the interpolation kernels (also what a user-supplied device
 // functor implements): `common(x0,x1,x2)` computes the part shared by all range entries
 // (the transcendental), `comp(c, common, x0,x1,x2)` returns range entry c.  No arrays, so
 // everything stays in registers.
-struct RegistryFn {
+// ID >= 0: the function id is a compile-time constant (the switches below fold away: no indirect branch
+// and no dead transcendental code in the node loop); ID = -1 dispatches on f.id at run time.
+// LEAN (structured per-node kernels only): the caller passes 0.0 for coordinates beyond the grid's
+// dimension — adding their squares / products changes no bit, so the dimension tests go — and the
+// host has bounded the Gaussian's argument over the grid box by 700 (expTabT<false>).
+template <int ID, bool LEAN = false>
+struct RegistryFnT {
   dfx_function f;
   int dim;
+  __device__ __forceinline__ int id() const { return ID >= 0 ? ID : f.id; }
   __device__ __forceinline__ int ncomp() const { return f.n_comp; }
   __device__ __forceinline__ double norm2(double x0, double x1, double x2) const {
     double s = __dmul_rn(x0, x0);                                   // x.two_norm2(): sum in index order
-    if (dim > 1) s = __dadd_rn(s, __dmul_rn(x1, x1));
-    if (dim > 2) s = __dadd_rn(s, __dmul_rn(x2, x2));
+    if (LEAN || dim > 1) s = __dadd_rn(s, __dmul_rn(x1, x1));
+    if (LEAN || dim > 2) s = __dadd_rn(s, __dmul_rn(x2, x2));
     return s;
   }
   __device__ __forceinline__ double common(double x0, double x1, double x2) const {
-    switch (f.id) {
+    switch (id()) {
       case DFX_FN_GAUSSIAN:
       case DFX_FN_GAUSSIAN_VEC:
-        return expTab(__dmul_rn(-f.p[0], norm2(x0, x1, x2)));
+        return expTabT<!LEAN>(__dmul_rn(-f.p[0], norm2(x0, x1, x2)));
       case DFX_FN_QUADRATIC: {
-        const double xx[3] = {x0, dim > 1 ? x1 : 0.0, dim > 2 ? x2 : 0.0};
+        const double xx[3] = {x0, (LEAN || dim > 1) ? x1 : 0.0, (LEAN || dim > 2) ? x2 : 0.0};
         double r = f.p[0];
 #pragma unroll
         for (int j = 0; j < 3; ++j) r = __dadd_rn(r, __dmul_rn(f.p[1 + j], xx[j]));
@@ -146,7 +161,7 @@ struct RegistryFn {
     return 0.0;
   }
   __device__ __forceinline__ double comp(int c, double cm, double x0, double x1, double x2) const {
-    switch (f.id) {
+    switch (id()) {
       case DFX_FN_CONSTANT: return f.p[c];
       case DFX_FN_IDENTITY: return c >= dim ? 0.0 : (c == 0 ? x0 : (c == 1 ? x1 : x2));
       case DFX_FN_GAUSSIAN_VEC: return __dmul_rn(c >= dim ? 1.0 : (c == 0 ? x0 : (c == 1 ? x1 : x2)), cm);
@@ -154,5 +169,6 @@ struct RegistryFn {
     return cm;
   }
 };
+typedef RegistryFnT<-1, false> RegistryFn;
 
 }  // namespace dfx

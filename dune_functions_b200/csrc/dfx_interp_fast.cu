@@ -19,6 +19,7 @@
 // Replaces the interpolate element loop (interpolate.hh:254-259 with :151-173) and
 // DefaultLocalView::bind -> PreBasis::indices (defaultlocalview.hh:95-101).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "dfx_device.cuh"
@@ -235,6 +236,85 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
   }
 }
 
+// ---- per-node evaluation, scalar case: ONE leaf on the lattice, no mask ------------------------------
+// The same sweep as k_interp_rows<F, 0, KT, true> with everything that is not the function taken out of
+// the node loop: a row's record holds the ADDRESS of x-entity 0's vertex-type / first edge-type node and
+// the byte stride between x-entities, so a node's store address is one 32 x 32 + 64-bit multiply-add;
+// reference coordinates alpha / k are compile-time constants; the functor sits in the constant bank.
+// With exp from expTab a Gaussian node is 14 FP64 issues + about 12 others, below the HBM time of the
+// 8 bytes it writes.
+struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsigned a8, pad; };
+int g_rowsLean = 32;    // lattice rows per block of the lean kernel (tuning knob DFX_OP_TUNE_ROWS; measured 1..32:
+                        // 256^3 0.43 -> 0.19 ms, 512^3 flat from 4 rows on, profiles/README.md)
+
+template <class F, int KT>
+__global__ void __launch_bounds__(256)
+k_interp_rows_lean(const __grid_constant__ DevBasis B, const __grid_constant__ RowArgs A, const __grid_constant__ F f,
+                   double* __restrict__ coeff) {
+  __shared__ LeanRow rows[kRowsPerBlock];
+  const DevGrid& g = B.grid;
+  const DevLayout& L = B.layouts[A.layoutId];
+  constexpr int k = KT;
+  const unsigned nRows = (unsigned)A.LX[1] * (unsigned)A.LX[2];
+  const unsigned row0 = blockIdx.x * (unsigned)A.rowsPerBlock;
+  const unsigned nr = min((unsigned)A.rowsPerBlock, nRows - row0);
+  if (threadIdx.x < nr) {
+    const unsigned rI = threadIdx.x;
+    unsigned Z, Y;
+    A.divLY.divmod(row0 + rI, Z, Y);
+    const Dir dy = latticeDir(g, A.divK, k, 1, (int)Y);
+    const Dir dz = latticeDir(g, A.divK, k, 2, (int)Z);
+    unsigned syz = 0;
+    u64 fyz = 0, fs = 1;
+    if (g.dim > 1 && dy.inner) { syz |= 2u; fyz += (u64)(dy.inner - 1) * fs; fs *= (u64)(k - 1); }
+    if (g.dim > 2 && dz.inner) { syz |= 4u; fyz += (u64)(dz.inner - 1) * fs; }
+    const unsigned sV = syz, sE = syz | 1u;
+    const u64 rowV = L.compOffset[sV] + (u64)L.blk[sV] * ((u64)L.csize[sV][0] * ((u64)dy.c + (u64)L.csize[sV][1] * (u64)dz.c)) + fyz;
+    const u64 rowE = L.compOffset[sE] + (u64)L.blk[sE] * ((u64)L.csize[sE][0] * ((u64)dy.c + (u64)L.csize[sE][1] * (u64)dz.c)) + fyz * (u64)(k - 1);
+    const DevLeaf& leaf = B.leaves[A.leafId[0]];
+    LeanRow r;
+    r.pV = coeff + (leaf.posA * rowV + leaf.posB);
+    r.pE = coeff + (leaf.posA * rowE + leaf.posB);
+    r.sV8 = (unsigned)(leaf.posA * (u64)L.blk[sV]) * 8u;
+    r.sE8 = (unsigned)(leaf.posA * (u64)L.blk[sE]) * 8u;
+    r.a8 = (unsigned)leaf.posA * 8u; r.pad = 0;
+    r.u1 = g.dim > 1 ? nodeCoord(g, k, 1, dy.ie, dy.a) : 0.0;
+    r.u2 = g.dim > 2 ? nodeCoord(g, k, 2, dz.ie, dz.a) : 0.0;
+    rows[rI] = r;
+  }
+  __syncthreads();
+  const int comp0 = f.ncomp() == 1 ? 0 : A.leafComp[0];
+  for (unsigned c0 = threadIdx.x; c0 < (unsigned)g.N[0]; c0 += blockDim.x) {
+    // nodes X = k c0 + a of x-entity c0: a = 0 vertex-type, 1 .. k-1 edge-type; owner element = c0 itself
+    const double lo = gridCoordinate(g, 0, g.off[0] + (int)c0), up = gridCoordinate(g, 0, g.off[0] + (int)c0 + 1);
+    const double d = __dsub_rn(up, lo);
+    double hx[KT];
+#pragma unroll
+    for (int a = 0; a < KT; ++a) hx[a] = __dadd_rn(lo, __dmul_rn((double)a / (double)KT, d));   // alpha / k folded at compile time
+#pragma unroll 4
+    for (unsigned rI = 0; rI < nr; ++rI) {
+      const LeanRow r = rows[rI];
+#pragma unroll
+      for (int a = 0; a < KT; ++a) {
+        const double v = f.comp(comp0, f.common(hx[a], r.u1, r.u2), hx[a], r.u1, r.u2);
+        char* p = a == 0 ? reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * c0
+                         : reinterpret_cast<char*>(r.pE) + (size_t)r.sE8 * c0 + (size_t)r.a8 * (unsigned)(a - 1);
+        *reinterpret_cast<double*>(p) = v;
+      }
+    }
+  }
+  // the closing vertex plane x-entity N_x: one node per row; its owner is the element right of it if
+  // the grid has one, else the last element with alpha = k (interpolate.hh:254-259, last writer)
+  if (threadIdx.x < nr) {
+    const LeanRow r = rows[threadIdx.x];
+    int ie = g.off[0] + g.N[0], aa = 0;
+    if (ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }
+    const double xc = nodeCoord(g, k, 0, ie, aa);
+    const double v = f.comp(comp0, f.common(xc, r.u1, r.u2), xc, r.u1, r.u2);
+    *reinterpret_cast<double*>(reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * (unsigned)g.N[0]) = v;
+  }
+}
+
 struct CellArgs {
   int k, dim, nloc;              // direct copies: no indexed-constant loads in the kernel
   int off[3];
@@ -334,12 +414,23 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
         // elementGlobal(g, 0, ie, xhat) with the element's end points hoisted out of the pass loop
         const double lo = gridCoordinate(g, 0, g.off[0] + (int)ec0), up = gridCoordinate(g, 0, g.off[0] + (int)ec0 + 1);
         const double d = __dsub_rn(up, lo);
+        if (SIMPLE) {
+          double* po = coeff + A.posB[0] + tBase;
+          const int c0 = scalar ? 0 : A.comp[0];
 #pragma unroll
-        for (int t = 0; t < NP; ++t)
-          if (lane + 32 * t < nloc) {
-            const double x0 = __dadd_rn(lo, __dmul_rn(xh0[t], d));
-            emit(tBase + 32 * t, f.common(x0, u1[t], u2[t]), x0, u1[t], u2[t]);
-          }
+          for (int t = 0; t < NP; ++t)
+            if (lane + 32 * t < nloc) {
+              const double x0 = __dadd_rn(lo, __dmul_rn(xh0[t], d));
+              po[32 * t] = f.comp(c0, f.common(x0, u1[t], u2[t]), x0, u1[t], u2[t]);
+            }
+        } else {
+#pragma unroll
+          for (int t = 0; t < NP; ++t)
+            if (lane + 32 * t < nloc) {
+              const double x0 = __dadd_rn(lo, __dmul_rn(xh0[t], d));
+              emit(tBase + 32 * t, f.common(x0, u1[t], u2[t]), x0, u1[t], u2[t]);
+            }
+        }
       }
       if (++ec0 >= N0) { ec0 = 0; newRow = true; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
     }
@@ -370,6 +461,61 @@ k_interp_cell(const __grid_constant__ DevGrid g, const __grid_constant__ CellArg
       if (++ec0 >= N0) { ec0 = 0; newRow = true; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
     }
   }
+}
+
+// |argument of exp(-a |x|^2)| <= 700 over the whole grid box: expTabT<false> applies
+static bool gaussianBounded(const DevGrid& g, const dfx_function& fn) {
+  double r2 = 0;
+  for (int j = 0; j < g.dim; ++j) {
+    const double lo = g.lower[j], up = g.lower[j] + g.h[j] * g.G[j];
+    r2 += std::max(lo * lo, up * up);
+  }
+  return std::abs(fn.p[0]) * r2 * 1.001 <= 700.0;
+}
+// per-node kernels with a compile-time function id (orders 1 and 2 / up to 8 passes of 32 local indices)
+template <int ID>
+static void launchRowsNode(int k, bool one, unsigned grid, unsigned bs, cudaStream_t st, const DevBasis& D, RowArgs A,
+                           const dfx_function& fn, double* coeff, const uint8_t* mask) {
+  RegistryFnT<ID> f; f.f = fn; f.dim = D.grid.dim;
+  // LEAN functor: |argument of exp| bounded by 700 over the whole grid box
+  const bool bounded = ID != DFX_FN_GAUSSIAN || gaussianBounded(D.grid, fn);
+  if (one && mask == nullptr && bounded) {
+    // scalar, unmasked: the lean kernel, a few rows per block (its blocks in flight then cover a compact band
+    // of every index-set component, like the table-driven kernel)
+    RegistryFnT<ID, true> fl; fl.f = fn; fl.dim = D.grid.dim;
+    const u64 nRows = (u64)A.LX[1] * A.LX[2];
+    A.rowsPerBlock = std::max(1, std::min(g_rowsLean, kRowsPerBlock));
+    const unsigned gridL = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
+    if (k == 1) k_interp_rows_lean<RegistryFnT<ID, true>, 1><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
+    else k_interp_rows_lean<RegistryFnT<ID, true>, 2><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
+    return;
+  }
+  if (k == 1) {
+    if (one) k_interp_rows<RegistryFnT<ID>, 0, 1, true><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
+    else k_interp_rows<RegistryFnT<ID>, 0, 1, false><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
+  } else {
+    if (one) k_interp_rows<RegistryFnT<ID>, 0, 2, true><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
+    else k_interp_rows<RegistryFnT<ID>, 0, 2, false><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
+  }
+}
+template <int ID>
+static void launchCellNode(int passes, unsigned blocks, cudaStream_t st, const DevGrid& g, const CellArgs& C, const dfx_function& fn,
+                           double* coeff, const uint8_t* mask) {
+  const bool lean = C.nActive == 1 && C.posA[0] == 1 && mask == nullptr && (ID != DFX_FN_GAUSSIAN || gaussianBounded(g, fn));
+  if (lean) {
+    // one leaf, unit stride, no mask: running store pointer, zero-padded coordinates, bounded exp argument
+    RegistryFnT<ID, true> f; f.f = fn; f.dim = g.dim;
+    if (passes <= 1) k_interp_cell<RegistryFnT<ID, true>, 0, 1, true><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+    else if (passes <= 2) k_interp_cell<RegistryFnT<ID, true>, 0, 2, true><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+    else if (passes <= 4) k_interp_cell<RegistryFnT<ID, true>, 0, 4, true><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+    else k_interp_cell<RegistryFnT<ID, true>, 0, 8, true><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+    return;
+  }
+  RegistryFnT<ID> f; f.f = fn; f.dim = g.dim;
+  if (passes <= 1) k_interp_cell<RegistryFnT<ID>, 0, 1, false><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+  else if (passes <= 2) k_interp_cell<RegistryFnT<ID>, 0, 2, false><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+  else if (passes <= 4) k_interp_cell<RegistryFnT<ID>, 0, 4, false><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
+  else k_interp_cell<RegistryFnT<ID>, 0, 8, false><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
 }
 
 static bool separable(const dfx_function& f) {
@@ -447,17 +593,29 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
       const unsigned nEnt = (unsigned)g.N[0] * (A.interleaved ? (unsigned)A.nActive : 1u), chunks = (nEnt + 255) / 256;
       const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
+      // per-node evaluation with the function id known at compile time for the functions the BASELINE
+      // configs interpolate (no switch in the node loop); everything else dispatches on f.id at run time
+      bool launched = false;
+      if (!sep && k <= 2) {
+        switch (fn.id) {
+          case DFX_FN_GAUSSIAN: launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_QUADRATIC: launchRowsNode<DFX_FN_QUADRATIC>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_IDENTITY: launchRowsNode<DFX_FN_IDENTITY>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          default: break;
+        }
+      }
 #define DFX_ROWS2(KT_, ONE_)                                                                                 \
   { if (sep) k_interp_rows<RegistryFn, 1, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask);      \
     else k_interp_rows<RegistryFn, 0, KT_, ONE_><<<grid, bs, 0, st>>>(D, A, f, tab, coeff, mask); }
 #define DFX_ROWS(KT_) { if (A.nActive == 1) DFX_ROWS2(KT_, true) else DFX_ROWS2(KT_, false) }
-      switch (k) {
-        case 1: DFX_ROWS(1) break;
-        case 2: DFX_ROWS(2) break;
-        case 3: DFX_ROWS(3) break;
-        case 4: DFX_ROWS(4) break;
-        default: DFX_ROWS(0)
-      }
+      if (!launched)
+        switch (k) {
+          case 1: DFX_ROWS(1) break;
+          case 2: DFX_ROWS(2) break;
+          case 3: DFX_ROWS(3) break;
+          case 4: DFX_ROWS(4) break;
+          default: DFX_ROWS(0)
+        }
 #undef DFX_ROWS2
 #undef DFX_ROWS
       int rc = postLaunch("k_interp_rows");
@@ -481,13 +639,22 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "basis too large for one launch");
       const int passes = (L.nloc + 31) / 32;
       const bool simple = sep && C.nActive == 1 && C.posA[0] == 1 && mask == nullptr;
+      bool launched = false;
+      if (!sep && passes <= 8) {
+        switch (fn.id) {
+          case DFX_FN_GAUSSIAN: launchCellNode<DFX_FN_GAUSSIAN>(passes, (unsigned)blocks, st, g, C, fn, coeff, mask); launched = true; break;
+          case DFX_FN_QUADRATIC: launchCellNode<DFX_FN_QUADRATIC>(passes, (unsigned)blocks, st, g, C, fn, coeff, mask); launched = true; break;
+          default: break;
+        }
+      }
 #define DFX_CELL(NP_)                                                                                              \
   {                                                                                                                \
     if (simple) k_interp_cell<RegistryFn, 1, NP_, true><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);       \
     else if (sep) k_interp_cell<RegistryFn, 1, NP_, false><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);   \
     else k_interp_cell<RegistryFn, 0, NP_, false><<<(unsigned)blocks, kCellWarps * 32, 0, st>>>(g, C, f, tab, coeff, mask);             \
   }
-      if (passes <= 1) DFX_CELL(1)
+      if (launched) {}
+      else if (passes <= 1) DFX_CELL(1)
       else if (passes <= 2) DFX_CELL(2)
       else if (passes <= 4) DFX_CELL(4)
       else if (passes <= 8) DFX_CELL(8)

@@ -79,6 +79,7 @@ int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* co
                 cudaStream_t st);
 int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
                     const uint8_t* mask, bool wantSep, cudaStream_t st);
+extern int g_rowsLean;
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st);
 int boundaryDofs(const dfx_basis* b, int firstLeaf, int nLeaves, uint8_t* mask, cudaStream_t st);

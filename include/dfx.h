@@ -319,6 +319,7 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
 #define DFX_OP_INDICES 2
 #define DFX_OP_HOST_BAND_KIB 3
 #define DFX_OP_SMEM_GRADIENT 4
+#define DFX_OP_TUNE_ROWS 5      /* lattice rows per block of the per-node interpolation kernel (-1 = default) */
 void dfx_set_kernel_path(int32_t op, int32_t path);
 
 /* ---- host-buffer entry points (what a CPU caller of the reference uses) ----

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Round-2 tuning probes (development tool): rows per block of the lean per-node interpolation kernel,
+DG4 per-node interpolation, and the accuracy of the two DG4 gradient forms against the analytic gradient."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import dune_functions_b200 as dfx  # noqa: E402
+from dune_functions_b200 import _capi as capi  # noqa: E402
+
+L = capi.lib()
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    what = set(sys.argv[1:]) or {"rows", "dg4", "jac"}
+    if "rows" in what:
+        for n in (256, 512):
+            b = dfx.makeBasis(dfx.YaspGrid([n, n, n]), dfx.lagrange(2))
+            x = b.newVector(0.0)
+            nd = b.dimension()
+            for rows in (1, 2, 4, 8, 16, 32):
+                L.dfx_set_kernel_path(capi.OP_TUNE_ROWS, rows)
+                ms = timeit(lambda: dfx.interpolate(b, x, dfx.gaussian(1.0)))
+                print(json.dumps({"probe": "lean rows", "n": n, "rows": rows, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
+            L.dfx_set_kernel_path(capi.OP_TUNE_ROWS, -1)
+            ms = timeit(lambda: dfx.interpolate(b, x, dfx.quadratic(0.5, [1, 2, 3], [1, 2, 3, 4, 5, 6])))
+            print(json.dumps({"probe": "quadratic per node", "n": n, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
+            ms = timeit(lambda: dfx.interpolate(b, x, dfx.gaussian(1.0), separable=True))
+            print(json.dumps({"probe": "separable tables", "n": n, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
+            del b, x
+            torch.cuda.empty_cache()
+    if "dg4" in what or "jac" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
+        x = b.newVector(0.0)
+        nd = b.dimension()
+        quad = dfx.quadratic(0.0, [0, 0, 0], [42, 7, 0, 13, 0, 5])
+        if "dg4" in what:
+            for name, f in (("quadratic", quad), ("gaussian", dfx.gaussian(1.0))):
+                ms = timeit(lambda: dfx.interpolate(b, x, f), reps=5)
+                print(json.dumps({"probe": "dg4 per node " + name, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
+        if "jac" in what:
+            import orc
+            dfx.interpolate(b, x, quad)
+            pts, _ = dfx.tensor_gauss(3, 5)
+            tp = torch.from_numpy(pts).cuda()
+            o = orc.OracleBasis(b.grid, dfx.lagrangeDG(4))
+            u = dfx.makeDiscreteGlobalBasisFunction(b, x)
+            ne = b.numElements()
+            for e0 in (0, ne // 2 // 128 * 128, ne - 4096):
+                e1 = e0 + 4096
+                e = torch.arange(e0, e1, device="cuda")
+                ec = torch.stack([e % 192, (e // 192) % 192, e // (192 * 192)], 1).double()
+                P = (ec[:, None, :] + tp[None]) / 192
+                X, Y, Z = P[..., 0], P[..., 1], P[..., 2]
+                exact = torch.stack([84 * X + 7 * Y, 26 * Y + 7 * X, 10 * Z], -1).cpu().numpy()
+                idx = b.flatIndices(e0, e1, dtype=torch.int64)
+                h = np.zeros(o.dimension())
+                h[idx.cpu().numpy()] = x[idx].cpu().numpy()
+                _, jo = o.evaluate(h, pts, jacobians=True, e0=e0, e1=e1, nthreads=8)
+                scale = max(1.0, np.abs(exact).max())
+                row = {"probe": "dg4 jac accuracy", "e0": e0, "oracle_vs_exact": float(np.abs(jo[:, :, 0, :] - exact).max() / scale)}
+                for grad, label in ((-1, "collocation"), (1, "differentiated_tables")):
+                    L.dfx_set_kernel_path(capi.OP_SMEM_GRADIENT, grad)
+                    _, j = u.evaluate(pts, jacobians=True, elem_begin=e0, elem_end=e1)
+                    j = j.cpu().numpy()[:, :, 0, :]
+                    row[label + "_vs_exact"] = float(np.abs(j - exact).max() / scale)
+                    row[label + "_vs_oracle"] = float(np.abs(j - jo[:, :, 0, :]).max() / scale)
+                L.dfx_set_kernel_path(capi.OP_SMEM_GRADIENT, -1)
+                print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
