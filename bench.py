@@ -348,10 +348,13 @@ class Runner:
     def interpolate(self, separable=False):
         if self.node_fns is None:
             self.dfx.interpolate(self.basis, self.coeff, self.f, separable=separable)
-        else:
-            entry = self.L.dfx_interpolate_separable if separable else self.L.dfx_interpolate
+        elif separable:
             for node, fn in self.node_fns:
-                self.capi.check(entry(self.basis._h, node, C.byref(fn), C.c_void_p(self.coeff.data_ptr()), None, self.stream_ptr()))
+                self.capi.check(self.L.dfx_interpolate_separable(self.basis._h, node, C.byref(fn), C.c_void_p(self.coeff.data_ptr()),
+                                                                 None, self.stream_ptr()))
+        else:
+            # velocity and pressure sub-spaces as one batched call (one launch for the two lattices)
+            self.dfx.interpolateBatch(self.basis, self.coeff, self.node_fns)
 
     def step(self, timed):
         torch, capi, L = self.torch, self.capi, self.L

@@ -7,7 +7,7 @@ load the CUDA library; the first call that needs it does, and fails loudly if
 from .basis import (  # noqa: F401
     YaspGrid, makeBasis, GlobalBasis, LocalView, lagrange, lagrangeDG, power, composite, taylorHood,
     flatLexicographic, flatInterleaved, blockedLexicographic, blockedInterleaved,
-    subspaceBasis, SubspaceBasis, interpolate, interpolationPoints, interpolateFromValues,
+    subspaceBasis, SubspaceBasis, interpolate, interpolateBatch, interpolationPoints, interpolateFromValues,
     makeDiscreteGlobalBasisFunction, DiscreteGlobalBasisFunction, subEntityDOFs, boundaryDOFs,
     gaussian, identity, constant, coord, quadratic, sinprod, gaussian_vec, make_function,
     tensor_gauss, gauss_points_1d, tree_array,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "dfx_indices_flat_u64": (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     "dfx_interpolate": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp, _vp]),
     "dfx_interpolate_separable": (C.c_int, [_vp, _i32, C.POINTER(Function), _vp, _vp, _vp]),
+    "dfx_interpolate_batch": (C.c_int, [_vp, _i32, _pi32, C.POINTER(Function), _vp, _vp, _vp]),
     "dfx_interpolation_points": (C.c_int, [_vp, _vp, _vp, _vp]),
     "dfx_interpolate_from_values": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "dfx_interpolate_dgbf": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),

@@ -566,6 +566,34 @@ def interpolate(basis, coeff, f, mask=None, separable=False):
     return coeff
 
 
+def interpolateBatch(basis, coeff, parts, mask=None):
+    """several interpolate calls on one vector as one call (dfx_interpolate_batch): parts = [(space, f), ...]
+    with `space` the basis, a sub-space basis of it, or a tree-node id; equivalent to interpolate(space, coeff, f)
+    for each part in order.  Two parts whose kernels are shorter than a launch gap share one launch."""
+    root, _ = _root_and_node(basis)
+    if coeff.numel() != root.dimension():
+        raise capi.RangeError("coefficient vector size does not match basis.dimension()")
+    nodes, fns = [], []
+    for space, f in parts:
+        if isinstance(space, int):
+            nodes.append(space)
+        else:
+            r, node = _root_and_node(space)
+            if r is not root:
+                raise capi.DfxError("all parts must be sub-spaces of the same basis")
+            nodes.append(node)
+        fns.append(f)
+    n = len(nodes)
+    arr_n = (C.c_int32 * max(1, n))(*nodes)
+    arr_f = (capi.Function * max(1, n))(*fns)
+    m = None
+    if mask is not None:
+        import torch
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    capi.check(root._lib.dfx_interpolate_batch(root._h, n, arr_n, arr_f, _ptr(coeff), _ptr(m), _stream()))
+    return coeff
+
+
 def interpolationPoints(basis):
     """positions of all interpolation nodes and the leaf of every coefficient (form 2 of f)"""
     import torch

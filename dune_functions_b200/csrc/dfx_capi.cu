@@ -403,6 +403,38 @@ int dfx_interpolate(const dfx_basis* b, int32_t node, const dfx_function* f, dou
   return interpolateImpl(b, node, f, coeff, mask, false, stream);
 }
 
+// several interpolate calls on one vector; two lean lattice sweeps share one launch
+int dfx_interpolate_batch(const dfx_basis* b, int32_t n_parts, const int32_t* nodes_host, const dfx_function* fns_host, double* coeff,
+                          const uint8_t* mask, void* stream) {
+  DFX_RANGE("dfx_interpolate_batch");
+  int rc = ensureDevice(b); if (rc) return rc;
+  if (n_parts < 0 || (n_parts > 0 && (!nodes_host || !fns_host))) return fail(DFX_ERR_INVALID, "null argument");
+  if (!coeff) return fail(DFX_ERR_INVALID, "null coefficient vector");
+  // validate everything before anything is written
+  std::vector<std::pair<int, int>> leaves((size_t)n_parts);
+  for (int p = 0; p < n_parts; ++p) {
+    if ((rc = subtree(b, nodes_host[p], leaves[p].first, leaves[p].second))) return rc;
+    if ((rc = checkFunction(&fns_host[p], leaves[p].second))) return rc;
+  }
+  int p = 0;
+  while (p < n_parts) {
+    if (p + 1 < n_parts && mask == nullptr && g_interpPath.load() == -1) {
+      // the pair must not overlap (then the order of the two calls would matter): disjoint leaf ranges
+      const bool disjoint = leaves[p].first + leaves[p].second <= leaves[p + 1].first ||
+                            leaves[p + 1].first + leaves[p + 1].second <= leaves[p].first;
+      if (disjoint) {
+        rc = interpolateBatch2(const_cast<dfx_basis*>(b), leaves[p].first, leaves[p].second, fns_host[p], leaves[p + 1].first,
+                               leaves[p + 1].second, fns_host[p + 1], coeff, (cudaStream_t)stream);
+        if (rc == DFX_OK) { p += 2; continue; }
+        if (rc > 0) return rc;
+      }
+    }
+    if ((rc = interpolateImpl(b, nodes_host[p], &fns_host[p], coeff, mask, false, stream))) return rc;
+    ++p;
+  }
+  return DFX_OK;
+}
+
 int dfx_interpolate_separable(const dfx_basis* b, int32_t node, const dfx_function* f, double* coeff, const uint8_t* mask,
                               void* stream) {
   DFX_RANGE("dfx_interpolate_separable");
@@ -633,6 +665,12 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
       allFast = planFastEval(b, fl + l, r - l, xhat_host, n_q, out_jac != nullptr, -1, plans.back()) > 0;
       runs.push_back({l, r - l});
       l = r;
+    }
+    if (allFast && runs.size() == 2) {
+      // Taylor-Hood shape (order-2 run + order-1 run): one launch that stages whole points
+      rc = runSplitEval(b, plans[0], fl + runs[0].first, runs[0].second, &plans[1], fl + runs[1].first, runs[1].second, coeff,
+                        e0, e1, out_values, out_jac, st);
+      if (rc >= 0) return rc;
     }
     if (allFast && runs.size() > 1) {
       for (size_t q = 0; q < runs.size(); ++q)

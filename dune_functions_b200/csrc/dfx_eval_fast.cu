@@ -131,6 +131,37 @@ __device__ __forceinline__ void bulkStore(double* gdst, const double* ssrc, unsi
 __device__ __forceinline__ void bulkStoreWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// LocalFunctionBase::bind for one leaf (discreteglobalbasisfunction.hh:140-147): the (KK+1)^DIM coefficients of
+// element e, located by the closed form of MCMGMapper::subIndex on the structured grid
+template <int DIM, int KK>
+__device__ __forceinline__ void gatherLeaf(const DevLayout& L, const double* __restrict__ coeff, u64 posA, u64 posB, u64 e,
+                                           const int (&ec)[3], double* __restrict__ c) {
+  constexpr int N1 = KK + 1;
+  constexpr int NLOC = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  if (L.kind == DFX_NODE_LAGRANGE_DG) {
+    const u64 base = posA * (e * (u64)NLOC) + posB;
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) c[i] = __ldg(coeff + base + posA * (u64)i);
+    return;
+  }
+#pragma unroll
+  for (int a2 = 0; a2 < (DIM == 3 ? N1 : 1); ++a2)
+#pragma unroll
+    for (int a1 = 0; a1 < N1; ++a1)
+#pragma unroll
+      for (int a0 = 0; a0 < N1; ++a0) {
+        const int s = ((a0 > 0 && a0 < KK) ? 1 : 0) | ((a1 > 0 && a1 < KK) ? 2 : 0) | ((DIM == 3 && a2 > 0 && a2 < KK) ? 4 : 0);
+        const int c0 = ec[0] + (a0 == KK ? 1 : 0);
+        const int c1 = ec[1] + (a1 == KK ? 1 : 0);
+        const int c2 = ec[2] + ((DIM == 3 && a2 == KK) ? 1 : 0);
+        // KK <= 2 here: at most one interior node per direction, so the in-entity index is 0
+        // (blk[s] = (KK-1)^|s| = 1); entity counts of one component stay below 2^32
+        const unsigned ent = (unsigned)c0 + (unsigned)L.csize[s][0] * ((unsigned)c1 + (unsigned)L.csize[s][1] * (unsigned)c2);
+        const u64 j = L.compOffset[s] + (u64)ent;
+        c[a0 + N1 * (a1 + N1 * a2)] = __ldg(coeff + posA * j + posB);
+      }
+}
+
 // resident blocks per SM the register allocator is asked to allow (values-only kernels):
 // 6 x 128 threads = 24 warps at <= 80 registers, no spills for any instantiated (DIM, K, M)
 #ifndef DFX_EVAL_MINB
@@ -273,6 +304,239 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Several leaves per point (power / composite subtrees): ONE THREAD PER (element, leaf).  A block takes
+// epb elements and G = nGroup + nGroup2 leaves, blockDim = epb * G with the leaf fastest, so
+//  * the lanes of a warp gather neighbouring elements' coefficients of all leaves at once — for an
+//    interleaved power node (position = C j + c) those are consecutive addresses;
+//  * every thread contracts one leaf (sum factorisation in registers, as k_eval_reg) and writes its column of
+//    the staged tile [epb][NQ][G], which then holds WHOLE points in output order and leaves as one TMA bulk
+//    store per block — no 8-byte stores at a G * 8-byte stride;
+//  * a block keeps G warps busy per 32 elements of staging tile instead of one.
+// K2 >= 0: the last nGroup2 leaves have order K2 on their own lattice L2 (Taylor-Hood: three Q2 velocity
+// components + the Q1 pressure, taylorhoodbasis.hh:229-251); the warp then runs both branches.
+struct SplitArgs {
+  int nGroup, nGroup2, epb;
+  int compOffset, ncompTotal;
+  int qs[3];
+  unsigned long long e0, ne;
+  FastDiv divN0, divN1, divG;
+  int bulk;
+  unsigned long long posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES];    // all G leaves, group 2 behind group 1
+};
+constexpr int kSplitThreads = 128;
+
+template <int DIM, int K, int M, bool JAC, int K2>
+__global__ void __launch_bounds__(kSplitThreads, JAC ? 2 : 5)
+k_eval_split(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout L,
+             const __grid_constant__ Tables<K + 1, M> T, const __grid_constant__ SplitArgs R,
+             const double* __restrict__ coeff, double* __restrict__ values, double* __restrict__ jac,
+             const __grid_constant__ DevLayout L2, const __grid_constant__ Tables<(K2 >= 0 ? K2 : 0) + 1, M> T2) {
+  constexpr int N1 = K + 1;
+  constexpr int NLOC = DIM == 3 ? N1 * N1 * N1 : N1 * N1;
+  constexpr int NQ = DIM == 3 ? M * M * M : M * M;
+  constexpr int KB = K2 >= 0 ? K2 : 0;
+  constexpr int N1B = KB + 1;
+  constexpr int NLOCB = DIM == 3 ? N1B * N1B * N1B : N1B * N1B;
+  extern __shared__ __align__(128) double stage[];       // values tile [epb][NQ][G], then jac tile [epb][NQ][G][DIM]
+  const int G = R.nGroup + R.nGroup2;
+  const int epb = R.epb;
+  const int tid = threadIdx.x;
+  unsigned elL, leaf;
+  R.divG.divmod((unsigned)tid, elL, leaf);
+  const u64 blk0 = (u64)blockIdx.x * (u64)epb;
+  const u64 el = blk0 + elL;
+  const bool active = el < R.ne && (int)elL < epb;
+  const u64 e = R.e0 + (active ? el : 0);
+  int ec[3];
+  {
+    const unsigned e32 = (unsigned)e;       // numElements < 2^32 checked on the host
+    unsigned q, r;
+    R.divN0.divmod(e32, q, r);
+    ec[0] = (int)r;
+    unsigned q2;
+    R.divN1.divmod(q, q2, r);
+    ec[1] = (int)r; ec[2] = (int)q2;
+  }
+  const int rowLen = NQ * G;
+  double* vTile = stage;
+  double* jTile = stage + (size_t)epb * rowLen;
+  double jinv[3] = {0, 0, 0};
+  if (JAC) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) jinv[d] = elementJacInv(g, d, g.off[d] + ec[d]);
+  }
+  const u64 posA = R.posA[leaf], posB = R.posB[leaf];
+  double* vOut = vTile + (size_t)elL * rowLen + leaf;
+  double* jOut = jTile + ((size_t)elL * rowLen + leaf) * DIM;
+  if ((int)elL < epb) {
+    if (K2 < 0 || (int)leaf < R.nGroup) {
+      double c[NLOC];
+      gatherLeaf<DIM, K>(L, coeff, posA, posB, e, ec, c);
+      double u[NQ];
+      if (values) {
+        sumFactor<DIM, N1, M>(T.A[0], T.A[1], T.A[2], c, u);
+#pragma unroll
+        for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+          for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+            for (int q0 = 0; q0 < M; ++q0)
+              vOut[(q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2]) * G] = u[q0 + M * (q1 + M * q2)];
+      }
+      if (JAC) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          sumFactor<DIM, N1, M>(d == 0 ? T.D[0] : T.A[0], d == 1 ? T.D[1] : T.A[1], d == 2 ? T.D[2] : T.A[2], c, u);
+#pragma unroll
+          for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+            for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+              for (int q0 = 0; q0 < M; ++q0)
+                jOut[(q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2]) * G * DIM + d] = u[q0 + M * (q1 + M * q2)] * jinv[d];
+        }
+      }
+    } else {
+      double c[NLOCB];
+      gatherLeaf<DIM, KB>(L2, coeff, posA, posB, e, ec, c);
+      double u[NQ];
+      if (values) {
+        sumFactor<DIM, N1B, M>(T2.A[0], T2.A[1], T2.A[2], c, u);
+#pragma unroll
+        for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+          for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+            for (int q0 = 0; q0 < M; ++q0)
+              vOut[(q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2]) * G] = u[q0 + M * (q1 + M * q2)];
+      }
+      if (JAC) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          sumFactor<DIM, N1B, M>(d == 0 ? T2.D[0] : T2.A[0], d == 1 ? T2.D[1] : T2.A[1], d == 2 ? T2.D[2] : T2.A[2], c, u);
+#pragma unroll
+          for (int q2 = 0; q2 < (DIM == 3 ? M : 1); ++q2)
+#pragma unroll
+            for (int q1 = 0; q1 < M; ++q1)
+#pragma unroll
+              for (int q0 = 0; q0 < M; ++q0)
+                jOut[(q0 * R.qs[0] + q1 * R.qs[1] + q2 * R.qs[2]) * G * DIM + d] = u[q0 + M * (q1 + M * q2)] * jinv[d];
+        }
+      }
+    }
+  }
+  // ---- the block's results leave in output order ----
+  const u64 nAct = R.ne - blk0 < (u64)epb ? R.ne - blk0 : (u64)epb;
+  if (R.bulk && nAct == (u64)epb) {
+    fenceProxyAsync();          // generic-proxy smem writes -> visible to the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      if (values) bulkStore(values + blk0 * (u64)rowLen, vTile, (unsigned)(epb * rowLen * sizeof(double)));
+      if (JAC) bulkStore(jac + blk0 * (u64)rowLen * DIM, jTile, (unsigned)(epb * rowLen * DIM * sizeof(double)));
+      bulkStoreWaitRead();      // shared memory must outlive the copy
+    }
+    return;
+  }
+  __syncthreads();
+  // partial tile, unaligned output or a sub-range of the range entries: cooperative stores
+  const int nT = R.ncompTotal, cOff = R.compOffset;
+  if (values) {
+    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen;
+    double* dst = values + blk0 * (u64)NQ * (u64)nT + cOff;
+    for (unsigned i = tid; i < cnt; i += blockDim.x) {
+      const unsigned row = i / (unsigned)G, gI = i - row * (unsigned)G;       // row = el_local*NQ + q
+      dst[(size_t)row * nT + gI] = vTile[i];
+    }
+  }
+  if (JAC) {
+    const unsigned cnt = (unsigned)nAct * (unsigned)rowLen * DIM;
+    double* dst = jac + (blk0 * (u64)NQ * (u64)nT + cOff) * DIM;
+    for (unsigned i = tid; i < cnt; i += blockDim.x) {
+      const unsigned rg = i / DIM, d = i - rg * DIM;
+      const unsigned row = rg / (unsigned)G, gI = rg - row * (unsigned)G;
+      dst[((size_t)row * nT + gI) * DIM + d] = jTile[i];
+    }
+  }
+}
+
+template <int DIM, int K, int M, bool JAC, int K2>
+static int launchSplit(dfx_basis* b, const FastPlan& plan, const FastPlan* plan2, SplitArgs& R, int firstLeaf, int firstLeaf2,
+                       const double* coeff, double* values, double* jac, cudaStream_t st) {
+  constexpr int NQ = DIM == 3 ? M * M * M : M * M;
+  constexpr int KB = K2 >= 0 ? K2 : 0;
+  Tables<K + 1, M> T;
+  for (int j = 0; j < 3; ++j)
+    for (int q = 0; q < M; ++q)
+      for (int a = 0; a <= K; ++a) { T.A[j][q][a] = plan.A[j][q][a]; T.D[j][q][a] = plan.Dm[j][q][a]; }
+  Tables<KB + 1, M> T2{};
+  if (K2 >= 0)
+    for (int j = 0; j < 3; ++j)
+      for (int q = 0; q < M; ++q)
+        for (int a = 0; a <= KB; ++a) { T2.A[j][q][a] = plan2->A[j][q][a]; T2.D[j][q][a] = plan2->Dm[j][q][a]; }
+  const int G = R.nGroup + R.nGroup2;
+  // elements per block: as many as kSplitThreads threads cover, even (16-byte tiles), tile <= 56 KB
+  int epb = kSplitThreads / G;
+  const size_t perEl = (size_t)NQ * G * sizeof(double) * (JAC ? 1 + DIM : 1);
+  while (epb > 2 && (size_t)epb * perEl > 56 * 1024) epb /= 2;
+  epb &= ~1;
+  if (epb < 2) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
+  R.epb = epb; R.divG = FastDiv((unsigned)G);
+  const size_t smem = (size_t)epb * perEl;
+  auto kern = k_eval_split<DIM, K, M, JAC, K2>;
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
+  const u64 blocks = (R.ne + epb - 1) / epb;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  const DevLayout& L1 = b->dev.layouts[b->dev.leaves[firstLeaf].layout];
+  const DevLayout& L2 = K2 >= 0 ? b->dev.layouts[b->dev.leaves[firstLeaf2].layout] : L1;
+  const unsigned threads = (unsigned)(((epb * G) + 31) / 32 * 32);
+  kern<<<(unsigned)blocks, threads, smem, st>>>(b->dev.grid, L1, T, R, coeff, values, jac, L2, T2);
+  return postLaunch("k_eval_split");
+}
+
+// [firstA, firstA + nA): leaves of one order on one lattice; [firstB, firstB + nB) (nB may be 0): the run behind it,
+// order 1 behind order 2 (the fused Taylor-Hood case).  -1 = not a configuration of this kernel.
+int runSplitEval(dfx_basis* b, const FastPlan& planA, int firstA, int nA, const FastPlan* planB, int firstB, int nB,
+                 const double* coeff, u64 e0, u64 e1, double* values, double* jac, cudaStream_t st, int compBase, int compTotal) {
+  if (e1 == e0) return DFX_OK;
+  const DevBasis& D = b->dev;
+  if (planA.path != 1 || nA + nB > DFX_MAX_LEAVES || nA + nB < 2) return -1;
+  if (nB > 0 && (planB == nullptr || planB->path != 1 || planA.k != 2 || planB->k != 1 || planA.m != planB->m ||
+                 planA.firstFastest != planB->firstFastest || planA.jac != planB->jac)) return -1;
+  for (int l = 1; l < nA; ++l) if (D.leaves[firstA + l].layout != D.leaves[firstA].layout) return -1;
+  for (int l = 1; l < nB; ++l) if (D.leaves[firstB + l].layout != D.leaves[firstB].layout) return -1;
+  if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull) return -1;
+  SplitArgs R;
+  R.nGroup = nA; R.nGroup2 = nB;
+  for (int q = 0; q < nA; ++q) { R.posA[q] = D.leaves[firstA + q].posA; R.posB[q] = D.leaves[firstA + q].posB; }
+  for (int q = 0; q < nB; ++q) { R.posA[nA + q] = D.leaves[firstB + q].posA; R.posB[nA + q] = D.leaves[firstB + q].posB; }
+  const int m = planA.m, dim = planA.dim;
+  if (planA.firstFastest) { R.qs[0] = 1; R.qs[1] = m; R.qs[2] = m * m; }
+  else { int s = 1; R.qs[0] = R.qs[1] = R.qs[2] = 0; for (int j = dim - 1; j >= 0; --j) { R.qs[j] = s; s *= m; } }
+  R.e0 = e0; R.ne = e1 - e0;
+  R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
+  R.compOffset = compBase; R.ncompTotal = compTotal < 0 ? nA + nB : compTotal;
+  const bool whole = nA + nB == R.ncompTotal;
+  const bool aligned = (!values || ((uintptr_t)values & 15) == 0) && (!jac || ((uintptr_t)jac & 15) == 0);
+  R.bulk = whole && aligned ? 1 : 0;
+  int rc = -1;
+#define DFX_SPLIT(DIM_, K_, M_)                                                                                              \
+  if (nB == 0 && dim == DIM_ && planA.k == K_ && m == M_)                                                                    \
+    rc = planA.jac ? launchSplit<DIM_, K_, M_, true, -1>(b, planA, nullptr, R, firstA, firstA, coeff, values, jac, st)       \
+                   : launchSplit<DIM_, K_, M_, false, -1>(b, planA, nullptr, R, firstA, firstA, coeff, values, jac, st);
+  DFX_SPLIT(2, 1, 2) DFX_SPLIT(2, 1, 3) DFX_SPLIT(2, 2, 2) DFX_SPLIT(2, 2, 3)
+  DFX_SPLIT(3, 1, 2) DFX_SPLIT(3, 1, 3) DFX_SPLIT(3, 2, 2) DFX_SPLIT(3, 2, 3)
+#undef DFX_SPLIT
+#define DFX_FUSED(DIM_, M_)                                                                                                  \
+  if (nB > 0 && dim == DIM_ && m == M_)                                                                                      \
+    rc = planA.jac ? launchSplit<DIM_, 2, M_, true, 1>(b, planA, planB, R, firstA, firstB, coeff, values, jac, st)           \
+                   : launchSplit<DIM_, 2, M_, false, 1>(b, planA, planB, R, firstA, firstB, coeff, values, jac, st);
+  DFX_FUSED(2, 2) DFX_FUSED(2, 3) DFX_FUSED(3, 2) DFX_FUSED(3, 3)
+#undef DFX_FUSED
+  return rc;
+}
+
 template <int DIM, int K, int M, bool JAC, int EPB>
 static int launchRegE(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const double* coeff, double* values,
                       double* jac, cudaStream_t st) {
@@ -322,6 +586,11 @@ int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
       const size_t perLeaf = (size_t)(plan.jac ? 64 : 32) * nq * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
       const int maxG = (int)std::max<size_t>(1, (96 * 1024) / perLeaf);
       if (r - l > maxG) r = l + maxG;
+    }
+    if (r - l >= 2) {
+      // several leaves on one lattice: one thread per (element, leaf), whole range entries staged together
+      const int rcS = runSplitEval(b, plan, firstLeaf + l, r - l, nullptr, 0, 0, coeff, e0, e1, values, jac, st, compBase + l, compTotal);
+      if (rcS >= 0) { if (rcS) return rcS; l = r; continue; }
     }
     RegArgs R;
     R.firstLeaf = firstLeaf + l; R.nGroup = r - l; R.compOffset = compBase + l; R.ncompTotal = compTotal;

@@ -43,4 +43,10 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 
+// one thread per (element, leaf): a run of >= 2 leaves on one lattice, optionally followed by an order-1 run
+// behind an order-2 run (Taylor-Hood) in the same launch; -1 = not a configuration of this kernel
+int runSplitEval(dfx_basis* b, const FastPlan& planA, int firstA, int nA, const FastPlan* planB, int firstB, int nB,
+                 const double* coeff, u64 e0, u64 e1, double* values, double* jac, cudaStream_t st, int compBase = 0,
+                 int compTotal = -1);
+
 }  // namespace dfx

@@ -38,6 +38,7 @@ struct RowArgs {
   int vectorTables;        // separable mode: one table set per range entry (vector-valued f)
   int interleaved;         // the active leaves are the components of an interleaved power node (position = C j + c)
   int nActive;             // leaves of the subtree that live on this lattice
+  FastDiv divC;            // lean kernel: thread -> (x-entity, leaf) for an interleaved group of nActive leaves
   int leafId[DFX_MAX_LEAVES];     // their ids, range entries and in-entity position stride
   int leafComp[DFX_MAX_LEAVES];
   unsigned leafPosA[DFX_MAX_LEAVES];
@@ -247,16 +248,18 @@ struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsig
 int g_rowsLean = 32;    // lattice rows per block of the lean kernel (tuning knob DFX_OP_TUNE_ROWS; measured 1..32:
                         // 256^3 0.43 -> 0.19 ms, 512^3 flat from 4 rows on, profiles/README.md)
 
+// Body shared by the single and the two-part kernel.  The active leaves are either ONE leaf (any position
+// stride) or the C components of an interleaved power node (position = C j + c, FlatInterleaved /
+// BlockedInterleaved): thread u owns (x-entity u / C, leaf u % C), so consecutive lanes write consecutive
+// addresses whatever C is.
 template <class F, int KT>
-__global__ void __launch_bounds__(256)
-k_interp_rows_lean(const __grid_constant__ DevBasis B, const __grid_constant__ RowArgs A, const __grid_constant__ F f,
-                   double* __restrict__ coeff) {
-  __shared__ LeanRow rows[kRowsPerBlock];
+__device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A, const F& f, double* __restrict__ coeff,
+                                             unsigned blockId, LeanRow* rows) {
   const DevGrid& g = B.grid;
   const DevLayout& L = B.layouts[A.layoutId];
   constexpr int k = KT;
   const unsigned nRows = (unsigned)A.LX[1] * (unsigned)A.LX[2];
-  const unsigned row0 = blockIdx.x * (unsigned)A.rowsPerBlock;
+  const unsigned row0 = blockId * (unsigned)A.rowsPerBlock;
   const unsigned nr = min((unsigned)A.rowsPerBlock, nRows - row0);
   if (threadIdx.x < nr) {
     const unsigned rI = threadIdx.x;
@@ -283,8 +286,13 @@ k_interp_rows_lean(const __grid_constant__ DevBasis B, const __grid_constant__ R
     rows[rI] = r;
   }
   __syncthreads();
-  const int comp0 = f.ncomp() == 1 ? 0 : A.leafComp[0];
-  for (unsigned c0 = threadIdx.x; c0 < (unsigned)g.N[0]; c0 += blockDim.x) {
+  const unsigned C = (unsigned)A.nActive;                         // 1, or the components of an interleaved group
+  const bool scalar = f.ncomp() == 1;
+  for (unsigned u = threadIdx.x; u < (unsigned)g.N[0] * C; u += blockDim.x) {
+    unsigned c0, lI;
+    A.divC.divmod(u, c0, lI);
+    const int comp = scalar ? 0 : A.leafComp[lI];
+    const unsigned off8 = 8u * lI;                                 // leaf lI sits lI entries behind leaf 0
     // nodes X = k c0 + a of x-entity c0: a = 0 vertex-type, 1 .. k-1 edge-type; owner element = c0 itself
     const double lo = gridCoordinate(g, 0, g.off[0] + (int)c0), up = gridCoordinate(g, 0, g.off[0] + (int)c0 + 1);
     const double d = __dsub_rn(up, lo);
@@ -296,23 +304,46 @@ k_interp_rows_lean(const __grid_constant__ DevBasis B, const __grid_constant__ R
       const LeanRow r = rows[rI];
 #pragma unroll
       for (int a = 0; a < KT; ++a) {
-        const double v = f.comp(comp0, f.common(hx[a], r.u1, r.u2), hx[a], r.u1, r.u2);
+        const double v = f.comp(comp, f.common(hx[a], r.u1, r.u2), hx[a], r.u1, r.u2);
         char* p = a == 0 ? reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * c0
                          : reinterpret_cast<char*>(r.pE) + (size_t)r.sE8 * c0 + (size_t)r.a8 * (unsigned)(a - 1);
-        *reinterpret_cast<double*>(p) = v;
+        *reinterpret_cast<double*>(p + off8) = v;
       }
     }
   }
-  // the closing vertex plane x-entity N_x: one node per row; its owner is the element right of it if
+  // the closing vertex plane x-entity N_x: one node per row and leaf; its owner is the element right of it if
   // the grid has one, else the last element with alpha = k (interpolate.hh:254-259, last writer)
-  if (threadIdx.x < nr) {
-    const LeanRow r = rows[threadIdx.x];
+  for (unsigned w = threadIdx.x; w < nr * C; w += blockDim.x) {
+    unsigned rI, lI;
+    A.divC.divmod(w, rI, lI);
+    const LeanRow r = rows[rI];
     int ie = g.off[0] + g.N[0], aa = 0;
     if (ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }
     const double xc = nodeCoord(g, k, 0, ie, aa);
-    const double v = f.comp(comp0, f.common(xc, r.u1, r.u2), xc, r.u1, r.u2);
-    *reinterpret_cast<double*>(reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * (unsigned)g.N[0]) = v;
+    const double v = f.comp(scalar ? 0 : A.leafComp[lI], f.common(xc, r.u1, r.u2), xc, r.u1, r.u2);
+    *reinterpret_cast<double*>(reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * (unsigned)g.N[0] + 8u * lI) = v;
   }
+}
+
+template <class F, int KT>
+__global__ void __launch_bounds__(256)
+k_interp_rows_lean(const __grid_constant__ DevBasis B, const __grid_constant__ RowArgs A, const __grid_constant__ F f,
+                   double* __restrict__ coeff) {
+  __shared__ LeanRow rows[kRowsPerBlock];
+  leanRowsBody<F, KT>(B, A, f, coeff, blockIdx.x, rows);
+}
+
+// Two interpolate calls in ONE launch (dfx_interpolate_batch): the blocks [0, blocksA) sweep part A's lattice,
+// the rest part B's — e.g. the Taylor-Hood velocity (Q2 lattice, x -> x) and pressure (Q1 lattice,
+// exp(-|x|^2)) of examples/interpolation.cc:89-96, whose kernels are each shorter than a launch gap.
+template <class FA, int KTA, class FB, int KTB>
+__global__ void __launch_bounds__(256)
+k_interp_rows_lean2(const __grid_constant__ DevBasis B, const __grid_constant__ RowArgs A, const __grid_constant__ FA fa,
+                    const __grid_constant__ RowArgs A2, const __grid_constant__ FB fb, unsigned blocksA,
+                    double* __restrict__ coeff) {
+  __shared__ LeanRow rows[kRowsPerBlock];
+  if (blockIdx.x < blocksA) leanRowsBody<FA, KTA>(B, A, fa, coeff, blockIdx.x, rows);
+  else leanRowsBody<FB, KTB>(B, A2, fb, coeff, blockIdx.x - blocksA, rows);
 }
 
 struct CellArgs {
@@ -474,14 +505,13 @@ static bool gaussianBounded(const DevGrid& g, const dfx_function& fn) {
 }
 // per-node kernels with a compile-time function id (orders 1 and 2 / up to 8 passes of 32 local indices)
 template <int ID>
-static void launchRowsNode(int k, bool one, unsigned grid, unsigned bs, cudaStream_t st, const DevBasis& D, RowArgs A,
+static void launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsigned bs, cudaStream_t st, const DevBasis& D, RowArgs A,
                            const dfx_function& fn, double* coeff, const uint8_t* mask) {
   RegistryFnT<ID> f; f.f = fn; f.dim = D.grid.dim;
   // LEAN functor: |argument of exp| bounded by 700 over the whole grid box
   const bool bounded = ID != DFX_FN_GAUSSIAN || gaussianBounded(D.grid, fn);
-  if (one && mask == nullptr && bounded) {
-    // scalar, unmasked: the lean kernel, a few rows per block (its blocks in flight then cover a compact band
-    // of every index-set component, like the table-driven kernel)
+  if (leanShape && bounded) {
+    // one leaf or an interleaved group, unmasked: the lean kernel
     RegistryFnT<ID, true> fl; fl.f = fn; fl.dim = D.grid.dim;
     const u64 nRows = (u64)A.LX[1] * A.LX[2];
     A.rowsPerBlock = std::max(1, std::min(g_rowsLean, kRowsPerBlock));
@@ -581,7 +611,8 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       A.rowsPerBlock = sep ? (L.dimension >= 50000000ull ? 4 : 16) : kRowsPerBlock;    // L2-resident vectors like more rows
       // interleaved group: C leaves with position stride C and consecutive offsets
       A.interleaved = 0;
-      if (sep && A.nActive > 1) {
+      A.divC = FastDiv((unsigned)std::max(1, A.nActive));
+      if (A.nActive > 1) {
         bool il = true;
         for (int q2 = 0; q2 < A.nActive; ++q2) {
           const DevLeaf& lf = D.leaves[A.leafId[q2]];
@@ -591,16 +622,18 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       }
       const unsigned grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
-      const unsigned nEnt = (unsigned)g.N[0] * (A.interleaved ? (unsigned)A.nActive : 1u), chunks = (nEnt + 255) / 256;
+      // (the generic per-node kernel walks x-entities, only the table kernel and the lean kernel spread the leaves)
+      const bool leanShape = !sep && k <= 2 && mask == nullptr && (A.nActive == 1 || A.interleaved);
+      const unsigned nEnt = (unsigned)g.N[0] * (((sep || leanShape) && A.interleaved) ? (unsigned)A.nActive : 1u), chunks = (nEnt + 255) / 256;
       const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
       // per-node evaluation with the function id known at compile time for the functions the BASELINE
       // configs interpolate (no switch in the node loop); everything else dispatches on f.id at run time
       bool launched = false;
       if (!sep && k <= 2) {
         switch (fn.id) {
-          case DFX_FN_GAUSSIAN: launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
-          case DFX_FN_QUADRATIC: launchRowsNode<DFX_FN_QUADRATIC>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
-          case DFX_FN_IDENTITY: launchRowsNode<DFX_FN_IDENTITY>(k, A.nActive == 1, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_GAUSSIAN: launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_QUADRATIC: launchRowsNode<DFX_FN_QUADRATIC>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_IDENTITY: launchRowsNode<DFX_FN_IDENTITY>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
           default: break;
         }
       }
@@ -665,6 +698,79 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
     }
   }
   return DFX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dfx_interpolate_batch: several (subtree, f) pairs on one coefficient vector.  Two parts that are each one
+// lean lattice sweep (continuous order 1 / 2, one leaf or an interleaved group, no mask) run as ONE launch.
+static bool leanPlan(const dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, RowArgs& A, int& k, unsigned& bs,
+                     unsigned& grid) {
+  const DevBasis& D = b->dev;
+  const DevGrid& g = D.grid;
+  if (b->oriented || b->dimension > 0xffffffffull) return false;
+  const int q = D.leaves[firstLeaf].layout;
+  for (int l = 1; l < nLeaves; ++l) if (D.leaves[firstLeaf + l].layout != q) return false;
+  const DevLayout& L = D.layouts[q];
+  k = L.k;
+  if (L.kind != DFX_NODE_LAGRANGE || k < 1 || k > 2) return false;
+  if ((fn.id == DFX_FN_GAUSSIAN || fn.id == DFX_FN_GAUSSIAN_VEC) && !gaussianBounded(g, fn)) return false;
+  A.layoutId = q; A.firstLeaf = firstLeaf; A.nLeaves = nLeaves;
+  for (int j = 0; j < 3; ++j) A.LX[j] = j < g.dim ? k * g.N[j] + 1 : 1;
+  A.tabOff[0] = 0; A.tabOff[1] = A.LX[0]; A.tabOff[2] = A.LX[0] + A.LX[1];
+  A.divK = FastDiv((unsigned)k);
+  A.tabN = 0; A.vectorTables = 0;
+  const u64 nRows = (u64)A.LX[1] * A.LX[2];
+  if (nRows > 0x7fffffffull) return false;
+  A.divLY = FastDiv((unsigned)A.LX[1]);
+  A.nActive = nLeaves;
+  bool il = true;
+  for (int l = 0; l < nLeaves; ++l) {
+    const DevLeaf& lf = D.leaves[firstLeaf + l];
+    A.leafId[l] = firstLeaf + l; A.leafComp[l] = l; A.leafPosA[l] = (unsigned)lf.posA;
+    il = il && lf.posA == (u64)nLeaves && lf.posB == D.leaves[firstLeaf].posB + (u64)l;
+  }
+  if (nLeaves > 1 && !il) return false;
+  A.interleaved = nLeaves > 1 ? 1 : 0;
+  A.divC = FastDiv((unsigned)nLeaves);
+  A.rowsPerBlock = std::max(1, std::min(g_rowsLean, kRowsPerBlock));
+  grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
+  const unsigned nEnt = (unsigned)g.N[0] * (unsigned)nLeaves, chunks = (nEnt + 255) / 256;
+  bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
+  return true;
+}
+
+template <int IDA, int IDB>
+static bool launchLean2(int kA, int kB, unsigned gridA, unsigned gridB, unsigned bs, cudaStream_t st, const DevBasis& D,
+                        const RowArgs& A, const dfx_function& fa, const RowArgs& A2, const dfx_function& fb, double* coeff) {
+  RegistryFnT<IDA, true> FA; FA.f = fa; FA.dim = D.grid.dim;
+  RegistryFnT<IDB, true> FB; FB.f = fb; FB.dim = D.grid.dim;
+  const unsigned grid = gridA + gridB;
+#define DFX_L2(KA_, KB_)                                                                                         \
+  if (kA == KA_ && kB == KB_) {                                                                                  \
+    k_interp_rows_lean2<RegistryFnT<IDA, true>, KA_, RegistryFnT<IDB, true>, KB_><<<grid, bs, 0, st>>>(D, A, FA, A2, FB, gridA, coeff); \
+    return true;                                                                                                 \
+  }
+  DFX_L2(2, 1) DFX_L2(1, 1) DFX_L2(2, 2) DFX_L2(1, 2)
+#undef DFX_L2
+  return false;
+}
+
+// -1: not two lean sweeps (the caller runs the parts one after the other)
+int interpolateBatch2(dfx_basis* b, int flA, int nlA, const dfx_function& fa, int flB, int nlB, const dfx_function& fb,
+                      double* coeff, cudaStream_t st) {
+  RowArgs A, A2;
+  int kA, kB;
+  unsigned bsA, bsB, gridA, gridB;
+  if (!leanPlan(b, flA, nlA, fa, A, kA, bsA, gridA) || !leanPlan(b, flB, nlB, fb, A2, kB, bsB, gridB)) return -1;
+  if ((u64)gridA + gridB > 0x7fffffffull) return -1;
+  const unsigned bs = std::max(bsA, bsB);
+  bool ok;
+  if (fa.id == DFX_FN_IDENTITY && fb.id == DFX_FN_GAUSSIAN)
+    ok = launchLean2<DFX_FN_IDENTITY, DFX_FN_GAUSSIAN>(kA, kB, gridA, gridB, bs, st, b->dev, A, fa, A2, fb, coeff);
+  else
+    ok = launchLean2<-1, -1>(kA, kB, gridA, gridB, bs, st, b->dev, A, fa, A2, fb, coeff);
+  if (!ok) return -1;
+  return postLaunch("k_interp_rows_lean2");
 }
 
 // ---------------------------------------------------------------------------

@@ -249,6 +249,13 @@ int dfx_interpolate(const dfx_basis* b, int32_t subtree_node, const dfx_function
  * function without such a form is interpolated exactly like dfx_interpolate.                        */
 int dfx_interpolate_separable(const dfx_basis* b, int32_t subtree_node, const dfx_function* f_host,
                               double* coeff, const uint8_t* mask, void* stream);
+/* Several interpolate calls on the same vector as one call: part p interpolates fns_host[p] into the leaves
+ * below subtree_nodes_host[p], in order, exactly like n_parts dfx_interpolate calls (the reference's
+ * examples do this by hand: interpolate(subspaceBasis(basis, _0), x, f_velocity); interpolate(subspaceBasis(
+ * basis, _1), x, f_pressure), examples/interpolation.cc:89-96).  Consecutive parts on disjoint subtrees whose
+ * kernels would each be shorter than a launch gap share ONE launch (Taylor-Hood velocity + pressure).      */
+int dfx_interpolate_batch(const dfx_basis* b, int32_t n_parts, const int32_t* subtree_nodes_host,
+                          const dfx_function* fns_host, double* coeff, const uint8_t* mask, void* stream);
 /* form (2): positions of the interpolation nodes and range entry of every
  * coefficient, in flat container order; then a masked copy of caller values. */
 int dfx_interpolation_points(const dfx_basis* b, double* out_xyz /*[dimension][dim]*/,

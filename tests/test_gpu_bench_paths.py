@@ -181,3 +181,63 @@ def test_taylor_hood_128_subranges():
     check_evaluate_ranges(b, o, pts, 2048, jac=True, seed=6)
     check_evaluate_ranges(dfx.subspaceBasis(b, 0), o, pts, 4096, jac=False, onode=1, seed=7)  # velocity sub-space
     check_evaluate_ranges(dfx.subspaceBasis(b, 1), o, pts, 4096, jac=False, onode=5, seed=8)  # pressure sub-space
+
+
+# ---- batched interpolation (dfx_interpolate_batch) and the thread-per-(element, leaf) evaluation --------------
+@pytest.mark.parametrize("n", [[5, 4, 3], [40, 9, 7], [300, 3, 2]])
+def test_interpolate_batch_equals_the_sequence_of_calls(n):
+    """one fused launch for two lean lattice sweeps (interleaved velocity + scalar pressure), the plain sequence
+    for everything else — bit-identical to calling interpolate part by part, and equal to the oracle"""
+    from cases import th_variant
+    from dune_functions_b200 import (blockedLexicographic as BL, flatLexicographic as FL, flatInterleaved as FI,
+                                     blockedInterleaved as BI)
+    grid = dfx.YaspGrid(n, upper=[1.0, 0.5, 2.0])
+    trees = {"taylorHood": dfx.taylorHood()}
+    for on, o_ in (("BL", BL), ("FL", FL)):
+        for inn, i_ in (("FI", FI), ("BI", BI), ("BL", BL), ("FL", FL)):
+            trees[f"TH_{on}({inn})"] = th_variant(o_, i_, 3)
+    for name, tree in trees.items():
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        vel, pre = dfx.subspaceBasis(b, 0), dfx.subspaceBasis(b, 1)
+        for fv, fp in ((dfx.identity(3), dfx.gaussian(1.0)), (dfx.gaussian_vec(3, 0.5), dfx.quadratic(0.5, [1, -2, 3], [1, 0.5, -1, 2, 0.25, -0.5]))):
+            x = dfx.interpolateBatch(b, b.newVector(-7.0), [(vel, fv), (pre, fp)])
+            y = b.newVector(-7.0)
+            dfx.interpolate(vel, y, fv)
+            dfx.interpolate(pre, y, fp)
+            assert bool((x == y).all()), name
+            ref = np.full(o.dimension(), -7.0)
+            o.interpolate(fv, coeff=ref, node=1)
+            o.interpolate(fp, coeff=ref, node=o.numTreeNodes() - 1)
+            assert rel(x.cpu().numpy(), ref) <= TOL, name
+        # overlapping parts keep their order: the whole tree first, then the pressure again
+        x = dfx.interpolateBatch(b, b.newVector(0.0), [(b, dfx.constant(1.0, 2.0, 3.0, 4.0)), (pre, dfx.constant(9.0))])
+        ref = np.zeros(o.dimension())
+        o.interpolate(dfx.constant(1.0, 2.0, 3.0, 4.0), coeff=ref)
+        o.interpolate(dfx.constant(9.0), coeff=ref, node=o.numTreeNodes() - 1)
+        assert np.array_equal(x.cpu().numpy(), ref), name
+
+
+@pytest.mark.parametrize("n", [[16, 8, 8], [33, 5, 4]])
+def test_multi_leaf_evaluation_whole_points(n):
+    """power / composite subtrees go through the thread-per-(element, leaf) kernel: full blocks (bulk store) and
+    ragged ends, values and Jacobians, every Taylor-Hood merging variant and plain power nodes"""
+    import torch
+    from cases import trees as case_trees
+    grid = dfx.YaspGrid(n, upper=[1.0, 0.75, 1.25])
+    rng = np.random.default_rng(21)
+    for name, tree in case_trees(3).items():
+        if not (name.startswith("TH_") or name in ("taylorHood", "power3_q2_BI", "power2_q2_BL", "nested_pow_of_comp")):
+            continue
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        xr = rng.uniform(-1, 1, o.dimension())
+        xt = torch.from_numpy(xr).cuda()
+        for m in (2, 3):
+            pts, _ = tensor_gauss(3, m)
+            v, j = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, jacobians=True)
+            vr, jr = o.evaluate(xr, pts, jacobians=True, nthreads=4)
+            assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL, (name, m)
+            e0, e1 = 3, b.numElements() - 5
+            vs = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, elem_begin=e0, elem_end=e1)
+            assert rel(vs.cpu().numpy(), vr[e0:e1]) <= TOL, (name, m)
