@@ -560,10 +560,10 @@ int dfx_interpolate_dgbf_host(const dfx_basis* target, int32_t target_node, cons
 void dfx_set_kernel_path(int32_t op, int32_t path) {
   if (op == DFX_OP_EVALUATE) g_forcedPath = path;
   else if (op == DFX_OP_INTERPOLATE) g_interpPath = path;
-  else if (op == DFX_OP_INDICES) g_indicesPath = path;
+  else if (op == DFX_OP_INDICES) { g_indicesPath = path == 2 ? 1 : path; g_indicesTile = path == 2 ? 0 : 1; }
   else if (op == DFX_OP_HOST_BAND_KIB) g_hostBandKiB = path;
   else if (op == DFX_OP_SMEM_GRADIENT) g_smemGrad = path;
-  else if (op == DFX_OP_TUNE_ROWS) g_rowsLean = path > 0 ? path : 32;
+  else if (op == DFX_OP_TUNE_ROWS) g_rowsLean = path > 0 ? path : -1;
 }
 
 // Companion of a basis with permuted face DOFs: the same tree with every Lagrange leaf replaced by the

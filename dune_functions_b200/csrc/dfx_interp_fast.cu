@@ -245,8 +245,16 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
 // With exp from expTab a Gaussian node is 14 FP64 issues + about 12 others, below the HBM time of the
 // 8 bytes it writes.
 struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsigned a8, pad; };
-int g_rowsLean = 32;    // lattice rows per block of the lean kernel (tuning knob DFX_OP_TUNE_ROWS; measured 1..32:
-                        // 256^3 0.43 -> 0.19 ms, 512^3 flat from 4 rows on, profiles/README.md)
+int g_rowsLean = -1;    // lattice rows per block of the lean kernel; -1: leanRows() (tuning knob DFX_OP_TUNE_ROWS)
+
+// Many rows per block amortise the per-thread x-data (measured 1 .. 32 rows: 256^3 0.43 -> 0.19 ms, 512^3 flat
+// from 4 rows on), but a small lattice must still give every SM several waves of blocks (Taylor-Hood 128^3
+// has 66 049 + 16 641 rows: 32 rows per block are 2.2 waves with a 0.2-full tail; measured 2 .. 32 rows:
+// 0.107 / 0.090 (4 rows) / 0.097 / 0.124 ms): about 128 blocks per SM.
+static int leanRows(u64 nRows) {
+  if (g_rowsLean > 0) return std::min(g_rowsLean, kRowsPerBlock);
+  return (int)std::max<u64>(4, std::min<u64>(kRowsPerBlock, nRows / (148 * 128)));
+}
 
 // Body shared by the single and the two-part kernel.  The active leaves are either ONE leaf (any position
 // stride) or the C components of an interleaved power node (position = C j + c, FlatInterleaved /
@@ -514,7 +522,7 @@ static void launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsig
     // one leaf or an interleaved group, unmasked: the lean kernel
     RegistryFnT<ID, true> fl; fl.f = fn; fl.dim = D.grid.dim;
     const u64 nRows = (u64)A.LX[1] * A.LX[2];
-    A.rowsPerBlock = std::max(1, std::min(g_rowsLean, kRowsPerBlock));
+    A.rowsPerBlock = leanRows(nRows);
     const unsigned gridL = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
     if (k == 1) k_interp_rows_lean<RegistryFnT<ID, true>, 1><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
     else k_interp_rows_lean<RegistryFnT<ID, true>, 2><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
@@ -732,7 +740,7 @@ static bool leanPlan(const dfx_basis* b, int firstLeaf, int nLeaves, const dfx_f
   if (nLeaves > 1 && !il) return false;
   A.interleaved = nLeaves > 1 ? 1 : 0;
   A.divC = FastDiv((unsigned)nLeaves);
-  A.rowsPerBlock = std::max(1, std::min(g_rowsLean, kRowsPerBlock));
+  A.rowsPerBlock = leanRows(nRows);
   grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
   const unsigned nEnt = (unsigned)g.N[0] * (unsigned)nLeaves, chunks = (nEnt + 255) / 256;
   bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
@@ -912,6 +920,144 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same table through a shared-memory tile (identity orientations, the case of every BASELINE config):
+// a block owns `epb` consecutive elements, i.e. ONE contiguous run of the table; the threads keep their
+// local index as above but write into the tile (32-bit shared-memory address arithmetic instead of 64-bit
+// global pointers), and the run leaves as TMA bulk stores (cp.async.bulk.global.shared::cta, SASS UBLKCP) in
+// whole 16-byte units — the direct version's 4-byte stores at odd multiples of 4 left partially written
+// 32-byte sectors at both ends of every warp's run, which the L2 filled from DRAM (0.64 GB read for 0.69 GB
+// written on Taylor-Hood 128^3, profiles/README.md).
+struct IdxTileArgs {
+  u64 e0, ne;
+  FastDiv divN0, divN1;
+  int stride;          // digits per multi-index (MULTI), else 1
+  int lpb, m, epb;     // local indices per pass, elements in flight, elements per block
+  int bulk;            // output run of every full block is 16-byte aligned
+};
+
+template <class T, bool MULTI>
+__global__ void __launch_bounds__(256)
+k_indices_tile(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxTileArgs A,
+               const unsigned* __restrict__ localTab, T* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char tileRaw[];
+  T* tile = reinterpret_cast<T*>(tileRaw);
+  const DevGrid& g = Bp->grid;
+  const int nloc = Bp->nlocTotal;
+  const int sub = threadIdx.x / A.lpb, lane = threadIdx.x - sub * A.lpb;
+  const u64 blkEl0 = (u64)blockIdx.x * (u64)A.epb;
+  const u64 left = A.ne - blkEl0;
+  const unsigned nEl = left < (u64)A.epb ? (unsigned)left : (unsigned)A.epb;       // elements of this block
+  const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
+  const unsigned m = (unsigned)A.m;
+  const unsigned rowW = (unsigned)nloc * (unsigned)A.stride;                        // table entries (T) per element
+  if ((unsigned)sub < m)
+    for (int li = lane; li < nloc; li += A.lpb) {
+      const unsigned packed = __ldg(localTab + li);
+      const DevLeaf& leaf = Bp->leaves[packed & 31u];
+      const DevLayout& L = Bp->layouts[leaf.layout];
+      const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
+      const int zero[3] = {0, 0, 0};
+      const u64 jbase = layoutIndex(L, g, zero, a, li - leaf.localOffset);
+      unsigned s = 0;
+      if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << g.dim) - 1u;
+      else
+        for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
+      const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1];
+      const u64 blk = (u64)L.blk[s];
+      if ((unsigned)sub >= nEl) continue;
+      unsigned ec0, ec1, ec2;
+      {
+        unsigned q;
+        A.divN0.divmod((unsigned)(A.e0 + blkEl0 + (u64)sub), q, ec0);
+        A.divN1.divmod(q, ec2, ec1);
+      }
+      const unsigned nIt = (nEl - (unsigned)sub + m - 1) / m;
+      unsigned ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+      if (MULTI) {
+        T dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
+#pragma unroll
+        for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
+          dA[p] = p < leaf.ndig ? (T)(leaf.digA[p] * blk) : (T)0;
+          dB[p] = p < leaf.ndig ? (T)(leaf.digA[p] * jbase + leaf.digB[p]) : (T)0;
+        }
+        T* po = tile + ((unsigned)sub * (unsigned)nloc + (unsigned)li) * (unsigned)A.stride;
+        const unsigned step = m * rowW;
+        for (unsigned it = 0; it < nIt; ++it) {
+#pragma unroll
+          for (int p = 0; p < DFX_MAX_DIGITS; ++p)
+            if (p < A.stride) po[p] = (T)(dB[p] + dA[p] * (T)ent);
+          po += step; ec0 += m; ent += m;
+          if (ec0 >= N0) {
+            do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
+            ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+          }
+        }
+      } else {
+        // all per-entry arithmetic runs in the output type (wrapping 32-bit multiply-adds give the same bits
+        // as 64-bit ones when the true value fits, which the caller checked)
+        const T P0 = (T)(leaf.posA * jbase + leaf.posB);
+        const T S = (T)(leaf.posA * blk);
+        T* po = tile + ((unsigned)sub * (unsigned)nloc + (unsigned)li);
+        const unsigned step = m * (unsigned)nloc;
+        T v = (T)(P0 + S * (T)ent);
+        const T dv = (T)(S * (T)m);
+        for (unsigned it = 0; it < nIt; ++it) {
+          *po = v;
+          po += step; ec0 += m; v += dv;
+          if (ec0 >= N0) {
+            do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
+            v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
+          }
+        }
+      }
+    }
+  // ---- the block's run of the table leaves in one piece ----
+  T* dst = out + blkEl0 * (u64)rowW;
+  const unsigned bytes = nEl * rowW * (unsigned)sizeof(T);
+  if (A.bulk && (bytes & 15u) == 0u) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                   "r"((unsigned)__cvta_generic_to_shared(tile)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < nEl * rowW; i += blockDim.x) dst[i] = tile[i];
+}
+
+template <class T, bool MULTI>
+static int launchIndicesTile(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
+  IdxTileArgs A;
+  A.e0 = e0; A.ne = e1 - e0; A.stride = MULTI ? stride : 1;
+  if (A.ne == 0) return DFX_OK;
+  const int nloc = b->dev.nlocTotal;
+  A.lpb = std::min(nloc, 256);
+  A.m = std::max(1, 256 / A.lpb);
+  const size_t rowBytes = (size_t)nloc * A.stride * sizeof(T);
+  // elements per block: a tile of about 24 KB (9 blocks per SM), a multiple of 4 elements and of m
+  int epb = (int)std::max<size_t>(1, (24 * 1024) / rowBytes);
+  epb = std::max(4, epb / 4 * 4);
+  epb = std::max(A.m, epb / A.m * A.m);
+  if ((size_t)epb * rowBytes > 96 * 1024) return -1;                // huge elements: the direct kernel
+  A.epb = epb;
+  A.divN0 = FastDiv((unsigned)b->dev.grid.N[0]); A.divN1 = FastDiv((unsigned)b->dev.grid.N[1]);
+  // every full block's run starts at out + blockIdx * epb * rowBytes: aligned if the base and the block pitch are
+  A.bulk = (((uintptr_t)out & 15) == 0 && (((size_t)epb * rowBytes) & 15) == 0) ? 1 : 0;
+  const u64 blocks = (A.ne + epb - 1) / epb;
+  if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  const size_t smem = (size_t)epb * rowBytes;
+  auto kern = k_indices_tile<T, MULTI>;
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
+  kern<<<(unsigned)blocks, A.lpb * A.m, smem, st>>>((const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out);
+  return postLaunch("k_indices_tile");
+}
+
 template <class T, bool MULTI, bool ORIENT, bool GATHER>
 static int launchIndicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, int liBegin, int liEnd, const double* src,
                              double* dst, const GatherTab& G, cudaStream_t st) {
@@ -932,10 +1078,16 @@ static int launchIndicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int str
   return postLaunch("k_indices_fast");
 }
 
+int g_indicesTile = 1;     // 0: the direct-store walking kernel (dfx_set_kernel_path(DFX_OP_INDICES, 2))
+
 template <class T, bool MULTI>
 int indicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
   GatherTab G{};
   if (b->oriented) return launchIndicesFast<T, MULTI, true, false>(b, e0, e1, out, stride, 0, b->dev.nlocTotal, nullptr, nullptr, G, st);
+  if (g_indicesTile) {
+    const int rc = launchIndicesTile<T, MULTI>(b, e0, e1, out, stride, st);
+    if (rc >= 0) return rc;
+  }
   return launchIndicesFast<T, MULTI, false, false>(b, e0, e1, out, stride, 0, b->dev.nlocTotal, nullptr, nullptr, G, st);
 }
 

@@ -315,7 +315,8 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
  * behaviour per call, e.g. dfx_interpolate vs dfx_interpolate_separable).
  * op DFX_OP_EVALUATE: paths as above; DFX_OP_INTERPOLATE: 0 generic per-DOF
  * kernel, 1 structured kernel evaluating f at every node (the automatic choice), 2 structured
- * kernel with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast;
+ * kernel with per-direction tables for separable f; DFX_OP_INDICES: 0 generic, 1 fast (shared-memory tile + bulk stores),
+ * 2 fast with direct stores;
  * DFX_OP_HOST_BAND_KIB: `path` = KiB of results per pipeline band of dfx_evaluate_host
  * (-1 = default 192 MiB); DFX_OP_SMEM_GRADIENT: how the shared-memory evaluation kernel
  * forms gradients: 1 = differentiated shape tables in every stage, -1 = automatic

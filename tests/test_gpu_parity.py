@@ -625,9 +625,11 @@ def kernel_path():
         capi.lib().dfx_set_kernel_path(op, -1)
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [0, 1, 2])
 @pytest.mark.parametrize("gname", ["1d_5", "2d_3x2", "3d_3x4x5"])
 def test_indices_kernel_families(kernel_path, gname, path):
+    """0 generic per-entry kernel, 1 walking kernel through a shared-memory tile (bulk stores), 2 walking kernel
+    with direct stores"""
     import torch
     kernel_path(capi.OP_INDICES, path)
     grid = GRIDS[gname]

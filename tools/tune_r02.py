@@ -48,6 +48,39 @@ def main():
             print(json.dumps({"probe": "separable tables", "n": n, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
             del b, x
             torch.cuda.empty_cache()
+    if "c3" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([128, 128, 128]), dfx.taylorHood())
+        ne, nl = b.numElements(), b.maxNodeSize()
+        x = b.newVector(0.0)
+        nd = b.dimension()
+        parts = [(dfx.subspaceBasis(b, 0), dfx.identity(3)), (dfx.subspaceBasis(b, 1), dfx.gaussian(1.0))]
+        for rows in (-1, 2, 4, 6, 8, 12, 16, 32):
+            L.dfx_set_kernel_path(capi.OP_TUNE_ROWS, rows)
+            ms = timeit(lambda: dfx.interpolateBatch(b, x, parts))
+            print(json.dumps({"probe": "TH batch interpolate", "rows": rows, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_TUNE_ROWS, -1)
+        idx = torch.empty((ne, nl), dtype=torch.int32, device="cuda")
+        mi = torch.empty((ne, nl, 2), dtype=torch.int32, device="cuda")
+        st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+        for path, label in ((1, "tile + bulk store"), (2, "direct stores")):
+            L.dfx_set_kernel_path(capi.OP_INDICES, path)
+            ms = timeit(lambda: capi.check(L.dfx_indices_flat(b._h, 0, ne, C.c_void_p(idx.data_ptr()), st())))
+            print(json.dumps({"probe": "TH indices flat " + label, "ms": ms, "frac": idx.numel() * 4 / ms / 1e6 / PEAK}), flush=True)
+            ms = timeit(lambda: capi.check(L.dfx_indices_multi(b._h, 0, ne, C.c_void_p(mi.data_ptr()), 2, st())))
+            print(json.dumps({"probe": "TH indices 2 digits " + label, "ms": ms, "frac": mi.numel() * 4 / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_INDICES, -1)
+        del b, x, idx, mi
+        torch.cuda.empty_cache()
+        b = dfx.makeBasis(dfx.YaspGrid([256, 256, 256]), dfx.lagrange(2))
+        ne = b.numElements()
+        idx = torch.empty((ne, 27), dtype=torch.int32, device="cuda")
+        for path, label in ((1, "tile + bulk store"), (2, "direct stores")):
+            L.dfx_set_kernel_path(capi.OP_INDICES, path)
+            ms = timeit(lambda: capi.check(L.dfx_indices_flat(b._h, 0, ne, C.c_void_p(idx.data_ptr()), st())))
+            print(json.dumps({"probe": "Q2 256^3 indices flat " + label, "ms": ms, "frac": idx.numel() * 4 / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_INDICES, -1)
+        del b, idx
+        torch.cuda.empty_cache()
     if "dg4" in what or "jac" in what:
         b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
         x = b.newVector(0.0)
