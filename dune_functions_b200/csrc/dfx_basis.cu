@@ -454,6 +454,32 @@ int buildBasis(const dfx_grid_desc* gd, const dfx_tree_node* t, int n, int devic
       b->localTab[D.leaves[l].localOffset + i] = (unsigned)l | (a[0] << 5) | (a[1] << 10) | (a[2] << 15);
     }
   }
+  // ... and everything else of the index table that depends on the local index only (IdxLi)
+  b->idxTab.resize(offset);
+  for (int l = 0; l < D.nLeaves; ++l) {
+    const DevLeaf& leaf = D.leaves[l];
+    const DevLayout& L = D.layouts[leaf.layout];
+    for (int i = 0; i < leaf.nloc; ++i) {
+      int ii = i, a[3];
+      for (int j = 0; j < 3; ++j) { a[j] = ii % (L.k + 1); ii /= (L.k + 1); }
+      const int zero[3] = {0, 0, 0};
+      const u64 jbase = layoutIndex(L, D.grid, zero, a, i);
+      unsigned s = 0;
+      if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << D.grid.dim) - 1u;
+      else
+        for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
+      IdxLi& t = b->idxTab[leaf.localOffset + i];
+      const u64 blk = (u64)L.blk[s];
+      t.P0 = leaf.posA * jbase + leaf.posB;
+      t.S = (unsigned)(leaf.posA * blk);
+      t.cs0 = (unsigned)L.csize[s][0]; t.cs1 = (unsigned)L.csize[s][1];
+      t.ndig = (unsigned)leaf.ndig;
+      for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
+        t.dA[p] = p < leaf.ndig ? leaf.digA[p] * blk : 0;
+        t.dB[p] = p < leaf.ndig ? leaf.digA[p] * jbase + leaf.digB[p] : 0;
+      }
+    }
+  }
   *out = b.release();
   return DFX_OK;
 }

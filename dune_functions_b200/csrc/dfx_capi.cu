@@ -43,6 +43,8 @@ int ensureDevice(const dfx_basis* b) {
     dfx_basis* mb = const_cast<dfx_basis*>(b);
     DFX_CUDA(cudaMalloc(&mb->dLocalTab, b->localTab.size() * sizeof(unsigned)));
     DFX_CUDA(cudaMemcpy(mb->dLocalTab, b->localTab.data(), b->localTab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    DFX_CUDA(cudaMalloc(&mb->dIdxTab, b->idxTab.size() * sizeof(IdxLi)));
+    DFX_CUDA(cudaMemcpy(mb->dIdxTab, b->idxTab.data(), b->idxTab.size() * sizeof(IdxLi), cudaMemcpyHostToDevice));
     DFX_CUDA(cudaMalloc(&mb->dDev, sizeof(DevBasis)));
     DFX_CUDA(cudaMemcpy(mb->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice));
   }
@@ -189,12 +191,12 @@ static void releaseResources(dfx_basis_impl* b) {
   if (b->companion) { dfx_basis_destroy(static_cast<dfx_basis*>(b->companion)); b->companion = nullptr; }
   b->companionTried = false;
   const bool any = b->dLocalCoeff || b->dDense || b->dJinv || b->dNodal || b->dVid || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
-                   b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream;
+                   b->dIdxTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream;
   if (!any) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize((cudaStream_t)b->stream);
   if (b->dLocalCoeff) { cudaFree(b->dLocalCoeff); b->dLocalCoeff = nullptr; b->dLocalCoeffBytes = 0; }
-  for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dShape, &b->dLocalTab, &b->dDev, &b->dSep,
+  for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dShape, &b->dLocalTab, &b->dIdxTab, &b->dDev, &b->dSep,
                    &b->dScratch[0], &b->dScratch[1], &b->dScratch[2]})
     if (*p) { cudaFree(*p); *p = nullptr; }
   if (b->pinned) { cudaFreeHost(b->pinned); b->pinned = nullptr; }
@@ -564,6 +566,8 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_HOST_BAND_KIB) g_hostBandKiB = path;
   else if (op == DFX_OP_SMEM_GRADIENT) g_smemGrad = path;
   else if (op == DFX_OP_TUNE_ROWS) g_rowsLean = path > 0 ? path : -1;
+  else if (op == DFX_OP_TUNE_STREAM_HINT) g_evalStreamHint = path == 0 ? 0 : 1;
+  else if (op == DFX_OP_TUNE_SWIZZLE) g_evalSwizzle = path == 0 ? 0 : (path == 2 ? 2 : 1);
 }
 
 // Companion of a basis with permuted face DOFs: the same tree with every Lagrange leaf replaced by the

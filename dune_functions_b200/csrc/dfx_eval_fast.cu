@@ -40,6 +40,10 @@ static bool regPathHas(int dim, int k, int m) {
   return (dim == 2 || dim == 3) && (k == 1 || k == 2) && (m == 2 || m == 3);
 }
 
+int g_evalStreamHint = 1;  // bulk stores of results with the L2 evict-first policy (DFX_OP_TUNE_STREAM_HINT)
+int g_evalSwizzle = 1;     // dfx_set_kernel_path(DFX_OP_TUNE_SWIZZLE, .): 0 blocks in grid-view order, 1 strip schedule when a
+                           // z-layer outgrows the L2, 2 strip schedule whenever the shape allows (tests)
+
 int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* xhat, int nq, bool wantJac, int forced,
                  FastPlan& plan) {
   if (forced == 0) return 0;
@@ -118,6 +122,15 @@ struct RegArgs {
   FastDiv divN0, divN1;
   int bulk;                    // 1: the block's output tile is contiguous and 16-byte aligned
   unsigned long long posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES];   // flat position map of the group's leaves
+  // Block schedule (swz = 1): blocks do not walk the elements in grid-view order (x, then y, then z) but strip
+  // by strip — a strip is `stripH` element rows in y, taken through ALL z-layers before the next strip starts.
+  // The coefficients two z-neighbours share are then re-used after one strip-layer (a few MB) instead of after
+  // a whole z-layer of elements: at 512^3 that layer is 73 MB of coefficients + results, more than the L2 keeps,
+  // and ncu counted 11.3 GB of DRAM reads for 8.6 GB of coefficients (profiles/r02_ncu_configs.csv).  Every block
+  // still writes its own contiguous run of the element-major output.
+  int swz;
+  unsigned n0, n1, stripH, fullStrips;
+  FastDiv divBpr, divStripVol, divStripH, divLastH;
 };
 
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -125,6 +138,16 @@ __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)_
 // contiguous shared -> global copy by the TMA engine (SASS: UBLKCP)
 __device__ __forceinline__ void bulkStore(double* gdst, const double* ssrc, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smemAddr(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the same with an L2 evict-first policy: results are written once and never read by this kernel, so they
+// should not push the coefficients that neighbouring elements still need out of the L2
+__device__ __forceinline__ void bulkStoreStreaming(double* gdst, const double* ssrc, unsigned bytes) {
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smemAddr(ssrc)),
+               "r"(bytes), "l"(policy)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -180,7 +203,15 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
   // g and L (the group's DOF lattice) are direct kernel parameters: every access below has a
   // compile-time offset into the constant bank (no indexed-constant loads in the hot path)
   const int tid = threadIdx.x;
-  const u64 blk0 = (u64)blockIdx.x * EPB;
+  u64 blk0 = (u64)blockIdx.x * EPB;
+  if (R.swz) {
+    unsigned r, xb, strip, rem, z, yy;
+    R.divBpr.divmod(blockIdx.x, r, xb);                  // r: row slot in strip order, xb: block inside the row
+    R.divStripVol.divmod(r, strip, rem);                 // strip volume = stripH rows x all layers of the range
+    if (strip < R.fullStrips) R.divStripH.divmod(rem, z, yy);
+    else R.divLastH.divmod(rem, z, yy);                  // the last, lower strip
+    blk0 = ((u64)z * R.n1 + (u64)strip * R.stripH + yy) * (u64)R.n0 + (u64)xb * EPB;
+  }
   const u64 el = blk0 + tid;
   const bool active = el < R.ne;
   const u64 e = R.e0 + (active ? el : 0);
@@ -269,8 +300,13 @@ k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout 
     fenceProxyAsync();          // generic-proxy smem writes -> visible to the async proxy
     __syncthreads();
     if (tid == 0) {
-      if (values) bulkStore(values + blk0 * (u64)rowLen, vTile, (unsigned)(EPB * rowLen * sizeof(double)));
-      if (JAC) bulkStore(jac + blk0 * (u64)rowLen * DIM, jTile, (unsigned)(EPB * rowLen * DIM * sizeof(double)));
+      if (R.bulk == 2) {
+        if (values) bulkStoreStreaming(values + blk0 * (u64)rowLen, vTile, (unsigned)(EPB * rowLen * sizeof(double)));
+        if (JAC) bulkStoreStreaming(jac + blk0 * (u64)rowLen * DIM, jTile, (unsigned)(EPB * rowLen * DIM * sizeof(double)));
+      } else {
+        if (values) bulkStore(values + blk0 * (u64)rowLen, vTile, (unsigned)(EPB * rowLen * sizeof(double)));
+        if (JAC) bulkStore(jac + blk0 * (u64)rowLen * DIM, jTile, (unsigned)(EPB * rowLen * DIM * sizeof(double)));
+      }
       bulkStoreWaitRead();      // shared memory must outlive the copy
     }
     return;
@@ -602,7 +638,27 @@ int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
     const bool whole = R.nGroup == compTotal;
     const bool aligned = (!values || ((uintptr_t)values & 15) == 0) && (!jac || ((uintptr_t)jac & 15) == 0);
-    R.bulk = whole && aligned ? 1 : 0;
+    R.bulk = whole && aligned ? (g_evalStreamHint ? 2 : 1) : 0;
+    {
+      // strip schedule: 3-d, whole z-layers, rows that are whole blocks, and a z-layer too big for the L2 to keep
+      const u64 n0 = (u64)D.grid.N[0], n1 = (u64)D.grid.N[1], layer = n0 * n1;
+      const unsigned epb = plan.jac ? 64u : (R.nGroup >= 2 ? 32u : 128u);
+      int nqp = 1; for (int j = 0; j < plan.dim; ++j) nqp *= plan.m;
+      const u64 layerBytes = layer * (u64)nqp * R.nGroup * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
+      constexpr unsigned kStripH = 32;
+      R.swz = 0;
+      if (g_evalSwizzle && plan.dim == 3 && n0 % epb == 0 && e0 % layer == 0 && (e1 - e0) % layer == 0 && (e1 - e0) >= 2 * layer &&
+          n1 >= 2 * kStripH && (layerBytes > (24ull << 20) || g_evalSwizzle == 2)) {
+        const unsigned nz = (unsigned)((e1 - e0) / layer);
+        R.swz = 1;
+        R.n0 = (unsigned)n0; R.n1 = (unsigned)n1; R.stripH = kStripH;
+        R.fullStrips = (unsigned)(n1 / kStripH);
+        R.divBpr = FastDiv((unsigned)(n0 / epb));
+        R.divStripVol = FastDiv(kStripH * nz);
+        R.divStripH = FastDiv(kStripH);
+        R.divLastH = FastDiv(std::max(1u, (unsigned)(n1 % kStripH)));
+      }
+    }
     int rc = DFX_OK;
 #define DFX_REG(DIM_, K_, M_)                                                                      \
   if (dim == DIM_ && plan.k == K_ && m == M_)                                                      \

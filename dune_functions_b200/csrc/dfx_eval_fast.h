@@ -33,6 +33,8 @@ int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* x
                  FastPlan& plan);
 bool smemPathHas(int dim, int k, int m);
 extern int g_smemGrad;
+extern int g_evalSwizzle;
+extern int g_evalStreamHint;
 bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);
 int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, const double* coeff,
                 u64 e0, u64 e1, double* values, double* jac, cudaStream_t st);

@@ -208,6 +208,15 @@ DFX_HD void dofOwnerNode(const DevBasis& B, const DevLayout& L, u64 t, int ie[3]
   }
 }
 
+// ---- per local index, folded once on the host for the index-table kernel (csrc/dfx_interp_fast.cu) ----
+// flat position of local index li in element (ec0, ec1, ec2): P0 + S * ent with ent = ec0 + cs0 (ec1 + cs1 ec2);
+// digit p of its multi-index: dB[p] + dA[p] * ent  (identity orientations)
+struct IdxLi {
+  u64 P0;
+  unsigned S, cs0, cs1, ndig;
+  u64 dB[DFX_MAX_DIGITS], dA[DFX_MAX_DIGITS];
+};
+
 // ---- host-side basis --------------------------------------------------------
 struct HostNode {           // expanded local ansatz tree, preorder
   int kind, order, ims;
@@ -229,6 +238,7 @@ struct dfx_basis_impl {
   // device scratch owned by the handle
   std::vector<unsigned> localTab;                       // per local index: leaf | alpha (see k_indices_fast)
   void* dLocalTab = nullptr;                            // uploaded on first use
+  std::vector<IdxLi> idxTab; void* dIdxTab = nullptr;   // per local index: folded constants of the index table
   void* dDev = nullptr;                                 // device copy of `dev`
   void* dVid = nullptr;                                 // vertex ids (dev.vid points here)
   // evaluation with permuted face DOFs: the same tree with every leaf discontinuous, and the

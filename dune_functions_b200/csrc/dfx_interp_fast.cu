@@ -244,6 +244,14 @@ k_interp_rows(const __grid_constant__ DevBasis B, const __grid_constant__ RowArg
 // reference coordinates alpha / k are compile-time constants; the functor sits in the constant bank.
 // With exp from expTab a Gaussian node is 14 FP64 issues + about 12 others, below the HBM time of the
 // 8 bytes it writes.
+// alpha / k for alpha in 0 .. KT as the compiler folds it (IEEE division at compile time: the bits of __ddiv_rn)
+template <int KT>
+__device__ __forceinline__ double xhatOf(int a) {
+  double r = 0.0;
+#pragma unroll
+  for (int i = 1; i <= KT; ++i) if (a == i) r = (double)i / (double)KT;
+  return r;
+}
 struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsigned a8, pad; };
 int g_rowsLean = -1;    // lattice rows per block of the lean kernel; -1: leanRows() (tuning knob DFX_OP_TUNE_ROWS)
 
@@ -289,24 +297,28 @@ __device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A
     r.sV8 = (unsigned)(leaf.posA * (u64)L.blk[sV]) * 8u;
     r.sE8 = (unsigned)(leaf.posA * (u64)L.blk[sE]) * 8u;
     r.a8 = (unsigned)leaf.posA * 8u; r.pad = 0;
-    r.u1 = g.dim > 1 ? nodeCoord(g, k, 1, dy.ie, dy.a) : 0.0;
-    r.u2 = g.dim > 2 ? nodeCoord(g, k, 2, dz.ie, dz.a) : 0.0;
+    r.u1 = g.dim > 1 ? elementGlobal(g, 1, dy.ie, xhatOf<KT>(dy.a)) : 0.0;
+    r.u2 = g.dim > 2 ? elementGlobal(g, 2, dz.ie, xhatOf<KT>(dz.a)) : 0.0;
     rows[rI] = r;
   }
-  __syncthreads();
   const unsigned C = (unsigned)A.nActive;                         // 1, or the components of an interleaved group
   const bool scalar = f.ncomp() == 1;
-  for (unsigned u = threadIdx.x; u < (unsigned)g.N[0] * C; u += blockDim.x) {
-    unsigned c0, lI;
-    A.divC.divmod(u, c0, lI);
-    const int comp = scalar ? 0 : A.leafComp[lI];
-    const unsigned off8 = 8u * lI;                                 // leaf lI sits lI entries behind leaf 0
-    // nodes X = k c0 + a of x-entity c0: a = 0 vertex-type, 1 .. k-1 edge-type; owner element = c0 itself
+  const unsigned lim = (unsigned)g.N[0] * C;
+  unsigned u = threadIdx.x, c0 = 0, lI = 0;
+  double hx[KT];
+  // x-data of x-entity c0: nodes X = k c0 + a, a = 0 vertex-type, 1 .. k-1 edge-type; owner element = c0 itself
+  auto xprep = [&](unsigned uu) {
+    A.divC.divmod(uu, c0, lI);
     const double lo = gridCoordinate(g, 0, g.off[0] + (int)c0), up = gridCoordinate(g, 0, g.off[0] + (int)c0 + 1);
     const double d = __dsub_rn(up, lo);
-    double hx[KT];
 #pragma unroll
     for (int a = 0; a < KT; ++a) hx[a] = __dadd_rn(lo, __dmul_rn((double)a / (double)KT, d));   // alpha / k folded at compile time
+  };
+  if (u < lim) xprep(u);            // before the barrier: overlaps the row set-up of the first warp
+  __syncthreads();
+  while (u < lim) {
+    const int comp = scalar ? 0 : A.leafComp[lI];
+    const unsigned off8 = 8u * lI;                                 // leaf lI sits lI entries behind leaf 0
 #pragma unroll 4
     for (unsigned rI = 0; rI < nr; ++rI) {
       const LeanRow r = rows[rI];
@@ -318,6 +330,8 @@ __device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A
         *reinterpret_cast<double*>(p + off8) = v;
       }
     }
+    u += blockDim.x;
+    if (u < lim) xprep(u);
   }
   // the closing vertex plane x-entity N_x: one node per row and leaf; its owner is the element right of it if
   // the grid has one, else the last element with alpha = k (interpolate.hh:254-259, last writer)
@@ -327,7 +341,7 @@ __device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A
     const LeanRow r = rows[rI];
     int ie = g.off[0] + g.N[0], aa = 0;
     if (ie >= g.G[0]) { ie = g.G[0] - 1; aa = k; }
-    const double xc = nodeCoord(g, k, 0, ie, aa);
+    const double xc = elementGlobal(g, 0, ie, xhatOf<KT>(aa));
     const double v = f.comp(scalar ? 0 : A.leafComp[lI], f.common(xc, r.u1, r.u2), xc, r.u1, r.u2);
     *reinterpret_cast<double*>(reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * (unsigned)g.N[0] + 8u * lI) = v;
   }
@@ -930,16 +944,19 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
 // written on Taylor-Hood 128^3, profiles/README.md).
 struct IdxTileArgs {
   u64 e0, ne;
-  FastDiv divN0, divN1;
-  int stride;          // digits per multi-index (MULTI), else 1
+  FastDiv divN0, divN1, divM;
+  int stride;          // digits per multi-index (NDIG != 0), else 1
   int lpb, m, epb;     // local indices per pass, elements in flight, elements per block
   int bulk;            // output run of every full block is 16-byte aligned
 };
 
-template <class T, bool MULTI>
+// NDIG: 0 flat positions; 2, 3 multi-indices with that many digits per entry (compile time); -1 run-time stride.
+// Everything that depends on the local index only comes folded from the host (IdxLi); a thread walks its
+// elements row segment by row segment, so the inner loop is store / advance pointer / advance value.
+template <class T, int NDIG>
 __global__ void __launch_bounds__(256)
 k_indices_tile(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxTileArgs A,
-               const unsigned* __restrict__ localTab, T* __restrict__ out) {
+               const IdxLi* __restrict__ idxTab, T* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char tileRaw[];
   T* tile = reinterpret_cast<T*>(tileRaw);
   const DevGrid& g = Bp->grid;
@@ -950,68 +967,66 @@ k_indices_tile(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxTileA
   const unsigned nEl = left < (u64)A.epb ? (unsigned)left : (unsigned)A.epb;       // elements of this block
   const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
   const unsigned m = (unsigned)A.m;
-  const unsigned rowW = (unsigned)nloc * (unsigned)A.stride;                        // table entries (T) per element
-  if ((unsigned)sub < m)
+  const int stride = NDIG == 0 ? 1 : (NDIG > 0 ? NDIG : A.stride);
+  const unsigned rowW = (unsigned)nloc * (unsigned)stride;                          // table entries (T) per element
+  if ((unsigned)sub < nEl) {
+    unsigned s0, s1, s2;                          // coordinates of this thread's first element
+    {
+      unsigned q;
+      A.divN0.divmod((unsigned)(A.e0 + blkEl0 + (u64)sub), q, s0);
+      A.divN1.divmod(q, s2, s1);
+    }
+    const unsigned nIt = (nEl - (unsigned)sub + m - 1) / m;
     for (int li = lane; li < nloc; li += A.lpb) {
-      const unsigned packed = __ldg(localTab + li);
-      const DevLeaf& leaf = Bp->leaves[packed & 31u];
-      const DevLayout& L = Bp->layouts[leaf.layout];
-      const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
-      const int zero[3] = {0, 0, 0};
-      const u64 jbase = layoutIndex(L, g, zero, a, li - leaf.localOffset);
-      unsigned s = 0;
-      if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << g.dim) - 1u;
-      else
-        for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
-      const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1];
-      const u64 blk = (u64)L.blk[s];
-      if ((unsigned)sub >= nEl) continue;
-      unsigned ec0, ec1, ec2;
-      {
-        unsigned q;
-        A.divN0.divmod((unsigned)(A.e0 + blkEl0 + (u64)sub), q, ec0);
-        A.divN1.divmod(q, ec2, ec1);
-      }
-      const unsigned nIt = (nEl - (unsigned)sub + m - 1) / m;
-      unsigned ent = ec0 + cs0 * (ec1 + cs1 * ec2);
-      if (MULTI) {
-        T dA[DFX_MAX_DIGITS], dB[DFX_MAX_DIGITS];
-#pragma unroll
-        for (int p = 0; p < DFX_MAX_DIGITS; ++p) {
-          dA[p] = p < leaf.ndig ? (T)(leaf.digA[p] * blk) : (T)0;
-          dB[p] = p < leaf.ndig ? (T)(leaf.digA[p] * jbase + leaf.digB[p]) : (T)0;
-        }
-        T* po = tile + ((unsigned)sub * (unsigned)nloc + (unsigned)li) * (unsigned)A.stride;
-        const unsigned step = m * rowW;
-        for (unsigned it = 0; it < nIt; ++it) {
-#pragma unroll
-          for (int p = 0; p < DFX_MAX_DIGITS; ++p)
-            if (p < A.stride) po[p] = (T)(dB[p] + dA[p] * (T)ent);
-          po += step; ec0 += m; ent += m;
-          if (ec0 >= N0) {
-            do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
-            ent = ec0 + cs0 * (ec1 + cs1 * ec2);
-          }
-        }
-      } else {
+      const IdxLi* __restrict__ t = idxTab + li;
+      const unsigned cs0 = __ldg(&t->cs0), cs1 = __ldg(&t->cs1);
+      unsigned ec0 = s0, ec1 = s1, ec2 = s2, it = 0;
+      if (NDIG == 0) {
         // all per-entry arithmetic runs in the output type (wrapping 32-bit multiply-adds give the same bits
         // as 64-bit ones when the true value fits, which the caller checked)
-        const T P0 = (T)(leaf.posA * jbase + leaf.posB);
-        const T S = (T)(leaf.posA * blk);
+        const T P0 = (T)__ldg(&t->P0), S = (T)__ldg(&t->S);
+        const T dv = (T)(S * (T)m);
         T* po = tile + ((unsigned)sub * (unsigned)nloc + (unsigned)li);
         const unsigned step = m * (unsigned)nloc;
-        T v = (T)(P0 + S * (T)ent);
-        const T dv = (T)(S * (T)m);
-        for (unsigned it = 0; it < nIt; ++it) {
-          *po = v;
-          po += step; ec0 += m; v += dv;
-          if (ec0 >= N0) {
-            do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
-            v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
+        while (it < nIt) {
+          unsigned run = A.divM.div(N0 - 1u - ec0) + 1u;         // steps until the walk leaves this element row
+          run = min(run, nIt - it);
+          T v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
+#pragma unroll 4
+          for (unsigned r = 0; r < run; ++r) { *po = v; po += step; v += dv; }
+          it += run; ec0 += run * m;
+          while (ec0 >= N0) { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
+        }
+      } else {
+        constexpr int ND = NDIG > 0 ? NDIG : DFX_MAX_DIGITS;
+        T dB[ND], dA[ND], dv[ND];
+#pragma unroll
+        for (int p = 0; p < ND; ++p) {
+          dA[p] = (T)__ldg(&t->dA[p]); dB[p] = (T)__ldg(&t->dB[p]);
+          dv[p] = (T)(dA[p] * (T)m);
+        }
+        T* po = tile + ((unsigned)sub * (unsigned)nloc + (unsigned)li) * (unsigned)stride;
+        const unsigned step = m * rowW;
+        while (it < nIt) {
+          unsigned run = A.divM.div(N0 - 1u - ec0) + 1u;
+          run = min(run, nIt - it);
+          const T ent = (T)(ec0 + cs0 * (ec1 + cs1 * ec2));
+          T v[ND];
+#pragma unroll
+          for (int p = 0; p < ND; ++p) v[p] = (T)(dB[p] + dA[p] * ent);
+#pragma unroll 2
+          for (unsigned r = 0; r < run; ++r) {
+#pragma unroll
+            for (int p = 0; p < ND; ++p)
+              if (NDIG > 0 || p < stride) { po[p] = v[p]; v[p] += dv[p]; }
+            po += step;
           }
+          it += run; ec0 += run * m;
+          while (ec0 >= N0) { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
         }
       }
     }
+  }
   // ---- the block's run of the table leaves in one piece ----
   T* dst = out + blkEl0 * (u64)rowW;
   const unsigned bytes = nEl * rowW * (unsigned)sizeof(T);
@@ -1030,6 +1045,15 @@ k_indices_tile(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxTileA
   for (unsigned i = threadIdx.x; i < nEl * rowW; i += blockDim.x) dst[i] = tile[i];
 }
 
+template <class T, int NDIG>
+static int launchTileKernel(const dfx_basis* b, const IdxTileArgs& A, size_t smem, u64 blocks, T* out, cudaStream_t st) {
+  auto kern = k_indices_tile<T, NDIG>;
+  static std::atomic<unsigned long long> configured{0};
+  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
+  kern<<<(unsigned)blocks, A.lpb * A.m, smem, st>>>((const DevBasis*)b->dDev, A, (const IdxLi*)b->dIdxTab, out);
+  return postLaunch("k_indices_tile");
+}
+
 template <class T, bool MULTI>
 static int launchIndicesTile(const dfx_basis* b, u64 e0, u64 e1, T* out, int stride, cudaStream_t st) {
   IdxTileArgs A;
@@ -1046,16 +1070,16 @@ static int launchIndicesTile(const dfx_basis* b, u64 e0, u64 e1, T* out, int str
   if ((size_t)epb * rowBytes > 96 * 1024) return -1;                // huge elements: the direct kernel
   A.epb = epb;
   A.divN0 = FastDiv((unsigned)b->dev.grid.N[0]); A.divN1 = FastDiv((unsigned)b->dev.grid.N[1]);
+  A.divM = FastDiv((unsigned)A.m);
   // every full block's run starts at out + blockIdx * epb * rowBytes: aligned if the base and the block pitch are
   A.bulk = (((uintptr_t)out & 15) == 0 && (((size_t)epb * rowBytes) & 15) == 0) ? 1 : 0;
   const u64 blocks = (A.ne + epb - 1) / epb;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
   const size_t smem = (size_t)epb * rowBytes;
-  auto kern = k_indices_tile<T, MULTI>;
-  static std::atomic<unsigned long long> configured{0};
-  if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
-  kern<<<(unsigned)blocks, A.lpb * A.m, smem, st>>>((const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out);
-  return postLaunch("k_indices_tile");
+  if (!MULTI) return launchTileKernel<T, 0>(b, A, smem, blocks, out, st);
+  if (stride == 2) return launchTileKernel<T, 2>(b, A, smem, blocks, out, st);
+  if (stride == 3) return launchTileKernel<T, 3>(b, A, smem, blocks, out, st);
+  return launchTileKernel<T, -1>(b, A, smem, blocks, out, st);
 }
 
 template <class T, bool MULTI, bool ORIENT, bool GATHER>

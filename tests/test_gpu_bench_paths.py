@@ -241,3 +241,34 @@ def test_multi_leaf_evaluation_whole_points(n):
             e0, e1 = 3, b.numElements() - 5
             vs = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, elem_begin=e0, elem_end=e1)
             assert rel(vs.cpu().numpy(), vr[e0:e1]) <= TOL, (name, m)
+
+
+@pytest.mark.parametrize("n", [[128, 70, 3], [256, 65, 2]])
+def test_strip_schedule_of_the_evaluation_blocks(n):
+    """k_eval_reg walks big grids strip by strip (32 element rows through all z-layers) so that z-neighbours
+    share coefficients out of the L2; forced here on grids the oracle runs whole: full strips, a lower last strip,
+    values (128-element blocks) and Jacobians (64-element blocks), whole range and a range of whole layers"""
+    import torch
+    L = capi.lib()
+    grid = dfx.YaspGrid(n, upper=[1.0, 0.75, 1.25])
+    tree = dfx.lagrange(2)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    xr = np.random.default_rng(5).uniform(-1, 1, o.dimension())
+    xt = torch.from_numpy(xr).cuda()
+    pts, _ = tensor_gauss(3, 3)
+    vr, jr = o.evaluate(xr, pts, jacobians=True, nthreads=8)
+    layer = n[0] * n[1]
+    try:
+        for mode in (2, 0):
+            L.dfx_set_kernel_path(capi.OP_TUNE_SWIZZLE, mode)
+            f = dfx.makeDiscreteGlobalBasisFunction(b, xt)
+            v = f.evaluate(pts)
+            assert rel(v.cpu().numpy(), vr) <= TOL, mode
+            v, j = f.evaluate(pts, jacobians=True)
+            assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL, mode
+            if n[2] > 2:
+                v = f.evaluate(pts, elem_begin=layer, elem_end=3 * layer)
+                assert rel(v.cpu().numpy(), vr[layer:3 * layer]) <= TOL, mode
+    finally:
+        L.dfx_set_kernel_path(capi.OP_TUNE_SWIZZLE, -1)

@@ -48,6 +48,25 @@ def main():
             print(json.dumps({"probe": "separable tables", "n": n, "ms": ms, "frac": nd * 8 / ms / 1e6 / PEAK}), flush=True)
             del b, x
             torch.cuda.empty_cache()
+    if "swz" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([512, 512, 512]), dfx.lagrange(2))
+        x = b.newVector(0.0)
+        dfx.interpolate(b, x, dfx.gaussian(1.0))
+        pts, _ = dfx.tensor_gauss(3, 3)
+        v = torch.empty((b.numElements(), 27, 1), dtype=torch.float64, device="cuda")
+        f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+        nb = b.dimension() * 8 + v.numel() * 8
+        for rep in range(2):
+            for swz in (0, 1):
+                for hint in (0, 1):
+                    L.dfx_set_kernel_path(capi.OP_TUNE_SWIZZLE, swz)
+                    L.dfx_set_kernel_path(capi.OP_TUNE_STREAM_HINT, hint)
+                    ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=10)
+                    print(json.dumps({"probe": "eval 512^3", "strip_schedule": swz, "evict_first_stores": hint, "ms": ms, "frac": nb / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SWIZZLE, -1)
+        L.dfx_set_kernel_path(capi.OP_TUNE_STREAM_HINT, -1)
+        del b, x, v, f
+        torch.cuda.empty_cache()
     if "c3" in what:
         b = dfx.makeBasis(dfx.YaspGrid([128, 128, 128]), dfx.taylorHood())
         ne, nl = b.numElements(), b.maxNodeSize()
