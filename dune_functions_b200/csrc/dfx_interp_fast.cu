@@ -527,7 +527,7 @@ static bool gaussianBounded(const DevGrid& g, const dfx_function& fn) {
 }
 // per-node kernels with a compile-time function id (orders 1 and 2 / up to 8 passes of 32 local indices)
 template <int ID>
-static void launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsigned bs, cudaStream_t st, const DevBasis& D, RowArgs A,
+static bool launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsigned bs, cudaStream_t st, const DevBasis& D, RowArgs A,
                            const dfx_function& fn, double* coeff, const uint8_t* mask) {
   RegistryFnT<ID> f; f.f = fn; f.dim = D.grid.dim;
   // LEAN functor: |argument of exp| bounded by 700 over the whole grid box
@@ -539,9 +539,12 @@ static void launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsig
     A.rowsPerBlock = leanRows(nRows);
     const unsigned gridL = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
     if (k == 1) k_interp_rows_lean<RegistryFnT<ID, true>, 1><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
-    else k_interp_rows_lean<RegistryFnT<ID, true>, 2><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
-    return;
+    else if (k == 2) k_interp_rows_lean<RegistryFnT<ID, true>, 2><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
+    else if (k == 3) k_interp_rows_lean<RegistryFnT<ID, true>, 3><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
+    else k_interp_rows_lean<RegistryFnT<ID, true>, 4><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
+    return true;
   }
+  if (k > 2) return false;            // orders 3, 4 outside the lean shape: the run-time-id kernels of the caller
   if (k == 1) {
     if (one) k_interp_rows<RegistryFnT<ID>, 0, 1, true><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
     else k_interp_rows<RegistryFnT<ID>, 0, 1, false><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
@@ -549,6 +552,7 @@ static void launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsig
     if (one) k_interp_rows<RegistryFnT<ID>, 0, 2, true><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
     else k_interp_rows<RegistryFnT<ID>, 0, 2, false><<<grid, bs, 0, st>>>(D, A, f, nullptr, coeff, mask);
   }
+  return true;
 }
 template <int ID>
 static void launchCellNode(int passes, unsigned blocks, cudaStream_t st, const DevGrid& g, const CellArgs& C, const dfx_function& fn,
@@ -645,17 +649,17 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       const unsigned grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
       // threads per block: the row's x-entities split evenly over the fewest <= 256-wide chunks
       // (the generic per-node kernel walks x-entities, only the table kernel and the lean kernel spread the leaves)
-      const bool leanShape = !sep && k <= 2 && mask == nullptr && (A.nActive == 1 || A.interleaved);
+      const bool leanShape = !sep && k <= 4 && mask == nullptr && (A.nActive == 1 || A.interleaved);
       const unsigned nEnt = (unsigned)g.N[0] * (((sep || leanShape) && A.interleaved) ? (unsigned)A.nActive : 1u), chunks = (nEnt + 255) / 256;
       const unsigned bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);
       // per-node evaluation with the function id known at compile time for the functions the BASELINE
       // configs interpolate (no switch in the node loop); everything else dispatches on f.id at run time
       bool launched = false;
-      if (!sep && k <= 2) {
+      if (!sep && (k <= 2 || leanShape)) {
         switch (fn.id) {
-          case DFX_FN_GAUSSIAN: launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
-          case DFX_FN_QUADRATIC: launchRowsNode<DFX_FN_QUADRATIC>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
-          case DFX_FN_IDENTITY: launchRowsNode<DFX_FN_IDENTITY>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); launched = true; break;
+          case DFX_FN_GAUSSIAN: launched = launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); break;
+          case DFX_FN_QUADRATIC: launched = launchRowsNode<DFX_FN_QUADRATIC>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); break;
+          case DFX_FN_IDENTITY: launched = launchRowsNode<DFX_FN_IDENTITY>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); break;
           default: break;
         }
       }

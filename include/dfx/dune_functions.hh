@@ -598,10 +598,62 @@ template <class R, class B, class C> class DiscreteGlobalBasisFunction;
 namespace Impl {
 template <class T> struct IsDiscreteGlobalBasisFunction : std::false_type {};
 template <class R, class B, class C> struct IsDiscreteGlobalBasisFunction<DiscreteGlobalBasisFunction<R, B, C>> : std::true_type {};
-// flat view of a range value: scalar or anything indexable (HierarchicNodeToRangeMap + flatVectorView)
-template <class Y> double rangeEntry(const Y& y, int leaf, int nLeaves) {
-  if constexpr (std::is_arithmetic_v<Y>) { (void)leaf; (void)nLeaves; return (double)y; }
-  else return (double)y[leaf];
+template <class T> struct IsStdTuple : std::false_type {};
+template <class... T> struct IsStdTuple<std::tuple<T...>> : std::true_type {};
+// flatVectorView(entry)[0] (flatvectorview.hh:27-222): the first scalar of a range entry in flat lexicographic
+// order — FieldMatrix row-major (:63-78), so [0][0]; a scalar is its own view.  Every leaf in scope is a
+// scalar-valued Lagrange element, whose one range component lands there.
+template <class Y> decltype(auto) flatFirst(Y& y) {
+  if constexpr (std::is_arithmetic_v<std::remove_cv_t<Y>>) return (y);
+  else if constexpr (IsStdTuple<std::remove_cv_t<Y>>::value) return flatFirst(std::get<0>(y));
+  else return flatFirst(y[0]);
+}
+// HierarchicNodeToRangeMap (hierarchicnodetorangemap.hh:33-48): the leaf with tree path (i0, ..., in) — relative
+// to the root of the interpolated (sub)tree — takes y[i0]...[in] (resolveStaticMultiIndex); a range without
+// index access is forwarded whole for all nodes.  std::tuple levels (TupleVector-like ranges such as
+// tuple<FieldVector<double,3>, double> of examples/stokes-taylorhood.cc) are indexed by position.  The visitor
+// receives the scalar the leaf's single range component maps to (flatVectorView of the entry).
+template <class Y, class Visitor>
+void visitRangeEntry(Y& y, const int* path, int len, Visitor&& visit) {
+  using T = std::remove_cv_t<Y>;
+  if constexpr (std::is_arithmetic_v<T>) { (void)path; (void)len; visit(y); }
+  else if (len == 0) visit(flatFirst(y));
+  else if constexpr (IsStdTuple<T>::value) {
+    bool found = false;
+    int i = 0;
+    std::apply([&](auto&... e) { ((i++ == path[0] ? (void)(found = true, visitRangeEntry(e, path + 1, len - 1, visit)) : (void)0), ...); }, y);
+    if (!found) throw RangeError("tree path leaves the range type (tuple index " + std::to_string(path[0]) + ")");
+  } else {
+    if ((std::size_t)path[0] >= y.size()) throw RangeError("tree path leaves the range type (index " + std::to_string(path[0]) + ")");
+    visitRangeEntry(y[path[0]], path + 1, len - 1, visit);
+  }
+}
+template <class Y> double rangeEntry(const Y& y, const std::vector<int>& path) {
+  double r = 0;
+  visitRangeEntry(y, path.data(), (int)path.size(), [&](const auto& v) { r = (double)v; });
+  return r;
+}
+template <class Y> void assignRangeEntry(Y& y, const std::vector<int>& path, double value) {
+  visitRangeEntry(y, path.data(), (int)path.size(), [&](auto& v) { v = (std::remove_reference_t<decltype(v)>)value; });
+}
+// tree paths of the leaves below `node`, relative to it, in leaf order (TypeTree::forEachLeafNode)
+inline void collectLeafPaths(const dfx_basis* h, int node, std::vector<int>& prefix, std::vector<std::vector<int>>& out) {
+  int off, size, firstLeaf, nLeaves;
+  check(dfx_basis_node_info(h, node, &off, &size, &firstLeaf, &nLeaves));
+  if (dfx_basis_node_child(h, node, 0) < 0) { out.push_back(prefix); return; }
+  for (int c = 0;; ++c) {
+    const int child = dfx_basis_node_child(h, node, c);
+    if (child < 0) break;
+    prefix.push_back(c);
+    collectLeafPaths(h, child, prefix, out);
+    prefix.pop_back();
+  }
+}
+inline std::vector<std::vector<int>> leafPaths(const dfx_basis* h, int node) {
+  std::vector<std::vector<int>> out;
+  std::vector<int> prefix;
+  collectLeafPaths(h, node, prefix, out);
+  return out;
 }
 template <class C> double* coeffData(C& c, std::size_t n) {
   using V = typename C::value_type;
@@ -783,12 +835,13 @@ void interpolate(const B& basis, C&& coeff, const F& f, const BV& bv) {
     Impl::check(dfx_interpolation_points_host(h, xyz.data(), leaf.data()));
     int off, size, firstLeaf, nLeaves;
     Impl::check(dfx_basis_node_info(h, basis.rootNode(), &off, &size, &firstLeaf, &nLeaves));
+    const auto paths = Impl::leafPaths(h, basis.rootNode());      // HierarchicNodeToRangeMap: leaf -> y[treePath]
     for (std::size_t p = 0; p < n; ++p) {
       const int l = leaf[p] - firstLeaf;
       if (l < 0 || l >= nLeaves || (mask && !mask[p])) continue;
       FieldVector<double, dim> pos;
       for (int j = 0; j < dim; ++j) pos[j] = xyz[p * dim + j];
-      x[p] = Impl::rangeEntry(f(pos), l, nLeaves);
+      x[p] = Impl::rangeEntry(f(pos), paths[l]);
     }
   }
   }
@@ -1010,6 +1063,17 @@ class DiscreteGlobalBasisFunction {
   friend LocalFunction localFunction(const DiscreteGlobalBasisFunction& f) { return LocalFunction(f); }
   int numComponents() const { return ncomp_; }
   const B& basis() const { return basis_; }
+  // The value as the Range type R of makeDiscreteGlobalBasisFunction<R> (discreteglobalbasisfunction.hh:358-368):
+  // leaf l of the (sub)tree contributes to nodeToRangeEntry(node, treePath, y), i.e. y[i0]...[in] for its tree
+  // path — nested ranges such as tuple<FieldVector<double,3>, double> or FieldMatrix<double,2,2> included.
+  using Range = R;
+  R toRange(const std::vector<double>& flatEntries) const {
+    R y{};
+    const auto paths = Impl::leafPaths(basis_.handle(), basis_.rootNode());
+    for (std::size_t l = 0; l < paths.size() && l < flatEntries.size(); ++l) Impl::assignRangeEntry(y, paths[l], flatEntries[l]);
+    return y;
+  }
+  R range(const Domain& xGlobal) const { return toRange((*this)(xGlobal)); }
   // flat container order of the coefficients: the container itself if it is one contiguous run, else its
   // flat image, rebuilt at every use because the vector is referenced, not copied (:389-395)
   const double* coefficientData() const {

@@ -295,6 +295,45 @@ int main() {
       makeDiscreteGlobalBasisFunction<FieldVector<double, 3>>(subspaceBasis(th, Indices::_0), x).evaluateAll(pts, vn);
       makeDiscreteGlobalBasisFunction<FieldVector<double, 3>>(subspaceBasis(th, Indices::_0), flat).evaluateAll(pts, vf);
       CHECK(vn == vf && !vn.empty(), "DiscreteGlobalBasisFunction over a nested coefficient container");
+      // HierarchicNodeToRangeMap on a nested range (hierarchicnodetorangemap.hh:33-48): the WHOLE Taylor-Hood tree
+      // with f returning tuple<FieldVector<double,3>, double> — leaf (0, c) takes get<0>(y)[c], leaf (1) takes
+      // get<1>(y) (the range type of examples/stokes-taylorhood.cc:419-438) — equals the two sub-space calls
+      {
+        using Range = std::tuple<FieldVector<double, 3>, double>;
+        auto both = [&](const FieldVector<double, 3>& p) { return Range{velocity(p), pressure(p)}; };
+        std::vector<double> whole;
+        interpolate(th, whole, both);
+        CHECK(whole == flat, "interpolate(tree, f -> tuple<FieldVector<3>, double>) resolves y[treePath]");
+        VectorType xw;
+        interpolate(th, xw, both);
+        CHECK(std::get<0>(xw) == std::get<0>(x) && std::get<1>(xw) == std::get<1>(x), "the same into the nested container");
+        // and back: the typed Range of the discrete function of the whole tree
+        auto uh = makeDiscreteGlobalBasisFunction<Range>(th, flat);
+        const FieldVector<double, 3> xg{0.4, 0.55, 0.3};
+        const Range y = uh.range(xg);
+        const auto flatValues = uh(xg);
+        CHECK(flatValues.size() == 4, "four range entries");
+        CHECK(std::get<0>(y)[0] == flatValues[0] && std::get<0>(y)[1] == flatValues[1] && std::get<0>(y)[2] == flatValues[2] &&
+              std::get<1>(y) == flatValues[3], "DiscreteGlobalBasisFunction<tuple<FieldVector<3>, double>>::range assigns y[treePath]");
+        // velocity (p1, -p0, p2 p0) is reproduced exactly by Q2, the pressure by Q1
+        CHECK(std::abs(std::get<0>(y)[0] - xg[1]) < 1e-13 && std::abs(std::get<0>(y)[2] - xg[2] * xg[0]) < 1e-13 &&
+              std::abs(std::get<1>(y) - (xg[0] + 2 * xg[1])) < 1e-13, "values of the typed range");
+      }
+      // power<2>(power<2>(lagrange<1>)): tree path (i, j) -> y[i][j], a FieldMatrix range (row-major, flatvectorview.hh:63-78)
+      {
+        auto pp = makeBasis(gv3, power<2>(power<2>(lagrange<1>(), flatInterleaved()), flatLexicographic()));
+        auto m = [](const FieldVector<double, 3>& p) { return FieldMatrix<double, 2, 2>{{{p[0], p[1]}, {p[2], 1.0 + p[0] * p[1]}}}; };
+        std::vector<double> xm, xs(pp.dimension(), 0.0);
+        interpolate(pp, xm, m);
+        interpolate(subspaceBasis(pp, Indices::_0, Indices::_0), xs, [](const FieldVector<double, 3>& p) { return p[0]; });
+        interpolate(subspaceBasis(pp, Indices::_0, Indices::_1), xs, [](const FieldVector<double, 3>& p) { return p[1]; });
+        interpolate(subspaceBasis(pp, Indices::_1, Indices::_0), xs, [](const FieldVector<double, 3>& p) { return p[2]; });
+        interpolate(subspaceBasis(pp, Indices::_1, Indices::_1), xs, [](const FieldVector<double, 3>& p) { return 1.0 + p[0] * p[1]; });
+        CHECK(xm == xs && !xm.empty(), "FieldMatrix range: leaf (i, j) takes y[i][j]");
+        auto um = makeDiscreteGlobalBasisFunction<FieldMatrix<double, 2, 2>>(pp, xm);
+        const auto ym = um.range(FieldVector<double, 3>{0.25, 0.5, 0.75});
+        CHECK(std::abs(ym[0][0] - 0.25) < 1e-13 && std::abs(ym[0][1] - 0.5) < 1e-13 && std::abs(ym[1][0] - 0.75) < 1e-13, "FieldMatrix range of the discrete function");
+      }
       // masked interpolation with a nested bit vector of the same shape
       std::tuple<std::vector<std::array<char, 3>>, std::vector<char>> bits;
       std::get<0>(bits).assign(n2, std::array<char, 3>{1, 0, 1});

@@ -96,7 +96,38 @@ double integrateGridViewFunction(const GridView& gridView, const F& f) {
 }
 static double x_component_A(const FieldVector<double, 2>& x) { return x[0]; }
 
+// HierarchicNodeToRangeMap + flatVectorView on nested range types (hierarchicnodetorangemap.hh:33-48,
+// flatvectorview.hh:63-100): pure host templates, checked without a device
+static void checkNodeToRangeMap() {
+  using namespace Dune::Functions::Impl;
+  using TH = std::tuple<FieldVector<double, 3>, double>;
+  const TH y{FieldVector<double, 3>{1.0, 2.0, 3.0}, 4.0};
+  CHECK(rangeEntry(y, {0, 0}) == 1.0 && rangeEntry(y, {0, 2}) == 3.0 && rangeEntry(y, {1}) == 4.0, "tuple<FieldVector<3>, double>[treePath]");
+  CHECK(rangeEntry(5.5, {0, 1}) == 5.5 && rangeEntry(5.5, {}) == 5.5, "a range without index access is used whole");
+  const FieldMatrix<double, 2, 3> m{{{1, 2, 3}, {4, 5, 6}}};
+  CHECK(rangeEntry(m, {1, 2}) == 6.0 && rangeEntry(m, {0, 1}) == 2.0, "FieldMatrix[i][j]");
+  CHECK(rangeEntry(m, {1}) == 4.0 && rangeEntry(m, {}) == 1.0, "a path that ends early takes the flat view's first entry (row-major)");
+  const std::array<FieldVector<double, 2>, 2> a{{FieldVector<double, 2>{1, 2}, FieldVector<double, 2>{3, 4}}};
+  CHECK(rangeEntry(a, {1, 0}) == 3.0, "array<FieldVector<2>, 2>[i][j]");
+  const FieldVector<double, 1> one{7.0};
+  CHECK(rangeEntry(one, {}) == 7.0, "FieldVector<double,1> as a scalar entry");
+  bool threw = false;
+  try { rangeEntry(y, {2}); } catch (const RangeError&) { threw = true; }
+  CHECK(threw, "tree path beyond the tuple throws RangeError");
+  threw = false;
+  try { rangeEntry(m, {2, 0}); } catch (const RangeError&) { threw = true; }
+  CHECK(threw, "tree path beyond the matrix rows throws RangeError");
+  TH z{};
+  assignRangeEntry(z, {0, 1}, 2.5);
+  assignRangeEntry(z, {1}, -1.0);
+  CHECK(std::get<0>(z)[1] == 2.5 && std::get<0>(z)[0] == 0.0 && std::get<1>(z) == -1.0, "assignment into y[treePath]");
+  double s = 0;
+  assignRangeEntry(s, {0, 0}, 3.0);
+  CHECK(s == 3.0, "assignment into a scalar range");
+}
+
 int main() {
+  checkNodeToRangeMap();
   using Grid = YaspGrid<2>;
   Grid grid(FieldVector<double, 2>(1.0), {{2, 2}});
   auto gv = grid.leafGridView();
