@@ -33,6 +33,7 @@ int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* x
                  FastPlan& plan);
 bool smemPathHas(int dim, int k, int m);
 extern int g_smemGrad;
+extern int g_smemTma;
 extern int g_evalSwizzle;
 extern int g_evalStreamHint;
 bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);

@@ -725,6 +725,38 @@ def test_halo_pack_unpack_and_owned_ranges():
 
 
 @pytest.mark.parametrize("k", [2, 3, 4, 5])
+@pytest.mark.parametrize("last_fastest", [True, False])
+def test_evaluate_shared_memory_tma_pair_loads(kernel_path, k, last_fastest):
+    """element-local DOFs: the coefficients of element pairs arrive by TMA bulk loads (two buffers per warp,
+    mbarrier completion); both point orders (the permuted one reads the natural layout with a stride), values and —
+    forced — gradients, several pairs per warp, ranges that start on an even / odd element (the odd one is not
+    16-byte aligned and takes the register path)"""
+    import torch
+    L = capi.lib()
+    grid = YaspGrid([6, 5, 4], upper=[1.0, 2.0, 0.5])
+    tree = lagrangeDG(k)
+    b = dfx.makeBasis(grid, tree)
+    o = orc.OracleBasis(grid, tree)
+    c = random_coeff(b.dimension())
+    f = dfx.makeDiscreteGlobalBasisFunction(b, torch.from_numpy(c).cuda())
+    ne = b.numElements()
+    kernel_path(capi.OP_EVALUATE, 2)
+    try:
+        for m in (k + 1, k + 2):
+            pts, _ = tensor_gauss(3, m, last_fastest)
+            vr, jr = o.evaluate(c, pts, jacobians=True)
+            for mode in (2, 1, 0):
+                L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, mode)
+                v, j = f.evaluate(pts, jacobians=True)
+                assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL, (m, mode)
+                assert rel(f.evaluate(pts).cpu().numpy(), vr) <= TOL, (m, mode)
+                for e0, e1 in ((2, ne), (1, ne - 1), (4, 6)):
+                    assert rel(f.evaluate(pts, elem_begin=e0, elem_end=e1).cpu().numpy(), vr[e0:e1]) <= TOL, (m, mode, e0)
+    finally:
+        L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, -1)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
 @pytest.mark.parametrize("dm", [-1, 0, 1])
 @pytest.mark.parametrize("last_fastest", [True, False])
 def test_evaluate_shared_memory_path(kernel_path, k, dm, last_fastest):

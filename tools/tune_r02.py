@@ -100,6 +100,26 @@ def main():
         L.dfx_set_kernel_path(capi.OP_INDICES, -1)
         del b, idx
         torch.cuda.empty_cache()
+    if "c4eval" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
+        x = b.newVector(0.0).uniform_(-1, 1)
+        ne = b.numElements()
+        pts, _ = dfx.tensor_gauss(3, 5)
+        v = torch.empty((ne, 125, 1), dtype=torch.float64, device="cuda")
+        j = torch.empty((ne, 125, 1, 3), dtype=torch.float64, device="cuda")
+        f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+        nbv = b.dimension() * 8 + v.numel() * 8
+        nbj = nbv + j.numel() * 8
+        for rep in range(2):
+            for tma in (0, 1):
+                L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, tma)
+                ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=5)
+                print(json.dumps({"probe": "DG4 192^3 values", "tma_pair_loads": tma, "ms": ms, "frac": nbv / ms / 1e6 / PEAK}), flush=True)
+                ms = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), reps=5)
+                print(json.dumps({"probe": "DG4 192^3 values+gradients", "tma_pair_loads": tma, "ms": ms, "frac": nbj / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, -1)
+        del b, x, v, j, f
+        torch.cuda.empty_cache()
     if "dg4" in what or "jac" in what:
         b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
         x = b.newVector(0.0)
