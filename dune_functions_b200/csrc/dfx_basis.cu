@@ -85,8 +85,13 @@ static std::shared_ptr<PreNode> parseTree(const DevGrid& g, const dfx_tree_node*
     case DFX_NODE_LAGRANGE:
       // RangeError of LagrangePreBasis ctor, lagrangebasis.hh:789-796
       if (nd.order < 0) { err = DFX_ERR_RANGE; msg = "Lagrange order must be >= 0"; return nullptr; }
+      // :795 restricts order > 17 in 3-d only ("in 1d and 2d any order is supported"); here the bound holds in every
+      // dimension: the kernels' per-direction tables and the packed lattice multi-indices are sized for it
+      // (documented in include/dfx.h, dfx_basis_create)
       if (nd.order > kMaxContinuousOrder) {
-        err = DFX_ERR_RANGE; msg = "Polynomial order >17 is not supported"; return nullptr; }
+        err = DFX_ERR_RANGE;
+        msg = g.dim == 3 ? "Polynomial order >17 is not supported" : "Polynomial order >17 is not supported by this library (kernel table bound; the reference restricts 3-d only)";
+        return nullptr; }
       return p;
     case DFX_NODE_LAGRANGE_DG:
       if (nd.order < 0 || nd.order > kMaxDGOrder) { err = DFX_ERR_RANGE; msg = "LagrangeDG order out of range"; return nullptr; }

@@ -140,7 +140,10 @@ const char* dfx_last_error(void);
 uint64_t    dfx_kernel_launch_count(void);
 
 /* makeBasis(gridView, preBasisFactory): defaultglobalbasis.hh:205-209, ctor :89-95.
- * `device` is the CUDA ordinal the handle is bound to.                        */
+ * `device` is the CUDA ordinal the handle is bound to.
+ * Deliberate restrictions (DFX_ERR_RANGE): continuous Lagrange order <= 17 in EVERY dimension (the reference
+ * restricts 3-d only, lagrangebasis.hh:795; the kernels' tables are sized for 17), LagrangeDG order <= 12,
+ * at most DFX_MAX_LEAVES leaves and DFX_MAX_DIGITS multi-index digits.                                  */
 int  dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_host,
                       int32_t n_nodes, int32_t device, dfx_basis** out);
 void dfx_basis_destroy(dfx_basis* b);

@@ -81,11 +81,9 @@ def main():
         basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.lagrange(k))
         x = basis.newVector(0.0)
         nd = basis.dimension()
-        for mode, label in ((-1, "separable tables"), (1, "f at every node")):
-            L.dfx_set_kernel_path(capi.OP_INTERPOLATE, mode)
-            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0)), args.reps)
+        for sep, label in ((True, "separable tables (opt-in)"), (False, "f at every node")):
+            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0), separable=sep), args.reps)
             report("interpolate exp(-|x|^2) [" + label + "]", cfg, ms, best, nd * 8, {"dofs_per_s": nd / ms * 1e3})
-        L.dfx_set_kernel_path(capi.OP_INTERPOLATE, -1)
         ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.quadratic(0.5, [1, 2, 3], [1, 2, 3, 4, 5, 6])), args.reps)
         report("interpolate quadratic [f at every node]", cfg, ms, best, nd * 8, {"dofs_per_s": nd / ms * 1e3})
         m = 3 if k <= 2 else k + 1
@@ -158,7 +156,15 @@ def main():
             dfx.interpolate(vel, x, dfx.identity(3))
             dfx.interpolate(pre, x, dfx.gaussian(1.0))
         ms, best = timeit(interp, args.reps)
-        report("interpolate velocity x + pressure exp", "c3", ms, best, basis.dimension() * 8)
+        report("interpolate velocity x + pressure exp [two calls]", "c3", ms, best, basis.dimension() * 8)
+        ms, best = timeit(lambda: dfx.interpolateBatch(basis, x, [(vel, dfx.identity(3)), (pre, dfx.gaussian(1.0))]), args.reps)
+        report("interpolate velocity x + pressure exp [dfx_interpolate_batch, one launch]", "c3", ms, best, basis.dimension() * 8)
+        fw = dfx.makeDiscreteGlobalBasisFunction(basis, x)
+        v4 = torch.empty((ne, 27, 4), dtype=torch.float64, device="cuda")
+        pts3, _ = dfx.tensor_gauss(3, 3)
+        ms, best = timeit(lambda: fw.evaluate(pts3, out_values=v4), args.reps)
+        report("evaluate whole tree (3 x Q2 + Q1) values 3^3 [one launch, whole points]", "c3", ms, best, basis.dimension() * 8 + v4.numel() * 8)
+        del v4, fw
         pts, _ = dfx.tensor_gauss(3, 3)
         fv = dfx.makeDiscreteGlobalBasisFunction(vel, x)
         v = torch.empty((ne, 27, 3), dtype=torch.float64, device="cuda")
@@ -172,11 +178,9 @@ def main():
         basis = dfx.makeBasis(dfx.YaspGrid(n), dfx.lagrangeDG(4))
         x = basis.newVector(0.0)
         nd, ne = basis.dimension(), basis.numElements()
-        for mode, label in ((-1, "separable tables"), (1, "f at every node")):
-            L.dfx_set_kernel_path(capi.OP_INTERPOLATE, mode)
-            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0)), args.reps)
+        for sep, label in ((True, "separable tables (opt-in)"), (False, "f at every node")):
+            ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0), separable=sep), args.reps)
             report("interpolate DG4 exp(-|x|^2) [" + label + "]", "c4", ms, best, nd * 8)
-        L.dfx_set_kernel_path(capi.OP_INTERPOLATE, -1)
         x.uniform_(-1, 1)
         pts, _ = dfx.tensor_gauss(3, 5)
         f = dfx.makeDiscreteGlobalBasisFunction(basis, x)

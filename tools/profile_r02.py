@@ -14,12 +14,24 @@ import dune_functions_b200 as dfx  # noqa: E402
 from dune_functions_b200 import _capi as capi  # noqa: E402
 
 L = capi.lib()
-which = set(sys.argv[1:]) or {"c5w", "c3", "c4"}
+which = set(sys.argv[1:]) or {"c5w", "c2", "c3", "c4"}
 st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
 REPS = int(os.environ.get("DFX_PROFILE_REPS", "1"))
 
 if "c5w" in which:
     b = dfx.makeBasis(dfx.YaspGrid([512, 512, 512]), dfx.lagrange(2))
+    x = b.newVector(0.0)
+    pts, _ = dfx.tensor_gauss(3, 3)
+    v = torch.empty((b.numElements(), 27, 1), dtype=torch.float64, device="cuda")
+    f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+    for _ in range(REPS):
+        dfx.interpolate(b, x, dfx.gaussian(1.0))
+        f.evaluate(pts, out_values=v)
+    torch.cuda.synchronize()
+    del b, x, v, f
+    torch.cuda.empty_cache()
+if "c2" in which:
+    b = dfx.makeBasis(dfx.YaspGrid([256, 256, 256]), dfx.lagrange(2))
     x = b.newVector(0.0)
     pts, _ = dfx.tensor_gauss(3, 3)
     v = torch.empty((b.numElements(), 27, 1), dtype=torch.float64, device="cuda")
