@@ -52,15 +52,18 @@ WORKLOADS = {
                 desc="LagrangeBasis Q2, 3-d YaspGrid 512^3 per GPU (z-slabs; ~1.08e9 DOFs per GPU), interpolate exp(-|x|^2) "
                      "at every node + DiscreteGlobalBasisFunction eval at 3^3 Gauss points"),
 }
+WORKLOADS["q3"] = dict(n=[128, 128, 128], tree="lagrange3", m=4, jac=False, scaling="weak",
+                       desc="(not a BASELINE config; SURVEY.md section 8(f) row 3's base case) LagrangeBasis Q3, 3-d YaspGrid 128^3 per GPU, "
+                            "interpolate exp(-|x|^2) at every node + eval at 4^3 Gauss points")
 HEADLINE = "c5w"
-SUB_CONFIGS = ("c2", "c3", "c4")
+SUB_CONFIGS = ("c2", "c3", "c4", "q3")
 METRIC = "DOFs/s through interpolate + DiscreteGlobalBasisFunction evaluation (FP64)"
 TOL = 1e-12
 
 
 def make_tree(name):
     import dune_functions_b200 as dfx
-    return {"lagrange1": lambda: dfx.lagrange(1), "lagrange2": lambda: dfx.lagrange(2),
+    return {"lagrange1": lambda: dfx.lagrange(1), "lagrange2": lambda: dfx.lagrange(2), "lagrange3": lambda: dfx.lagrange(3),
             "taylorhood": lambda: dfx.taylorHood(), "lagrangedg4": lambda: dfx.lagrangeDG(4)}[name]()
 
 
@@ -445,7 +448,7 @@ class Runner:
         torch = self.torch
         basis, ne = self.basis, self.ne
         if count is None:
-            count = {"lagrangedg4": 4096, "taylorhood": 8192}.get(self.wl["tree"], 32768)
+            count = {"lagrangedg4": 4096, "taylorhood": 8192, "lagrange3": 8192}.get(self.wl["tree"], 32768)
         count = min(count, ne)
         count -= count % 128 if count >= 128 else 0
         starts = sorted({0, ((ne - count) // 2) // 128 * 128, ne - count})[:n_ranges]

@@ -368,6 +368,103 @@ k_interp_rows_lean2(const __grid_constant__ DevBasis B, const __grid_constant__ 
   else leanRowsBody<FB, KTB>(B, A2, fb, coeff, blockIdx.x - blocksA, rows);
 }
 
+// ---- per-node evaluation for continuous orders >= 3: sweep RUNS of the numbering, not lattice rows ----------
+// For order k >= 3 an edge / facet / element carries (k-1)^m interior DOFs that the reference numbers entity by
+// entity (dofLayout, lagrangebasis.hh:747-762), so a lattice row touches 16 of every 64 bytes of the interior
+// component and 4 different rows complete a sector.  In every index-set component the entities of one
+// (c1, c2) row are consecutive, so their DOFs form ONE contiguous run of csize[s][0] * blk[s] entries: a block
+// takes a few such runs of one component, thread (tx, ty) owns in-entity DOF fr = tx % blk — its lattice offsets
+// (a0, a1, a2) are constants — and x-entities tx / blk, + TX / blk, ...; the x-coordinate is computed once per
+// (thread, x-entity) and swept over the block's runs, whose y / z node coordinates sit in shared memory.  Every
+// warp store is 256 contiguous bytes.
+struct RunArgs {
+  int layoutId, leafId, comp;
+  int runsPerBlock[8];          // per component (index = shift mask s)
+  unsigned blockStart[9];       // first block of component order[q], q = 0 .. ncomp
+  FastDiv divBlk[8], divCs1[8];
+};
+constexpr int kRunRows = 32;
+template <int K> struct RunRow { double* base; double y[K - 1], z[K - 1]; };
+
+template <class F, int K, int TX, int TY>
+__global__ void __launch_bounds__(TX * TY)
+k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArgs A, const __grid_constant__ F f,
+              double* __restrict__ coeff) {
+  __shared__ RunRow<K> rows[kRunRows];
+  const DevGrid& g = B.grid;
+  const DevLayout& L = B.layouts[A.layoutId];
+  const DevLeaf& leaf = B.leaves[A.leafId];
+  // component of this block
+  int q = 0;
+  while (q + 1 < L.ncomp && blockIdx.x >= A.blockStart[q + 1]) ++q;
+  const int s = L.order[q];
+  const unsigned blk = (unsigned)L.blk[s];
+  const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1], cs2 = (unsigned)L.csize[s][2];
+  const unsigned nRuns = cs1 * cs2;
+  const unsigned R = (unsigned)A.runsPerBlock[s];
+  const unsigned row0 = (blockIdx.x - A.blockStart[q]) * R;
+  const unsigned nr = min(R, nRuns - row0);
+  const unsigned tid = threadIdx.y * TX + threadIdx.x;
+  // coordinate of node `a` (1 .. K-1) of entity c along a free direction / of lattice plane c along a pinned one
+  auto freeCoord = [&](int j, unsigned c, int a) { return elementGlobal(g, j, g.off[j] + (int)c, xhatOf<K>(a)); };
+  auto planeCoord = [&](int j, unsigned c) {
+    // shared by the elements on both sides: the later one in iteration order writes last (interpolate.hh:254-259)
+    const int gc = g.off[j] + (int)c;
+    return gc < g.G[j] ? elementGlobal(g, j, gc, 0.0) : elementGlobal(g, j, g.G[j] - 1, 1.0);
+  };
+  if (tid < nr) {
+    unsigned c1, c2;
+    A.divCs1[s].divmod(row0 + tid, c2, c1);
+    RunRow<K> r;
+    const u64 j0 = L.compOffset[s] + (u64)blk * ((u64)cs0 * ((u64)c1 + (u64)cs1 * (u64)c2));
+    r.base = coeff + (leaf.posA * j0 + leaf.posB);
+#pragma unroll
+    for (int a = 1; a < K; ++a) {
+      r.y[a - 1] = g.dim > 1 ? ((s & 2) ? freeCoord(1, c1, a) : planeCoord(1, c1)) : 0.0;
+      r.z[a - 1] = g.dim > 2 ? ((s & 4) ? freeCoord(2, c2, a) : planeCoord(2, c2)) : 0.0;
+    }
+    rows[tid] = r;
+  }
+  // this thread's in-entity DOF: digits of fr over the free directions, x first (LocalKey::index order)
+  unsigned fr = threadIdx.x % blk;
+  int a0 = 0, yi = 0, zi = 0;
+  if (s & 1) { a0 = 1 + (int)(fr % (K - 1)); fr /= (K - 1); }
+  if (s & 2) { yi = (int)(fr % (K - 1)); fr /= (K - 1); }
+  if (s & 4) { zi = (int)(fr % (K - 1)); }
+  const unsigned stride8 = (unsigned)leaf.posA * 8u;
+  const int comp = f.ncomp() == 1 ? 0 : A.comp;
+  const unsigned len = cs0 * blk;
+  const unsigned mainLen = len - len % TX;       // whole passes of TX entries; the rest (a few entries of the closing
+                                                 // lattice plane when x is pinned) goes item by item below
+  __syncthreads();
+  for (unsigned u = threadIdx.x; u < mainLen; u += TX) {
+    const unsigned c0 = A.divBlk[s].div(u);
+    const double x = (s & 1) ? freeCoord(0, c0, a0) : planeCoord(0, c0);
+    const size_t off = (size_t)stride8 * u;
+#pragma unroll 4
+    for (unsigned r = threadIdx.y; r < nr; r += TY) {
+      const RunRow<K>& row = rows[r];
+      const double y = row.y[yi], z = row.z[zi];
+      *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, f.common(x, y, z), x, y, z);
+    }
+  }
+  // ---- the last len % TX entries of every run: one (run, entry) item per thread ----
+  const unsigned rem = len - mainLen;
+  for (unsigned t = tid; t < rem * nr; t += TX * TY) {
+    const unsigned r = t / rem, u = mainLen + (t - r * rem);
+    const unsigned c0 = A.divBlk[s].div(u);
+    unsigned fu = u - c0 * blk;
+    int b0 = 0, yj = 0, zj = 0;
+    if (s & 1) { b0 = 1 + (int)(fu % (K - 1)); fu /= (K - 1); }
+    if (s & 2) { yj = (int)(fu % (K - 1)); fu /= (K - 1); }
+    if (s & 4) { zj = (int)(fu % (K - 1)); }
+    const double x = (s & 1) ? freeCoord(0, c0, b0) : planeCoord(0, c0);
+    const RunRow<K>& row = rows[r];
+    const double y = row.y[yj], z = row.z[zj];
+    *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + (size_t)stride8 * u) = f.comp(comp, f.common(x, y, z), x, y, z);
+  }
+}
+
 struct CellArgs {
   int k, dim, nloc;              // direct copies: no indexed-constant loads in the kernel
   int off[3];
@@ -574,6 +671,38 @@ static void launchCellNode(int passes, unsigned blocks, cudaStream_t st, const D
   else k_interp_cell<RegistryFnT<ID>, 0, 8, false><<<blocks, kCellWarps * 32, 0, st>>>(g, C, f, nullptr, coeff, mask);
 }
 
+// continuous orders 3 .. 5, one leaf, no mask: the run sweep (k_interp_runs)
+template <int ID>
+static bool launchRunsNode(const DevBasis& D, int q, int leafId, int comp, const dfx_function& fn, double* coeff, cudaStream_t st) {
+  const DevLayout& L = D.layouts[q];
+  const int k = L.k;
+  if (k < 3 || k > 5) return false;
+  if ((fn.id == DFX_FN_GAUSSIAN || fn.id == DFX_FN_GAUSSIAN_VEC) && !gaussianBounded(D.grid, fn)) return false;
+  RunArgs A;
+  A.layoutId = q; A.leafId = leafId; A.comp = comp;
+  u64 blocks = 0;
+  for (int s = 0; s < 8; ++s) { A.runsPerBlock[s] = 1; A.divBlk[s] = FastDiv(1); A.divCs1[s] = FastDiv(1); }
+  for (int qq = 0; qq < L.ncomp; ++qq) {
+    const int s = L.order[qq];
+    const u64 len = (u64)L.csize[s][0] * (u64)L.blk[s];
+    const u64 runs = (u64)L.csize[s][1] * (u64)L.csize[s][2];
+    const int R = (int)std::max<u64>(1, std::min<u64>(kRunRows, 8192 / std::max<u64>(1, len)));
+    A.runsPerBlock[s] = R;
+    A.blockStart[qq] = (unsigned)blocks;
+    blocks += (runs + R - 1) / R;
+    A.divBlk[s] = FastDiv((unsigned)L.blk[s]);
+    A.divCs1[s] = FastDiv((unsigned)std::max(1, L.csize[s][1]));
+    if (len > 0xffffffffull || runs > 0xffffffffull) return false;
+  }
+  for (int qq = L.ncomp; qq <= 8; ++qq) A.blockStart[qq] = (unsigned)blocks;
+  if (blocks == 0 || blocks > 0x7fffffffull) return false;
+  RegistryFnT<ID, true> f; f.f = fn; f.dim = D.grid.dim;
+  if (k == 3) k_interp_runs<RegistryFnT<ID, true>, 3, 128, 2><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+  else if (k == 4) k_interp_runs<RegistryFnT<ID, true>, 4, 108, 2><<<(unsigned)blocks, dim3(108, 2), 0, st>>>(D, A, f, coeff);
+  else k_interp_runs<RegistryFnT<ID, true>, 5, 128, 2><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+  return true;
+}
+
 static bool separable(const dfx_function& f) {
   if (f.n_comp == 1) return f.id == DFX_FN_GAUSSIAN || f.id == DFX_FN_SINPROD || f.id == DFX_FN_COORD || f.id == DFX_FN_CONSTANT;
   // vector-valued: every range entry is a product of per-direction factors (one table set each)
@@ -655,6 +784,15 @@ int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function
       // per-node evaluation with the function id known at compile time for the functions the BASELINE
       // configs interpolate (no switch in the node loop); everything else dispatches on f.id at run time
       bool launched = false;
+      if (!sep && k >= 3 && k <= 5 && A.nActive == 1 && mask == nullptr) {
+        // orders 3 .. 5: sweep the contiguous runs of the numbering (entity-blocked interior DOFs)
+        switch (fn.id) {
+          case DFX_FN_GAUSSIAN: launched = launchRunsNode<DFX_FN_GAUSSIAN>(D, q, A.leafId[0], A.leafComp[0], fn, coeff, st); break;
+          case DFX_FN_QUADRATIC: launched = launchRunsNode<DFX_FN_QUADRATIC>(D, q, A.leafId[0], A.leafComp[0], fn, coeff, st); break;
+          default: launched = launchRunsNode<-1>(D, q, A.leafId[0], A.leafComp[0], fn, coeff, st); break;
+        }
+        if (launched) { int rc = postLaunch("k_interp_runs"); if (rc) return rc; continue; }
+      }
       if (!sep && (k <= 2 || leanShape)) {
         switch (fn.id) {
           case DFX_FN_GAUSSIAN: launched = launchRowsNode<DFX_FN_GAUSSIAN>(k, A.nActive == 1, leanShape, grid, bs, st, D, A, fn, coeff, mask); break;
