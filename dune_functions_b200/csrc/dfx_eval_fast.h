@@ -36,6 +36,7 @@ extern int g_smemGrad;
 extern int g_smemTma;
 extern int g_evalSwizzle;
 extern int g_evalStreamHint;
+extern int g_evalBlock;
 bool dmmaPathHas(const dfx_basis* b, int firstLeaf, int nLeaves);
 int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double* xhat, int nq, const double* coeff,
                 u64 e0, u64 e1, double* values, double* jac, cudaStream_t st);

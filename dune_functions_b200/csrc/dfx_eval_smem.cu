@@ -47,6 +47,7 @@ struct SmemArgs {
   int isDG;                           // element-local DOFs: scalar index = e * NLOC + i
   int perm;                           // 1: contract direction 2 first (points ordered last-coordinate-fastest)
   int tma;                            // 1 (TMA instantiation): coefficients of element pairs arrive by bulk copies
+  int n0, n1;                         // elements per direction (offsets into the diag(J^-1) table)
 };
 
 __device__ __forceinline__ unsigned smemAddr2(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -133,14 +134,18 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
 
   // ---- the three contractions of one item whose coefficients sit in shared memory at cin[cidx(p) + cstr * a]
   // (p: pencil of stage x, a: index along the contracted direction), and the flush of a finished pair ----
-  auto contractItem = [&](const double* cin, bool natural, u64 el, int eI, int gI, const unsigned (&ec)[3]) {
-    double jinv[3] = {0, 0, 0};
+  // diag(J^-1) of an element (AxisAlignedCubeGeometry::jacobianInverse per direction, tabulated once per handle).
+  // Loaded ONE ITEM AHEAD like the coefficients: the first use is a select / multiply at the top of the item, and
+  // ncu's source view charged 48 % of all stall samples (long scoreboard) to exactly those instructions when the
+  // loads were issued there.
+  auto loadJinv = [&](const unsigned (&ec)[3], double (&jinv)[3]) {
     if (OUTJ) {
-      // AxisAlignedCubeGeometry::jacobianInverse per direction, tabulated once per handle
       jinv[0] = __ldg(jinvTab + ec[0]);
-      jinv[1] = __ldg(jinvTab + g.N[0] + ec[1]);
-      jinv[2] = __ldg(jinvTab + g.N[0] + g.N[1] + ec[2]);
+      jinv[1] = __ldg(jinvTab + R.n0 + ec[1]);
+      jinv[2] = __ldg(jinvTab + R.n0 + R.n1 + ec[2]);
     }
+  };
+  auto contractItem = [&](const double* cin, bool natural, u64 el, int eI, int gI, const double (&jinv)[3]) {
     // physical direction of the kernel's first / last contraction and its inverse-Jacobian entry
     const int dFirst = R.perm ? 2 : 0, dLast = R.perm ? 0 : 2;
     const double jFirst = R.perm ? jinv[2] : jinv[0], jLast = R.perm ? jinv[0] : jinv[2];
@@ -317,6 +322,12 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
       bulkLoad(pairBuf, src + warpId * (u64)PAIRBUF, pairBytes, &mbar[0]);
     }
     __syncwarp();
+    double jcur[3] = {0, 0, 0}, jnxt[3] = {0, 0, 0};
+    {
+      unsigned ec0[3];
+      elementCoords(warpId * 2, ec0);
+      loadJinv(ec0, jcur);
+    }
     unsigned it = 0;
     for (u64 pair = warpId; pair < nPairs; pair += nWarps, ++it) {
       const unsigned b = it & 1u;
@@ -332,10 +343,17 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
 #pragma unroll 1
       for (int eI = 0; eI < 2; ++eI) {
         const u64 el = pair * 2 + (u64)eI;
-        unsigned ec[3];
-        elementCoords(el, ec);
+        // diag(J^-1) of the element after this one (the pair's second, or the next pair's first)
+        const u64 elN = eI == 0 ? el + 1 : pairN * 2;
+        if (OUTJ && elN < R.ne) {
+          unsigned ecN[3];
+          elementCoords(elN, ecN);
+          loadJinv(ecN, jnxt);
+        }
         __syncwarp();
-        contractItem(cpair + eI * NLOC, true, el, eI, 0, ec);
+        contractItem(cpair + eI * NLOC, true, el, eI, 0, jcur);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) jcur[j] = jnxt[j];
       }
     }
     if (lane == 0 && pendingStore) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -379,8 +397,9 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
     e_ = 0; pr += nWarps;
   };
   // gather of one item into registers (LocalFunctionBase::bind, :140-147)
-  auto fetch = [&](u64 el, int gI, double (&c)[SETS], unsigned (&ec)[3]) {
+  auto fetch = [&](u64 el, int gI, double (&c)[SETS], unsigned (&ec)[3], double (&jinv)[3]) {
     elementCoords(el, ec);
+    loadJinv(ec, jinv);
     const unsigned e = (unsigned)(R.e0 + el);
     const DevLeaf& leaf = Bp->leaves[R.firstLeaf + gI];
     const u64 posA = leaf.posA, posB = leaf.posB;
@@ -404,29 +423,30 @@ k_eval_smem(const DevBasis* __restrict__ Bp, const __grid_constant__ Tables3<N1,
   };
 
   double cur[SETS], nxt[SETS];
+  double jcur[3] = {0, 0, 0}, jnxt[3] = {0, 0, 0};
   unsigned ec[3], ecN[3];
   u64 pair = warpId, pairN;
   int eI = 0, gI = 0, eIN, gIN;
-  fetch(pair * 2, 0, cur, ec);
+  fetch(pair * 2, 0, cur, ec, jcur);
 
   while (true) {
     const u64 el = pair * 2 + (u64)eI;
     pairN = pair; eIN = eI; gIN = gI;
     advance(pairN, eIN, gIN);
     const bool haveN = pairN < nPairs;
-    if (haveN) fetch(pairN * 2 + (u64)eIN, gIN, nxt, ecN);       // in flight while this item is contracted
+    if (haveN) fetch(pairN * 2 + (u64)eIN, gIN, nxt, ecN, jnxt);       // in flight while this item is contracted
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < SETS; ++t) { const int i = lane + 32 * t; if (i < NLOC) cbuf[cpos[t]] = cur[t]; }
     __syncwarp();
-    contractItem(cbuf, false, el, eI, gI, ec);
+    contractItem(cbuf, false, el, eI, gI, jcur);
     if (!haveN) break;
     // rotate the prefetched item in
     pair = pairN; eI = eIN; gI = gIN;
 #pragma unroll
     for (int t = 0; t < SETS; ++t) cur[t] = nxt[t];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) ec[j] = ecN[j];
+    for (int j = 0; j < 3; ++j) { ec[j] = ecN[j]; jcur[j] = jnxt[j]; }
   }
   // shared memory must outlive the last bulk store's read
   if (lane == 0 && pendingStore) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -520,6 +540,7 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     R.perm = plan.firstFastest ? 0 : 1;
     R.isDG = D.layouts[D.leaves[firstLeaf + l].layout].kind == DFX_NODE_LAGRANGE_DG ? 1 : 0;
     R.e0 = e0; R.ne = e1 - e0;
+    R.n0 = D.grid.N[0]; R.n1 = D.grid.N[1];
     {
       // TMA pair loads: element-local DOFs, one leaf with unit position stride, whole pairs, every pair a 16-byte
       // aligned run of the vector

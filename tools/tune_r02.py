@@ -67,6 +67,23 @@ def main():
         L.dfx_set_kernel_path(capi.OP_TUNE_STREAM_HINT, -1)
         del b, x, v, f
         torch.cuda.empty_cache()
+    if "evalblock" in what:
+        for n in (512, 256):
+            b = dfx.makeBasis(dfx.YaspGrid([n, n, n]), dfx.lagrange(2))
+            x = b.newVector(0.0)
+            dfx.interpolate(b, x, dfx.gaussian(1.0))
+            pts, _ = dfx.tensor_gauss(3, 3)
+            v = torch.empty((b.numElements(), 27, 1), dtype=torch.float64, device="cuda")
+            f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+            nb = b.dimension() * 8 + v.numel() * 8
+            for rep in range(2):
+                for epb in (128, 64):
+                    L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_BLOCK, epb)
+                    ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=10)
+                    print(json.dumps({"probe": "eval Q2 values", "n": n, "elements_per_block": epb, "ms": ms, "frac": nb / ms / 1e6 / PEAK}), flush=True)
+            L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_BLOCK, -1)
+            del b, x, v, f
+            torch.cuda.empty_cache()
     if "c3" in what:
         b = dfx.makeBasis(dfx.YaspGrid([128, 128, 128]), dfx.taylorHood())
         ne, nl = b.numElements(), b.maxNodeSize()
