@@ -34,6 +34,8 @@ int planFastEval(const dfx_basis* b, int firstLeaf, int nLeaves, const double* x
 bool smemPathHas(int dim, int k, int m);
 extern int g_smemGrad;
 extern int g_smemTma;
+extern int g_smemPair;
+extern int g_smemMaxBlocks;
 extern int g_evalSwizzle;
 extern int g_evalStreamHint;
 extern int g_evalBlock;
@@ -44,6 +46,9 @@ int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double
 // number of range entries per point (a mixed-order subtree is evaluated run by run)
 int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
+// LagrangeDG leaf, whole element pairs, both elements of a pair contracted at once; -1 = not a configuration of it
+int runPairEval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coeff, u64 e0, u64 e1, double* values,
+                double* jac, cudaStream_t st);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 

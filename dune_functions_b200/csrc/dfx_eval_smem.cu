@@ -499,7 +499,8 @@ static int launchSmemT(dfx_basis* b, const FastPlan& plan, const SmemArgs& R, co
   DFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
   const u64 pairs = (R.ne + 1) / 2;
   const u64 want = (pairs + kSmemWarps - 1) / kSmemWarps;
-  const u64 blocks = std::min<u64>(want, (u64)std::max(1, perSM) * (u64)std::max(1, sms));
+  u64 blocks = std::min<u64>(want, (u64)std::max(1, perSM) * (u64)std::max(1, sms));
+  if (g_smemMaxBlocks > 0) blocks = std::min<u64>(blocks, (u64)g_smemMaxBlocks);
   kern<<<(unsigned)blocks, kSmemWarps * 32, smem, st>>>((const DevBasis*)b->dDev, T, R, (const unsigned*)b->dLocalTab,
                                                          (const double*)b->dJinv, coeff, values, jac);
   return postLaunch("k_eval_smem");
@@ -521,6 +522,11 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull)
     return fail(DFX_ERR_RANGE, "more than 2^32 elements in one box");
   const int n1 = plan.k + 1, m = plan.m;
+  if (nLeaves == 1 && compTotal == 1 && compBase == 0) {
+    // element-local DOFs, one leaf, whole pairs: both elements of a pair at once (dfx_eval_pair.cu)
+    const int rc = runPairEval(b, plan, firstLeaf, coeff, e0, e1, values, jac, st);
+    if (rc >= 0) return rc;
+  }
   if (plan.jac) { int rc = ensureJinvTable(b, st); if (rc) return rc; }
   int l = 0;
   while (l < nLeaves) {

@@ -745,15 +745,25 @@ def test_evaluate_shared_memory_tma_pair_loads(kernel_path, k, last_fastest):
         for m in (k + 1, k + 2):
             pts, _ = tensor_gauss(3, m, last_fastest)
             vr, jr = o.evaluate(c, pts, jacobians=True)
-            for mode in (2, 1, 0):
+            # k_eval_pair (both elements of a pair at once; 8 / 4 warps per block, block tiles), then k_eval_smem with its TMA modes
+            # grids of 2 blocks: every warp walks through 8-15 items (buffer reuse, mbarrier phases, store waits)
+            for pair, mode, cap in ((1, 1, 2), (4, 1, 2), (4, 1, 1), (-1, 1, -1), (0, 2, 2), (0, 1, 2), (0, 0, 2), (0, 1, -1)):
+                L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, pair)
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, mode)
+                L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_BLOCKS, cap)
                 v, j = f.evaluate(pts, jacobians=True)
-                assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL, (m, mode)
-                assert rel(f.evaluate(pts).cpu().numpy(), vr) <= TOL, (m, mode)
-                for e0, e1 in ((2, ne), (1, ne - 1), (4, 6)):
-                    assert rel(f.evaluate(pts, elem_begin=e0, elem_end=e1).cpu().numpy(), vr[e0:e1]) <= TOL, (m, mode, e0)
+                assert rel(v.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL, (m, pair, mode)
+                assert rel(f.evaluate(pts).cpu().numpy(), vr) <= TOL, (m, pair, mode)
+                j2 = f.evaluate(pts, values=False, jacobians=True)
+                assert rel(j2.cpu().numpy(), jr) <= TOL, (m, pair, mode)
+                for e0, e1 in ((2, ne), (1, ne - 1), (4, 6), (3, 4)):
+                    assert rel(f.evaluate(pts, elem_begin=e0, elem_end=e1).cpu().numpy(), vr[e0:e1]) <= TOL, (m, pair, mode, e0)
+                    js = f.evaluate(pts, values=False, jacobians=True, elem_begin=e0, elem_end=e1)
+                    assert rel(js.cpu().numpy(), jr[e0:e1]) <= TOL, (m, pair, mode, e0)
     finally:
         L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, -1)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, -1)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_BLOCKS, -1)
 
 
 @pytest.mark.parametrize("k", [2, 3, 4, 5])

@@ -128,13 +128,16 @@ def main():
         nbv = b.dimension() * 8 + v.numel() * 8
         nbj = nbv + j.numel() * 8
         for rep in range(2):
-            for tma in (0, 1):
+            # pair: 0 = k_eval_smem (one element per warp at a time), 4 / 1 = k_eval_pair with 4 / 8 warps per block
+            for pair, tma in ((0, 1), (4, 1), (1, 1)):
+                L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, pair)
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, tma)
                 ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=5)
-                print(json.dumps({"probe": "DG4 192^3 values", "tma_pair_loads": tma, "ms": ms, "frac": nbv / ms / 1e6 / PEAK}), flush=True)
+                print(json.dumps({"probe": "DG4 192^3 values", "pair_kernel_warps": pair, "tma_pair_loads": tma, "ms": ms, "frac": nbv / ms / 1e6 / PEAK}), flush=True)
                 ms = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), reps=5)
-                print(json.dumps({"probe": "DG4 192^3 values+gradients", "tma_pair_loads": tma, "ms": ms, "frac": nbj / ms / 1e6 / PEAK}), flush=True)
+                print(json.dumps({"probe": "DG4 192^3 values+gradients", "pair_kernel_warps": pair, "tma_pair_loads": tma, "ms": ms, "frac": nbj / ms / 1e6 / PEAK}), flush=True)
         L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, -1)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, -1)
         del b, x, v, j, f
         torch.cuda.empty_cache()
     if "dg4" in what or "jac" in what:
