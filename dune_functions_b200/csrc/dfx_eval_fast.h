@@ -36,6 +36,7 @@ extern int g_smemGrad;
 extern int g_smemTma;
 extern int g_smemPair;
 extern int g_smemMaxBlocks;
+extern int g_evalQ3;
 extern int g_evalSwizzle;
 extern int g_evalStreamHint;
 extern int g_evalBlock;
@@ -49,6 +50,9 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
 // LagrangeDG leaf, whole element pairs, both elements of a pair contracted at once; -1 = not a configuration of it
 int runPairEval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coeff, u64 e0, u64 e1, double* values,
                 double* jac, cudaStream_t st);
+// continuous Lagrange order 3 at 4^3 points, values only, one leaf; -1 = not a configuration of it
+int runQ3Eval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coeff, u64 e0, u64 e1, double* values,
+              cudaStream_t st);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 

@@ -524,8 +524,10 @@ int runSmemEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
   const int n1 = plan.k + 1, m = plan.m;
   if (nLeaves == 1 && compTotal == 1 && compBase == 0) {
     // element-local DOFs, one leaf, whole pairs: both elements of a pair at once (dfx_eval_pair.cu)
-    const int rc = runPairEval(b, plan, firstLeaf, coeff, e0, e1, values, jac, st);
+    int rc = runPairEval(b, plan, firstLeaf, coeff, e0, e1, values, jac, st);
     if (rc >= 0) return rc;
+    // continuous order 3 at 4^3 points, values only: thread per element in registers (dfx_eval_q3.cu)
+    if (!jac) { rc = runQ3Eval(b, plan, firstLeaf, coeff, e0, e1, values, st); if (rc >= 0) return rc; }
   }
   if (plan.jac) { int rc = ensureJinvTable(b, st); if (rc) return rc; }
   int l = 0;

@@ -139,6 +139,39 @@ def test_q2_baseline_grids_subranges(n):
         check_interpolate_ranges(b, o, [(0, 0, dfx.gaussian(1.0))], 1 << 16, separable=sep)
 
 
+@pytest.mark.parametrize("n", [[70, 3, 2], [16, 8, 8], [5, 4, 3]])
+@pytest.mark.parametrize("last_fastest", [False, True])
+def test_q3_register_kernel_against_oracle(n, last_fastest):
+    """continuous order 3 at 4^3 points, values only: k_eval_q3 (thread per element, 64 coefficients in registers,
+    staged copy-out) — whole grids with full and partial 64-element blocks, sub-ranges with odd starts, both point
+    orders, a sub-space of a power tree (position stride 2) and the shared-memory kernel on the same numbers"""
+    import torch
+    L = capi.lib()
+    grid = dfx.YaspGrid(n, upper=[1.0, 0.75, 1.25])
+    pts, _ = tensor_gauss(3, 4, last_fastest)
+    rng = np.random.default_rng(5)
+    for tree, node, onode in ((dfx.lagrange(3), 0, 0), (dfx.power(dfx.lagrange(3), 2, dfx.flatInterleaved()), None, None)):
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        xr = rng.uniform(-1, 1, o.dimension())
+        xt = torch.from_numpy(xr).cuda()
+        ne = b.numElements()
+        if node is None:
+            space, onode = dfx.subspaceBasis(b, 1), b.child(0, 1)
+        else:
+            space = b
+        f = dfx.makeDiscreteGlobalBasisFunction(space, xt)
+        ref = o.evaluate(xr, pts, node=onode, nthreads=4)
+        try:
+            for q3 in (1, 0):
+                L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_Q3, q3)
+                assert rel(f.evaluate(pts).cpu().numpy(), ref) <= TOL, (n, q3)
+                for e0, e1 in ((1, ne), (3, ne - 2), (ne // 2, ne // 2 + 1)):
+                    assert rel(f.evaluate(pts, elem_begin=e0, elem_end=e1).cpu().numpy(), ref[e0:e1]) <= TOL, (n, q3, e0)
+        finally:
+            L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_Q3, -1)
+
+
 def test_dg4_192_subranges():
     """configs[3]: k_eval_smem<5,5,0> (values) and <5,5,2> (values + collocation gradients), element
     pairs leaving by TMA bulk stores; k_interp_cell"""
