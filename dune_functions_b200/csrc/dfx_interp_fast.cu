@@ -259,9 +259,15 @@ int g_rowsLean = -1;    // lattice rows per block of the lean kernel; -1: leanRo
 // from 4 rows on), but a small lattice must still give every SM several waves of blocks (Taylor-Hood 128^3
 // has 66 049 + 16 641 rows: 32 rows per block are 2.2 waves with a 0.2-full tail; measured 2 .. 32 rows:
 // 0.107 / 0.090 (4 rows) / 0.097 / 0.124 ms): about 128 blocks per SM.
-static int leanRows(u64 nRows) {
+// ... and the rows the resident blocks write at one time should stay a compact band of every index-set component:
+// at 512^3 (8.2 KB per lattice row) 32 rows per block put 310 MB in flight and the
+// kernel takes 1.82 ms, 8 rows (78 MB) 1.71 ms, 4 rows 1.76 ms (`profiles/r02_interp_row_hoist_ab.jsonl`); at
+// 256^3 the optimum is flat from 16 rows on.  rowBytes: bytes one lattice row writes.
+static int leanRows(u64 nRows, u64 rowBytes) {
   if (g_rowsLean > 0) return std::min(g_rowsLean, kRowsPerBlock);
-  return (int)std::max<u64>(4, std::min<u64>(kRowsPerBlock, nRows / (148 * 128)));
+  const u64 bySize = std::max<u64>(4, std::min<u64>(kRowsPerBlock, nRows / (148 * 128)));
+  const u64 byBand = std::max<u64>(4, (80ull << 20) / (148ull * 8 * std::max<u64>(1, rowBytes)));
+  return (int)std::min(bySize, byBand);
 }
 
 // Body shared by the single and the two-part kernel.  The active leaves are either ONE leaf (any position
@@ -633,7 +639,7 @@ static bool launchRowsNode(int k, bool one, bool leanShape, unsigned grid, unsig
     // one leaf or an interleaved group, unmasked: the lean kernel
     RegistryFnT<ID, true> fl; fl.f = fn; fl.dim = D.grid.dim;
     const u64 nRows = (u64)A.LX[1] * A.LX[2];
-    A.rowsPerBlock = leanRows(nRows);
+    A.rowsPerBlock = leanRows(nRows, (u64)A.LX[0] * (u64)A.nActive * sizeof(double));
     const unsigned gridL = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
     if (k == 1) k_interp_rows_lean<RegistryFnT<ID, true>, 1><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
     else if (k == 2) k_interp_rows_lean<RegistryFnT<ID, true>, 2><<<gridL, bs, 0, st>>>(D, A, fl, coeff);
@@ -896,7 +902,7 @@ static bool leanPlan(const dfx_basis* b, int firstLeaf, int nLeaves, const dfx_f
   if (nLeaves > 1 && !il) return false;
   A.interleaved = nLeaves > 1 ? 1 : 0;
   A.divC = FastDiv((unsigned)nLeaves);
-  A.rowsPerBlock = leanRows(nRows);
+  A.rowsPerBlock = leanRows(nRows, (u64)A.LX[0] * (u64)nLeaves * sizeof(double));
   grid = (unsigned)((nRows + A.rowsPerBlock - 1) / A.rowsPerBlock);
   const unsigned nEnt = (unsigned)g.N[0] * (unsigned)nLeaves, chunks = (nEnt + 255) / 256;
   bs = std::max(32u, (((nEnt + chunks - 1) / chunks + 31) / 32) * 32);

@@ -74,4 +74,16 @@ if "c4" in which:
         f.evaluate(pts, out_values=v)
         f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j)
     torch.cuda.synchronize()
+if "q3" in which:
+    b = dfx.makeBasis(dfx.YaspGrid([128, 128, 128]), dfx.lagrange(3))
+    x = b.newVector(0.0)
+    pts, _ = dfx.tensor_gauss(3, 4)
+    v = torch.empty((b.numElements(), 64, 1), dtype=torch.float64, device="cuda")
+    f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+    for _ in range(REPS):
+        dfx.interpolate(b, x, dfx.gaussian(1.0))
+        f.evaluate(pts, out_values=v)
+    torch.cuda.synchronize()
+    del b, x, v, f
+    torch.cuda.empty_cache()
 print("profile pass done, launches:", L.dfx_kernel_launch_count())
