@@ -173,8 +173,8 @@ def test_q3_register_kernel_against_oracle(n, last_fastest):
 
 
 def test_dg4_192_subranges():
-    """configs[3]: k_eval_smem<5,5,0> (values) and <5,5,2> (values + collocation gradients), element
-    pairs leaving by TMA bulk stores; k_interp_cell"""
+    """configs[3]: k_eval_smem<5,5,0,TMA> (values) and k_eval_pair<5,5,...> (values + collocation gradients; the
+    8 pairs of a block leave as one block tile per array by TMA bulk stores); k_interp_cell"""
     grid = dfx.YaspGrid([192, 192, 192])
     tree = dfx.lagrangeDG(4)
     b = dfx.makeBasis(grid, tree)
