@@ -36,6 +36,7 @@ int ensureDevice(const dfx_basis* b) {
     if (!mb->dVid) DFX_CUDA(cudaMalloc(&mb->dVid, b->vidHost.size() * sizeof(u64)));
     DFX_CUDA(cudaMemcpy(mb->dVid, b->vidHost.data(), b->vidHost.size() * sizeof(u64), cudaMemcpyHostToDevice));
     mb->dev.vid = (const u64*)mb->dVid;
+    mb->dev.orient = nullptr; mb->orientValid = false;
     mb->vidPending = false;
     if (mb->dDev) DFX_CUDA(cudaMemcpy(mb->dDev, &mb->dev, sizeof(DevBasis), cudaMemcpyHostToDevice));
   }
@@ -190,13 +191,13 @@ int dfx_basis_create(const dfx_grid_desc* grid_host, const dfx_tree_node* tree_h
 static void releaseResources(dfx_basis_impl* b) {
   if (b->companion) { dfx_basis_destroy(static_cast<dfx_basis*>(b->companion)); b->companion = nullptr; }
   b->companionTried = false;
-  const bool any = b->dLocalCoeff || b->dDense || b->dJinv || b->dNodal || b->dVid || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
+  const bool any = b->dLocalCoeff || b->dDense || b->dJinv || b->dNodal || b->dVid || b->dOrient || b->evStream[0] || b->evStream[1] || b->dLocalTab || b->dDev ||
                    b->dIdxTab || b->dSep || b->dShape || b->pinned || b->dScratch[0] || b->dScratch[1] || b->dScratch[2] || b->stream;
   if (!any) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize((cudaStream_t)b->stream);
   if (b->dLocalCoeff) { cudaFree(b->dLocalCoeff); b->dLocalCoeff = nullptr; b->dLocalCoeffBytes = 0; }
-  for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dShape, &b->dLocalTab, &b->dIdxTab, &b->dDev, &b->dSep,
+  for (void** p : {&b->dDense, &b->dJinv, &b->dNodal, &b->dVid, &b->dOrient, &b->dShape, &b->dLocalTab, &b->dIdxTab, &b->dDev, &b->dSep,
                    &b->dScratch[0], &b->dScratch[1], &b->dScratch[2]})
     if (*p) { cudaFree(*p); *p = nullptr; }
   if (b->pinned) { cudaFreeHost(b->pinned); b->pinned = nullptr; }
@@ -244,6 +245,7 @@ static int setVertexIds(dfx_basis* b, const uint64_t* ids, uint64_t n, bool from
   if (ids && n != numVertices(b)) return fail(DFX_ERR_RANGE, "one id per vertex of the local box expected");
   if (!ids) {
     b->dev.vid = nullptr;                  // the table itself stays allocated until destroy: kernels in flight may read it
+    b->dev.orient = nullptr; b->orientValid = false;
     b->oriented = false;
     b->vidPending = false;
     b->vidHost.clear();
@@ -257,6 +259,7 @@ static int setVertexIds(dfx_basis* b, const uint64_t* ids, uint64_t n, bool from
     // host bookkeeping only; the upload happens in ensureDevice() at the next device call
     b->vidHost.assign(ids, ids + n);
     b->vidPending = true;
+    b->dev.orient = nullptr; b->orientValid = false;
     b->oriented = wantsOrientation(b);
     return DFX_OK;
   }
@@ -266,6 +269,7 @@ static int setVertexIds(dfx_basis* b, const uint64_t* ids, uint64_t n, bool from
   b->vidPending = false;
   b->vidHost.clear();
   b->dev.vid = (const u64*)b->dVid;
+  b->dev.orient = nullptr; b->orientValid = false;
   b->oriented = wantsOrientation(b);
   if (b->dDev) DFX_CUDA(cudaMemcpyAsync(b->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice, st));
   return DFX_OK;
@@ -395,6 +399,11 @@ static int interpolateImpl(const dfx_basis* b, int32_t node, const dfx_function*
   if (path != 0 && !b->oriented && b->dimension <= 0xffffffffull && dfx_basis_num_elements(b) <= 0xffffffffull) {
     const bool wantSep = path == 2 || (path == -1 && separable);
     return interpolateFast(const_cast<dfx_basis*>(b), fl, nl, *f, coeff, mask, wantSep, (cudaStream_t)stream);
+  }
+  if (path != 0 && b->oriented && nl == 1 && mask == nullptr) {
+    // permuted face DOFs, one continuous leaf of order 3 .. 5: the run sweep with one orientation byte per entity
+    rc = interpolateRunsOriented(const_cast<dfx_basis*>(b), fl, *f, coeff, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
   }
   return interpolateRegistry(b, fl, nl, *f, coeff, mask, (cudaStream_t)stream);
 }
@@ -643,6 +652,15 @@ int dfx_evaluate(const dfx_basis* cb, int32_t node, const double* coeff, const d
     // apply.  LocalFunction::bind as its own pass — the element-local coefficients are gathered through
     // layoutIndexOriented into the layout of the companion basis (same tree, discontinuous leaves) —
     // then the companion evaluates on the element-local fast kernels.
+    if (g_forcedPath != 0 && nl == 1 && !out_jac) {
+      // continuous order 3 at 4^3 points: the register kernel reads one orientation byte per edge / facet of the
+      // element and permutes the in-entity index of its gathers — no separate gather pass, no companion
+      FastPlan plan;
+      if (planFastEval(b, fl, nl, xhat_host, n_q, false, 2, plan) == 2) {
+        rc = runQ3Eval(b, plan, fl, coeff, e0, e1, out_values, st);
+        if (rc >= 0) return rc;
+      }
+    }
     if (g_forcedPath != 0 && orientedCompanion(b)) {
       dfx_basis* c = static_cast<dfx_basis*>(b->companion);
       // the gather walks like the fast index table (path 1 of DFX_OP_INDICES) or like k_indices (path 0)

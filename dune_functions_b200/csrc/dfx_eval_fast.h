@@ -53,6 +53,8 @@ int runPairEval(dfx_basis* b, const FastPlan& plan, int leafId, const double* co
 // continuous Lagrange order 3 at 4^3 points, values only, one leaf; -1 = not a configuration of it
 int runQ3Eval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coeff, u64 e0, u64 e1, double* values,
               cudaStream_t st);
+// orientation codes of the local box's edges / facets (handles with permuted face DOFs)
+int ensureOrientTable(dfx_basis* b, cudaStream_t st);
 int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, const double* coeff, u64 e0, u64 e1,
                 double* values, double* jac, cudaStream_t st, int compBase = 0, int compTotal = -1);
 

@@ -41,11 +41,47 @@ struct Q3Args {
   unsigned long long e0, ne;
   FastDiv divN0, divN1;
   unsigned long long posA, posB;
+  const unsigned char* orient;   // ORIENT: orientation code per edge / facet of the local box (DevBasis::orient)
+  unsigned ooff[8];
 };
 
+// Orientation codes of every edge and quadrilateral facet of the local box from the vertex ids (orientCode,
+// dfx_internal.h; FaceOrientations, lagrangebasis.hh:207-331): one thread per entity, one byte each.
+struct OrientArgs { unsigned off[8], cnt[8][3]; unsigned total; };
+__global__ void __launch_bounds__(256)
+k_orient_codes(const __grid_constant__ DevGrid g, const __grid_constant__ OrientArgs A, const u64* __restrict__ vid,
+               unsigned char* __restrict__ tab) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.total) return;
+  unsigned s = 0;                     // offsets ascend with the component number over the components that exist
+#pragma unroll
+  for (unsigned q = 1; q < 7; ++q)
+    if (A.cnt[q][0] != 0 && t >= A.off[q]) s = q;
+  const unsigned r = t - A.off[s];
+  int c[3];
+  c[0] = (int)(r % A.cnt[s][0]);
+  const unsigned r2 = r / A.cnt[s][0];
+  c[1] = (int)(r2 % A.cnt[s][1]);
+  c[2] = (int)(r2 / A.cnt[s][1]);
+  tab[t] = (unsigned char)orientCode(g, vid, s, c);
+}
+
+// all eight codes of a facet (edges: two) applied to the in-entity indices of order 3, two bits each: the
+// permuted index of `fr` under `code` is (word >> (8 code + 2 fr)) & 3
+constexpr unsigned long long q3OrientWord(int nfree) {
+  unsigned long long w = 0;
+  for (unsigned code = 0; code < 8; ++code)
+    for (unsigned fr = 0; fr < (nfree == 2 ? 4u : 2u); ++fr)
+      w |= (unsigned long long)applyOrientCode<false>(nfree == 1 ? (code & 1u) : code, nfree, 3, fr) << (8 * code + 2 * fr);
+  return w;
+}
+constexpr unsigned long long kQ3WordEdge = q3OrientWord(1), kQ3WordFace = q3OrientWord(2);
+
 // UNIT: flat container position = scalar index + posB (a root leaf, or a blocked-lexicographic child)
-template <int M, bool UNIT>
-__global__ void __launch_bounds__(kQ3Threads, 6)
+// ORIENT (dfx_basis_set_vertex_ids): the DOFs of an edge / facet sit in the entity's globally unique orientation
+// (lagrangebasis.hh:863-869); the thread reads the entity's code and permutes the in-entity index of its load.
+template <int M, bool UNIT, bool ORIENT>
+__global__ void __launch_bounds__(kQ3Threads, ORIENT ? 5 : 6)
 k_eval_q3(const __grid_constant__ DevLayout L, const __grid_constant__ Q3Tables<M> T, const __grid_constant__ Q3Args R,
           const double* __restrict__ coeff, double* __restrict__ values) {
   constexpr int K = 3, N1 = 4, NLOC = 64, NQ = M * M * M;
@@ -80,6 +116,11 @@ k_eval_q3(const __grid_constant__ DevLayout L, const __grid_constant__ Q3Tables<
         if (i2) { fr += (a2 - 1) * frs; }
         const unsigned c0 = ec0 + (a0 == K ? 1u : 0u), c1 = ec1 + (a1 == K ? 1u : 0u), c2 = ec2 + (a2 == K ? 1u : 0u);
         const unsigned ent = c0 + (unsigned)L.csize[s][0] * (c1 + (unsigned)L.csize[s][1] * c2);
+        if (ORIENT && blk > 1 && blk < 8) {
+          const unsigned long long word = blk == 4 ? kQ3WordFace : kQ3WordEdge;
+          const unsigned code = __ldg(R.orient + R.ooff[s] + ent);
+          fr = (int)((word >> (8u * code + 2u * (unsigned)fr)) & 3ull);
+        }
         if (UNIT) {
           c[a0 + N1 * (a1 + N1 * a2)] = __ldg(src + L.compOffset[s] + fr + (u64)(ent * (unsigned)blk));
         } else {
@@ -109,7 +150,44 @@ k_eval_q3(const __grid_constant__ DevLayout L, const __grid_constant__ Q3Tables<
 
 }  // namespace
 
-// -1: not a configuration of this kernel (the caller goes on to k_eval_smem)
+// Builds (once per set of vertex ids) the orientation codes of the local box and publishes them in the handle's
+// DevBasis.  Stream-ordered on `st` like every other per-handle cache (one stream per handle, include/dfx.h).
+int ensureOrientTable(dfx_basis* b, cudaStream_t st) {
+  if (b->orientValid && b->dev.orient) return DFX_OK;
+  if (!b->dev.vid) return fail(DFX_ERR_INVALID, "orientation table without vertex ids");
+  const DevGrid& g = b->dev.grid;
+  OrientArgs A{};
+  u64 total = 0;
+  for (unsigned s = 1; s < 7; ++s) {
+    const int nfree = (int)((s & 1u) + ((s >> 1) & 1u) + ((s >> 2) & 1u));
+    bool exists = (nfree == 1 && g.dim > 1) || (nfree == 2 && g.dim == 3);
+    for (int j = g.dim; j < 3; ++j) if ((s >> j) & 1u) exists = false;       // no free direction beyond the dimension
+    if (!exists) continue;
+    u64 n = 1;
+    for (int j = 0; j < 3; ++j) { A.cnt[s][j] = (unsigned)(j < g.dim ? g.N[j] + (((s >> j) & 1u) ? 0 : 1) : 1); n *= A.cnt[s][j]; }
+    A.off[s] = (unsigned)total;
+    total += n;
+  }
+  if (total == 0 || total > 0xffffffffull) return fail(DFX_ERR_RANGE, "orientation table: entity count out of range");
+  A.total = (unsigned)total;
+  if (b->dOrientBytes < total) {
+    if (b->dOrient) DFX_CUDA(cudaFree(b->dOrient));
+    b->dOrient = nullptr; b->dOrientBytes = 0;
+    DFX_CUDA(cudaMalloc(&b->dOrient, total));
+    b->dOrientBytes = total;
+  }
+  k_orient_codes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, A, b->dev.vid, (unsigned char*)b->dOrient);
+  int rc = postLaunch("k_orient_codes");
+  if (rc) return rc;
+  b->dev.orient = (const unsigned char*)b->dOrient;
+  for (int s = 0; s < 8; ++s) b->dev.orientOff[s] = A.off[s];
+  b->orientValid = true;
+  if (b->dDev) DFX_CUDA(cudaMemcpyAsync(b->dDev, &b->dev, sizeof(DevBasis), cudaMemcpyHostToDevice, st));
+  return DFX_OK;
+}
+
+// -1: not a configuration of this kernel (the caller goes on to k_eval_smem, or to the gather + companion route
+// when the handle has permuted face DOFs)
 int runQ3Eval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coeff, u64 e0, u64 e1, double* values,
               cudaStream_t st) {
   if (!g_evalQ3 || plan.dim != 3 || plan.k != 3 || plan.m != 4 || plan.jac || !values) return -1;
@@ -126,20 +204,36 @@ int runQ3Eval(dfx_basis* b, const FastPlan& plan, int leafId, const double* coef
   for (int j = 0; j < 3; ++j)
     for (int q = 0; q < M; ++q)
       for (int a = 0; a < 4; ++a) T.A[j][q][a] = plan.A[j][q][a];
-  Q3Args R;
+  Q3Args R{};
   if (plan.firstFastest) { R.qs[0] = 1; R.qs[1] = M; R.qs[2] = M * M; }
   else { R.qs[2] = 1; R.qs[1] = M; R.qs[0] = M * M; }
   R.e0 = e0; R.ne = e1 - e0;
   R.divN0 = FastDiv((unsigned)D.grid.N[0]); R.divN1 = FastDiv((unsigned)D.grid.N[1]);
   R.posA = lf.posA; R.posB = lf.posB;
+  if (b->oriented) {
+    int rc = ensureOrientTable(b, st);
+    if (rc) return rc;
+    // the table numbers entities like the DOF layout does
+    for (unsigned s = 1; s < 7; ++s)
+      for (int j = 0; j < 3; ++j)
+        if ((int)(D.grid.N[j] + (((s >> j) & 1u) ? 0 : 1)) != L.csize[s][j]) return -1;
+    R.orient = b->dev.orient;
+    for (int s = 0; s < 8; ++s) R.ooff[s] = b->dev.orientOff[s];
+  }
   const size_t smem = (size_t)kQ3Threads * ((M * M * M) | 1) * sizeof(double);
   const u64 blocks = (R.ne + kQ3Threads - 1) / kQ3Threads;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
   // UNIT multiplies entity index and block size in 32 bits: every component's DOF count must fit
   bool unit = lf.posA == 1;
   for (int s = 0; s < 8; ++s) if (L.compCount[s] > 0xffffffffull) unit = false;
-  if (unit) k_eval_q3<M, true><<<(unsigned)blocks, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
-  else k_eval_q3<M, false><<<(unsigned)blocks, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
+  const unsigned nb = (unsigned)blocks;
+  if (b->oriented) {
+    if (unit) k_eval_q3<M, true, true><<<nb, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
+    else k_eval_q3<M, false, true><<<nb, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
+  } else {
+    if (unit) k_eval_q3<M, true, false><<<nb, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
+    else k_eval_q3<M, false, false><<<nb, kQ3Threads, smem, st>>>(L, T, R, coeff, values);
+  }
   return postLaunch("k_eval_q3");
 }
 

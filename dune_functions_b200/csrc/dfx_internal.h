@@ -70,8 +70,14 @@ struct DevBasis {
   // ids of the grid's globalIdSet for the vertices of the local box, lexicographic (device memory,
   // owned by the handle); nullptr = the structured grid's own ids, monotone in lexicographic
   // position, for which every face orientation is the identity (lagrangebasis.hh:787, :615-634).
-  // Last member on purpose: the offsets of everything the tuned kernels read stay what they were.
+  // Last members on purpose: the offsets of everything the tuned kernels read stay what they were.
   const u64* vid;
+  // orientation codes (orientCode) of the local box's edges and quadrilateral facets, one byte per entity:
+  // component s (bit j set = direction j is free) starts at orientOff[s], entities lexicographic with
+  // N_j (free) or N_j + 1 (fixed) per direction — the entity index of the DOF layout.  nullptr until built
+  // (ensureOrientTable, after dfx_basis_set_vertex_ids).
+  const unsigned char* orient;
+  unsigned orientOff[8];
 };
 
 // scalar index of local node alpha of element e in a continuous/DG layout
@@ -109,15 +115,18 @@ DFX_HD u64 layoutIndex(const DevLayout& L, const DevGrid& g, const int e[3], con
 // smaller id than its first; the vertex with the smallest id is found directly (the reference derives
 // it from the edge bits to save comparisons, ":291-297 ... is equivalent to").  The orientation depends
 // on the entity only, so every element that contains it computes the same one.
-template <bool INVERSE>
-DFX_HD unsigned orientFaceDOF(const DevGrid& g, const u64* vid, int k, unsigned s, const int c[3], unsigned fr) {
+// The orientation depends on the entity only, so it splits into a CODE per entity (edges: 1 = flipped; facets:
+// rotations r in bits 0-1, reflection in bit 2; 0 = identity) and the permutation the code stands for.  The code
+// table of the local box is built once per dfx_basis_set_vertex_ids (k_orient_codes), after which the kernels
+// read one byte per entity instead of two or four 64-bit ids.
+DFX_HD unsigned orientCode(const DevGrid& g, const u64* vid, unsigned s, const int c[3]) {
   const u64 v0s = (u64)(g.N[0] + 1), v1s = v0s * (u64)(g.N[1] + 1);
   const u64 base = (u64)c[0] + v0s * (u64)c[1] + v1s * (u64)c[2];
   const u64 st[3] = {1, v0s, v1s};
   const int nfree = ((s >> 0) & 1) + ((s >> 1) & 1) + ((s >> 2) & 1);
   if (nfree == 1 && g.dim > 1) {
     const int f = (s & 1u) ? 0 : ((s & 2u) ? 1 : 2);
-    return vid[base] > vid[base + st[f]] ? (unsigned)(k - 2) - fr : fr;
+    return vid[base] > vid[base + st[f]] ? 1u : 0u;
   }
   if (nfree == 2 && g.dim == 3) {
     const int f0 = (s & 1u) ? 0 : 1, f1 = (s & 4u) ? 2 : 1;
@@ -127,8 +136,20 @@ DFX_HD unsigned orientFaceDOF(const DevGrid& g, const u64* vid, int k, unsigned 
     else if (id1 < id2 && id1 < id3) { r = 3; refl = id0 < id3; }
     else if (id2 < id3) { r = 1; refl = id3 < id0; }
     else { r = 2; refl = id1 < id2; }
+    return r | (refl << 2);
+  }
+  return 0u;
+}
+
+// nfree: free directions of the entity (1 edge, 2 quadrilateral facet); anything else is the identity
+template <bool INVERSE>
+DFX_HD constexpr unsigned applyOrientCode(unsigned code, int nfree, int k, unsigned fr) {
+  if (nfree == 1) return code ? (unsigned)(k - 2) - fr : fr;
+  if (nfree == 2) {
+    unsigned r = code & 3u;
+    const unsigned refl = code >> 2;
     const unsigned m = (unsigned)(k - 1);
-    unsigned c0 = fr % m, c1 = fr / m, t;
+    unsigned c0 = fr % m, c1 = fr / m, t = 0;
     if (INVERSE) {
       if (refl) { t = c0; c0 = c1; c1 = t; }
       r = (4u - r) & 3u;
@@ -140,6 +161,13 @@ DFX_HD unsigned orientFaceDOF(const DevGrid& g, const u64* vid, int k, unsigned 
     return c0 + m * c1;
   }
   return fr;
+}
+
+template <bool INVERSE>
+DFX_HD unsigned orientFaceDOF(const DevGrid& g, const u64* vid, int k, unsigned s, const int c[3], unsigned fr) {
+  const int nfree = ((s >> 0) & 1) + ((s >> 1) & 1) + ((s >> 2) & 1);
+  if (!((nfree == 1 && g.dim > 1) || (nfree == 2 && g.dim == 3))) return fr;
+  return applyOrientCode<INVERSE>(orientCode(g, vid, s, c), nfree, k, fr);
 }
 
 // layoutIndex with the face-DOF permutation applied (PreBasis::indices, lagrangebasis.hh:863-869)
@@ -241,6 +269,7 @@ struct dfx_basis_impl {
   std::vector<IdxLi> idxTab; void* dIdxTab = nullptr;   // per local index: folded constants of the index table
   void* dDev = nullptr;                                 // device copy of `dev`
   void* dVid = nullptr;                                 // vertex ids (dev.vid points here)
+  void* dOrient = nullptr; size_t dOrientBytes = 0; bool orientValid = false;   // orientation codes (dev.orient)
   // evaluation with permuted face DOFs: the same tree with every leaf discontinuous, and the
   // element-local coefficients gathered for it (csrc/dfx_kernels.cu, k_gather_local)
   dfx_basis_impl* companion = nullptr; bool companionTried = false;

@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "dfx_device.cuh"
+#include "dfx_eval_fast.h"
 #include "dfx_launch.h"
 
 namespace dfx {
@@ -390,9 +391,12 @@ struct RunArgs {
   FastDiv divBlk[8], divCs1[8];
 };
 constexpr int kRunRows = 32;
-template <int K> struct RunRow { double* base; double y[K - 1], z[K - 1]; };
+template <int K> struct RunRow { double* base; double y[K - 1], z[K - 1]; unsigned obase, pad; };   // obase: ORIENT, entity index of the run's first entity
 
-template <class F, int K, int TX, int TY>
+// ORIENT (dfx_basis_set_vertex_ids): slot t of an edge / facet block holds the node the entity's globally unique
+// orientation numbers t; the element numbers it applyOrientCode<INVERSE>(code, t) (lagrangebasis.hh:863-869 read
+// backwards, as dofOwnerNode does), so the thread reads the entity's code byte and picks its node's offsets per entity.
+template <class F, int K, int TX, int TY, bool ORIENT>
 __global__ void __launch_bounds__(TX * TY)
 k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArgs A, const __grid_constant__ F f,
               double* __restrict__ coeff) {
@@ -424,6 +428,7 @@ k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArg
     RunRow<K> r;
     const u64 j0 = L.compOffset[s] + (u64)blk * ((u64)cs0 * ((u64)c1 + (u64)cs1 * (u64)c2));
     r.base = coeff + (leaf.posA * j0 + leaf.posB);
+    r.obase = cs0 * (c1 + cs1 * c2); r.pad = 0;
 #pragma unroll
     for (int a = 1; a < K; ++a) {
       r.y[a - 1] = g.dim > 1 ? ((s & 2) ? freeCoord(1, c1, a) : planeCoord(1, c1)) : 0.0;
@@ -443,15 +448,43 @@ k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArg
   const unsigned mainLen = len - len % TX;       // whole passes of TX entries; the rest (a few entries of the closing
                                                  // lattice plane when x is pinned) goes item by item below
   __syncthreads();
-  for (unsigned u = threadIdx.x; u < mainLen; u += TX) {
-    const unsigned c0 = A.divBlk[s].div(u);
-    const double x = (s & 1) ? freeCoord(0, c0, a0) : planeCoord(0, c0);
-    const size_t off = (size_t)stride8 * u;
+  // ORIENT: edges (one free direction, 2-d and 3-d) and quadrilateral facets (two free directions, 3-d)
+  const int nfree = (s & 1) + ((s >> 1) & 1) + ((s >> 2) & 1);
+  const bool permuted = ORIENT && B.orient != nullptr && ((nfree == 1 && g.dim > 1) || (nfree == 2 && g.dim == 3));
+  const unsigned char* __restrict__ otab = permuted ? B.orient + B.orientOff[s] : nullptr;
+  const unsigned slot = threadIdx.x % blk;
+  if (permuted) {
+    for (unsigned u = threadIdx.x; u < mainLen; u += TX) {
+      const unsigned c0 = A.divBlk[s].div(u);
+      double xs[K - 1];                            // x of the node for every in-entity offset along x (x free), else one value
+#pragma unroll
+      for (int a = 1; a < K; ++a) xs[a - 1] = (s & 1) ? freeCoord(0, c0, a) : planeCoord(0, c0);
+      const size_t off = (size_t)stride8 * u;
+      for (unsigned r = threadIdx.y; r < nr; r += TY) {
+        const RunRow<K>& row = rows[r];
+        unsigned fl = applyOrientCode<true>((unsigned)__ldg(otab + row.obase + c0), nfree, K, slot);
+        int b0 = 0, yj = 0, zj = 0;
+        if (s & 1) { b0 = (int)(fl % (K - 1)); fl /= (K - 1); }
+        if (s & 2) { yj = (int)(fl % (K - 1)); fl /= (K - 1); }
+        if (s & 4) { zj = (int)(fl % (K - 1)); }
+        double x = xs[0];
+#pragma unroll
+        for (int a = 1; a < K - 1; ++a) x = b0 == a ? xs[a] : x;
+        const double y = row.y[yj], z = row.z[zj];
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, f.common(x, y, z), x, y, z);
+      }
+    }
+  } else {
+    for (unsigned u = threadIdx.x; u < mainLen; u += TX) {
+      const unsigned c0 = A.divBlk[s].div(u);
+      const double x = (s & 1) ? freeCoord(0, c0, a0) : planeCoord(0, c0);
+      const size_t off = (size_t)stride8 * u;
 #pragma unroll 4
-    for (unsigned r = threadIdx.y; r < nr; r += TY) {
-      const RunRow<K>& row = rows[r];
-      const double y = row.y[yi], z = row.z[zi];
-      *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, f.common(x, y, z), x, y, z);
+      for (unsigned r = threadIdx.y; r < nr; r += TY) {
+        const RunRow<K>& row = rows[r];
+        const double y = row.y[yi], z = row.z[zi];
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, f.common(x, y, z), x, y, z);
+      }
     }
   }
   // ---- the last len % TX entries of every run: one (run, entry) item per thread ----
@@ -460,6 +493,7 @@ k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArg
     const unsigned r = t / rem, u = mainLen + (t - r * rem);
     const unsigned c0 = A.divBlk[s].div(u);
     unsigned fu = u - c0 * blk;
+    if (permuted) fu = applyOrientCode<true>((unsigned)__ldg(otab + rows[r].obase + c0), nfree, K, fu);
     int b0 = 0, yj = 0, zj = 0;
     if (s & 1) { b0 = 1 + (int)(fu % (K - 1)); fu /= (K - 1); }
     if (s & 2) { yj = (int)(fu % (K - 1)); fu /= (K - 1); }
@@ -679,7 +713,8 @@ static void launchCellNode(int passes, unsigned blocks, cudaStream_t st, const D
 
 // continuous orders 3 .. 5, one leaf, no mask: the run sweep (k_interp_runs)
 template <int ID>
-static bool launchRunsNode(const DevBasis& D, int q, int leafId, int comp, const dfx_function& fn, double* coeff, cudaStream_t st) {
+static bool launchRunsNode(const DevBasis& D, int q, int leafId, int comp, const dfx_function& fn, double* coeff, cudaStream_t st,
+                           bool orient = false) {
   const DevLayout& L = D.layouts[q];
   const int k = L.k;
   if (k < 3 || k > 5) return false;
@@ -703,10 +738,39 @@ static bool launchRunsNode(const DevBasis& D, int q, int leafId, int comp, const
   for (int qq = L.ncomp; qq <= 8; ++qq) A.blockStart[qq] = (unsigned)blocks;
   if (blocks == 0 || blocks > 0x7fffffffull) return false;
   RegistryFnT<ID, true> f; f.f = fn; f.dim = D.grid.dim;
-  if (k == 3) k_interp_runs<RegistryFnT<ID, true>, 3, 128, 2><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
-  else if (k == 4) k_interp_runs<RegistryFnT<ID, true>, 4, 108, 2><<<(unsigned)blocks, dim3(108, 2), 0, st>>>(D, A, f, coeff);
-  else k_interp_runs<RegistryFnT<ID, true>, 5, 128, 2><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+  if (orient) {
+    if (k == 3) k_interp_runs<RegistryFnT<ID, true>, 3, 128, 2, true><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+    else if (k == 4) k_interp_runs<RegistryFnT<ID, true>, 4, 108, 2, true><<<(unsigned)blocks, dim3(108, 2), 0, st>>>(D, A, f, coeff);
+    else k_interp_runs<RegistryFnT<ID, true>, 5, 128, 2, true><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+    return true;
+  }
+  if (k == 3) k_interp_runs<RegistryFnT<ID, true>, 3, 128, 2, false><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
+  else if (k == 4) k_interp_runs<RegistryFnT<ID, true>, 4, 108, 2, false><<<(unsigned)blocks, dim3(108, 2), 0, st>>>(D, A, f, coeff);
+  else k_interp_runs<RegistryFnT<ID, true>, 5, 128, 2, false><<<(unsigned)blocks, dim3(128, 2), 0, st>>>(D, A, f, coeff);
   return true;
+}
+
+// Handles with permuted face DOFs (dfx_basis_set_vertex_ids): ONE continuous leaf of order 3 .. 5, no mask — the run
+// sweep with one orientation byte per entity.  -1: not this configuration (the caller takes the general kernel).
+int interpolateRunsOriented(dfx_basis* b, int leafId, const dfx_function& fn, double* coeff, cudaStream_t st) {
+  const DevBasis& D0 = b->dev;
+  const int q = D0.leaves[leafId].layout;
+  const DevLayout& L = D0.layouts[q];
+  if (L.kind != DFX_NODE_LAGRANGE || L.k < 3 || L.k > 5 || fn.n_comp != 1) return -1;
+  if (b->dimension > 0xffffffffull) return -1;
+  if (ensureOrientTable(b, st) != DFX_OK) return -1;
+  for (unsigned s = 1; s < 7; ++s)                                  // the table numbers entities like the DOF layout
+    for (int j = 0; j < D0.grid.dim; ++j)
+      if ((int)(D0.grid.N[j] + (((s >> j) & 1u) ? 0 : 1)) != L.csize[s][j] && L.compCount[s] > 0) return -1;
+  const DevBasis& D = b->dev;                                       // with the table published
+  bool launched = false;
+  switch (fn.id) {
+    case DFX_FN_GAUSSIAN: launched = launchRunsNode<DFX_FN_GAUSSIAN>(D, q, leafId, 0, fn, coeff, st, true); break;
+    case DFX_FN_QUADRATIC: launched = launchRunsNode<DFX_FN_QUADRATIC>(D, q, leafId, 0, fn, coeff, st, true); break;
+    default: launched = launchRunsNode<-1>(D, q, leafId, 0, fn, coeff, st, true); break;
+  }
+  if (!launched) return -1;
+  return postLaunch("k_interp_runs");
 }
 
 static bool separable(const dfx_function& f) {
@@ -1010,15 +1074,25 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
     const T PA = (T)leaf.posA;
     const u64* __restrict__ vid = ORIENT ? Bp->vid : nullptr;
     const int kOrd = L.k;
+    int nfree = 0;
+    // the entity's orientation code: one byte from the handle's table (built once per set of ids by
+    // k_orient_codes; entity index = the DOF layout's), else derived from the 2 / 4 vertex ids on the spot
+    const unsigned char* __restrict__ otab = nullptr;
     if (ORIENT && vid != nullptr && L.kind == DFX_NODE_LAGRANGE && kOrd > 2 && g.dim > 1) {
-      const int nfree = (int)((s & 1u) + ((s >> 1) & 1u) + ((s >> 2) & 1u));
+      nfree = (int)((s & 1u) + ((s >> 1) & 1u) + ((s >> 2) & 1u));
       perm = nfree == 1 || (nfree == 2 && g.dim == 3);
       unsigned frs = 1;
       for (int j = 0; j < 3; ++j) {
         if ((s >> j) & 1u) { fr += (unsigned)(a[j] - 1) * frs; frs *= (unsigned)(kOrd - 1); }
         else sh[j] = a[j] == kOrd ? 1 : 0;
       }
+      if (perm && Bp->orient != nullptr) otab = Bp->orient + Bp->orientOff[s] + (unsigned)sh[0] + cs0 * ((unsigned)sh[1] + cs1 * (unsigned)sh[2]);
     }
+    auto permuted = [&](unsigned entNow, unsigned e0_, unsigned e1_, unsigned e2_) -> unsigned {
+      if (otab != nullptr) return applyOrientCode<false>((unsigned)__ldg(otab + entNow), nfree, kOrd, fr);
+      const int c[3] = {(int)e0_ + sh[0], (int)e1_ + sh[1], (int)e2_ + sh[2]};
+      return orientFaceDOF<false>(g, vid, kOrd, s, c, fr);
+    };
     // walk this thread's elements el = blkEl0 + sub, + m, + 2m, ...: coordinates advance with carry,
     // the value and the output pointer advance by constant steps between carries
     const u64 el = blkEl0 + (u64)sub;
@@ -1039,10 +1113,7 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
       const size_t step = (size_t)m * nloc * A.stride;
       for (int it = 0; it < nIt; ++it) {
         T df = (T)0;
-        if (ORIENT && perm) {
-          const int c[3] = {(int)ec0 + sh[0], (int)ec1 + sh[1], (int)ec2 + sh[2]};
-          df = (T)orientFaceDOF<false>(g, vid, kOrd, s, c, fr) - (T)fr;
-        }
+        if (ORIENT && perm) df = (T)permuted(ent, ec0, ec1, ec2) - (T)fr;
 #pragma unroll
         for (int p = 0; p < DFX_MAX_DIGITS; ++p)
           if (p < A.stride) po[p] = ORIENT ? (T)(dB[p] + dA[p] * (T)ent + dF[p] * df) : (T)(dB[p] + dA[p] * (T)ent);
@@ -1066,16 +1137,14 @@ k_indices_fast(const DevBasis* __restrict__ Bp, const __grid_constant__ IdxArgs 
       const T dv = (T)(S * (T)m);
       for (int it = 0; it < nIt; ++it) {
         T w = v;
-        if (ORIENT && perm) {
-          const int c[3] = {(int)ec0 + sh[0], (int)ec1 + sh[1], (int)ec2 + sh[2]};
-          w = (T)(v + PA * ((T)orientFaceDOF<false>(g, vid, kOrd, s, c, fr) - (T)fr));
-        }
+        if (ORIENT && perm) w = (T)(v + PA * ((T)permuted(ent, ec0, ec1, ec2) - (T)fr));
         if (GATHER) { *pd = src[w]; pd += step; }
         else { *po = w; po += step; }
-        ec0 += m; v += dv;
+        ec0 += m; v += dv; ent += m;
         if (ec0 >= N0) {
           do { ec0 -= N0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } } while (ec0 >= N0);
-          v = (T)(P0 + S * (T)(ec0 + cs0 * (ec1 + cs1 * ec2)));
+          ent = ec0 + cs0 * (ec1 + cs1 * ec2);
+          v = (T)(P0 + S * (T)ent);
         }
       }
     }
@@ -1245,6 +1314,9 @@ static int launchIndicesFast(const dfx_basis* b, u64 e0, u64 e1, T* out, int str
   const u64 perBlock = (u64)A.m * A.iters;
   const u64 blocks = (A.ne + perBlock - 1) / perBlock;
   if (blocks > 0x7fffffffull) return fail(DFX_ERR_RANGE, "element range too large for one launch");
+  // permuted face DOFs: one orientation byte per entity instead of 2 - 4 vertex ids per DOF (the kernel derives the
+  // code from the ids itself when the table cannot be built)
+  if (ORIENT && b->oriented) (void)ensureOrientTable(const_cast<dfx_basis*>(b), st);
   k_indices_fast<T, MULTI, ORIENT, GATHER><<<(unsigned)blocks, A.lpb * A.m, 0, st>>>(
       (const DevBasis*)b->dDev, A, (const unsigned*)b->dLocalTab, out, src, dst, G);
   return postLaunch("k_indices_fast");

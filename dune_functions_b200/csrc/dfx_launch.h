@@ -79,6 +79,7 @@ int evalGeneric(const dfx_basis* b, int firstLeaf, int nLeaves, const double* co
                 cudaStream_t st);
 int interpolateFast(dfx_basis* b, int firstLeaf, int nLeaves, const dfx_function& fn, double* coeff,
                     const uint8_t* mask, bool wantSep, cudaStream_t st);
+int interpolateRunsOriented(dfx_basis* b, int leafId, const dfx_function& fn, double* coeff, cudaStream_t st);
 extern int g_rowsLean;
 extern int g_indicesTile;
 int interpolateBatch2(dfx_basis* b, int flA, int nlA, const dfx_function& fa, int flB, int nlB, const dfx_function& fb,

@@ -335,3 +335,44 @@ def test_index_kernel_families_with_permuted_face_dofs(n):
                     assert (b.flatIndices(2, ne - 1, dtype=dt).cpu().numpy().astype(np.uint64) == flat[2:ne - 1]).all()
     finally:
         capi.lib().dfx_set_kernel_path(capi.OP_INDICES, -1)
+
+
+@pytest.mark.parametrize("n", [(70, 3, 2), (9, 5, 4), (1, 1, 1)], ids=str)
+@pytest.mark.parametrize("last_fastest", [False, True])
+def test_q3_register_kernel_with_permuted_face_dofs(n, last_fastest):
+    """order 3 at 4^3 points, values only, with vertex ids: k_eval_q3<.., ORIENT> reads one orientation byte per
+    edge / facet (the code table k_orient_codes builds once per set of ids) and permutes the in-entity index of
+    its gathers.  Against the oracle — whole grid, sub-ranges, a component of an interleaved power tree — against
+    the gather + companion route, and again after the ids have been replaced (the table is rebuilt) and removed."""
+    import torch
+    L = capi.lib()
+    rng = np.random.default_rng(31)
+    pts, _ = tensor_gauss(3, 4, last_fastest)
+    for tree, sub in ((lagrange(3), None), (power(lagrange(3), 2, FI()), 1)):
+        grid = grid_with_ids(n, 41, upper=[1.0, 0.7, 1.3])
+        b = dfx.makeBasis(grid, tree)
+        o = orc.OracleBasis(grid, tree)
+        c = rng.uniform(-1, 1, b.dimension())
+        ct = torch.from_numpy(c).cuda()
+        ne = b.numElements()
+        space = b if sub is None else dfx.subspaceBasis(b, sub)
+        node = 0 if sub is None else b.child(0, sub)
+        f = dfx.makeDiscreteGlobalBasisFunction(space, ct)
+        ref = o.evaluate(c, pts, node=node)
+        try:
+            for q3 in (1, 0):
+                L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_Q3, q3)
+                assert rel(f.evaluate(pts).cpu().numpy(), ref) <= TOL, (n, q3)
+                if ne > 2:
+                    assert rel(f.evaluate(pts, elem_begin=1, elem_end=ne - 1).cpu().numpy(), ref[1:ne - 1]) <= TOL, (n, q3)
+        finally:
+            L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_Q3, -1)
+        # other ids: the numbering changes, the code table with it
+        ids2 = ids_for(n, 77)
+        b.setVertexIds(ids2)
+        o2 = orc.OracleBasis(YaspGrid(list(n), vertex_ids=ids2, upper=[1.0, 0.7, 1.3]), tree)
+        assert rel(f.evaluate(pts).cpu().numpy(), o2.evaluate(c, pts, node=node)) <= TOL
+        # no ids: the plain kernel
+        b.setVertexIds(None)
+        o3 = orc.OracleBasis(YaspGrid(list(n), upper=[1.0, 0.7, 1.3]), tree)
+        assert rel(f.evaluate(pts).cpu().numpy(), o3.evaluate(c, pts, node=node)) <= TOL

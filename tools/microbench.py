@@ -125,16 +125,16 @@ def main():
         nd, ne = basis.dimension(), basis.numElements()
         x = basis.newVector(0.0)
         ms, best = timeit(lambda: dfx.interpolate(basis, x, dfx.gaussian(1.0)), args.reps)
-        report("interpolate exp(-|x|^2) [permuted face DOFs, general kernel]", "q3_128_oriented", ms, best, nd * 8,
+        report("interpolate exp(-|x|^2) [permuted face DOFs: run sweep + orientation bytes]", "q3_128_oriented", ms, best, nd * 8,
                {"dofs_per_s": nd / ms * 1e3})
         pts, _ = dfx.tensor_gauss(3, 4)
         f = dfx.makeDiscreteGlobalBasisFunction(basis, x)
         v = torch.empty((ne, len(pts), 1), dtype=torch.float64, device="cuda")
         ms, best = timeit(lambda: f.evaluate(pts, out_values=v), args.reps)
-        report("evaluate values 4^3 [permuted face DOFs: gather + companion basis]", "q3_128_oriented", ms, best, nd * 8 + v.numel() * 8)
+        report("evaluate values 4^3 [permuted face DOFs: k_eval_q3 + orientation bytes]", "q3_128_oriented", ms, best, nd * 8 + v.numel() * 8)
         idx = torch.empty((ne, 64), dtype=torch.int32, device="cuda")
         ms, best = timeit(lambda: capi.check(L.dfx_indices_flat(basis._h, 0, ne, C.c_void_p(idx.data_ptr()), st())), args.reps)
-        report("indices flat u32 [permuted face DOFs, walking kernel]", "q3_128_oriented", ms, best, idx.numel() * 4)
+        report("indices flat u32 [permuted face DOFs: walking kernel + orientation bytes]", "q3_128_oriented", ms, best, idx.numel() * 4)
         del basis, x, v, f, idx, ids
         torch.cuda.empty_cache()
 
