@@ -680,6 +680,33 @@ def run_e2e(run, steps):
     return out
 
 
+def copy_bandwidth_here(run, seconds=0.3):
+    """device-to-device copy bandwidth (read + write bytes) measured on this GPU right after the sustained loop, i.e.
+    under the clocks and the power state the step itself ran at — MEASURED_PEAKS.json's figure is a best-of-10 burst.
+    Uses two disjoint 1 GiB pieces of the step's own output buffer (recomputed by the next step), larger than the L2."""
+    torch = run.torch
+    flat = run.values.view(-1)
+    n = int(min(1 << 27, flat.numel() // 2))
+    if n * 8 < (256 << 20):
+        return None
+    a, b = flat[:n], flat[n:2 * n]
+    for _ in range(3):
+        b.copy_(a)
+    torch.cuda.synchronize()
+    per = 2.0 * n * 8
+    reps = int(max(10, min(4000, seconds * 6.0e12 / per)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"gbs": per * reps / ms / 1e6, "seconds": ms / 1e3, "copies": reps, "bytes_per_copy": int(per),
+            "how": "torch copy_ between two disjoint 1 GiB pieces of the output buffer, back to back right after the sustained "
+                   "loop (same clocks / power state as the step); read + write bytes"}
+
+
 def time_workload(run, steps, warmup, sustain_s=0.0, sampler=None):
     """W warm-up steps, exactly K timed steps (CUDA events, barrier + synchronize on both sides), optional
     sustained continuation; returns (ms_per_step max over ranks, launches, sustained dict, t_end of the timed steps)"""
@@ -847,6 +874,7 @@ def main():
     # NVML is polled by rank 0 only: queries from every process contend in the driver and delay launches
     sampler = ClockSampler(physical_gpu_index(local_rank))
     ms_per_step, launches, sustained, t_end = time_workload(run, args.steps, warmup, args.sustain, sampler)
+    copy_here = copy_bandwidth_here(run) if args.sustain > 0 else None
     sampler.stop_flag.set()
     if rank == 0:
         sampler.join()
@@ -972,6 +1000,11 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes": eval_bytes,
                          "traffic": traffic_from_profiles("evaluate", args.workload),
+                         "copy_bandwidth_after_sustained_loop": copy_here,
+                         # evaluate inside the sustained loop (its share of the step as in the timed steps) against the copy
+                         # bandwidth measured right after that loop: both under the settled clocks
+                         "frac_of_copy_bandwidth_after_sustained_loop":
+                             (achieved * ms_per_step / sustained["ms_per_step"] / copy_here["gbs"]) if (copy_here and sustained) else None,
                          "interpolate": {"achieved": interp_bytes / t_interp / 1e9 if t_interp > 0 else None,
                                          "frac": interp_bytes / t_interp / 1e9 / peak if t_interp > 0 else None,
                                          "frac_separable_tables": interp_bytes / (t_sep / 1e3) / 1e9 / peak if t_sep > 0 else None,
