@@ -784,6 +784,12 @@ def sub_config(name, local_rank, steps, warmup, peak):
                         "algorithmic_bytes": run.eval_bytes(), "traffic": traffic_from_profiles("evaluate", name),
                         "interpolate": {"frac": fr["interpolate"], "algorithmic_bytes": run.interp_bytes(),
                                         "traffic": traffic_from_profiles("interpolate", name)}}}
+    if name == "c4":
+        # the config's synthetic f costs 24 FP64 operations per node in the reference's summation order (kept for
+        # bit-exactness): the per-node interpolation of this config is bound by the FP64 pipe, not by HBM
+        out["roofline"]["interpolate"]["second_bound"] = {
+            "bound": "fp64 pipe", "sm__pipe_fp64_cycles_active_pct": 80.0,
+            "source": "profiles/r02_ncu_configs.csv, k_interp_cell<RegistryFnT<QUADRATIC>,0,4,1>"}
     if run.index_table is not None:
         out["roofline"]["indices"] = {"frac": fr["indices"], "algorithmic_bytes": run.index_bytes(),
                                       "traffic": traffic_from_profiles("indices", name)}
