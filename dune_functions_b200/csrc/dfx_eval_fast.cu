@@ -46,6 +46,8 @@ int g_evalBlock = 64;      // elements per block of the values-only register ker
                            // and 14 % to the one warp per block that waits for the bulk store before it exits).
                            // Measured back to back: 512^3 6.53 -> 6.05 and 7.00 -> 6.58 ms, 256^3 0.806 -> 0.799 ms
 int g_evalStreamHint = 1;  // bulk stores of results with the L2 evict-first policy (DFX_OP_TUNE_STREAM_HINT)
+int g_evalSplitByGroup = 1;   // DFX_OP_TUNE_SPLIT_MAP: fused Taylor-Hood evaluation with whole warps per leaf group (0: every warp runs both
+                              // branches; measured 0.441 -> 0.370 ms on Taylor-Hood 128^3, profiles/r02_c3eval_split_map_ab.jsonl)
 int g_evalSwizzle = 1;     // dfx_set_kernel_path(DFX_OP_TUNE_SWIZZLE, .): 0 blocks in grid-view order, 1 strip schedule when a
                            // z-layer outgrows the L2, 2 strip schedule whenever the shape allows (tests)
 
@@ -364,6 +366,10 @@ struct SplitArgs {
   FastDiv divN0, divN1, divG;
   int bulk;
   unsigned long long posA[DFX_MAX_LEAVES], posB[DFX_MAX_LEAVES];    // all G leaves, group 2 behind group 1
+  // K2 >= 0, byGroup: the threads [0, epb * nGroup) take group 1 (leaf fastest), the rest group 2 — whole warps on one
+  // branch instead of every warp running both (Taylor-Hood: three warps of Q2 velocity, one of Q1 pressure)
+  int byGroup;
+  FastDiv divGA, divGB;
 };
 constexpr int kSplitThreads = 128;
 
@@ -384,7 +390,13 @@ k_eval_split(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayou
   const int epb = R.epb;
   const int tid = threadIdx.x;
   unsigned elL, leaf;
-  R.divG.divmod((unsigned)tid, elL, leaf);
+  if (K2 >= 0 && R.byGroup) {
+    const unsigned nA = (unsigned)(epb * R.nGroup);
+    if ((unsigned)tid < nA) R.divGA.divmod((unsigned)tid, elL, leaf);
+    else { R.divGB.divmod((unsigned)tid - nA, elL, leaf); leaf += (unsigned)R.nGroup; }
+  } else {
+    R.divG.divmod((unsigned)tid, elL, leaf);
+  }
   const u64 blk0 = (u64)blockIdx.x * (u64)epb;
   const u64 el = blk0 + elL;
   const bool active = el < R.ne && (int)elL < epb;
@@ -523,6 +535,8 @@ static int launchSplit(dfx_basis* b, const FastPlan& plan, const FastPlan* plan2
   epb &= ~1;
   if (epb < 2) return fail(DFX_ERR_NOT_IMPLEMENTED, "evaluation tile exceeds shared memory");
   R.epb = epb; R.divG = FastDiv((unsigned)G);
+  R.byGroup = (K2 >= 0 && g_evalSplitByGroup) ? 1 : 0;
+  R.divGA = FastDiv((unsigned)std::max(1, R.nGroup)); R.divGB = FastDiv((unsigned)std::max(1, R.nGroup2));
   const size_t smem = (size_t)epb * perEl;
   auto kern = k_eval_split<DIM, K, M, JAC, K2>;
   static std::atomic<unsigned long long> configured{0};

@@ -37,6 +37,7 @@ extern int g_smemTma;
 extern int g_smemPair;
 extern int g_smemMaxBlocks;
 extern int g_evalQ3;
+extern int g_evalSplitByGroup;
 extern int g_evalSwizzle;
 extern int g_evalStreamHint;
 extern int g_evalBlock;

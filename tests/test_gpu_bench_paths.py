@@ -210,8 +210,14 @@ def test_taylor_hood_128_subranges():
     check_interpolate_ranges(b, o, fns, 8192)
     check_interpolate_ranges(b, o, fns, 8192, separable=True)
     pts, _ = tensor_gauss(3, 3)
-    check_evaluate_ranges(b, o, pts, 4096, jac=False)                            # whole tree: Q2 x 3 + Q1
+    check_evaluate_ranges(b, o, pts, 4096, jac=False)                            # whole tree: Q2 x 3 + Q1, warps per leaf group
     check_evaluate_ranges(b, o, pts, 2048, jac=True, seed=6)
+    capi.lib().dfx_set_kernel_path(capi.OP_TUNE_SPLIT_MAP, 0)                    # every warp runs the Q2 and the Q1 branch
+    try:
+        check_evaluate_ranges(b, o, pts, 4096, jac=False)
+        check_evaluate_ranges(b, o, pts, 2048, jac=True, seed=6)
+    finally:
+        capi.lib().dfx_set_kernel_path(capi.OP_TUNE_SPLIT_MAP, -1)
     check_evaluate_ranges(dfx.subspaceBasis(b, 0), o, pts, 4096, jac=False, onode=1, seed=7)  # velocity sub-space
     check_evaluate_ranges(dfx.subspaceBasis(b, 1), o, pts, 4096, jac=False, onode=5, seed=8)  # pressure sub-space
 

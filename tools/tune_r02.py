@@ -117,6 +117,26 @@ def main():
         L.dfx_set_kernel_path(capi.OP_INDICES, -1)
         del b, idx
         torch.cuda.empty_cache()
+    if "c3eval" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([128, 128, 128]), dfx.taylorHood())
+        ne = b.numElements()
+        x = b.newVector(0.0).uniform_(-1, 1)
+        pts, _ = dfx.tensor_gauss(3, 3)
+        v = torch.empty((ne, 27, 4), dtype=torch.float64, device="cuda")
+        f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+        nb = b.dimension() * 8 + v.numel() * 8
+        ref = None
+        for rep in range(3):
+            for mode in (0, 1):
+                L.dfx_set_kernel_path(capi.OP_TUNE_SPLIT_MAP, mode)
+                ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=10)
+                if ref is None:
+                    ref = v.clone()
+                print(json.dumps({"probe": "Taylor-Hood 128^3 whole-tree evaluate", "warps_per_leaf_group": mode, "ms": ms,
+                                  "frac": nb / ms / 1e6 / PEAK, "same_values": bool(torch.equal(v, ref))}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_TUNE_SPLIT_MAP, -1)
+        del b, x, v, f
+        torch.cuda.empty_cache()
     if "c4eval" in what:
         b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
         x = b.newVector(0.0).uniform_(-1, 1)
