@@ -205,9 +205,17 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
         }
       }
     }
-    // the previous iteration's stores must have read the block tiles stage z is about to overwrite
-    if (threadIdx.x == 0 && pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
+    // the previous iteration's stores must have read the block tiles before they are overwritten.  EARLY (one pass of
+    // stage-z pencils): the values tile — the older, four times smaller bulk group — is awaited here, the Jacobian
+    // tile only behind stage z, whose derivative along the last direction waits in registers meanwhile; the 48 KB of
+    // Jacobians then drain under stages x, y AND z of the next iteration instead of x and y only
+    constexpr bool EARLY = GRAD && P3 <= 32;
+    if (threadIdx.x == 0 && pending) {
+      if (EARLY) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
+    }
     __syncthreads();
+    double gz0[EARLY ? M : 1], gz1[EARLY ? M : 1];
     if (have) {
       // ---- stage z: pencil p = q0 + M q1; t2[(q1 M + q0) S + a2] = t2[S p + a2]; point p + P3 q2 ----
 #pragma unroll
@@ -234,9 +242,27 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
               double g0 = T.C[2][q][0] * u0[0], g1 = T.C[2][q][0] * u1[0];
 #pragma unroll
               for (int r = 1; r < M; ++r) { g0 = fma(T.C[2][q][r], u0[r], g0); g1 = fma(T.C[2][q][r], u1[r], g1); }
-              jst[(p + q * P3) * 3 + dLast] = g0 * jc[0][dLast];
-              jst[(NQ + p + q * P3) * 3 + dLast] = g1 * jc[1][dLast];
+              if (EARLY) { gz0[q] = g0 * jc[0][dLast]; gz1[q] = g1 * jc[1][dLast]; }
+              else {
+                jst[(p + q * P3) * 3 + dLast] = g0 * jc[0][dLast];
+                jst[(NQ + p + q * P3) * 3 + dLast] = g1 * jc[1][dLast];
+              }
             }
+          }
+        }
+      }
+    }
+    if (EARLY) {
+      if (threadIdx.x == 0 && pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
+      __syncthreads();
+    }
+    if (have) {
+      if (EARLY) {
+        if (lane < P3) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) {
+            jst[(lane + q * P3) * 3 + dLast] = gz0[q];
+            jst[(NQ + lane + q * P3) * 3 + dLast] = gz1[q];
           }
         }
       }
@@ -296,6 +322,7 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
       if (values)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(values + first * (u64)(2 * NQ)),
                      "r"(sa(tileV)), "r"((unsigned)(n * 2 * NQ * sizeof(double))) : "memory");
+      if (GRAD && P3 <= 32) asm volatile("cp.async.bulk.commit_group;" ::: "memory");     // EARLY: values in their own, older group
       if (GRAD)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(jac + first * (u64)(6 * NQ)),
                      "r"(sa(tileJ)), "r"((unsigned)(n * 6 * NQ * sizeof(double))) : "memory");
