@@ -20,10 +20,12 @@
 //   per warp: TMA bulk load (mbarrier) of the pair's 2 (k+1)^3 coefficients — one 16-byte aligned run of the
 //     vector — into `pb`; the load of the warp's NEXT pair is issued as soon as stage x has read `pb`
 //   stage x: pb -> t1[e][q0][a2][a1]      stage y: t1 -> t2[e][q1][q0][a2]            (warp-private, __syncwarp)
-//   barrier: the previous iteration's bulk stores have read the block tiles (thread 0 waits, __syncthreads)
-//   stage z: t2 -> u = vst[warp][e][point]; gradients = collocation derivative of u along the three grid lines
-//     (jst[warp][e][point][3], scaled by diag(J^-1))
-//   barrier, then thread 0 issues two bulk stores: WARPS * 2 m^3 values and three times as many Jacobian entries.
+//   barrier: the previous iteration's VALUES store (the older, smaller bulk group) has read its tile
+//   stage z: t2 -> u = vst[warp][e][point]; the derivative of u along the last direction stays in registers
+//   barrier: the previous iteration's JACOBIAN store has read its tile (thread 0 waits, __syncthreads)
+//   gradients = collocation derivative of u along the three grid lines (jst[warp][e][point][3], scaled by diag(J^-1))
+//   barrier, then thread 0 issues two bulk stores in two groups: WARPS * 2 m^3 values, then three times as many
+//     Jacobian entries.
 // Two blocks per SM run out of phase: one contracts stages x / y while the other's tile drains.
 //
 // Replaces LocalFunction::operator() / derivative (discreteglobalbasisfunction.hh:336-371, :583-627) for
