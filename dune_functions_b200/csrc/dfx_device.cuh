@@ -160,6 +160,16 @@ struct RegistryFnT {
     }
     return 0.0;
   }
+  // `common` from the SQUARES of the coordinates, for the functions that only need those (the Gaussians): the lattice
+  // sweeps keep x0^2 per x-entity and x1^2, x2^2 per row, so a node costs the two additions, not three more
+  // multiplications — the same operations in the same order as `common`, hence the same bits.
+  static constexpr bool kFromSquares = ID == DFX_FN_GAUSSIAN || ID == DFX_FN_GAUSSIAN_VEC;
+  __device__ __forceinline__ double commonSq(double q0, double q1, double q2) const {
+    double s = q0;                                                  // x.two_norm2(): sum in index order
+    if (LEAN || dim > 1) s = __dadd_rn(s, q1);
+    if (LEAN || dim > 2) s = __dadd_rn(s, q2);
+    return expTabT<!LEAN>(__dmul_rn(-f.p[0], s));
+  }
   __device__ __forceinline__ double comp(int c, double cm, double x0, double x1, double x2) const {
     switch (id()) {
       case DFX_FN_CONSTANT: return f.p[c];

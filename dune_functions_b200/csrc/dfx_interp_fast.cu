@@ -253,7 +253,7 @@ __device__ __forceinline__ double xhatOf(int a) {
   for (int i = 1; i <= KT; ++i) if (a == i) r = (double)i / (double)KT;
   return r;
 }
-struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsigned a8, pad; };
+struct LeanRow { double* pV; double* pE; unsigned sV8, sE8; double u1, u2; unsigned a8, pad; double q1, q2; };   // q1, q2: u1^2, u2^2 (F::kFromSquares)
 int g_rowsLean = -1;    // lattice rows per block of the lean kernel; -1: leanRows() (tuning knob DFX_OP_TUNE_ROWS)
 
 // Many rows per block amortise the per-thread x-data (measured 1 .. 32 rows: 256^3 0.43 -> 0.19 ms, 512^3 flat
@@ -306,20 +306,24 @@ __device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A
     r.a8 = (unsigned)leaf.posA * 8u; r.pad = 0;
     r.u1 = g.dim > 1 ? elementGlobal(g, 1, dy.ie, xhatOf<KT>(dy.a)) : 0.0;
     r.u2 = g.dim > 2 ? elementGlobal(g, 2, dz.ie, xhatOf<KT>(dz.a)) : 0.0;
+    r.q1 = __dmul_rn(r.u1, r.u1); r.q2 = __dmul_rn(r.u2, r.u2);
     rows[rI] = r;
   }
   const unsigned C = (unsigned)A.nActive;                         // 1, or the components of an interleaved group
   const bool scalar = f.ncomp() == 1;
   const unsigned lim = (unsigned)g.N[0] * C;
   unsigned u = threadIdx.x, c0 = 0, lI = 0;
-  double hx[KT];
+  double hx[KT], hq[KT];            // hq: squares of hx (F::kFromSquares)
   // x-data of x-entity c0: nodes X = k c0 + a, a = 0 vertex-type, 1 .. k-1 edge-type; owner element = c0 itself
   auto xprep = [&](unsigned uu) {
     A.divC.divmod(uu, c0, lI);
     const double lo = gridCoordinate(g, 0, g.off[0] + (int)c0), up = gridCoordinate(g, 0, g.off[0] + (int)c0 + 1);
     const double d = __dsub_rn(up, lo);
 #pragma unroll
-    for (int a = 0; a < KT; ++a) hx[a] = __dadd_rn(lo, __dmul_rn((double)a / (double)KT, d));   // alpha / k folded at compile time
+    for (int a = 0; a < KT; ++a) {
+      hx[a] = __dadd_rn(lo, __dmul_rn((double)a / (double)KT, d));   // alpha / k folded at compile time
+      hq[a] = __dmul_rn(hx[a], hx[a]);
+    }
   };
   if (u < lim) xprep(u);            // before the barrier: overlaps the row set-up of the first warp
   __syncthreads();
@@ -331,7 +335,8 @@ __device__ __forceinline__ void leanRowsBody(const DevBasis& B, const RowArgs& A
       const LeanRow r = rows[rI];
 #pragma unroll
       for (int a = 0; a < KT; ++a) {
-        const double v = f.comp(comp, f.common(hx[a], r.u1, r.u2), hx[a], r.u1, r.u2);
+        const double cm = F::kFromSquares ? f.commonSq(hq[a], r.q1, r.q2) : f.common(hx[a], r.u1, r.u2);
+        const double v = f.comp(comp, cm, hx[a], r.u1, r.u2);
         char* p = a == 0 ? reinterpret_cast<char*>(r.pV) + (size_t)r.sV8 * c0
                          : reinterpret_cast<char*>(r.pE) + (size_t)r.sE8 * c0 + (size_t)r.a8 * (unsigned)(a - 1);
         *reinterpret_cast<double*>(p + off8) = v;
@@ -391,7 +396,7 @@ struct RunArgs {
   FastDiv divBlk[8], divCs1[8];
 };
 constexpr int kRunRows = 32;
-template <int K> struct RunRow { double* base; double y[K - 1], z[K - 1]; unsigned obase, pad; };   // obase: ORIENT, entity index of the run's first entity
+template <int K> struct RunRow { double* base; double y[K - 1], z[K - 1]; unsigned obase, pad; double yq[K - 1], zq[K - 1]; };   // yq, zq: squares (F::kFromSquares)   // obase: ORIENT, entity index of the run's first entity
 
 // ORIENT (dfx_basis_set_vertex_ids): slot t of an edge / facet block holds the node the entity's globally unique
 // orientation numbers t; the element numbers it applyOrientCode<INVERSE>(code, t) (lagrangebasis.hh:863-869 read
@@ -433,6 +438,7 @@ k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArg
     for (int a = 1; a < K; ++a) {
       r.y[a - 1] = g.dim > 1 ? ((s & 2) ? freeCoord(1, c1, a) : planeCoord(1, c1)) : 0.0;
       r.z[a - 1] = g.dim > 2 ? ((s & 4) ? freeCoord(2, c2, a) : planeCoord(2, c2)) : 0.0;
+      r.yq[a - 1] = __dmul_rn(r.y[a - 1], r.y[a - 1]); r.zq[a - 1] = __dmul_rn(r.z[a - 1], r.z[a - 1]);
     }
     rows[tid] = r;
   }
@@ -478,12 +484,14 @@ k_interp_runs(const __grid_constant__ DevBasis B, const __grid_constant__ RunArg
     for (unsigned u = threadIdx.x; u < mainLen; u += TX) {
       const unsigned c0 = A.divBlk[s].div(u);
       const double x = (s & 1) ? freeCoord(0, c0, a0) : planeCoord(0, c0);
+      const double xq = __dmul_rn(x, x);
       const size_t off = (size_t)stride8 * u;
 #pragma unroll 4
       for (unsigned r = threadIdx.y; r < nr; r += TY) {
         const RunRow<K>& row = rows[r];
         const double y = row.y[yi], z = row.z[zi];
-        *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, f.common(x, y, z), x, y, z);
+        const double cm = F::kFromSquares ? f.commonSq(xq, row.yq[yi], row.zq[zi]) : f.common(x, y, z);
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(row.base) + off) = f.comp(comp, cm, x, y, z);
       }
     }
   }
