@@ -173,7 +173,12 @@ int  dfx_basis_update(dfx_basis* b, const dfx_grid_desc* grid_host);
  * stream-ordered.                                                                                  */
 int     dfx_basis_set_vertex_ids(dfx_basis* b, const uint64_t* ids, uint64_t n, void* stream);
 int     dfx_basis_set_vertex_ids_host(dfx_basis* b, const uint64_t* ids_host, uint64_t n);
-/* 1 iff ids are set AND some continuous leaf has order >= 3 on a 2-d/3-d grid (the general kernels run) */
+/* 1 iff ids are set AND some continuous leaf has order >= 3 on a 2-d/3-d grid.  The orientation of every edge and
+ * quadrilateral facet of the local box is then computed ONCE per set of ids into a one-byte-per-entity table on the
+ * device (at the first index table / interpolate / evaluate call after the ids were set) and the kernels permute the
+ * in-entity index through it: index table and evaluation gather on the walking kernel, a single continuous leaf of
+ * order 3 - 5 interpolated by the run sweep, order 3 at 4^3 points evaluated in registers; everything else (masks,
+ * several leaves per call, other point sets) takes the general kernels or the gather + companion-basis route. */
 int32_t dfx_basis_has_permuted_face_dofs(const dfx_basis* b);
 
 /* ---- GlobalBasis concept: functionspacebases/concepts.hh:253-273 -----------*/
