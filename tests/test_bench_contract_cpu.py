@@ -36,3 +36,17 @@ def test_reference_arm_under_torchrun_env_only_rank0_prints():
                           "--steps", "1", "--warmup", "1", "--cpu-budget", "0.1"], capture_output=True, text=True, timeout=300,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_profiles_traffic_covers_every_bench_config():
+    """bench.py fills roofline.traffic from profiles/traffic.json: the headline workload and every sub-config must
+    have the kernels it reports, as positive byte counts with the ncu source named"""
+    sys.path.insert(0, ROOT)
+    import bench
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for name in (bench.HEADLINE,) + tuple(bench.SUB_CONFIGS):
+        assert name in t, name
+        for kernel in ("evaluate", "interpolate"):
+            assert t[name][kernel] > 0 and bench.traffic_from_profiles(kernel, name) == t[name][kernel], (name, kernel)
+        assert "ncu" in t[name]["source"]
+    assert t["c3"]["indices"] > 0 and t["c3"]["indices_multi"] > 0 and t["c4"]["evaluate_values_only"] > 0
