@@ -41,6 +41,8 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+struct GatherLi { u64 P0, S; unsigned cs0, cs1; };     // position of local index i in element e: P0 + S * lex(e; cs0, cs1)
+
 __global__ void __launch_bounds__(256)
 k_eval_dmma(const DevBasis* __restrict__ Bp, const __grid_constant__ DmmaArgs R, const unsigned* __restrict__ localTab,
             const double* __restrict__ coeff, const double* __restrict__ Bt, double* __restrict__ values,
@@ -48,64 +50,110 @@ k_eval_dmma(const DevBasis* __restrict__ Bp, const __grid_constant__ DmmaArgs R,
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                                   // [128][lda]
   double* Bs = smem + (size_t)kDmmaElems * R.lda;      // [kp][68]
+  GatherLi* li = reinterpret_cast<GatherLi*>(Bs + (size_t)R.kp * kDmmaLdb);    // [kp]
   const DevGrid& g = Bp->grid;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;
   const u64 el0 = (u64)blockIdx.x * kDmmaElems;
   const unsigned nEl = (R.ne - el0) < (u64)kDmmaElems ? (unsigned)(R.ne - el0) : (unsigned)kDmmaElems;
-  const unsigned N0 = (unsigned)g.N[0], N1g = (unsigned)g.N[1];
-  unsigned s0, s1, s2;                                 // coordinates of the CTA's first element
-  {
-    unsigned q;
-    R.divN0.divmod((unsigned)(R.e0 + el0), q, s0);
-    R.divN1.divmod(q, s2, s1);
-  }
   const DevLeaf& leaf0 = Bp->leaves[R.firstLeaf];
   const DevLayout& L = Bp->layouts[leaf0.layout];
 
+  // the two rows of this thread's accumulator fragments: element, diag(J^-1) (AxisAlignedCubeGeometry), once per kernel
+  // — the first version recomputed the three divisions in every pass of every leaf (31 % of the stall samples sat in
+  // the epilogue)
+  double jinvRow[2][3] = {{1, 1, 1}, {1, 1, 1}};
+  if (R.wantJac) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const unsigned n = (unsigned)(warp * 16 + mt * 8 + grp);
+      if (n >= nEl) continue;
+      unsigned q, ec0, ec1, ec2;
+      R.divN0.divmod((unsigned)(R.e0 + el0) + n, q, ec0);
+      R.divN1.divmod(q, ec2, ec1);
+      jinvRow[mt][0] = elementJacInv(g, 0, g.off[0] + (int)ec0);
+      if (R.dim > 1) jinvRow[mt][1] = elementJacInv(g, 1, g.off[1] + (int)ec1);
+      if (R.dim > 2) jinvRow[mt][2] = elementJacInv(g, 2, g.off[2] + (int)ec2);
+    }
+  }
   for (int gI = 0; gI < R.nGroup; ++gI) {
     const DevLeaf& leaf = Bp->leaves[R.firstLeaf + gI];
     __syncthreads();
-    // ---- gather: thread <-> local index, walk the CTA's elements (LocalFunctionBase::bind) ----
+    // ---- gather (LocalFunctionBase::bind): the per-local-index constants of the closed-form position go into shared
+    // memory once, then the 128 x kp entries of the tile are spread over ALL threads as independent loads (the first
+    // version let thread i walk its 128 elements one dependent iteration after the other: 125 threads, one load in
+    // flight each — about 40 us of the CTA's 217 us) ----
     for (int i = tid; i < R.kp; i += blockDim.x) {
-      if (i >= R.nloc) { for (unsigned n = 0; n < kDmmaElems; ++n) As[n * R.lda + i] = 0.0; continue; }
-      const unsigned packed = __ldg(localTab + leaf0.localOffset + i);
-      const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
-      const int zero[3] = {0, 0, 0};
-      const u64 jbase = layoutIndex(L, g, zero, a, i);
-      unsigned s = 0;
-      if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << g.dim) - 1u;
-      else
-        for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
-      const unsigned cs0 = (unsigned)L.csize[s][0], cs1 = (unsigned)L.csize[s][1];
-      const u64 P0 = leaf.posA * jbase + leaf.posB, S = leaf.posA * (u64)L.blk[s];
-      unsigned ec0 = s0, ec1 = s1, ec2 = s2;
-      for (unsigned n = 0; n < kDmmaElems; ++n) {
-        double v = 0.0;
-        if (n < nEl) v = __ldg(coeff + P0 + S * (u64)(ec0 + cs0 * (ec1 + cs1 * ec2)));
-        As[n * R.lda + i] = v;
-        if (++ec0 >= N0) { ec0 = 0; if (++ec1 >= N1g) { ec1 = 0; ++ec2; } }
+      GatherLi c; c.P0 = 0; c.S = 0; c.cs0 = 0; c.cs1 = 0;
+      if (i < R.nloc) {
+        const unsigned packed = __ldg(localTab + leaf0.localOffset + i);
+        const int a[3] = {(int)((packed >> 5) & 31u), (int)((packed >> 10) & 31u), (int)((packed >> 15) & 31u)};
+        const int zero[3] = {0, 0, 0};
+        const u64 jbase = layoutIndex(L, g, zero, a, i);
+        unsigned s = 0;
+        if (L.kind == DFX_NODE_LAGRANGE_DG || L.k == 0) s = (1u << g.dim) - 1u;
+        else
+          for (int j = 0; j < 3; ++j) if (a[j] > 0 && a[j] < L.k) s |= 1u << j;
+        c.cs0 = (unsigned)L.csize[s][0]; c.cs1 = (unsigned)L.csize[s][1];
+        c.P0 = leaf.posA * jbase + leaf.posB; c.S = leaf.posA * (u64)L.blk[s];
+      }
+      li[i] = c;
+    }
+    __syncthreads();
+    // eight independent loads in flight per thread (ncu: with one, 16 % of all stall samples sat on the store behind it)
+    for (int idx0 = tid; idx0 < kDmmaElems * R.kp; idx0 += 8 * 256) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = idx0 + u * 256;
+        const unsigned n = (unsigned)idx / (unsigned)R.kp, i = (unsigned)idx - n * (unsigned)R.kp;
+        v[u] = 0.0;
+        if (idx < kDmmaElems * R.kp && n < nEl && (int)i < R.nloc) {
+          unsigned q, ec0, ec1, ec2;                     // element coordinates of the CTA's n-th element (x fastest)
+          R.divN0.divmod((unsigned)(R.e0 + el0) + n, q, ec0);
+          R.divN1.divmod(q, ec2, ec1);
+          const GatherLi c = li[i];
+          v[u] = __ldg(coeff + c.P0 + c.S * (u64)(ec0 + c.cs0 * (ec1 + c.cs1 * ec2)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = idx0 + u * 256;
+        if (idx < kDmmaElems * R.kp) {
+          const unsigned n = (unsigned)idx / (unsigned)R.kp, i = (unsigned)idx - n * (unsigned)R.kp;
+          As[n * R.lda + i] = v[u];
+        }
       }
     }
     // ---- column blocks of the table ----
     for (int cb = 0; cb < R.ncolsPad; cb += kDmmaCols) {
       __syncthreads();
-      for (int idx = tid; idx < R.kp * kDmmaCols; idx += blockDim.x) {
-        const int kk = idx / kDmmaCols, nn = idx - kk * kDmmaCols;
-        Bs[kk * kDmmaLdb + nn] = __ldg(Bt + (size_t)kk * R.ncolsPad + cb + nn);
+      // 16-byte loads, eight in flight per thread (rows of the table and of Bs are 16-byte aligned: ncolsPad, cb and
+      // kDmmaLdb are even); one 8-byte load at a time left the table's L2 latency exposed in every pass (81 -> 63 ms).
+      // Two 32-column buffers filled by cp.async under the previous pass were measured too: 65.6 ms, no better.
+      {
+        constexpr int kVec = kDmmaCols / 2;
+        const int total = R.kp * kVec;
+#pragma unroll 8
+        for (int idx = tid; idx < total; idx += 256) {
+          const int kk = idx / kVec, nn = idx - kk * kVec;
+          const double2 v = __ldg(reinterpret_cast<const double2*>(Bt + (size_t)kk * R.ncolsPad + cb) + nn);
+          *reinterpret_cast<double2*>(Bs + kk * kDmmaLdb + 2 * nn) = v;
+        }
       }
       __syncthreads();
-      double acc[2][8][2];
+      constexpr int NT = kDmmaCols / 8;
+      double acc[2][NT][2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
       const int r0 = warp * 16;
       for (int ks = 0; ks < R.kp; ks += 4) {
         const double a0 = As[(r0 + grp) * R.lda + ks + tig];
         const double a1 = As[(r0 + 8 + grp) * R.lda + ks + tig];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
           const double bv = Bs[(ks + tig) * kDmmaLdb + nt * 8 + grp];
           dmma(acc[0][nt][0], acc[0][nt][1], a0, bv);
           dmma(acc[1][nt][0], acc[1][nt][1], a1, bv);
@@ -117,29 +165,24 @@ k_eval_dmma(const DevBasis* __restrict__ Bp, const __grid_constant__ DmmaArgs R,
         const unsigned n = (unsigned)(r0 + mt * 8 + grp);
         if (n >= nEl) continue;
         const u64 el = el0 + n;
-        double jinv[3] = {1, 1, 1};
-        if (R.wantJac) {
-          unsigned q, ec0, ec1, ec2;
-          R.divN0.divmod((unsigned)(R.e0 + el), q, ec0);
-          R.divN1.divmod(q, ec2, ec1);
-          jinv[0] = elementJacInv(g, 0, g.off[0] + (int)ec0);
-          if (R.dim > 1) jinv[1] = elementJacInv(g, 1, g.off[1] + (int)ec1);
-          if (R.dim > 2) jinv[2] = elementJacInv(g, 2, g.off[2] + (int)ec2);
-        }
+        const double jinv[3] = {jinvRow[mt][0], jinvRow[mt][1], jinvRow[mt][2]};
+        // row bases once per row; with one range entry per point (the scalar case) a column is a plain offset
+        const unsigned nT = (unsigned)R.ncompTotal, nvalCols = R.wantVal ? (unsigned)R.nq : 0u;
+        double* rowV = values ? values + (el * (u64)R.nq * nT + (u64)(R.compOffset + gI)) : nullptr;
+        double* rowJ = jac ? jac + (el * (u64)R.nq * nT + (u64)(R.compOffset + gI)) * (u64)R.dim : nullptr;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int col = cb + nt * 8 + 2 * tig + h;
-            if (col >= R.ncols) continue;
+            const unsigned col = (unsigned)(cb + nt * 8 + 2 * tig + h);
+            if (col >= (unsigned)R.ncols) continue;
             const double v = acc[mt][nt][h];
-            const int nvalCols = R.wantVal ? R.nq : 0;
             if (col < nvalCols) {
-              values[(el * (u64)R.nq + (u64)col) * (u64)R.ncompTotal + R.compOffset + gI] = v;
+              rowV[col * nT] = v;
             } else {
               unsigned q, d;
-              R.divDim.divmod((unsigned)(col - nvalCols), q, d);
-              jac[((el * (u64)R.nq + q) * (u64)R.ncompTotal + R.compOffset + gI) * (u64)R.dim + d] = v * jinv[d];
+              R.divDim.divmod(col - nvalCols, q, d);
+              rowJ[nT == 1u ? col - nvalCols : (q * nT) * (unsigned)R.dim + d] = v * (d == 0 ? jinv[0] : (d == 1 ? jinv[1] : jinv[2]));
             }
           }
       }
@@ -212,7 +255,7 @@ int runDmmaEval(dfx_basis* b, int node, int firstLeaf, int nLeaves, const double
     b->denseXhat.assign(xhat, xhat + (size_t)nq * dim);
     b->dDenseNode = node; b->dDenseCols = R.ncols; b->dDenseVal = R.wantVal;
   }
-  const size_t smem = ((size_t)kDmmaElems * R.lda + (size_t)R.kp * kDmmaLdb) * sizeof(double);
+  const size_t smem = ((size_t)kDmmaElems * R.lda + (size_t)R.kp * kDmmaLdb) * sizeof(double) + (size_t)R.kp * sizeof(GatherLi);
   static std::atomic<unsigned long long> configured{0};
   if (smem > 48 * 1024) { int rc = optInSharedMemory(k_eval_dmma, b->device, configured); if (rc) return rc; }
   const u64 blocks = (R.ne + kDmmaElems - 1) / kDmmaElems;
