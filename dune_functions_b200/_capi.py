@@ -127,7 +127,7 @@ SIGNATURES = {
     "dfx_owned_ranges": (C.c_int, [_vp, _pu64, _pu64, _pu64, _i32, _pi32]),
 }
 
-OP_EVALUATE, OP_INTERPOLATE, OP_INDICES, OP_HOST_BAND_KIB, OP_SMEM_GRADIENT, OP_TUNE_ROWS, OP_TUNE_SWIZZLE, OP_TUNE_STREAM_HINT, OP_TUNE_SMEM_TMA, OP_TUNE_EVAL_BLOCK, OP_TUNE_SMEM_PAIR, OP_TUNE_SMEM_BLOCKS, OP_TUNE_EVAL_Q3, OP_TUNE_SPLIT_MAP = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
+OP_EVALUATE, OP_INTERPOLATE, OP_INDICES, OP_HOST_BAND_KIB, OP_SMEM_GRADIENT, OP_TUNE_ROWS, OP_TUNE_SWIZZLE, OP_TUNE_STREAM_HINT, OP_TUNE_SMEM_TMA, OP_TUNE_EVAL_BLOCK, OP_TUNE_SMEM_PAIR, OP_TUNE_SMEM_BLOCKS, OP_TUNE_EVAL_Q3, OP_TUNE_SPLIT_MAP, OP_TUNE_PAIR_PREFETCH = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
 
 _lib = None
 

@@ -36,6 +36,7 @@ extern int g_smemGrad;
 extern int g_smemTma;
 extern int g_smemPair;
 extern int g_smemMaxBlocks;
+extern int g_pairL2Ahead;
 extern int g_evalQ3;
 extern int g_evalSplitByGroup;
 extern int g_evalSwizzle;

@@ -39,6 +39,7 @@
 namespace dfx {
 
 int g_smemPair = -1;  // DFX_OP_TUNE_SMEM_PAIR: -1 default (with gradients only), 0 off, 1 always (8 warps per block when they fit), 4 always with four
+int g_pairL2Ahead = 2;     // DFX_OP_TUNE_PAIR_PREFETCH: iterations ahead of the L2 prefetch of coefficients (0 / 1: none)
 int g_smemMaxBlocks = 0;   // DFX_OP_TUNE_SMEM_BLOCKS: > 0 caps the grid of the persistent-warp kernels (tests: many items per warp)
 
 template <int N1, int M>
@@ -48,6 +49,7 @@ struct PairTables {
 };
 
 struct PairArgs {
+  int l2ahead;            // > 0: the coefficients of the pair that many iterations ahead are prefetched into the L2
   u64 nPairs;
   unsigned e0;            // first element of the range (box-linear)
   unsigned n0, n1;        // elements per direction (offsets into the diag(J^-1) table)
@@ -186,6 +188,11 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
       if (lane == 0 && pairN < R.nPairs) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         pairLoad(pb, src + pairN * (u64)(2 * NLOC), pairBytes, bar);
+        // ... and the pair after that one starts its way from DRAM to the L2 now: under the write stream of this kernel
+        // a bulk load issued one iteration ahead still arrived late (ncu: 12 % of the stall samples on the mbarrier wait)
+        const u64 pairP = pair + (u64)R.l2ahead * stride;
+        if (R.l2ahead > 1 && pairP < R.nPairs)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + pairP * (u64)(2 * NLOC)), "r"(pairBytes) : "memory");
       }
       // ---- stage y: pencil p = a2 + N1 q0; t1[(q0 N1 + a2) S + a1] = t1[S p + a1] ----
 #pragma unroll
@@ -395,6 +402,7 @@ int runPairEval(dfx_basis* b, const FastPlan& plan, int leafId, const double* co
   if ((u64)D.grid.N[0] * D.grid.N[1] * D.grid.N[2] > 0xffffffffull) return -1;
   if (plan.jac) { int rc = ensureJinvTable(b, st); if (rc) return rc; }
   PairArgs R;
+  R.l2ahead = g_pairL2Ahead;
   R.nPairs = (e1 - e0) / 2;
   R.e0 = (unsigned)e0;
   R.n0 = (unsigned)D.grid.N[0]; R.n1 = (unsigned)D.grid.N[1];

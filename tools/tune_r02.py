@@ -137,6 +137,24 @@ def main():
         L.dfx_set_kernel_path(capi.OP_TUNE_SPLIT_MAP, -1)
         del b, x, v, f
         torch.cuda.empty_cache()
+    if "c4prefetch" in what:
+        b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
+        x = b.newVector(0.0).uniform_(-1, 1)
+        ne = b.numElements()
+        pts, _ = dfx.tensor_gauss(3, 5)
+        v = torch.empty((ne, 125, 1), dtype=torch.float64, device="cuda")
+        j = torch.empty((ne, 125, 1, 3), dtype=torch.float64, device="cuda")
+        f = dfx.makeDiscreteGlobalBasisFunction(b, x)
+        nbj = b.dimension() * 8 + v.numel() * 8 + j.numel() * 8
+        for rep in range(3):
+            for ahead in (0, 2, 3, 4):
+                L.dfx_set_kernel_path(capi.OP_TUNE_PAIR_PREFETCH, ahead)
+                ms = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), reps=7)
+                print(json.dumps({"probe": "DG4 192^3 values+gradients", "l2_prefetch_iterations_ahead": ahead, "ms": ms,
+                                  "frac": nbj / ms / 1e6 / PEAK}), flush=True)
+        L.dfx_set_kernel_path(capi.OP_TUNE_PAIR_PREFETCH, -1)
+        del b, x, v, j, f
+        torch.cuda.empty_cache()
     if "c4eval" in what:
         b = dfx.makeBasis(dfx.YaspGrid([192, 192, 192]), dfx.lagrangeDG(4))
         x = b.newVector(0.0).uniform_(-1, 1)
