@@ -146,12 +146,16 @@ def main():
         j = torch.empty((ne, 125, 1, 3), dtype=torch.float64, device="cuda")
         f = dfx.makeDiscreteGlobalBasisFunction(b, x)
         nbj = b.dimension() * 8 + v.numel() * 8 + j.numel() * 8
+        nbv = b.dimension() * 8 + v.numel() * 8
         for rep in range(3):
             for ahead in (0, 2, 3, 4):
                 L.dfx_set_kernel_path(capi.OP_TUNE_PAIR_PREFETCH, ahead)
                 ms = timeit(lambda: f.evaluate(pts, jacobians=True, out_values=v, out_jacobians=j), reps=7)
                 print(json.dumps({"probe": "DG4 192^3 values+gradients", "l2_prefetch_iterations_ahead": ahead, "ms": ms,
                                   "frac": nbj / ms / 1e6 / PEAK}), flush=True)
+                ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=7)
+                print(json.dumps({"probe": "DG4 192^3 values", "l2_prefetch_iterations_ahead": ahead, "ms": ms,
+                                  "frac": nbv / ms / 1e6 / PEAK}), flush=True)
         L.dfx_set_kernel_path(capi.OP_TUNE_PAIR_PREFETCH, -1)
         del b, x, v, j, f
         torch.cuda.empty_cache()
