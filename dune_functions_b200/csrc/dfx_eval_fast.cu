@@ -40,11 +40,13 @@ static bool regPathHas(int dim, int k, int m) {
   return (dim == 2 || dim == 3) && (k == 1 || k == 2) && (m == 2 || m == 3);
 }
 
-int g_evalBlock = 64;      // elements per block of the values-only register kernel (DFX_OP_TUNE_EVAL_BLOCK): 64 = 10 blocks of
-                           // 2 warps per SM at 96 registers (32 bytes of spill), 128 = 6 blocks of 4 warps at 80 registers
-                           // (64 / 72 bytes of spill, whose reloads ncu's source view charged 11 % of the stall samples to,
-                           // and 14 % to the one warp per block that waits for the bulk store before it exits).
-                           // Measured back to back: 512^3 6.53 -> 6.05 and 7.00 -> 6.58 ms, 256^3 0.806 -> 0.799 ms
+int g_evalBlock = 32;      // elements per block of the values-only register kernel (DFX_OP_TUNE_EVAL_BLOCK): 32 = 20 single-warp blocks per SM
+                           // at 96 registers (32 bytes of spill; no block barrier worth the name, one 6.9 KB tile per warp), 64 = 10
+                           // blocks of 2 warps, 128 = 6 blocks of 4 warps at 80 registers (64 / 72 bytes of spill, whose reloads ncu's
+                           // source view charged 11 % of the stall samples to, and 14 % to the one warp per block that waits for the
+                           // bulk store before it exits).  Measured back to back: 128 -> 64: 512^3 6.53 -> 6.05 and 7.00 -> 6.58 ms;
+                           // 64 -> 32: 256^3 0.740 -> 0.731 ms (three of three rounds), 512^3 6.12 -> 5.97, 6.64 -> 6.52, 6.93 -> 6.71 ms
+                           // (seven of eight rounds, profiles/r02_evalblock32_ab.jsonl; the GPU's thermal drift inside one run is larger)
 int g_evalStreamHint = 1;  // bulk stores of results with the L2 evict-first policy (DFX_OP_TUNE_STREAM_HINT)
 int g_evalSplitByGroup = 1;   // DFX_OP_TUNE_SPLIT_MAP: fused Taylor-Hood evaluation with whole warps per leaf group (0: every warp runs both
                               // branches; measured 0.441 -> 0.370 ms on Taylor-Hood 128^3, profiles/r02_c3eval_split_map_ab.jsonl)
@@ -199,7 +201,7 @@ __device__ __forceinline__ void gatherLeaf(const DevLayout& L, const double* __r
 #endif
 
 template <int DIM, int K, int M, bool JAC, int EPB>
-__global__ void __launch_bounds__(EPB, JAC ? 1 : (EPB == 64 ? 10 : DFX_EVAL_MINB))
+__global__ void __launch_bounds__(EPB, JAC ? 1 : (EPB == 64 ? 10 : (EPB == 32 ? 20 : DFX_EVAL_MINB)))
 k_eval_reg(const __grid_constant__ DevGrid g, const __grid_constant__ DevLayout L,
            const __grid_constant__ Tables<K + 1, M> T, const __grid_constant__ RegArgs R,
            const double* __restrict__ coeff, double* __restrict__ values, double* __restrict__ jac) {
@@ -619,6 +621,7 @@ static int launchReg(dfx_basis* b, const FastPlan& plan, const RegArgs& R, const
                      double* jac, cudaStream_t st) {
   if (JAC) return launchRegE<DIM, K, M, JAC, 64>(b, plan, R, coeff, values, jac, st);
   if (R.nGroup >= 2) return launchRegE<DIM, K, M, JAC, 32>(b, plan, R, coeff, values, jac, st);
+  if (g_evalBlock == 32) return launchRegE<DIM, K, M, JAC, 32>(b, plan, R, coeff, values, jac, st);
   if (g_evalBlock != 128) return launchRegE<DIM, K, M, JAC, 64>(b, plan, R, coeff, values, jac, st);
   return launchRegE<DIM, K, M, JAC, 128>(b, plan, R, coeff, values, jac, st);
 }
@@ -662,7 +665,7 @@ int runFastEval(dfx_basis* b, const FastPlan& plan, int firstLeaf, int nLeaves, 
     {
       // strip schedule: 3-d, whole z-layers, rows that are whole blocks, and a z-layer too big for the L2 to keep
       const u64 n0 = (u64)D.grid.N[0], n1 = (u64)D.grid.N[1], layer = n0 * n1;
-      const unsigned epb = plan.jac ? 64u : (R.nGroup >= 2 ? 32u : (g_evalBlock != 128 ? 64u : 128u));
+      const unsigned epb = plan.jac ? 64u : (R.nGroup >= 2 ? 32u : (g_evalBlock == 32 ? 32u : (g_evalBlock != 128 ? 64u : 128u)));
       int nqp = 1; for (int j = 0; j < plan.dim; ++j) nqp *= plan.m;
       const u64 layerBytes = layer * (u64)nqp * R.nGroup * sizeof(double) * (plan.jac ? 1 + plan.dim : 1);
       constexpr unsigned kStripH = 32;

@@ -112,7 +112,14 @@ def test_full_blocks_and_long_rows_against_oracle(n, k):
         pts, _ = tensor_gauss(3, m)
         assert eval_path(b, pts, False) == 1 and eval_path(b, pts, True) == 1
         v, j = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts, jacobians=True)     # 64-element blocks, bulk
-        vo = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts)                        # 128-element blocks, bulk
+        vo = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts)                        # 32-element blocks (default), bulk
+        for epb in (64, 128):                                                                # the other two tile sizes
+            capi.lib().dfx_set_kernel_path(capi.OP_TUNE_EVAL_BLOCK, epb)
+            try:
+                ve = dfx.makeDiscreteGlobalBasisFunction(b, xt).evaluate(pts)
+            finally:
+                capi.lib().dfx_set_kernel_path(capi.OP_TUNE_EVAL_BLOCK, -1)
+            assert torch.equal(ve, vo), (n, k, m, epb)
         vr, jr = o.evaluate(xr, pts, jacobians=True, nthreads=4)
         assert rel(v.cpu().numpy(), vr) <= TOL and rel(vo.cpu().numpy(), vr) <= TOL and rel(j.cpu().numpy(), jr) <= TOL
         # a sub-range that starts inside a block and ends inside another: partial tiles at both ends

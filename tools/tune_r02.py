@@ -68,7 +68,7 @@ def main():
         del b, x, v, f
         torch.cuda.empty_cache()
     if "evalblock" in what:
-        for n in (512, 256):
+        for n in (256, 512):
             b = dfx.makeBasis(dfx.YaspGrid([n, n, n]), dfx.lagrange(2))
             x = b.newVector(0.0)
             dfx.interpolate(b, x, dfx.gaussian(1.0))
@@ -76,8 +76,8 @@ def main():
             v = torch.empty((b.numElements(), 27, 1), dtype=torch.float64, device="cuda")
             f = dfx.makeDiscreteGlobalBasisFunction(b, x)
             nb = b.dimension() * 8 + v.numel() * 8
-            for rep in range(2):
-                for epb in (128, 64):
+            for rep in range(3):
+                for epb in (64, 32):
                     L.dfx_set_kernel_path(capi.OP_TUNE_EVAL_BLOCK, epb)
                     ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=10)
                     print(json.dumps({"probe": "eval Q2 values", "n": n, "elements_per_block": epb, "ms": ms, "frac": nb / ms / 1e6 / PEAK}), flush=True)
