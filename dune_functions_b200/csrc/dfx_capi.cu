@@ -577,7 +577,7 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_TUNE_ROWS) g_rowsLean = path > 0 ? path : -1;
   else if (op == DFX_OP_TUNE_EVAL_BLOCK) g_evalBlock = path == 128 ? 128 : (path == 64 ? 64 : 32);
   else if (op == DFX_OP_TUNE_SMEM_TMA) g_smemTma = path == 0 ? 0 : (path == 2 ? 2 : 1);
-  else if (op == DFX_OP_TUNE_SMEM_PAIR) g_smemPair = (path == 0 || path == 1 || path == 4) ? path : -1;
+  else if (op == DFX_OP_TUNE_SMEM_PAIR) g_smemPair = (path == 0 || path == 1 || path == 2 || path == 4) ? path : -1;
   else if (op == DFX_OP_TUNE_SMEM_BLOCKS) g_smemMaxBlocks = path > 0 ? path : 0;
   else if (op == DFX_OP_TUNE_EVAL_Q3) g_evalQ3 = path == 0 ? 0 : 1;
   else if (op == DFX_OP_TUNE_SPLIT_MAP) g_evalSplitByGroup = path == 0 ? 0 : 1;

@@ -17,8 +17,11 @@
 // collocation).
 //
 // Data flow per block iteration (WARPS consecutive pairs):
-//   per warp: TMA bulk load (mbarrier) of the pair's 2 (k+1)^3 coefficients — one 16-byte aligned run of the
-//     vector — into `pb`; the load of the warp's NEXT pair is issued as soon as stage x has read `pb`
+//   per block: ONE TMA bulk load (mbarrier) of the 8 pairs' 16 (k+1)^3 coefficients — one 16-byte aligned run of
+//     the vector, whole 128-byte lines for every k — into the landing area; the NEXT group's load is issued right
+//     behind the first barrier, when every warp is past stage x, and the group after that one is prefetched into
+//     the L2 (one load per warp, issued as soon as that warp had read its buffer, arrived late under the write
+//     stream and left the warps of a block out of step: 6.1-6.3 ms against 5.8-5.9 ms)
 //   stage x: pb -> t1[e][q0][a2][a1]      stage y: t1 -> t2[e][q1][q0][a2]            (warp-private, __syncwarp)
 //   barrier: the previous iteration's VALUES store (the older, smaller bulk group) has read its tile
 //   stage z: t2 -> u = vst[warp][e][point]; the derivative of u along the last direction stays in registers
@@ -38,7 +41,8 @@
 
 namespace dfx {
 
-int g_smemPair = -1;  // DFX_OP_TUNE_SMEM_PAIR: -1 default (with gradients only), 0 off, 1 always (8 warps per block when they fit), 4 always with four
+int g_smemPair = -1;  // DFX_OP_TUNE_SMEM_PAIR: -1 default (with gradients only), 0 off, 1 always (8 warps per block when they fit), 2 the
+                      // same with one bulk load per warp instead of one per block, 4 always with four warps
 int g_pairL2Ahead = 2;     // DFX_OP_TUNE_PAIR_PREFETCH: iterations ahead of the L2 prefetch of coefficients (0 / 1: none)
 int g_smemMaxBlocks = 0;   // DFX_OP_TUNE_SMEM_BLOCKS: > 0 caps the grid of the persistent-warp kernels (tests: many items per warp)
 
@@ -101,7 +105,9 @@ __device__ __forceinline__ void pairWait(unsigned long long* bar, unsigned parit
 
 // PERM: points ordered last-coordinate-fastest — the kernel's first contraction runs over z (tables arrive in
 // contraction order), stage x reads the natural layout with a stride, and the x / z gradient entries swap back.
-template <int N1, int M, bool GRAD, bool PERM, int WARPS>
+// BLK: the WARPS pairs of a block iteration are one run of the vector too — ONE bulk load per block (thread 0, one
+// mbarrier) into a contiguous landing area instead of one 2 (k+1)^3-entry load per warp.
+template <int N1, int M, bool GRAD, bool PERM, int WARPS, bool BLK>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 4)
 k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__ PairArgs R,
             const double* __restrict__ jinvTab, const double* __restrict__ src, double* __restrict__ values,
@@ -112,11 +118,14 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
   constexpr int dFirst = PERM ? 2 : 0, dLast = PERM ? 0 : 2;
   extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* base = smem + (size_t)warp * Lay::perWarp;
-  double* pb = base + Lay::oPB;
+  // BLK: [WARPS][2 NLOC] landing area first, then the warps' t1 / t2 / barrier slots (same total size)
+  double* base = BLK ? smem + (size_t)WARPS * (2 * Lay::NLOC) + (size_t)warp * (Lay::perWarp - 2 * Lay::NLOC) - 2 * Lay::NLOC
+                     : smem + (size_t)warp * Lay::perWarp;
+  double* pb = BLK ? smem + (size_t)warp * (2 * Lay::NLOC) : base + Lay::oPB;
   double* t1 = base + Lay::oT1;
   double* t2 = base + Lay::oT2;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + Lay::oBAR);
+  unsigned long long* bar = BLK ? reinterpret_cast<unsigned long long*>(smem + (size_t)WARPS * (2 * Lay::NLOC) + (Lay::oBAR - 2 * Lay::NLOC))
+                                : reinterpret_cast<unsigned long long*>(base + Lay::oBAR);      // BLK: warp 0's slot, for the block
   double* tileV = smem + (size_t)WARPS * Lay::perWarp;
   double* tileJ = tileV + WARPS * Lay::tileV;
   double* vst = tileV + warp * Lay::tileV;
@@ -127,12 +136,27 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
   constexpr unsigned pairBytes = (unsigned)(2 * NLOC * sizeof(double));
   u64 pair = (u64)blockIdx.x * WARPS + warp;
 
-  if (lane == 0) {
-    pairBarInit(bar);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (pair < R.nPairs) pairLoad(pb, src + pair * (u64)(2 * NLOC), pairBytes, bar);
+  // BLK: coefficients of the group's pairs (the last group may be short), by thread 0
+  auto groupLoad = [&](u64 grp) {
+    const u64 first = grp * WARPS;
+    const unsigned n = (unsigned)min((u64)WARPS, R.nPairs - first);
+    pairLoad(smem, src + first * (u64)(2 * NLOC), n * pairBytes, bar);
+  };
+  if (BLK) {
+    if (threadIdx.x == 0) {
+      pairBarInit(bar);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if ((u64)blockIdx.x < nGroups) groupLoad(blockIdx.x);
+    }
+    __syncthreads();
+  } else {
+    if (lane == 0) {
+      pairBarInit(bar);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (pair < R.nPairs) pairLoad(pb, src + pair * (u64)(2 * NLOC), pairBytes, bar);
+    }
+    __syncwarp();
   }
-  __syncwarp();
 
   // diag(J^-1) of both elements of a pair (AxisAlignedCubeGeometry::jacobianInverse, tabulated per handle), fetched
   // one pair ahead
@@ -185,7 +209,7 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
       }
       __syncwarp();
       // pb has been read: the warp's next pair can land while this one goes through stages y, z and the lines
-      if (lane == 0 && pairN < R.nPairs) {
+      if (!BLK && lane == 0 && pairN < R.nPairs) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         pairLoad(pb, src + pairN * (u64)(2 * NLOC), pairBytes, bar);
         // ... and the pair after that one starts its way from DRAM to the L2 now: under the write stream of this kernel
@@ -224,6 +248,20 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
       else { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
     }
     __syncthreads();
+    if (BLK && threadIdx.x == 0) {
+      // every warp is past stage x (it has passed the barrier): the landing area can take the next group
+      const u64 grpN = grp + gridDim.x;
+      if (grpN < nGroups) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        groupLoad(grpN);
+        const u64 grpP = grp + (u64)R.l2ahead * gridDim.x;
+        if (R.l2ahead > 1 && grpP < nGroups) {
+          const u64 first = grpP * WARPS;
+          const unsigned n = (unsigned)min((u64)WARPS, R.nPairs - first);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + first * (u64)(2 * NLOC)), "r"(n * pairBytes) : "memory");
+        }
+      }
+    }
     double gz0[EARLY ? M : 1], gz1[EARLY ? M : 1];
     if (have) {
       // ---- stage z: pencil p = q0 + M q1; t2[(q1 M + q0) S + a2] = t2[S p + a2]; point p + P3 q2 ----
@@ -345,7 +383,7 @@ k_eval_pair(const __grid_constant__ PairTables<N1, M> T, const __grid_constant__
 
 int ensureJinvTable(dfx_basis* b, cudaStream_t st);
 
-template <int N1, int M, bool GRAD, bool PERM, int WARPS>
+template <int N1, int M, bool GRAD, bool PERM, int WARPS, bool BLK>
 static int launchPairW(dfx_basis* b, const FastPlan& plan, const PairArgs& R, const double* src, double* values, double* jac,
                        cudaStream_t st) {
   using Lay = PairLayout<N1, M, GRAD>;
@@ -358,7 +396,7 @@ static int launchPairW(dfx_basis* b, const FastPlan& plan, const PairArgs& R, co
     }
   }
   const size_t smem = Lay::bytes(WARPS);
-  auto kern = k_eval_pair<N1, M, GRAD, PERM, WARPS>;
+  auto kern = k_eval_pair<N1, M, GRAD, PERM, WARPS, BLK>;
   static std::atomic<unsigned long long> configured{0};
   if (smem > 48 * 1024) { int rc = optInSharedMemory(kern, b->device, configured); if (rc) return rc; }
   int perSM = 0, sms = 0;
@@ -379,8 +417,10 @@ static int launchPair(dfx_basis* b, const FastPlan& plan, const PairArgs& R, con
   using Lay = PairLayout<N1, M, GRAD>;
   const size_t budget = 227 * 1024;
   const bool fits8 = 2 * (Lay::bytes(8) + 1024) <= budget, fits4 = 2 * (Lay::bytes(4) + 1024) <= budget;
-  if ((g_smemPair == 4 || !fits8) && fits4) return launchPairW<N1, M, GRAD, PERM, 4>(b, plan, R, src, values, jac, st);
-  if (fits8) return launchPairW<N1, M, GRAD, PERM, 8>(b, plan, R, src, values, jac, st);
+  if ((g_smemPair == 4 || !fits8) && fits4) return launchPairW<N1, M, GRAD, PERM, 4, false>(b, plan, R, src, values, jac, st);
+  // 8 warps: one bulk load per block (g_smemPair == 2: one per warp, the first version — 4-8 % slower)
+  if (fits8 && g_smemPair == 2) return launchPairW<N1, M, GRAD, PERM, 8, false>(b, plan, R, src, values, jac, st);
+  if (fits8) return launchPairW<N1, M, GRAD, PERM, 8, true>(b, plan, R, src, values, jac, st);
   return -1;
 }
 

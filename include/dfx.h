@@ -338,7 +338,7 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
 #define DFX_OP_TUNE_ROWS 5      /* lattice rows per block of the per-node interpolation kernel (-1 = default) */
 #define DFX_OP_TUNE_EVAL_BLOCK 9  /* elements per block of the values-only register evaluation kernel: 32, 64 or 128 (-1 = default: 32) */
 #define DFX_OP_TUNE_SMEM_TMA 8    /* shared-memory evaluation kernel: 0 no TMA pair loads of element-local coefficients, 2 also with gradients */
-#define DFX_OP_TUNE_SMEM_PAIR 10   /* element-local DOFs, one leaf: 0 one element per warp at a time (k_eval_smem), 1 / 4 = k_eval_pair also for values-only calls with 8 / 4 warps per block (-1 = default: k_eval_pair when gradients are asked for) */
+#define DFX_OP_TUNE_SMEM_PAIR 10   /* element-local DOFs, one leaf: 0 one element per warp at a time (k_eval_smem), 1 / 4 = k_eval_pair also for values-only calls with 8 / 4 warps per block, 2 = 8 warps with one bulk load per warp instead of one per block (-1 = default: k_eval_pair when gradients are asked for) */
 #define DFX_OP_TUNE_SMEM_BLOCKS 11 /* > 0: cap on the grid of the persistent-warp evaluation kernels (testing: many items per warp); -1 = none */
 #define DFX_OP_TUNE_EVAL_Q3 12     /* 0: continuous order 3 at 4^3 points stays on the shared-memory kernel (-1 = default: k_eval_q3) */
 #define DFX_OP_TUNE_SPLIT_MAP 13   /* fused Taylor-Hood evaluation: 0 = thread per (element, leaf) with the leaf fastest in every warp (-1 / 1 = default: whole warps per leaf group — velocity warps, pressure warp) */

@@ -747,7 +747,7 @@ def test_evaluate_shared_memory_tma_pair_loads(kernel_path, k, last_fastest):
             vr, jr = o.evaluate(c, pts, jacobians=True)
             # k_eval_pair (both elements of a pair at once; 8 / 4 warps per block, block tiles), then k_eval_smem with its TMA modes
             # grids of 2 blocks: every warp walks through 8-15 items (buffer reuse, mbarrier phases, store waits)
-            for pair, mode, cap in ((1, 1, 2), (4, 1, 2), (4, 1, 1), (-1, 1, -1), (0, 2, 2), (0, 1, 2), (0, 0, 2), (0, 1, -1)):
+            for pair, mode, cap in ((1, 1, 2), (2, 1, 2), (2, 1, 1), (4, 1, 2), (4, 1, 1), (-1, 1, -1), (0, 2, 2), (0, 1, 2), (0, 0, 2), (0, 1, -1)):
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, pair)
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, mode)
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_BLOCKS, cap)
