@@ -170,8 +170,8 @@ def main():
         nbv = b.dimension() * 8 + v.numel() * 8
         nbj = nbv + j.numel() * 8
         for rep in range(3):
-            # pair: 0 = k_eval_smem (one element per warp at a time), 4 / 1 = k_eval_pair with 4 / 8 warps per block
-            for pair, tma in ((1, 1), (2, 1)):
+            # pair: 0 = k_eval_smem (one element per warp at a time), 2 / 1 = k_eval_pair, 8 warps per block, one bulk load per warp / per block
+            for pair, tma in ((0, 1), (2, 1), (1, 1)):
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_PAIR, pair)
                 L.dfx_set_kernel_path(capi.OP_TUNE_SMEM_TMA, tma)
                 ms = timeit(lambda: f.evaluate(pts, out_values=v), reps=5)
