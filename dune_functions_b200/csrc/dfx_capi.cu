@@ -581,7 +581,7 @@ void dfx_set_kernel_path(int32_t op, int32_t path) {
   else if (op == DFX_OP_TUNE_SMEM_BLOCKS) g_smemMaxBlocks = path > 0 ? path : 0;
   else if (op == DFX_OP_TUNE_EVAL_Q3) g_evalQ3 = path == 0 ? 0 : 1;
   else if (op == DFX_OP_TUNE_SPLIT_MAP) g_evalSplitByGroup = path == 0 ? 0 : 1;
-  else if (op == DFX_OP_TUNE_PAIR_PREFETCH) g_pairL2Ahead = path < 0 ? 2 : path;
+  else if (op == DFX_OP_TUNE_PAIR_PREFETCH) g_pairL2Ahead = path < 0 ? 0 : path;
   else if (op == DFX_OP_TUNE_STREAM_HINT) g_evalStreamHint = path == 0 ? 0 : 1;
   else if (op == DFX_OP_TUNE_SWIZZLE) g_evalSwizzle = path == 0 ? 0 : (path == 2 ? 2 : 1);
 }

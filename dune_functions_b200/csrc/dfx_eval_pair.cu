@@ -19,8 +19,7 @@
 // Data flow per block iteration (WARPS consecutive pairs):
 //   per block: ONE TMA bulk load (mbarrier) of the 8 pairs' 16 (k+1)^3 coefficients — one 16-byte aligned run of
 //     the vector, whole 128-byte lines for every k — into the landing area; the NEXT group's load is issued right
-//     behind the first barrier, when every warp is past stage x, and the group after that one is prefetched into
-//     the L2 (one load per warp, issued as soon as that warp had read its buffer, arrived late under the write
+//     behind the first barrier, when every warp is past stage x (one load per warp, issued as soon as that warp had read its buffer, arrived late under the write
 //     stream and left the warps of a block out of step: 6.1-6.3 ms against 5.8-5.9 ms)
 //   stage x: pb -> t1[e][q0][a2][a1]      stage y: t1 -> t2[e][q1][q0][a2]            (warp-private, __syncwarp)
 //   barrier: the previous iteration's VALUES store (the older, smaller bulk group) has read its tile
@@ -43,7 +42,8 @@ namespace dfx {
 
 int g_smemPair = -1;  // DFX_OP_TUNE_SMEM_PAIR: -1 default (with gradients only), 0 off, 1 always (8 warps per block when they fit), 2 the
                       // same with one bulk load per warp instead of one per block, 4 always with four warps
-int g_pairL2Ahead = 2;     // DFX_OP_TUNE_PAIR_PREFETCH: iterations ahead of the L2 prefetch of coefficients (0 / 1: none)
+int g_pairL2Ahead = 0;     // DFX_OP_TUNE_PAIR_PREFETCH: iterations ahead of an L2 prefetch of coefficients (0 / 1: none).  Helped the
+                           // per-warp loads (2 ahead: 1-3 %), costs 3 % with one load per block (profiles/r02_c4eval_l2_prefetch_ab.jsonl)
 int g_smemMaxBlocks = 0;   // DFX_OP_TUNE_SMEM_BLOCKS: > 0 caps the grid of the persistent-warp kernels (tests: many items per warp)
 
 template <int N1, int M>

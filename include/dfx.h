@@ -342,7 +342,7 @@ int dfx_evaluate_path(const dfx_basis* b, int32_t subtree_node, const double* xh
 #define DFX_OP_TUNE_SMEM_BLOCKS 11 /* > 0: cap on the grid of the persistent-warp evaluation kernels (testing: many items per warp); -1 = none */
 #define DFX_OP_TUNE_EVAL_Q3 12     /* 0: continuous order 3 at 4^3 points stays on the shared-memory kernel (-1 = default: k_eval_q3) */
 #define DFX_OP_TUNE_SPLIT_MAP 13   /* fused Taylor-Hood evaluation: 0 = thread per (element, leaf) with the leaf fastest in every warp (-1 / 1 = default: whole warps per leaf group — velocity warps, pressure warp) */
-#define DFX_OP_TUNE_PAIR_PREFETCH 14 /* k_eval_pair: iterations ahead of the L2 prefetch of the coefficients (0: none; -1 = default 2) */
+#define DFX_OP_TUNE_PAIR_PREFETCH 14 /* k_eval_pair: iterations ahead of the L2 prefetch of the coefficients (-1 / 0 = default: none) */
 #define DFX_OP_TUNE_STREAM_HINT 7 /* 0: result stores without the L2 evict-first policy (-1 = default: with) */
 #define DFX_OP_TUNE_SWIZZLE 6   /* evaluation block schedule: 0 grid-view order, 2 strips whenever the shape allows, -1 / 1 = automatic */
 void dfx_set_kernel_path(int32_t op, int32_t path);
