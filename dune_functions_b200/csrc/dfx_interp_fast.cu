@@ -735,7 +735,10 @@ static bool launchRunsNode(const DevBasis& D, int q, int leafId, int comp, const
     const int s = L.order[qq];
     const u64 len = (u64)L.csize[s][0] * (u64)L.blk[s];
     const u64 runs = (u64)L.csize[s][1] * (u64)L.csize[s][2];
-    const int R = (int)std::max<u64>(1, std::min<u64>(kRunRows, 8192 / std::max<u64>(1, len)));
+    // runs per block: consecutive runs of a component are adjacent in memory, so a block's runs are ONE contiguous chunk —
+    // 32 K entries of it (was 8 K: the row set-up and its barrier weighed 15-20 % of a block; Q3 256^3 0.853 -> 0.639 ms,
+    // 128^3 0.112 -> 0.102 ms; 64 K entries / 64 runs: 0.654 / 0.101 ms)
+    const int R = (int)std::max<u64>(1, std::min<u64>(kRunRows, 32768 / std::max<u64>(1, len)));
     A.runsPerBlock[s] = R;
     A.blockStart[qq] = (unsigned)blocks;
     blocks += (runs + R - 1) / R;
